@@ -1,0 +1,184 @@
+/* moire_engine.h -- C ABI of the B200-native MCMC likelihood engine (libmoire_b200.so).
+ *
+ * This is the drop-in boundary for moire's data-parallel hot path: everything the reference's
+ * parallel-tempering driver (src/mcmc.cpp) and result packer (src/main.cpp) do with a `Chain`
+ * (src/chain.h:17-180) goes through these entry points.  One engine holds the device-resident
+ * state of a contiguous block of tempered chains on ONE GPU; the ladder shards over GPUs by
+ * creating one engine per rank with different `chain_offset`.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns 0 on success
+ * and a negative MOIRE_E* code otherwise (no exceptions cross the ABI); the caller owns every host
+ * buffer; the engine owns all device memory behind the opaque handle; one host thread per handle.
+ * There is NO CPU fallback: without a CUDA device `moire_engine_create` fails with
+ * MOIRE_ECUDA and `moire_last_error()` says why.
+ *
+ * Layouts (sample-major, like the reference's genotyping_llik_new[sample * L + locus],
+ * src/chain.cpp:1116):  per-cell arrays are [N][L]; per-sample arrays [N]; allele frequencies
+ * [L][a_pad] with a_pad = moire_engine_a_pad().  Allele sets (observed and latent) are 64-bit
+ * masks, bit a = allele a (sorted index list of the reference == ascending bit order).
+ */
+#ifndef MOIRE_ENGINE_H
+#define MOIRE_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOIRE_OK 0
+#define MOIRE_EINVAL (-1)   /* bad argument / unsupported shape */
+#define MOIRE_ECUDA (-2)    /* CUDA runtime error or no device */
+#define MOIRE_ENOMEM (-3)
+#define MOIRE_ESTATE (-4)   /* call order (e.g. step before init) */
+
+#define MOIRE_MAX_ALLELES 64 /* alleles per locus (one mask word) */
+#define MOIRE_MAX_COI 64     /* max_coi supported by the register tiers (reference LUT bound: 127) */
+
+/* The 8 Metropolis updates in the order MCMC::burnin runs them (src/mcmc.cpp:162-173). */
+enum moire_update_kind
+{
+    MOIRE_UPDATE_EPS_NEG = 0,  /* Chain::update_eps_neg   src/chain.cpp:632-695 */
+    MOIRE_UPDATE_EPS_POS = 1,  /* Chain::update_eps_pos   src/chain.cpp:567-630 */
+    MOIRE_UPDATE_P = 2,        /* Chain::update_p         src/chain.cpp:466-565 */
+    MOIRE_UPDATE_M = 3,        /* Chain::update_m         src/chain.cpp:165-224 */
+    MOIRE_UPDATE_R = 4,        /* Chain::update_r         src/chain.cpp:315-374 */
+    MOIRE_UPDATE_EFF_COI = 5,  /* Chain::update_eff_coi   src/chain.cpp:226-313 */
+    MOIRE_UPDATE_SAMPLES = 6,  /* Chain::update_samples   src/chain.cpp:697-807 */
+    MOIRE_UPDATE_MEAN_COI = 7  /* Chain::update_mean_coi  src/chain.cpp:809-856 */
+};
+
+/* Replaces GenotypingData (src/genotyping_data.h:15-24), repacked SoA + bit masks. */
+typedef struct moire_data
+{
+    int32_t num_samples;          /* N */
+    int32_t num_loci;             /* L */
+    const int32_t *num_alleles;   /* [L], 2..64 */
+    const uint64_t *obs_mask;     /* [N][L] observed alleles */
+    const uint8_t *is_missing;    /* [N][L] 0/1 */
+    const int32_t *observed_coi;  /* [N] or NULL (then derived as max_j popcount(obs_mask)) */
+} moire_data;
+
+/* POD mirror of the model half of Parameters (src/parameters.h:7-53, src/parameters.cpp:9-37). */
+typedef struct moire_params
+{
+    int32_t allow_relatedness;
+    int32_t burnin;  /* proposal-scale adaptation runs while iteration < burnin */
+    int32_t max_coi;
+    int32_t reserved0;
+    double mean_coi_shape, mean_coi_scale;
+    double max_eps_pos, eps_pos_alpha, eps_pos_beta;
+    double max_eps_neg, eps_neg_alpha, eps_neg_beta;
+    double r_alpha, r_beta;
+} moire_params;
+
+/* Full parameter state of one chain (public members of Chain, src/chain.h:84-142).
+ * Any pointer may be NULL to skip that field.  On load, fields not given keep their value and
+ * every likelihood/prior cache is rebuilt (Chain::initialize_likelihood, src/chain.cpp:1166-1223).
+ * Output-only fields are ignored on load. */
+typedef struct moire_chain_state
+{
+    int32_t *m;         /* [N] COI */
+    double *r;          /* [N] relatedness */
+    double *eps_pos;    /* [N] */
+    double *eps_neg;    /* [N] */
+    double *p;          /* [L][a_pad] allele frequencies (entries a >= A_j are 0) */
+    uint64_t *latent;   /* [N][L] latent genotypes */
+    double *lg_adj;     /* [N][L] log proposal density of the current latent genotype */
+    double *mean_coi;   /* [1] */
+    /* output only */
+    double *cell_t;     /* [N][L] transmission term (calc_transmission_process) */
+    double *cell_o;     /* [N][L] observation term (calc_observation_process); cell = t + o */
+    double *prior_eps_neg, *prior_eps_pos, *prior_coi, *prior_r; /* [N] */
+    double *mean_coi_hyper_prior;                                  /* [1] */
+} moire_chain_state;
+
+/* Acceptance counters and proposal scales returned at exit (src/main.cpp:99-136). */
+typedef struct moire_chain_diagnostics
+{
+    int32_t *eps_neg_accept, *eps_pos_accept, *m_accept, *r_accept, *m_r_accept,
+        *sample_accept;                                    /* [N] */
+    double *eps_neg_var, *eps_pos_var, *r_var, *m_r_var; /* [N] proposal sds */
+    int32_t *p_accept, *p_attempt;                       /* [L][a_pad] */
+    double *p_prop_var;                                  /* [L][a_pad] */
+    double *mean_coi_accept, *mean_coi_var;              /* [1] */
+} moire_chain_diagnostics;
+
+typedef struct moire_engine moire_engine;
+
+/* Last error of a failed call that had no handle (create), or of `e`. */
+const char *moire_last_error(void);
+const char *moire_engine_last_error(const moire_engine *e);
+
+/* Creates the engine for chains [chain_offset, chain_offset + num_chains) of a ladder, on CUDA
+ * device `device_id`, with the given starting temperatures (Chain::Chain(..., temp),
+ * src/chain.cpp:1294-1310).  `seed` keys every counter-based Philox stream; streams are keyed by
+ * GLOBAL chain id, so results do not depend on how the ladder is sharded. */
+int moire_engine_create(const moire_data *data, const moire_params *params, int32_t num_chains,
+                        int32_t chain_offset, const double *temps, int32_t device_id,
+                        uint64_t seed, moire_engine **out);
+int moire_engine_destroy(moire_engine *e);
+
+int32_t moire_engine_a_pad(const moire_engine *e);
+int32_t moire_engine_num_chains(const moire_engine *e);
+
+/* Chain::initialize_parameters with the retry loop of MCMC::MCMC (src/mcmc.cpp:68-104): draws a
+ * starting state per chain and retries chains whose log-likelihood is not finite, up to
+ * max_tries.  Per chain (arrays of num_chains, any may be NULL): number of ill-conditioned
+ * attempts, whether it is still ill-conditioned, the 1-based (sample, locus) of the first
+ * non-finite genotyping term of the LAST failed attempt (0,0 if none), and non-finite prior-term
+ * counts [num_chains][5] in the order eps_neg, eps_pos, relatedness, coi, mean_coi_hyper
+ * (Chain::first_nonfinite_genotyping_term / collect_nonfinite_prior_terms,
+ * src/chain.cpp:1032-1081). */
+int moire_engine_init_chains(moire_engine *e, int32_t max_tries, int32_t *ill_count,
+                             int32_t *still_ill, int32_t *first_bad_sample,
+                             int32_t *first_bad_locus, int32_t *prior_nonfinite);
+
+/* One sweep of all updates on every chain of the engine, in the reference's order, followed by
+ * the per-chain log-likelihood / prior reduction: the body of the OpenMP loops in
+ * MCMC::burnin / MCMC::sample (src/mcmc.cpp:159-174, 308-323).  `iteration` is what the
+ * reference passes to update_* (step during burn-in, burnin + step while sampling). */
+int moire_engine_step(moire_engine *e, int32_t iteration);
+/* A single update kind on every chain (parity tests, profiling). */
+int moire_engine_update(moire_engine *e, int32_t kind, int32_t iteration);
+/* Recompute every cell and prior from the current parameters, then reduce. */
+int moire_engine_eval_all(moire_engine *e);
+/* Per-chain sums only (Chain::calc_new_likelihood / calc_new_prior, src/chain.cpp:978-1026). */
+int moire_engine_reduce(moire_engine *e);
+
+/* Chain::get_llik / get_prior for every chain of the engine (synchronises the stream). */
+int moire_engine_get_scalars(moire_engine *e, double *llik, double *prior);
+/* Device addresses of the same [num_chains] arrays, for a collective (NCCL all-gather) that
+ * wants no host round trip.  Valid until destroy. */
+int moire_engine_device_scalars(moire_engine *e, void **dev_llik, void **dev_prior);
+/* Chain::set_temp / get_temp for every chain. */
+int moire_engine_set_temps(moire_engine *e, const double *temps);
+int moire_engine_get_temps(moire_engine *e, double *temps);
+
+int moire_engine_dump_state(moire_engine *e, int32_t chain, moire_chain_state *out);
+int moire_engine_load_state(moire_engine *e, int32_t chain, const moire_chain_state *in);
+int moire_engine_read_diagnostics(moire_engine *e, int32_t chain, moire_chain_diagnostics *out);
+/* Chain::get_llik(sample) for every sample (src/chain.cpp:1083-1097): [N]. */
+int moire_engine_read_sample_llik(moire_engine *e, int32_t chain, double *out);
+/* What MCMC::sample stores of the hot chain (src/mcmc.cpp:327-347) in one call: p [L][a_pad],
+ * m, eps_neg, eps_pos, r, per-sample llik [N], mean_coi[1], optional latent [N][L]. */
+int moire_engine_record_draw(moire_engine *e, int32_t chain, double *p, int32_t *m,
+                             double *eps_neg, double *eps_pos, double *r, double *sample_llik,
+                             double *mean_coi, uint64_t *latent);
+
+/* Work counters since create: non-missing cell likelihood evaluations, kernel launches. */
+int moire_engine_counters(moire_engine *e, uint64_t *cell_evals, uint64_t *kernel_launches);
+/* Device time (ms) spent in each update kind (CUDA events) since create; [9]: the 8 kinds + the
+ * reduction.  Enabled by moire_engine_set_timing(e, 1) (adds event records around each launch). */
+int moire_engine_set_timing(moire_engine *e, int32_t on);
+int moire_engine_read_timing(moire_engine *e, double *ms, uint64_t *launches);
+int moire_engine_synchronize(moire_engine *e);
+
+/* Philox4x32-10 block (counter, key) -> 4 words; exported so tests can pin the generator against
+ * the Random123 known-answer vectors. */
+void moire_philox4x32(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOIRE_ENGINE_H */

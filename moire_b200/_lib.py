@@ -1,0 +1,93 @@
+"""Loader for the CUDA engine's C-ABI shared library (libmoire_b200.so).
+
+The product path has no CPU fallback: if the library has not been built (``python -c "import
+__graft_entry__ as g; g.build()"`` or ``make -C moire_b200/csrc``) importing fails loudly, and if
+there is no CUDA device ``moire_engine_create`` returns MOIRE_ECUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmoire_b200.so")
+
+vp, i32, u64, dbl = C.c_void_p, C.c_int32, C.c_uint64, C.c_double
+
+
+class MoireData(C.Structure):
+    _fields_ = [("num_samples", i32), ("num_loci", i32), ("num_alleles", vp), ("obs_mask", vp),
+                ("is_missing", vp), ("observed_coi", vp)]
+
+
+class MoireParams(C.Structure):
+    _fields_ = [("allow_relatedness", i32), ("burnin", i32), ("max_coi", i32), ("reserved0", i32),
+                ("mean_coi_shape", dbl), ("mean_coi_scale", dbl),
+                ("max_eps_pos", dbl), ("eps_pos_alpha", dbl), ("eps_pos_beta", dbl),
+                ("max_eps_neg", dbl), ("eps_neg_alpha", dbl), ("eps_neg_beta", dbl),
+                ("r_alpha", dbl), ("r_beta", dbl)]
+
+
+class MoireChainState(C.Structure):
+    _fields_ = [(n, vp) for n in ("m", "r", "eps_pos", "eps_neg", "p", "latent", "lg_adj",
+                                  "mean_coi", "cell_t", "cell_o", "prior_eps_neg",
+                                  "prior_eps_pos", "prior_coi", "prior_r",
+                                  "mean_coi_hyper_prior")]
+
+
+class MoireChainDiagnostics(C.Structure):
+    _fields_ = [(n, vp) for n in ("eps_neg_accept", "eps_pos_accept", "m_accept", "r_accept",
+                                  "m_r_accept", "sample_accept", "eps_neg_var", "eps_pos_var",
+                                  "r_var", "m_r_var", "p_accept", "p_attempt", "p_prop_var",
+                                  "mean_coi_accept", "mean_coi_var")]
+
+
+# every symbol include/moire_engine.h declares: (restype, argtypes)
+ENGINE_SYMBOLS = {
+    "moire_last_error": (C.c_char_p, []),
+    "moire_engine_last_error": (C.c_char_p, [vp]),
+    "moire_engine_create": (C.c_int, [C.POINTER(MoireData), C.POINTER(MoireParams), i32, i32, vp,
+                                      i32, u64, C.POINTER(vp)]),
+    "moire_engine_destroy": (C.c_int, [vp]),
+    "moire_engine_a_pad": (i32, [vp]),
+    "moire_engine_num_chains": (i32, [vp]),
+    "moire_engine_init_chains": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
+    "moire_engine_step": (C.c_int, [vp, i32]),
+    "moire_engine_update": (C.c_int, [vp, i32, i32]),
+    "moire_engine_eval_all": (C.c_int, [vp]),
+    "moire_engine_reduce": (C.c_int, [vp]),
+    "moire_engine_get_scalars": (C.c_int, [vp, vp, vp]),
+    "moire_engine_device_scalars": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
+    "moire_engine_set_temps": (C.c_int, [vp, vp]),
+    "moire_engine_get_temps": (C.c_int, [vp, vp]),
+    "moire_engine_dump_state": (C.c_int, [vp, i32, C.POINTER(MoireChainState)]),
+    "moire_engine_load_state": (C.c_int, [vp, i32, C.POINTER(MoireChainState)]),
+    "moire_engine_read_diagnostics": (C.c_int, [vp, i32, C.POINTER(MoireChainDiagnostics)]),
+    "moire_engine_read_sample_llik": (C.c_int, [vp, i32, vp]),
+    "moire_engine_record_draw": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "moire_engine_counters": (C.c_int, [vp, vp, vp]),
+    "moire_engine_set_timing": (C.c_int, [vp, i32]),
+    "moire_engine_read_timing": (C.c_int, [vp, vp, vp]),
+    "moire_engine_synchronize": (C.c_int, [vp]),
+    "moire_philox4x32": (None, [vp, vp, vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Returns the ctypes handle of libmoire_b200.so with every prototype set."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA engine first "
+            "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in ENGINE_SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

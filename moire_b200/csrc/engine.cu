@@ -1,0 +1,841 @@
+// libmoire_b200.so: engine object + C ABI (include/moire_engine.h).
+//
+// Host-side responsibilities only: own the device allocations, lay the data out, launch the
+// kernels of kernels.cuh on one stream, move small results.  No arithmetic of the likelihood path
+// runs on the host: there is no CPU fallback (a missing device is an error).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/moire_engine.h"
+#include "kernels.cuh"
+
+namespace
+{
+thread_local std::string g_last_error;
+
+struct CudaError
+{
+    std::string msg;
+};
+
+#define CUDA_TRY(expr)                                                                        \
+    do                                                                                        \
+    {                                                                                         \
+        cudaError_t err__ = (expr);                                                           \
+        if (err__ != cudaSuccess)                                                             \
+            throw CudaError{std::string(#expr) + ": " + cudaGetErrorString(err__) + " (" +    \
+                            __FILE__ + ":" + std::to_string(__LINE__) + ")"};                 \
+    } while (0)
+
+struct InvalidArg
+{
+    std::string msg;
+};
+
+template <class T>
+struct DevBuf
+{
+    T *ptr = nullptr;
+    size_t n = 0;
+    void alloc(size_t count)
+    {
+        n = count;
+        CUDA_TRY(cudaMalloc(&ptr, std::max<size_t>(count, 1) * sizeof(T)));
+        CUDA_TRY(cudaMemset(ptr, 0, std::max<size_t>(count, 1) * sizeof(T)));
+    }
+    void upload(const T *src, size_t count, cudaStream_t s)
+    {
+        CUDA_TRY(cudaMemcpyAsync(ptr, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void release()
+    {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+    }
+};
+
+double log_binom_exact(unsigned n, unsigned k)
+{
+    // boost::math::binomial_coefficient<double> returns C(n,k) as an integer-valued double
+    // (src/sampler.cpp:270,305,327,330 take its log).
+    if (k > n) return -INFINITY;
+    if (k > n - k) k = n - k;
+    long double c = 1.0L;
+    for (unsigned i = 1; i <= k; ++i)
+    {
+        c = c * (long double)(n - k + i) / (long double)i;
+        c = floorl(c + 0.5L);
+    }
+    return std::log((double)c);
+}
+}  // namespace
+
+struct moire_engine
+{
+    moire::View v{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool initialised = false;
+    bool timing = false;
+    std::string last_error;
+    uint64_t launches = 0;
+    int tile_S = 1, tiles_per_chain = 1;
+    size_t sample_smem = 0, p_smem = 0;
+
+    // allocations
+    DevBuf<unsigned long long> obs, latent, evals;
+    DevBuf<unsigned char> missing;
+    DevBuf<int> nall, aclass, avals, obs_coi, m, acc6, p_acc, p_att, active;
+    DevBuf<double> logC, lgam, lgadj, cellT, cellO, persample, p, p_sd, perchain, scratchN;
+
+    struct TimedLaunch
+    {
+        cudaEvent_t a, b;
+        int kind;
+    };
+    std::vector<TimedLaunch> pending;
+    double kind_ms[9] = {0};
+    uint64_t kind_launches[9] = {0};
+
+    ~moire_engine()
+    {
+        cudaSetDevice(device);
+        for (auto &t : pending)
+        {
+            cudaEventDestroy(t.a);
+            cudaEventDestroy(t.b);
+        }
+        obs.release(); latent.release(); evals.release(); missing.release(); nall.release();
+        aclass.release(); avals.release(); obs_coi.release(); m.release(); acc6.release();
+        p_acc.release(); p_att.release(); active.release(); logC.release(); lgam.release();
+        lgadj.release(); cellT.release(); cellO.release(); persample.release(); p.release();
+        p_sd.release(); perchain.release(); scratchN.release();
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    void bind() { CUDA_TRY(cudaSetDevice(device)); }
+
+    void create(const moire_data *d, const moire_params *prm, int T, int chain_offset,
+                const double *temps, int device_id, uint64_t seed)
+    {
+        if (!d || !prm || !temps) throw InvalidArg{"null argument"};
+        const int N = d->num_samples, L = d->num_loci;
+        if (N < 1 || L < 1 || T < 1) throw InvalidArg{"num_samples, num_loci, num_chains must be >= 1"};
+        if (!d->num_alleles || !d->obs_mask || !d->is_missing) throw InvalidArg{"null data array"};
+        if (prm->max_coi < 1 || prm->max_coi > MOIRE_MAX_COI)
+            throw InvalidArg{"max_coi must be in 1.." + std::to_string(MOIRE_MAX_COI)};
+        if (chain_offset < 0 || chain_offset + T > 65535) throw InvalidArg{"chain id out of range"};
+        if (L > 65534) throw InvalidArg{"num_loci > 65534 unsupported"};
+        int amax = 0;
+        std::vector<int> avals_h, aclass_h(L);
+        for (int j = 0; j < L; ++j)
+        {
+            const int A = d->num_alleles[j];
+            if (A < 2 || A > MOIRE_MAX_ALLELES)
+                throw InvalidArg{"num_alleles[" + std::to_string(j) + "] = " + std::to_string(A) +
+                                 " outside 2.." + std::to_string(MOIRE_MAX_ALLELES)};
+            amax = std::max(amax, A);
+            auto it = std::find(avals_h.begin(), avals_h.end(), A);
+            if (it == avals_h.end())
+            {
+                avals_h.push_back(A);
+                it = avals_h.end() - 1;
+            }
+            aclass_h[j] = (int)(it - avals_h.begin());
+        }
+        std::vector<int> coi_h(N, 0);
+        for (int i = 0; i < N; ++i)
+        {
+            for (int j = 0; j < L; ++j)
+            {
+                const unsigned long long o = d->obs_mask[(size_t)i * L + j];
+                const int A = d->num_alleles[j];
+                if (A < 64 && (o >> A) != 0) throw InvalidArg{"obs_mask has bits above num_alleles"};
+                coi_h[i] = std::max(coi_h[i], __builtin_popcountll(o));
+            }
+            if (d->observed_coi) coi_h[i] = d->observed_coi[i];
+        }
+
+        int ndev = 0;
+        cudaError_t e0 = cudaGetDeviceCount(&ndev);
+        if (e0 != cudaSuccess || ndev == 0)
+            throw CudaError{std::string("no CUDA device: ") +
+                            (e0 == cudaSuccess ? "device count is 0" : cudaGetErrorString(e0)) +
+                            " -- libmoire_b200 has no CPU fallback"};
+        if (device_id < 0 || device_id >= ndev) throw InvalidArg{"device_id out of range"};
+        device = device_id;
+        bind();
+        CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+
+        v.N = N; v.L = L; v.T = T;
+        v.AP = (amax + 3) / 4 * 4;
+        v.nA = (int)avals_h.size();
+        v.allow_rel = prm->allow_relatedness != 0;
+        v.burnin = prm->burnin;
+        v.max_coi = prm->max_coi;
+        v.chain_offset = chain_offset;
+        v.seed = seed;
+        v.mean_coi_shape = prm->mean_coi_shape;
+        v.mean_coi_scale = prm->mean_coi_scale;
+        v.lg_shape = std::lgamma(prm->mean_coi_shape);
+        v.l_scale = std::log(prm->mean_coi_scale);
+        v.max_eps_pos = prm->max_eps_pos; v.eps_pos_a = prm->eps_pos_alpha; v.eps_pos_b = prm->eps_pos_beta;
+        v.max_eps_neg = prm->max_eps_neg; v.eps_neg_a = prm->eps_neg_alpha; v.eps_neg_b = prm->eps_neg_beta;
+        v.r_a = prm->r_alpha; v.r_b = prm->r_beta;
+        auto lbeta = [](double a, double b) { return std::lgamma(a) + std::lgamma(b) - std::lgamma(a + b); };
+        v.eps_pos_lbeta = lbeta(v.eps_pos_a, v.eps_pos_b);
+        v.eps_neg_lbeta = lbeta(v.eps_neg_a, v.eps_neg_b);
+        v.r_lbeta = lbeta(v.r_a, v.r_b);
+
+        const size_t NL = (size_t)N * L, TNL = (size_t)T * NL, TN = (size_t)T * N;
+        const size_t TLA = (size_t)T * L * v.AP;
+        obs.alloc(NL); missing.alloc(NL); nall.alloc(L); aclass.alloc(L); avals.alloc(v.nA);
+        obs_coi.alloc(N); logC.alloc(moire::kLogCDim * moire::kLogCDim); lgam.alloc(128);
+        latent.alloc(TNL); lgadj.alloc(TNL); cellT.alloc(TNL); cellO.alloc(TNL);
+        m.alloc(TN); acc6.alloc(6 * TN); persample.alloc(14 * TN);
+        p.alloc(TLA); p_sd.alloc(TLA); p_acc.alloc(TLA); p_att.alloc(TLA);
+        perchain.alloc(7 * (size_t)T); active.alloc(T); evals.alloc(1); scratchN.alloc(N);
+
+        std::vector<double> logC_h(moire::kLogCDim * moire::kLogCDim, -INFINITY), lgam_h(128);
+        for (int n = 0; n < moire::kLogCDim; ++n)
+            for (int k = 0; k <= n; ++k) logC_h[n * moire::kLogCDim + k] = log_binom_exact(n, k);
+        for (int i = 0; i < 128; ++i) lgam_h[i] = std::lgamma((double)(i + 1));  // sampler.cpp:22-25
+
+        obs.upload((const unsigned long long *)d->obs_mask, NL, stream);
+        missing.upload(d->is_missing, NL, stream);
+        nall.upload(d->num_alleles, L, stream);
+        aclass.upload(aclass_h.data(), L, stream);
+        avals.upload(avals_h.data(), v.nA, stream);
+        obs_coi.upload(coi_h.data(), N, stream);
+        logC.upload(logC_h.data(), logC_h.size(), stream);
+        lgam.upload(lgam_h.data(), 128, stream);
+
+        v.obs = obs.ptr; v.missing = missing.ptr; v.nall = nall.ptr; v.aclass = aclass.ptr;
+        v.avals = avals.ptr; v.obs_coi = obs_coi.ptr; v.logC = logC.ptr; v.lgam = lgam.ptr;
+        v.latent = latent.ptr; v.lgadj = lgadj.ptr; v.cellT = cellT.ptr; v.cellO = cellO.ptr;
+        v.m = m.ptr;
+        double *ps = persample.ptr;
+        v.r = ps + 0 * TN; v.log_r = ps + 1 * TN; v.log_1mr = ps + 2 * TN;
+        v.eps_pos = ps + 3 * TN; v.eps_neg = ps + 4 * TN;
+        v.sd_eps_neg = ps + 5 * TN; v.sd_eps_pos = ps + 6 * TN; v.sd_r = ps + 7 * TN; v.sd_mr = ps + 8 * TN;
+        v.pr_eps_neg = ps + 9 * TN; v.pr_eps_pos = ps + 10 * TN; v.pr_coi = ps + 11 * TN; v.pr_r = ps + 12 * TN;
+        int *ac = acc6.ptr;
+        v.acc_eps_neg = ac + 0 * TN; v.acc_eps_pos = ac + 1 * TN; v.acc_m = ac + 2 * TN;
+        v.acc_r = ac + 3 * TN; v.acc_mr = ac + 4 * TN; v.acc_samples = ac + 5 * TN;
+        v.p = p.ptr; v.p_sd = p_sd.ptr; v.p_acc = p_acc.ptr; v.p_att = p_att.ptr;
+        double *pc = perchain.ptr;
+        v.mean_coi = pc + 0 * T; v.mean_coi_sd = pc + 1 * T; v.mean_coi_acc = pc + 2 * T;
+        v.hyper = pc + 3 * T; v.temp = pc + 4 * T; v.llik = pc + 5 * T; v.prior = pc + 6 * T;
+        v.active = active.ptr; v.evals = evals.ptr;
+        CUDA_TRY(cudaMemcpyAsync(v.temp, temps, T * sizeof(double), cudaMemcpyHostToDevice, stream));
+
+        // tile shape of the per-sample kernel: S consecutive samples, S*L <= kThreads*kCpt cells
+        const int max_cells = moire::kThreads * moire::kCpt;
+        if (L > max_cells)
+            throw InvalidArg{"num_loci > " + std::to_string(max_cells) + " unsupported by the sample kernel"};
+        tile_S = std::max(1, std::min({moire::kMaxTileSamples, max_cells / L, N}));
+        tiles_per_chain = (N + tile_S - 1) / tile_S;
+        sample_smem = moire::sample_kernel_smem(tile_S, L, v.nA);
+        p_smem = moire::p_kernel_smem(N, v.AP);
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        const size_t smem_cap = prop.sharedMemPerBlockOptin;
+        if (sample_smem > smem_cap || p_smem > smem_cap)
+            throw InvalidArg{"problem shape needs " + std::to_string(std::max(sample_smem, p_smem)) +
+                             " B of shared memory per block; device allows " + std::to_string(smem_cap)};
+        set_smem_attr();
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+
+    void set_smem_attr()
+    {
+        using namespace moire;
+        const int ss = (int)sample_smem;
+        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EPS_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
+        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EPS_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
+        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
+        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
+        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EFF_COI>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
+        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_SAMPLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
+        CUDA_TRY(cudaFuncSetAttribute(k_update_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
+    }
+
+    struct Timed
+    {
+        moire_engine *e;
+        cudaEvent_t a = nullptr, b = nullptr;
+        int kind;
+        Timed(moire_engine *e_, int kind_) : e(e_), kind(kind_)
+        {
+            ++e->launches;
+            if (e->timing)
+            {
+                CUDA_TRY(cudaEventCreate(&a));
+                CUDA_TRY(cudaEventCreate(&b));
+                CUDA_TRY(cudaEventRecord(a, e->stream));
+            }
+        }
+        void done()
+        {
+            CUDA_TRY(cudaGetLastError());
+            if (e->timing)
+            {
+                CUDA_TRY(cudaEventRecord(b, e->stream));
+                e->pending.push_back({a, b, kind});
+            }
+        }
+    };
+
+    void resolve_timing()
+    {
+        if (pending.empty()) return;
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        for (auto &t : pending)
+        {
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, t.a, t.b));
+            kind_ms[t.kind] += ms;
+            kind_launches[t.kind] += 1;
+            cudaEventDestroy(t.a);
+            cudaEventDestroy(t.b);
+        }
+        pending.clear();
+    }
+
+    template <int KIND>
+    void launch_sample(int iteration)
+    {
+        Timed tm(this, KIND);
+        moire::k_update_sample<KIND><<<v.T * tiles_per_chain, moire::kThreads, sample_smem, stream>>>(
+            v, iteration, tile_S, tiles_per_chain);
+        tm.done();
+    }
+
+    void update(int kind, int iteration)
+    {
+        using namespace moire;
+        switch (kind)
+        {
+            case MOIRE_UPDATE_EPS_NEG: launch_sample<KIND_EPS_NEG>(iteration); break;
+            case MOIRE_UPDATE_EPS_POS: launch_sample<KIND_EPS_POS>(iteration); break;
+            case MOIRE_UPDATE_M: launch_sample<KIND_M>(iteration); break;
+            case MOIRE_UPDATE_R: launch_sample<KIND_R>(iteration); break;
+            case MOIRE_UPDATE_EFF_COI: launch_sample<KIND_EFF_COI>(iteration); break;
+            case MOIRE_UPDATE_SAMPLES: launch_sample<KIND_SAMPLES>(iteration); break;
+            case MOIRE_UPDATE_P:
+            {
+                Timed tm(this, kind);
+                k_update_p<<<v.T * v.L, kPThreads, p_smem, stream>>>(v, iteration);
+                tm.done();
+                break;
+            }
+            case MOIRE_UPDATE_MEAN_COI:
+            {
+                Timed tm(this, kind);
+                k_update_mean_coi<<<v.T, kThreads, 0, stream>>>(v, iteration);
+                tm.done();
+                break;
+            }
+            default: throw InvalidArg{"unknown update kind"};
+        }
+    }
+
+    void reduce()
+    {
+        Timed tm(this, 8);
+        moire::k_reduce<<<v.T, 1024, 0, stream>>>(v);
+        tm.done();
+    }
+
+    // MCMC::burnin / MCMC::sample loop body (src/mcmc.cpp:162-173, 311-322)
+    void step(int iteration)
+    {
+        update(MOIRE_UPDATE_EPS_NEG, iteration);
+        update(MOIRE_UPDATE_EPS_POS, iteration);
+        update(MOIRE_UPDATE_P, iteration);
+        update(MOIRE_UPDATE_M, iteration);
+        if (v.allow_rel)
+        {
+            update(MOIRE_UPDATE_R, iteration);
+            update(MOIRE_UPDATE_EFF_COI, iteration);
+        }
+        update(MOIRE_UPDATE_SAMPLES, iteration);
+        update(MOIRE_UPDATE_MEAN_COI, iteration);
+        reduce();
+    }
+
+    void eval_all(int chain_sel, int use_active)
+    {
+        using namespace moire;
+        const size_t nchains = chain_sel < 0 ? v.T : 1;
+        {
+            const size_t total = nchains * v.N;
+            ++launches;
+            k_eval_priors<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(v, chain_sel, use_active);
+            CUDA_TRY(cudaGetLastError());
+        }
+        {
+            const size_t total = nchains * (size_t)v.N * v.L;
+            ++launches;
+            k_eval_cells<<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
+                v, chain_sel, use_active);
+            CUDA_TRY(cudaGetLastError());
+        }
+        reduce();
+    }
+
+    void get_scalars(double *llik, double *prior)
+    {
+        if (llik) CUDA_TRY(cudaMemcpyAsync(llik, v.llik, v.T * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        if (prior) CUDA_TRY(cudaMemcpyAsync(prior, v.prior, v.T * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+
+    void init_chains(int max_tries, int32_t *ill_count, int32_t *still_ill, int32_t *bad_sample,
+                     int32_t *bad_locus, int32_t *prior_nonfinite)
+    {
+        using namespace moire;
+        const int T = v.T, N = v.N, L = v.L;
+        std::vector<int> act(T, 1), ill(T, 0);
+        std::vector<double> llik(T);
+        if (bad_sample) std::fill(bad_sample, bad_sample + T, 0);
+        if (bad_locus) std::fill(bad_locus, bad_locus + T, 0);
+        if (prior_nonfinite) std::fill(prior_nonfinite, prior_nonfinite + 5 * T, 0);
+        for (int attempt = 0; attempt <= max_tries; ++attempt)
+        {
+            CUDA_TRY(cudaMemcpyAsync(v.active, act.data(), T * sizeof(int), cudaMemcpyHostToDevice, stream));
+            const size_t TN = (size_t)T * N, TNL = TN * L, TL = (size_t)T * L;
+            launches += 3;
+            k_init_samples<<<(unsigned)((TN + 255) / 256), 256, 0, stream>>>(v, attempt);
+            k_init_latent<<<(unsigned)((TNL + 255) / 256), 256, 0, stream>>>(v, attempt);
+            k_init_p<<<(unsigned)((TL + 127) / 128), 128, 0, stream>>>(v, attempt);
+            CUDA_TRY(cudaGetLastError());
+            eval_all(-1, 1);
+            get_scalars(llik.data(), nullptr);
+            bool any = false;
+            for (int t = 0; t < T; ++t)
+            {
+                if (!act[t]) continue;
+                if (std::isfinite(llik[t]))
+                {
+                    act[t] = 0;
+                    continue;
+                }
+                ++ill[t];
+                any = true;
+                diagnose(t, bad_sample ? &bad_sample[t] : nullptr, bad_locus ? &bad_locus[t] : nullptr,
+                         prior_nonfinite ? &prior_nonfinite[5 * t] : nullptr);
+            }
+            if (!any) break;
+        }
+        for (int t = 0; t < T; ++t)
+        {
+            if (ill_count) ill_count[t] = ill[t];
+            if (still_ill) still_ill[t] = act[t];
+        }
+        initialised = true;
+    }
+
+    // first_nonfinite_genotyping_term / collect_nonfinite_prior_terms (src/chain.cpp:1032-1081);
+    // failure path only, so the scan runs on dumped arrays.
+    void diagnose(int t, int32_t *bad_sample, int32_t *bad_locus, int32_t *prior_counts)
+    {
+        const size_t NL = (size_t)v.N * v.L;
+        std::vector<double> T_(NL), O_(NL), pr(4 * (size_t)v.N);
+        double hyper = 0;
+        CUDA_TRY(cudaMemcpyAsync(T_.data(), v.cellT + t * NL, NL * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(O_.data(), v.cellO + t * NL, NL * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        const double *src[4] = {v.pr_eps_neg, v.pr_eps_pos, v.pr_r, v.pr_coi};
+        for (int q = 0; q < 4; ++q)
+            CUDA_TRY(cudaMemcpyAsync(pr.data() + (size_t)q * v.N, src[q] + (size_t)t * v.N,
+                                     v.N * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(&hyper, v.hyper + t, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (bad_sample && bad_locus)
+        {
+            *bad_sample = *bad_locus = 0;
+            for (size_t c = 0; c < NL; ++c)
+            {
+                if (!std::isfinite(T_[c] + O_[c]))
+                {
+                    *bad_sample = (int)(c / v.L) + 1;
+                    *bad_locus = (int)(c % v.L) + 1;
+                    break;
+                }
+            }
+        }
+        if (prior_counts)
+        {
+            for (int q = 0; q < 4; ++q)
+                for (int i = 0; i < v.N; ++i)
+                    if (!std::isfinite(pr[(size_t)q * v.N + i])) ++prior_counts[q];
+            if (!std::isfinite(hyper)) ++prior_counts[4];
+        }
+    }
+
+    template <class T>
+    void d2h(T *dst, const T *src, size_t n)
+    {
+        if (dst) CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+    }
+    template <class T>
+    void h2d(T *dst, const T *src, size_t n)
+    {
+        if (src) CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+    }
+
+    void dump_state(int t, moire_chain_state *o)
+    {
+        const size_t N = v.N, NL = N * v.L, LA = (size_t)v.L * v.AP;
+        d2h(o->m, v.m + t * N, N);
+        d2h(o->r, v.r + t * N, N);
+        d2h(o->eps_pos, v.eps_pos + t * N, N);
+        d2h(o->eps_neg, v.eps_neg + t * N, N);
+        d2h(o->p, v.p + t * LA, LA);
+        d2h((unsigned long long *)o->latent, v.latent + t * NL, NL);
+        d2h(o->lg_adj, v.lgadj + t * NL, NL);
+        d2h(o->mean_coi, v.mean_coi + t, 1);
+        d2h(o->cell_t, v.cellT + t * NL, NL);
+        d2h(o->cell_o, v.cellO + t * NL, NL);
+        d2h(o->prior_eps_neg, v.pr_eps_neg + t * N, N);
+        d2h(o->prior_eps_pos, v.pr_eps_pos + t * N, N);
+        d2h(o->prior_coi, v.pr_coi + t * N, N);
+        d2h(o->prior_r, v.pr_r + t * N, N);
+        d2h(o->mean_coi_hyper_prior, v.hyper + t, 1);
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+
+    void load_state(int t, const moire_chain_state *in)
+    {
+        const size_t N = v.N, NL = N * v.L, LA = (size_t)v.L * v.AP;
+        h2d(v.m + t * N, in->m, N);
+        h2d(v.r + t * N, in->r, N);
+        h2d(v.eps_pos + t * N, in->eps_pos, N);
+        h2d(v.eps_neg + t * N, in->eps_neg, N);
+        h2d(v.p + t * LA, in->p, LA);
+        h2d(v.latent + t * NL, (const unsigned long long *)in->latent, NL);
+        h2d(v.lgadj + t * NL, in->lg_adj, NL);
+        h2d(v.mean_coi + t, in->mean_coi, 1);
+        CUDA_TRY(cudaStreamSynchronize(stream));  // host buffers may go away after return
+        eval_all(t, 0);
+        initialised = true;
+    }
+
+    void read_diag(int t, moire_chain_diagnostics *o)
+    {
+        const size_t N = v.N, LA = (size_t)v.L * v.AP;
+        d2h(o->eps_neg_accept, v.acc_eps_neg + t * N, N);
+        d2h(o->eps_pos_accept, v.acc_eps_pos + t * N, N);
+        d2h(o->m_accept, v.acc_m + t * N, N);
+        d2h(o->r_accept, v.acc_r + t * N, N);
+        d2h(o->m_r_accept, v.acc_mr + t * N, N);
+        d2h(o->sample_accept, v.acc_samples + t * N, N);
+        d2h(o->eps_neg_var, v.sd_eps_neg + t * N, N);
+        d2h(o->eps_pos_var, v.sd_eps_pos + t * N, N);
+        d2h(o->r_var, v.sd_r + t * N, N);
+        d2h(o->m_r_var, v.sd_mr + t * N, N);
+        d2h(o->p_accept, v.p_acc + t * LA, LA);
+        d2h(o->p_attempt, v.p_att + t * LA, LA);
+        d2h(o->p_prop_var, v.p_sd + t * LA, LA);
+        d2h(o->mean_coi_accept, v.mean_coi_acc + t, 1);
+        d2h(o->mean_coi_var, v.mean_coi_sd + t, 1);
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+
+    void sample_llik_async(int t)
+    {
+        ++launches;
+        moire::k_sample_llik<<<(v.N + 127) / 128, 128, 0, stream>>>(v, t, scratchN.ptr);
+        CUDA_TRY(cudaGetLastError());
+    }
+};
+
+// ---- C ABI -------------------------------------------------------------------------------------
+namespace
+{
+template <class F>
+int guarded(moire_engine *e, F &&f)
+{
+    try
+    {
+        if (e) e->bind();
+        f();
+        return MOIRE_OK;
+    }
+    catch (const CudaError &ce)
+    {
+        g_last_error = ce.msg;
+        if (e) e->last_error = ce.msg;
+        return MOIRE_ECUDA;
+    }
+    catch (const InvalidArg &ia)
+    {
+        g_last_error = ia.msg;
+        if (e) e->last_error = ia.msg;
+        return MOIRE_EINVAL;
+    }
+    catch (const std::bad_alloc &)
+    {
+        g_last_error = "host allocation failed";
+        if (e) e->last_error = g_last_error;
+        return MOIRE_ENOMEM;
+    }
+    catch (...)
+    {
+        g_last_error = "unknown error";
+        if (e) e->last_error = g_last_error;
+        return MOIRE_EINVAL;
+    }
+}
+
+void need_chain(moire_engine *e, int chain)
+{
+    if (!e) throw InvalidArg{"null engine"};
+    if (chain < 0 || chain >= e->v.T) throw InvalidArg{"chain index out of range"};
+}
+}  // namespace
+
+extern "C"
+{
+const char *moire_last_error(void) { return g_last_error.c_str(); }
+
+const char *moire_engine_last_error(const moire_engine *e) { return e ? e->last_error.c_str() : ""; }
+
+int moire_engine_create(const moire_data *data, const moire_params *params, int32_t num_chains,
+                        int32_t chain_offset, const double *temps, int32_t device_id,
+                        uint64_t seed, moire_engine **out)
+{
+    if (!out)
+    {
+        g_last_error = "null out pointer";
+        return MOIRE_EINVAL;
+    }
+    *out = nullptr;
+    moire_engine *e = nullptr;
+    const int rc = guarded(nullptr, [&] {
+        e = new moire_engine();
+        e->create(data, params, num_chains, chain_offset, temps, device_id, seed);
+    });
+    if (rc != MOIRE_OK)
+    {
+        delete e;
+        return rc;
+    }
+    *out = e;
+    return MOIRE_OK;
+}
+
+int moire_engine_destroy(moire_engine *e)
+{
+    delete e;
+    return MOIRE_OK;
+}
+
+int32_t moire_engine_a_pad(const moire_engine *e) { return e ? e->v.AP : 0; }
+int32_t moire_engine_num_chains(const moire_engine *e) { return e ? e->v.T : 0; }
+
+int moire_engine_init_chains(moire_engine *e, int32_t max_tries, int32_t *ill_count,
+                             int32_t *still_ill, int32_t *first_bad_sample,
+                             int32_t *first_bad_locus, int32_t *prior_nonfinite)
+{
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        e->init_chains(max_tries, ill_count, still_ill, first_bad_sample, first_bad_locus,
+                       prior_nonfinite);
+    });
+}
+
+int moire_engine_step(moire_engine *e, int32_t iteration)
+{
+    if (e && !e->initialised)
+    {
+        e->last_error = g_last_error = "step before init_chains/load_state";
+        return MOIRE_ESTATE;
+    }
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        e->step(iteration);
+    });
+}
+
+int moire_engine_update(moire_engine *e, int32_t kind, int32_t iteration)
+{
+    if (e && !e->initialised)
+    {
+        e->last_error = g_last_error = "update before init_chains/load_state";
+        return MOIRE_ESTATE;
+    }
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        e->update(kind, iteration);
+    });
+}
+
+int moire_engine_eval_all(moire_engine *e)
+{
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        e->eval_all(-1, 0);
+    });
+}
+
+int moire_engine_reduce(moire_engine *e)
+{
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        e->reduce();
+    });
+}
+
+int moire_engine_get_scalars(moire_engine *e, double *llik, double *prior)
+{
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        e->get_scalars(llik, prior);
+    });
+}
+
+int moire_engine_device_scalars(moire_engine *e, void **dev_llik, void **dev_prior)
+{
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        if (dev_llik) *dev_llik = e->v.llik;
+        if (dev_prior) *dev_prior = e->v.prior;
+    });
+}
+
+int moire_engine_set_temps(moire_engine *e, const double *temps)
+{
+    return guarded(e, [&] {
+        if (!e || !temps) throw InvalidArg{"null argument"};
+        CUDA_TRY(cudaMemcpyAsync(e->v.temp, temps, e->v.T * sizeof(double), cudaMemcpyHostToDevice,
+                                 e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    });
+}
+
+int moire_engine_get_temps(moire_engine *e, double *temps)
+{
+    return guarded(e, [&] {
+        if (!e || !temps) throw InvalidArg{"null argument"};
+        CUDA_TRY(cudaMemcpyAsync(temps, e->v.temp, e->v.T * sizeof(double), cudaMemcpyDeviceToHost,
+                                 e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    });
+}
+
+int moire_engine_dump_state(moire_engine *e, int32_t chain, moire_chain_state *out)
+{
+    return guarded(e, [&] {
+        need_chain(e, chain);
+        if (!out) throw InvalidArg{"null state"};
+        e->dump_state(chain, out);
+    });
+}
+
+int moire_engine_load_state(moire_engine *e, int32_t chain, const moire_chain_state *in)
+{
+    return guarded(e, [&] {
+        need_chain(e, chain);
+        if (!in) throw InvalidArg{"null state"};
+        e->load_state(chain, in);
+    });
+}
+
+int moire_engine_read_diagnostics(moire_engine *e, int32_t chain, moire_chain_diagnostics *out)
+{
+    return guarded(e, [&] {
+        need_chain(e, chain);
+        if (!out) throw InvalidArg{"null diagnostics"};
+        e->read_diag(chain, out);
+    });
+}
+
+int moire_engine_read_sample_llik(moire_engine *e, int32_t chain, double *out)
+{
+    return guarded(e, [&] {
+        need_chain(e, chain);
+        if (!out) throw InvalidArg{"null output"};
+        e->sample_llik_async(chain);
+        e->d2h(out, e->scratchN.ptr, (size_t)e->v.N);
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    });
+}
+
+int moire_engine_record_draw(moire_engine *e, int32_t chain, double *p, int32_t *m,
+                             double *eps_neg, double *eps_pos, double *r, double *sample_llik,
+                             double *mean_coi, uint64_t *latent)
+{
+    return guarded(e, [&] {
+        need_chain(e, chain);
+        const moire::View &v = e->v;
+        const size_t N = v.N, NL = N * v.L, LA = (size_t)v.L * v.AP, t = chain;
+        if (sample_llik) e->sample_llik_async(chain);
+        e->d2h(p, v.p + t * LA, LA);
+        e->d2h(m, v.m + t * N, N);
+        e->d2h(eps_neg, v.eps_neg + t * N, N);
+        e->d2h(eps_pos, v.eps_pos + t * N, N);
+        e->d2h(r, v.r + t * N, N);
+        e->d2h(sample_llik, e->scratchN.ptr, N);
+        e->d2h(mean_coi, v.mean_coi + t, 1);
+        e->d2h((unsigned long long *)latent, v.latent + t * NL, NL);
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    });
+}
+
+int moire_engine_counters(moire_engine *e, uint64_t *cell_evals, uint64_t *kernel_launches)
+{
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        if (cell_evals)
+        {
+            unsigned long long ev = 0;
+            CUDA_TRY(cudaMemcpyAsync(&ev, e->v.evals, sizeof(ev), cudaMemcpyDeviceToHost, e->stream));
+            CUDA_TRY(cudaStreamSynchronize(e->stream));
+            *cell_evals = ev;
+        }
+        if (kernel_launches) *kernel_launches = e->launches;
+    });
+}
+
+int moire_engine_set_timing(moire_engine *e, int32_t on)
+{
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        e->resolve_timing();
+        e->timing = on != 0;
+    });
+}
+
+int moire_engine_read_timing(moire_engine *e, double *ms, uint64_t *launches)
+{
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        e->resolve_timing();
+        for (int k = 0; k < 9; ++k)
+        {
+            if (ms) ms[k] = e->kind_ms[k];
+            if (launches) launches[k] = e->kind_launches[k];
+        }
+    });
+}
+
+int moire_engine_synchronize(moire_engine *e)
+{
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    });
+}
+
+void moire_philox4x32(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4])
+{
+    moire::philox4x32_10(counter, key[0], key[1], out);
+}
+}  // extern "C"

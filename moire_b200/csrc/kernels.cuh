@@ -1,0 +1,886 @@
+// The Metropolis kernels of the engine (sm_100a).
+//
+// Parallel decomposition: given (p, mean_coi) the per-sample updates of the
+// reference are conditionally independent across samples, and given the sample state the
+// allele-frequency updates are independent across loci.  So
+//   * the six per-sample updates run as ONE templated kernel, one thread block per
+//     (chain, tile of S consecutive samples), threads across the S*L contiguous cells of the
+//     tile (coalesced), one warp owning each sample's accept decision (shuffle reductions);
+//   * update_p runs one block per (chain, locus), the A_j SALT proposals sequential inside the
+//     block, threads across samples, latent genotypes and likelihood terms staged in shared
+//     memory for all A_j proposals;
+//   * update_mean_coi and the per-chain reductions run one block per chain.
+// The Metropolis ratio uses the change of the affected cells only, summed in fp64 in a fixed
+// order (the reference re-reduces all N*L cells in fp32 per proposal, src/chain.cpp:978-1026;
+// the two are the same number up to the reference's rounding noise).
+#pragma once
+#include <cfloat>
+
+#include "likelihood.cuh"
+#include "state.cuh"
+
+namespace moire
+{
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kCpt = 4;             // cells per thread kept in registers by the sample kernel
+constexpr int kMaxTileSamples = 32;
+constexpr int kPThreads = 256;      // update_p block size
+
+struct Proposal
+{
+    int valid, adapt, m_new, accept;
+    double r_new, en_new, ep_new, log_r, log_1mr;
+    double adj;
+    double pr_en_new, pr_ep_new, pr_coi_new, pr_r_new, dprior;
+    double logu;
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block-wide sum; every thread gets the total.  s_red: >= 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double *s_red)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) s_red[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        double tot = 0.0;
+        for (int i = 0; i < nw; ++i) tot += s_red[i];
+        s_red[32] = tot;
+    }
+    __syncthreads();
+    return s_red[32];
+}
+
+// Robbins-Monro proposal-scale adaptation (e.g. src/chain.cpp:618-627).
+__device__ __forceinline__ double adapt_sd(double sd, double accepts, double denom, double root_arg,
+                                           double floor_)
+{
+    const double rate = accepts / denom;
+    const double upd = (rate - .23) / sqrt(root_arg);
+    const double nv = sd + upd;
+    return nv > floor_ ? nv : floor_;  // std::max(sd + update, floor)
+}
+
+__host__ __device__ inline size_t sample_kernel_smem(int S, int L, int nA)
+{
+    size_t b = 0;
+    b += 128 * sizeof(double);                      // lgam
+    b += (size_t)kIeMax * kThreads * sizeof(double); // qs scratch
+    b += (size_t)2 * S * L * sizeof(double);        // delta, adjd
+    b += (size_t)S * nA * sizeof(EpsLogs);
+    b += (size_t)S * sizeof(Proposal);
+    return b;
+}
+
+// ---- per-sample updates: eps_neg, eps_pos, m, r, eff_coi, samples ----------------------------
+template <int KIND>
+__global__ void __launch_bounds__(kThreads)
+    k_update_sample(const View v, const int iteration, const int S, const int tiles_per_chain)
+{
+    constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
+    constexpr bool NEED_T = RESAMPLE || KIND == KIND_R;
+    constexpr bool NEED_O = RESAMPLE || KIND == KIND_EPS_NEG || KIND == KIND_EPS_POS;
+
+    extern __shared__ double smem[];
+    double *s_lgam = smem;
+    double *s_qs = s_lgam + 128;
+    double *s_delta = s_qs + kIeMax * kThreads;
+    double *s_adjd = s_delta + S * v.L;
+    EpsLogs *s_elogs = reinterpret_cast<EpsLogs *>(s_adjd + S * v.L);
+    Proposal *s_prop = reinterpret_cast<Proposal *>(s_elogs + S * v.nA);
+    __shared__ unsigned int s_evals;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = blockIdx.x / tiles_per_chain;
+    const int s0 = (blockIdx.x - t * tiles_per_chain) * S;
+    const int ns = min(S, v.N - s0);
+    const int N = v.N, L = v.L, nA = v.nA;
+    const unsigned gchain = (unsigned)(v.chain_offset + t);
+    const double temp = v.temp[t];
+
+    for (int i = tid; i < 128; i += kThreads) s_lgam[i] = v.lgam[i];
+    if (tid == 0) s_evals = 0;
+    __syncthreads();
+
+    // ---- phase A: one proposal per sample -----------------------------------------------------
+    if (tid < ns)
+    {
+        const int i = s0 + tid;
+        const size_t si = (size_t)t * N + i;
+        Stream rng;
+        rng.open(v.seed, (uint32_t)iteration, KIND, gchain, (uint32_t)i, 0);
+        Proposal P;
+        P.valid = 1;
+        P.adapt = 0;
+        P.accept = 0;
+        P.m_new = v.m[si];
+        P.r_new = v.r[si];
+        P.en_new = v.eps_neg[si];
+        P.ep_new = v.eps_pos[si];
+        P.log_r = v.log_r[si];
+        P.log_1mr = v.log_1mr[si];
+        P.adj = 0.0;
+        P.dprior = 0.0;
+        P.pr_en_new = P.pr_ep_new = P.pr_coi_new = P.pr_r_new = 0.0;
+        const double min_sampled = DBL_MIN;  // std::numeric_limits<double>::min()
+        const double lambda = v.mean_coi[t];
+        const double log_geom = -0.40546510810816438;  // log(1 - 1/3): sample_coi_delta(2)
+
+        if (KIND == KIND_EPS_NEG || KIND == KIND_SAMPLES)
+        {
+            const double z = v.sd_eps_neg[si] * next_normal(rng);
+            double prop, adj;
+            constrained_proposal(z, P.en_new, min_sampled, 1.0, &prop, &adj);
+            const bool ok = prop < 1.0 && prop > 1e-32;
+            P.valid &= ok;
+            P.en_new = prop;
+            P.adj += adj;
+            P.pr_en_new = dbeta_log(prop, v.eps_neg_a, v.eps_neg_b, v.eps_neg_lbeta);
+            P.dprior += P.pr_en_new - v.pr_eps_neg[si];
+        }
+        if (KIND == KIND_EPS_POS || KIND == KIND_SAMPLES)
+        {
+            const double z = v.sd_eps_pos[si] * next_normal(rng);
+            double prop, adj;
+            constrained_proposal(z, P.ep_new, min_sampled, 1.0, &prop, &adj);
+            const bool ok = prop < 1.0 && prop > 1e-32;
+            P.valid &= ok;
+            P.ep_new = prop;
+            P.adj += adj;
+            P.pr_ep_new = dbeta_log(prop, v.eps_pos_a, v.eps_pos_b, v.eps_pos_lbeta);
+            P.dprior += P.pr_ep_new - v.pr_eps_pos[si];
+        }
+        if (KIND == KIND_R || (KIND == KIND_SAMPLES && v.allow_rel))
+        {
+            const double z = v.sd_r[si] * next_normal(rng);
+            double prop, adj;
+            constrained_proposal(z, P.r_new, min_sampled, .99, &prop, &adj);
+            if (KIND == KIND_SAMPLES) P.valid &= (prop < 1.0 && prop > 1e-32);
+            P.r_new = prop;
+            P.adj += adj;
+        }
+        if (KIND == KIND_SAMPLES && !v.allow_rel) P.r_new = 0.0;  // src/chain.cpp:719
+        if (KIND == KIND_EFF_COI)
+        {
+            const double curr_eff = (double)(P.m_new - 1) * (1.0 - P.r_new) + 1.0;
+            const double z = v.sd_mr[si] * next_normal(rng);
+            double prop_eff, adj;
+            constrained_proposal(z, curr_eff, 1.0, (double)v.max_coi, &prop_eff, &adj);
+            const int prop_m = P.m_new + next_coi_delta(rng, log_geom);
+            const double prop_r = 1.0 - (prop_eff - 1.0) / ((double)prop_m - 1.0);
+            // src/chain.cpp:244-246: skipped proposals neither evaluate nor adapt
+            if (prop_m <= 0 || prop_m > v.max_coi || prop_r > 1.0 || prop_r < 1e-32) P.valid = 0;
+            P.m_new = prop_m;
+            P.r_new = prop_r;
+            P.adj += adj;
+        }
+        if (KIND == KIND_M || KIND == KIND_SAMPLES)
+        {
+            const int prop_m = P.m_new + next_coi_delta(rng, log_geom);
+            P.valid &= (prop_m > 0 && prop_m <= v.max_coi);
+            P.m_new = prop_m;
+        }
+        if (KIND == KIND_R || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
+        {
+            P.pr_r_new = dbeta_log(P.r_new, v.r_a, v.r_b, v.r_lbeta);
+            P.dprior += P.pr_r_new - v.pr_r[si];
+            P.log_r = log(P.r_new);
+            P.log_1mr = log(1.0 - P.r_new);
+        }
+        if (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
+        {
+            const int mm = P.valid ? P.m_new : 1;  // keep the LUT index in range
+            P.pr_coi_new = dztpois_log(mm, log(lambda), log(exp(lambda) - 1.0), s_lgam);
+            P.dprior += P.pr_coi_new - v.pr_coi[si];
+        }
+        // which updates adapt, and when (src/chain.cpp:303-311, 364-372, 618-627, 683-692)
+        if (KIND == KIND_EPS_NEG || KIND == KIND_EPS_POS || KIND == KIND_EFF_COI)
+            P.adapt = P.valid;
+        if (KIND == KIND_R) P.adapt = 1;
+        P.logu = log(rng.next_uniform());
+        s_prop[tid] = P;
+    }
+    __syncthreads();
+
+    if (NEED_O)
+    {
+        for (int e = tid; e < ns * nA; e += kThreads)
+        {
+            const int sl = e / nA, a = e - sl * nA;
+            build_eps_logs(s_elogs[e], s_prop[sl].en_new, s_prop[sl].ep_new, v.max_eps_neg,
+                           v.max_eps_pos, v.avals[a]);
+        }
+        __syncthreads();
+    }
+
+    // ---- phase B: every cell of the tile ------------------------------------------------------
+    unsigned long long nlat[kCpt];
+    double nT[kCpt], nO[kCpt], nadj[kCpt];
+    unsigned my_evals = 0;
+    const size_t tile_base = ((size_t)t * N + s0) * L;  // first cell of the tile in [T][N][L]
+    const size_t data_base = (size_t)s0 * L;            // same in [N][L]
+    const int ncell = ns * L;
+#pragma unroll
+    for (int c = 0; c < kCpt; ++c)
+    {
+        const int cell = tid + c * kThreads;
+        nlat[c] = 0;
+        nT[c] = nO[c] = nadj[c] = 0.0;
+        if (cell < ncell)
+        {
+            const int sl = cell / L, j = cell - sl * L;
+            const Proposal &P = s_prop[sl];
+            double delta = 0.0, adjd = 0.0;
+            if (P.valid)
+            {
+                const size_t gi = tile_base + cell;
+                const unsigned long long obs = v.obs[data_base + cell];
+                const bool miss = v.missing[data_base + cell] != 0;
+                const int A = v.nall[j];
+                const double oldT = v.cellT[gi], oldO = v.cellO[gi];
+                unsigned long long lat = v.latent[gi];
+                const EpsLogs *el = NEED_O ? &s_elogs[sl * nA + v.aclass[j]] : nullptr;
+                if (RESAMPLE)
+                {
+                    Stream crng;
+                    crng.open(v.seed, (uint32_t)iteration, KIND, gchain, (uint32_t)(s0 + sl),
+                              (uint32_t)(j + 1));
+                    double lp;
+                    lat = sample_latent_genotype(crng, obs, A, P.m_new, *el, v.logC, &lp);
+                    nlat[c] = lat;
+                    nadj[c] = lp;
+                    adjd = lp - v.lgadj[gi];
+                }
+                if (!miss)
+                {
+                    double T = oldT, O = oldO;
+                    if (NEED_T)
+                        T = transmission_ll(lat, v.p + ((size_t)t * L + j) * v.AP, P.m_new, P.log_r,
+                                            P.log_1mr, v.allow_rel != 0, s_qs + tid, kThreads,
+                                            s_lgam);
+                    if (NEED_O) O = observation_ll(lat, obs, A, *el);
+                    nT[c] = T;
+                    nO[c] = O;
+                    delta = __dadd_rn(T, O) - __dadd_rn(oldT, oldO);
+                    ++my_evals;
+                }
+            }
+            s_delta[cell] = delta;
+            if (RESAMPLE) s_adjd[cell] = adjd;
+        }
+    }
+    if (my_evals) atomicAdd(&s_evals, my_evals);
+    __syncthreads();
+
+    // ---- phase C: one warp per sample decides -------------------------------------------------
+    for (int sl = warp; sl < ns; sl += kWarps)
+    {
+        double d = 0.0, a = 0.0;
+        for (int j = lane; j < L; j += 32)
+        {
+            d += s_delta[sl * L + j];
+            if (RESAMPLE) a += s_adjd[sl * L + j];
+        }
+        d = warp_sum(d);
+        if (RESAMPLE) a = warp_sum(a);
+        if (lane == 0)
+        {
+            Proposal &P = s_prop[sl];
+            const int i = s0 + sl;
+            const size_t si = (size_t)t * N + i;
+            bool accept = false;
+            if (P.valid)
+            {
+                const double dpost = temp * d + P.dprior;  // new_post - old_post
+                const double ratio = dpost + (P.adj + a);
+                if (KIND == KIND_M || KIND == KIND_SAMPLES)
+                    accept = !isnan(dpost) && P.logu <= ratio;
+                else if (KIND == KIND_EFF_COI)
+                    accept = !(isnan(dpost) || isnan(ratio) || P.logu > ratio);
+                else
+                    accept = !(isnan(dpost) || P.logu > ratio);
+            }
+            P.accept = accept;
+            int nacc = 0;
+            if (accept)
+            {
+                if (KIND == KIND_EPS_NEG || KIND == KIND_SAMPLES)
+                {
+                    v.eps_neg[si] = P.en_new;
+                    v.pr_eps_neg[si] = P.pr_en_new;
+                }
+                if (KIND == KIND_EPS_POS || KIND == KIND_SAMPLES)
+                {
+                    v.eps_pos[si] = P.ep_new;
+                    v.pr_eps_pos[si] = P.pr_ep_new;
+                }
+                if (KIND == KIND_R || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
+                {
+                    v.r[si] = P.r_new;
+                    v.log_r[si] = P.log_r;
+                    v.log_1mr[si] = P.log_1mr;
+                    v.pr_r[si] = P.pr_r_new;
+                }
+                if (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
+                {
+                    v.m[si] = P.m_new;
+                    v.pr_coi[si] = P.pr_coi_new;
+                }
+            }
+            int *accp = KIND == KIND_EPS_NEG   ? v.acc_eps_neg
+                        : KIND == KIND_EPS_POS ? v.acc_eps_pos
+                        : KIND == KIND_M       ? v.acc_m
+                        : KIND == KIND_R       ? v.acc_r
+                        : KIND == KIND_EFF_COI ? v.acc_mr
+                                               : v.acc_samples;
+            nacc = accp[si] + (accept ? 1 : 0);
+            if (accept) accp[si] = nacc;
+            if (P.adapt && iteration < v.burnin && iteration > 15)
+            {
+                double *sdp = KIND == KIND_EPS_NEG   ? v.sd_eps_neg
+                              : KIND == KIND_EPS_POS ? v.sd_eps_pos
+                              : KIND == KIND_R       ? v.sd_r
+                                                     : v.sd_mr;
+                sdp[si] = adapt_sd(sdp[si], (double)nacc, (double)iteration,
+                                   (double)iteration + 1.0, .01);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase D: commit the accepted samples' cells -----------------------------------------
+#pragma unroll
+    for (int c = 0; c < kCpt; ++c)
+    {
+        const int cell = tid + c * kThreads;
+        if (cell < ncell)
+        {
+            const int sl = cell / L;
+            if (s_prop[sl].accept)
+            {
+                const size_t gi = tile_base + cell;
+                const bool miss = v.missing[data_base + cell] != 0;
+                if (RESAMPLE)
+                {
+                    v.latent[gi] = nlat[c];
+                    v.lgadj[gi] = nadj[c];
+                }
+                if (!miss)
+                {
+                    if (NEED_T) v.cellT[gi] = nT[c];
+                    if (NEED_O) v.cellO[gi] = nO[c];
+                }
+            }
+        }
+    }
+    if (tid == 0 && s_evals) atomicAdd(v.evals, (unsigned long long)s_evals);
+}
+
+// ---- SALT proposal math (src/mcmc_utils.h:150-313) --------------------------------------------
+__device__ __forceinline__ double logit_d(double x)
+{
+    return x < .5 ? log(x) - log1p(-x) : log(x / (1.0 - x));
+}
+
+__device__ __forceinline__ void log_pq_d(double x, double &lp, double &lq)
+{
+    const double ex = exp(x);
+    if (x < 0.0)
+    {
+        lq = -log1p(ex);
+        lp = lq + x;
+    }
+    else
+    {
+        lp = -log1p(1.0 / ex);
+        lq = lp - x;
+    }
+}
+
+__device__ __forceinline__ double logit_scale_d(double x, double scale)
+{
+    const bool ok = (scale < 0.69314718055994530942) && (fabs(scale) < fabs(x + scale));
+    const double u = -scale - (ok ? 0.0 : x);
+    const double w = -scale - (ok ? x : 0.0);
+    const double ev = exp(w);
+    const double eumo = expm1(u);
+    double l2;
+    if (isinf(eumo))
+        l2 = fmax(u, w) + log1p(exp(-fabs(u - w)));
+    else
+        l2 = log(eumo + ev);
+    if (w > log(2.0 * fabs(eumo))) return -(w + log1p(eumo / ev));
+    return -l2;
+}
+
+__device__ __forceinline__ double expit_d(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+__host__ __device__ inline size_t p_kernel_smem(int N, int AP)
+{
+    size_t b = 0;
+    b += 128 * sizeof(double);                       // lgam
+    b += (size_t)kIeMax * kPThreads * sizeof(double); // qs scratch
+    b += (size_t)3 * N * sizeof(double);             // latent, Told, Tnew
+    b += (size_t)3 * AP * sizeof(double);            // p_cur, p_prop, p_sd
+    b += (size_t)2 * AP * sizeof(int);               // acc, att
+    b += 40 * sizeof(double);                        // reductions + scalars
+    return b;
+}
+
+// ---- update_p: SALT sampler, one block per (chain, locus) (src/chain.cpp:466-565) -------------
+__global__ void __launch_bounds__(kPThreads) k_update_p(const View v, const int iteration)
+{
+    extern __shared__ double smem[];
+    const int N = v.N, L = v.L, AP = v.AP;
+    double *s_lgam = smem;
+    double *s_qs = s_lgam + 128;
+    unsigned long long *s_lat = reinterpret_cast<unsigned long long *>(s_qs + kIeMax * kPThreads);
+    double *s_Told = reinterpret_cast<double *>(s_lat + N);
+    double *s_Tnew = s_Told + N;
+    double *s_pcur = s_Tnew + N;
+    double *s_pprop = s_pcur + AP;
+    double *s_psd = s_pprop + AP;
+    double *s_red = s_psd + AP;  // 40 doubles: [0..32] reduction, 33 logAdj, 34 flag, 35 accept
+    int *s_acc = reinterpret_cast<int *>(s_red + 40);
+    int *s_att = s_acc + AP;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = blockIdx.x / L, j = blockIdx.x - t * L;
+    const int A = v.nall[j];
+    const unsigned gchain = (unsigned)(v.chain_offset + t);
+    const double temp = v.temp[t];
+    const size_t prow = ((size_t)t * L + j) * AP;
+
+    for (int i = tid; i < 128; i += kPThreads) s_lgam[i] = v.lgam[i];
+    for (int a = tid; a < AP; a += kPThreads)
+    {
+        s_pcur[a] = v.p[prow + a];
+        s_psd[a] = v.p_sd[prow + a];
+        s_acc[a] = v.p_acc[prow + a];
+        s_att[a] = v.p_att[prow + a];
+    }
+    unsigned nonmissing = 0;
+    for (int i = tid; i < N; i += kPThreads)
+    {
+        const size_t gi = ((size_t)t * N + i) * L + j;
+        s_lat[i] = v.latent[gi];
+        s_Told[i] = v.cellT[gi];
+        nonmissing += v.missing[(size_t)i * L + j] == 0;
+    }
+    __syncthreads();
+
+    unsigned long long evals = 0;
+    for (int rep = 0; rep < A; ++rep)
+    {
+        // -- the proposal, warp 0, lanes across alleles
+        if (warp == 0)
+        {
+            Stream rng;
+            rng.open(v.seed, (uint32_t)iteration, KIND_P, gchain, (uint32_t)j, (uint32_t)rep);
+            const int idx = (int)mulhi32(rng.next_u32(), (uint32_t)A);
+            const double z = next_normal(rng);
+            const double logu = log(rng.next_uniform());
+            double lg[2], lp[2], lq[2];
+            bool rest[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+            {
+                const int a = lane + 32 * s;
+                const bool has = a < A;
+                lg[s] = has ? logit_d(s_pcur[a]) : 0.0;
+                lp[s] = lq[s] = 0.0;
+                if (has) log_pq_d(lg[s], lp[s], lq[s]);
+                rest[s] = has && a != idx;
+            }
+            const double lg_sel = (idx >> 5) ? lg[1] : lg[0];
+            const double logit_curr = __shfl_sync(0xffffffffu, lg_sel, idx & 31);
+            const double logit_prop = logit_curr + s_psd[idx] * z;
+            double clp, clq, plp, plq;
+            log_pq_d(logit_curr, clp, clq);
+            log_pq_d(logit_prop, plp, plq);
+            // logitSum over the other alleles (src/mcmc_utils.h:219-248): the largest logit
+            // leads; on ties the lowest allele index does.
+            double bv = -INFINITY;
+            int ba = 1 << 30;
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+                if (rest[s] && (lg[s] > bv)) { bv = lg[s]; ba = lane + 32 * s; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oa = __shfl_xor_sync(0xffffffffu, ba, o);
+                if (ov > bv || (ov == bv && oa < ba)) { bv = ov; ba = oa; }
+            }
+            const double lp_sel = (ba >> 5) ? lp[1] : lp[0];
+            const double lq_sel = (ba >> 5) ? lq[1] : lq[0];
+            const double lp1 = __shfl_sync(0xffffffffu, lp_sel, ba & 31);
+            const double lq1 = __shfl_sync(0xffffffffu, lq_sel, ba & 31);
+            double cum = 0.0;
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+                if (rest[s] && (lane + 32 * s) != ba) cum += (bv < 0.0) ? exp(lp[s] - lp1) : exp(lp[s]);
+            cum = warp_sum(cum);
+            const double lsum = (bv < 0.0) ? lp1 + log1p(cum) : log1p(-exp(lq1) + cum);
+            const double ls = plq - lsum;
+            bool below = false;
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+            {
+                const int a = lane + 32 * s;
+                if (a < A)
+                {
+                    const double np = expit_d(a == idx ? logit_prop : logit_scale_d(lg[s], ls));
+                    s_pprop[a] = np;
+                    below |= np < 1e-12;
+                }
+            }
+            below = __any_sync(0xffffffffu, below);
+            if (lane == 0)
+            {
+                ++s_att[idx];
+                s_red[33] = (clp - plp) + (double)(A - 1) * (clq - plq);
+                s_red[34] = below ? 1.0 : 0.0;
+                s_red[36] = logu;
+                s_red[37] = (double)idx;
+            }
+        }
+        __syncthreads();
+        if (s_red[34] != 0.0) break;  // src/chain.cpp:503-518: leaves the locus
+
+        // -- all N cells of the locus under the proposed frequencies
+        double dsum = 0.0;
+        for (int i = tid; i < N; i += kPThreads)
+        {
+            double Tn = 0.0;
+            if (v.missing[(size_t)i * L + j] == 0)
+            {
+                const size_t si = (size_t)t * N + i;
+                Tn = transmission_ll(s_lat[i], s_pprop, v.m[si], v.log_r[si], v.log_1mr[si],
+                                     v.allow_rel != 0, s_qs + tid, kPThreads, s_lgam);
+                dsum += Tn - s_Told[i];
+            }
+            s_Tnew[i] = Tn;
+        }
+        evals += nonmissing;
+        const double d = block_sum(dsum, s_red);
+        if (tid == 0)
+        {
+            const int idx = (int)s_red[37];
+            const double dpost = temp * d;  // the priors do not depend on p
+            const double ratio = dpost + s_red[33];
+            const bool accept = !(isnan(dpost) || s_red[36] > ratio);
+            if (accept) ++s_acc[idx];
+            if (iteration < v.burnin && s_att[idx] > 15)
+            {
+                // src/chain.cpp:555-562
+                const double rate = ((double)s_acc[idx] + 1.0) / ((double)s_att[idx] + 1.0);
+                double sd = s_psd[idx] + (rate - .23) / sqrt((double)s_att[idx] + 1.0);
+                s_psd[idx] = sd > .01 ? sd : .01;
+            }
+            s_red[35] = accept ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        if (s_red[35] != 0.0)
+        {
+            for (int i = tid; i < N; i += kPThreads) s_Told[i] = s_Tnew[i];
+            for (int a = tid; a < A; a += kPThreads) s_pcur[a] = s_pprop[a];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+
+    for (int i = tid; i < N; i += kPThreads)
+    {
+        if (v.missing[(size_t)i * L + j] == 0) v.cellT[((size_t)t * N + i) * L + j] = s_Told[i];
+    }
+    for (int a = tid; a < AP; a += kPThreads)
+    {
+        v.p[prow + a] = s_pcur[a];
+        v.p_sd[prow + a] = s_psd[a];
+        v.p_acc[prow + a] = s_acc[a];
+        v.p_att[prow + a] = s_att[a];
+    }
+    {
+        // per-thread partial counts -> one atomic per warp
+        unsigned long long e = evals;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        if (lane == 0 && e) atomicAdd(v.evals, e);
+    }
+}
+
+// ---- update_mean_coi: one block per chain (src/chain.cpp:809-856) ----------------------------
+__global__ void __launch_bounds__(kThreads) k_update_mean_coi(const View v, const int iteration)
+{
+    __shared__ double s_lgam[128];
+    __shared__ double s_red[40];
+    const int tid = threadIdx.x, t = blockIdx.x, N = v.N;
+    for (int i = tid; i < 128; i += kThreads) s_lgam[i] = v.lgam[i];
+    if (tid == 0)
+    {
+        Stream rng;
+        rng.open(v.seed, (uint32_t)iteration, KIND_MEAN_COI, (unsigned)(v.chain_offset + t), 0, 0);
+        const double z = v.mean_coi_sd[t] * next_normal(rng);
+        double prop, adj;
+        constrained_proposal(z, v.mean_coi[t], 1e-5, (double)v.max_coi, &prop, &adj);
+        s_red[33] = prop;
+        s_red[34] = adj;
+        s_red[35] = log(rng.next_uniform());
+    }
+    __syncthreads();
+    const double prop = s_red[33];
+    const double ll = log(prop), lem = log(exp(prop) - 1.0);
+    double dsum = 0.0;
+    for (int i = tid; i < N; i += kThreads)
+    {
+        const size_t si = (size_t)t * N + i;
+        dsum += dztpois_log(v.m[si], ll, lem, s_lgam) - v.pr_coi[si];
+    }
+    const double d = block_sum(dsum, s_red);
+    if (tid == 0)
+    {
+        const double hyper_new =
+            dgamma_log(prop, v.mean_coi_shape, v.mean_coi_scale, v.lg_shape, v.l_scale);
+        const double dpost = d + (hyper_new - v.hyper[t]);  // the likelihood does not change
+        const double ratio = dpost + s_red[34];
+        const bool accept = !isnan(dpost) && s_red[35] <= ratio;
+        if (accept)
+        {
+            v.mean_coi[t] = prop;
+            v.hyper[t] = hyper_new;
+            v.mean_coi_acc[t] += 1.0;
+        }
+        if (iteration < v.burnin && iteration > 15)
+        {
+            v.mean_coi_sd[t] = adapt_sd(v.mean_coi_sd[t], v.mean_coi_acc[t],
+                                        (double)(iteration + 1), (double)iteration + 1.0, .1);
+        }
+        s_red[36] = accept ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (s_red[36] != 0.0)
+    {
+        for (int i = tid; i < N; i += kThreads)
+        {
+            const size_t si = (size_t)t * N + i;
+            v.pr_coi[si] = dztpois_log(v.m[si], ll, lem, s_lgam);
+        }
+    }
+}
+
+// ---- per-chain sums (calc_new_likelihood / calc_new_prior, src/chain.cpp:978-1026) ------------
+__global__ void __launch_bounds__(1024) k_reduce(const View v)
+{
+    __shared__ double s_red[40];
+    const int tid = threadIdx.x, t = blockIdx.x;
+    const size_t ncell = (size_t)v.N * v.L;
+    const double *cT = v.cellT + (size_t)t * ncell;
+    const double *cO = v.cellO + (size_t)t * ncell;
+    double s = 0.0;
+    for (size_t c = tid; c < ncell; c += blockDim.x) s += __dadd_rn(cT[c], cO[c]);
+    const double llik = block_sum(s, s_red);
+    double q = 0.0;
+    for (int i = tid; i < v.N; i += blockDim.x)
+    {
+        const size_t si = (size_t)t * v.N + i;
+        q += ((v.pr_eps_neg[si] + v.pr_eps_pos[si]) + v.pr_r[si]) + v.pr_coi[si];
+    }
+    const double prior = block_sum(q, s_red);
+    if (tid == 0)
+    {
+        v.llik[t] = llik;
+        v.prior[t] = prior + v.hyper[t];
+    }
+}
+
+// Chain::get_llik(sample) for one chain (src/chain.cpp:1083-1097).
+__global__ void k_sample_llik(const View v, const int t, double *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.N) return;
+    const size_t base = ((size_t)t * v.N + i) * v.L;
+    double s = 0.0;
+    for (int j = 0; j < v.L; ++j) s += __dadd_rn(v.cellT[base + j], v.cellO[base + j]);
+    out[i] = s;
+}
+
+// ---- rebuild every cache from the parameters (initialize_likelihood, chain.cpp:1166-1223) ----
+// chain_sel < 0: all chains (optionally only the `active` ones); else one chain.
+__global__ void __launch_bounds__(kThreads)
+    k_eval_cells(const View v, const int chain_sel, const int use_active)
+{
+    __shared__ double s_lgam[128];
+    __shared__ double s_qs[kIeMax * kThreads];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 128; i += kThreads) s_lgam[i] = v.lgam[i];
+    __syncthreads();
+    const size_t ncell = (size_t)v.N * v.L;
+    const size_t total = (chain_sel < 0 ? (size_t)v.T : 1) * ncell;
+    const size_t g = (size_t)blockIdx.x * kThreads + tid;
+    if (g >= total) return;
+    const int t = chain_sel < 0 ? (int)(g / ncell) : chain_sel;
+    if (use_active && !v.active[t]) return;
+    const size_t cell = g % ncell;
+    const int i = (int)(cell / v.L), j = (int)(cell - (size_t)i * v.L);
+    const size_t gi = (size_t)t * ncell + cell;
+    double T = 0.0, O = 0.0;
+    if (!v.missing[cell])
+    {
+        const size_t si = (size_t)t * v.N + i;
+        EpsLogs el;
+        build_eps_logs(el, v.eps_neg[si], v.eps_pos[si], v.max_eps_neg, v.max_eps_pos, v.nall[j]);
+        T = transmission_ll(v.latent[gi], v.p + ((size_t)t * v.L + j) * v.AP, v.m[si], v.log_r[si],
+                            v.log_1mr[si], v.allow_rel != 0, s_qs + tid, kThreads, s_lgam);
+        O = observation_ll(v.latent[gi], v.obs[cell], v.nall[j], el);
+    }
+    v.cellT[gi] = T;
+    v.cellO[gi] = O;
+}
+
+__global__ void k_eval_priors(const View v, const int chain_sel, const int use_active)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (chain_sel < 0 ? (size_t)v.T : 1) * v.N;
+    if (g >= total) return;
+    const int t = chain_sel < 0 ? (int)(g / v.N) : chain_sel;
+    if (use_active && !v.active[t]) return;
+    const int i = (int)(g % v.N);
+    const size_t si = (size_t)t * v.N + i;
+    const double lambda = v.mean_coi[t];
+    v.log_r[si] = log(v.r[si]);
+    v.log_1mr[si] = log(1.0 - v.r[si]);
+    v.pr_eps_neg[si] = dbeta_log(v.eps_neg[si], v.eps_neg_a, v.eps_neg_b, v.eps_neg_lbeta);
+    v.pr_eps_pos[si] = dbeta_log(v.eps_pos[si], v.eps_pos_a, v.eps_pos_b, v.eps_pos_lbeta);
+    v.pr_r[si] = dbeta_log(v.r[si], v.r_a, v.r_b, v.r_lbeta);
+    const int mm = v.m[si];
+    v.pr_coi[si] = (mm >= 0 && mm < 128)
+                       ? dztpois_log(mm, log(lambda), log(exp(lambda) - 1.0), v.lgam)
+                       : NAN;
+    if (i == 0)
+        v.hyper[t] = dgamma_log(lambda, v.mean_coi_shape, v.mean_coi_scale, v.lg_shape, v.l_scale);
+}
+
+// ---- starting state (Chain::initialize_parameters, src/chain.cpp:21-163, 1294-1310) ----------
+// Gamma(shape, 1) by Marsaglia-Tsang, clamped like Sampler::rgamma (src/sampler.cpp:57-72).
+__device__ inline double next_gamma(Stream &rng, double shape)
+{
+    double boost = 1.0;
+    if (shape < 1.0)
+    {
+        boost = pow(rng.next_uniform(), 1.0 / shape);
+        shape += 1.0;
+    }
+    const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    double x = 1.0;
+    for (int guard = 0; guard < 1000; ++guard)
+    {
+        const double z = next_normal(rng);
+        double w = 1.0 + c * z;
+        if (w <= 0.0) continue;
+        w = w * w * w;
+        const double u = rng.next_uniform();
+        if (log(u) < 0.5 * z * z + d - d * w + d * log(w))
+        {
+            x = d * w;
+            break;
+        }
+    }
+    x *= boost;
+    return fmin(fmax(x, 1e-100), 1e100);
+}
+
+__global__ void k_init_samples(const View v, const int attempt)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)v.T * v.N) return;
+    const int t = (int)(g / v.N), i = (int)(g % v.N);
+    if (!v.active[t]) return;
+    const size_t si = g;
+    Stream rng;
+    rng.open(v.seed, 0xFFFF0000u + (uint32_t)attempt, KIND_INIT_SAMPLE,
+             (unsigned)(v.chain_offset + t), (uint32_t)i, 0);
+    // initialize_m (src/chain.cpp:77-96): observed COI + geometric(1/4) jitter, never below it
+    const int coi = v.obs_coi[i];
+    const int lower = min(max(coi, 1), v.max_coi);
+    const int jit = coi + next_coi_delta(rng, -0.28768207245178093 /* log(3/4) */);
+    v.m[si] = min(max(jit, lower), v.max_coi);
+    v.eps_neg[si] = rng.next_uniform() * .1;
+    v.eps_pos[si] = rng.next_uniform() * .1;
+    v.r[si] = v.allow_rel ? rng.next_uniform() * .99 : 0.0;
+    v.sd_eps_neg[si] = v.sd_eps_pos[si] = v.sd_r[si] = v.sd_mr[si] = 1.0;
+    v.acc_eps_neg[si] = v.acc_eps_pos[si] = v.acc_m[si] = 0;
+    v.acc_r[si] = v.acc_mr[si] = v.acc_samples[si] = 0;
+}
+
+__global__ void k_init_latent(const View v, const int attempt)
+{
+    const size_t ncell = (size_t)v.N * v.L;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)v.T * ncell) return;
+    const int t = (int)(g / ncell);
+    if (!v.active[t]) return;
+    const size_t cell = g % ncell;
+    const int i = (int)(cell / v.L), j = (int)(cell - (size_t)i * v.L);
+    Stream rng;
+    rng.open(v.seed, 0xFFFF0000u + (uint32_t)attempt, KIND_INIT_SAMPLE,
+             (unsigned)(v.chain_offset + t), (uint32_t)i, (uint32_t)(j + 1));
+    EpsLogs el;
+    build_eps_logs(el, .2, .2, v.max_eps_neg, v.max_eps_pos, v.nall[j]);  // src/chain.cpp:39
+    double lp;
+    v.latent[g] = sample_latent_genotype(rng, v.obs[cell], v.nall[j], v.m[(size_t)t * v.N + i], el,
+                                         v.logC, &lp);
+    v.lgadj[g] = lp;
+}
+
+__global__ void k_init_p(const View v, const int attempt)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)v.T * v.L) return;
+    const int t = (int)(g / v.L), j = (int)(g % v.L);
+    if (!v.active[t]) return;
+    const int A = v.nall[j];
+    const size_t row = g * v.AP;
+    // initialize_p: Dirichlet(10 * 1) via gamma draws (src/chain.cpp:51-75, sampler.cpp:79-98)
+    double tot = 0.0;
+    for (int a = 0; a < v.AP; ++a)
+    {
+        double x = 0.0;
+        if (a < A)
+        {
+            Stream rng;
+            rng.open(v.seed, 0xFFFF0000u + (uint32_t)attempt, KIND_INIT_P,
+                     (unsigned)(v.chain_offset + t), (uint32_t)j, (uint32_t)a);
+            x = next_gamma(rng, 10.0);
+        }
+        v.p[row + a] = x;
+        tot += x;
+        v.p_sd[row + a] = 1.0;
+        v.p_acc[row + a] = 0;
+        v.p_att[row + a] = 0;
+    }
+    const double inv = 1.0 / tot;
+    for (int a = 0; a < A; ++a) v.p[row + a] *= inv;
+    if (j == 0)
+    {
+        // Chain::Chain: mean_coi = Gamma(shape, scale) + 1 (src/chain.cpp:1300-1304)
+        Stream rng;
+        rng.open(v.seed, 0xFFFF0000u + (uint32_t)attempt, KIND_INIT_MEAN_COI,
+                 (unsigned)(v.chain_offset + t), 0, 0);
+        const double g0 = next_gamma(rng, v.mean_coi_shape) * v.mean_coi_scale;
+        v.mean_coi[t] = fmin(fmax(g0, 1e-100), 1e100) + 1.0;
+        v.mean_coi_sd[t] = 1.0;
+        v.mean_coi_acc[t] = 0.0;
+    }
+}
+}  // namespace moire

@@ -1,0 +1,515 @@
+// Device math of the hot path: per-cell transmission / observation log-likelihood,
+// prob_any_missing, the latent-genotype proposal, priors and the constrained proposal.
+//
+// Arithmetic is fp64 and follows the double variant of the reference (every `float` read as
+// `double`), operation for operation wherever the order decides the rounding: the
+// inclusion-exclusion sums, the EGF recurrence and the sequential sums use explicit
+// __d{add,sub,mul,div}_rn so that nvcc cannot contract them into FMAs.  What is left to differ
+// from the CPU is libm (log / log1p / exp), i.e. a couple of ulps.
+//
+// Reference (paths relative to /root/reference):
+//   calc_transmission_process   src/chain.cpp:858-921
+//   calc_observation_process    src/chain.cpp:923-961
+//   probAnyMissingFunctor       src/prob_any_missing.cpp:13-234
+//   CombinationIndicesGenerator src/combination_indices_generator.cpp:5-76  (as a bit trick)
+//   sample_latent_genotype      src/sampler.cpp:230-340
+//   sample_constrained          src/sampler.cpp:176-190
+//   dbinom / dztpois            src/sampler.cpp:38-50
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#include "rng.cuh"
+
+namespace moire
+{
+constexpr int kIeMax = 10;      // src/prob_any_missing.cpp:11
+constexpr int kMaxCoi = 64;     // MOIRE_MAX_COI
+constexpr int kLogCDim = 65;    // logC[n][k], 0 <= k <= n <= 64
+
+// Per (sample, distinct allele count) logs, built once per tile.
+struct EpsLogs
+{
+    // calc_observation_process: log(1 - en*Mn/A), log(en*Mn/A), log(1 - ep*Mp/A), log(ep*Mp/A)
+    double o_tp, o_fn, o_tn, o_fp;
+    // sample_latent_genotype: log(en/A), log(1 - en/A), log(ep/A), log(1 - ep/A), en/A, ep/A
+    double l_en, l_1men, l_ep, l_1mep, pr_en, pr_ep;
+};
+
+__device__ __forceinline__ void build_eps_logs(EpsLogs &e, double eps_neg, double eps_pos,
+                                               double max_eps_neg, double max_eps_pos, int A)
+{
+    const double norm = __ddiv_rn(1.0, (double)A);
+    const double xn = __dmul_rn(__dmul_rn(eps_neg, max_eps_neg), norm);
+    const double xp = __dmul_rn(__dmul_rn(eps_pos, max_eps_pos), norm);
+    e.o_tp = log(__dsub_rn(1.0, xn));
+    e.o_fn = log(xn);
+    e.o_tn = log(__dsub_rn(1.0, xp));
+    e.o_fp = log(xp);
+    e.pr_en = __ddiv_rn(eps_neg, (double)A);
+    e.pr_ep = __ddiv_rn(eps_pos, (double)A);
+    e.l_en = log(e.pr_en);
+    e.l_1men = log(__dsub_rn(1.0, e.pr_en));
+    e.l_ep = log(e.pr_ep);
+    e.l_1mep = log(__dsub_rn(1.0, e.pr_ep));
+}
+
+// ---- a7: observation process on masks --------------------------------------------------------
+__device__ __forceinline__ double observation_ll(uint64_t latent, uint64_t obs, int A,
+                                                 const EpsLogs &e)
+{
+    const int tp = __popcll(latent & obs);
+    const int fn = __popcll(latent & ~obs);
+    const int fp = __popcll(obs & ~latent);
+    const int tn = A - tp - fn - fp;
+    double res = 0.0;
+    res = __dadd_rn(res, __dmul_rn(e.o_tp, (double)tp));
+    res = __dadd_rn(res, __dmul_rn(e.o_fn, (double)fn));
+    res = __dadd_rn(res, __dmul_rn(e.o_tn, (double)tn));
+    res = __dadd_rn(res, __dmul_rn(e.o_fp, (double)fp));
+    return res;
+}
+
+__device__ __forceinline__ double clamp_pam(double x)
+{
+    // src/chain.cpp:890-893 in double: min(1 - eps, max(0, x))
+    const double max_pam = 1.0 - DBL_EPSILON;
+    const double lo = x > 0.0 ? x : 0.0;  // std::max(0., x): NaN -> 0
+    return max_pam < lo ? max_pam : lo;
+}
+
+__device__ __forceinline__ double pam_from_coverage(double cov)
+{
+    const double pam = __dsub_rn(1.0, cov);
+    if (pam <= 0.0) return 0.0;
+    if (pam >= 1.0) return 1.0;
+    return pam;
+}
+
+// Subsets of {0..k-1} of one size in the reference's lexicographic order.  Element e lives at
+// bit (k-1-e), so lexicographic-ascending == numerically descending; the successor is Gosper's
+// hack applied to the complement.
+__device__ __forceinline__ uint32_t next_subset_lex(uint32_t sub, uint32_t full)
+{
+    const uint32_t v = ~sub & full;
+    const uint32_t t = v | (v - 1u);
+    const uint32_t w = (t + 1u) | (((~t & (0u - ~t)) - 1u) >> __ffs(v));
+    return ~w & full;
+}
+
+// base = 1 - q[c0] - q[c1] - ... in ascending element order (src/prob_any_missing.cpp:27-31).
+// qs[b * qstride] holds q of the element at bit b.
+__device__ __forceinline__ double subset_base(uint32_t sub, const double *qs, int qstride)
+{
+    double base = 1.0;
+    while (sub)
+    {
+        const int b = 31 - __clz(sub);
+        base = __dsub_rn(base, qs[b * qstride]);
+        sub ^= 1u << b;
+    }
+    return base;
+}
+
+// ---- a4: vectorised inclusion-exclusion, k <= 10 (src/prob_any_missing.cpp:178-216) --------
+// acc[t] accumulates the PAM of n = k + t draws, t < cnt = m - k + 1 (entries n < k are never
+// read by the mixture).  NACC is the register tier (>= cnt).
+template <int NACC>
+__device__ __forceinline__ void ie_vectorized(const double *qs, int qstride, int k, int cnt,
+                                              double (&acc)[NACC])
+{
+#pragma unroll
+    for (int t = 0; t < NACC; ++t) acc[t] = 0.0;
+    const uint32_t full = (1u << k) - 1u;
+    int sign = -1;
+    int ncomb = 1;
+    for (int s = 1; s <= k; ++s)
+    {
+        sign = -sign;
+        ncomb = ncomb * (k - s + 1) / s;  // C(k, s), exact
+        uint32_t sub = ((1u << s) - 1u) << (k - s);
+        for (int c = 0; c < ncomb; ++c)
+        {
+            const double base = subset_base(sub, qs, qstride);
+            double r = (double)sign;
+            for (int j = 0; j < k - 1; ++j) r = __dmul_rn(r, base);
+#pragma unroll
+            for (int t = 0; t < NACC; ++t)
+            {
+                if (t < cnt)
+                {
+                    r = __dmul_rn(r, base);
+                    acc[t] = __dadd_rn(acc[t], r);
+                }
+            }
+            if (c + 1 < ncomb) sub = next_subset_lex(sub, full);
+        }
+    }
+}
+
+// ---- a3: scalar inclusion-exclusion, k <= 10 (src/prob_any_missing.cpp:13-53) ---------------
+__device__ __forceinline__ double ie_scalar(const double *qs, int qstride, int k, int n)
+{
+    const uint32_t full = (1u << k) - 1u;
+    double prob = 0.0;
+    int sign = -1;
+    int ncomb = 1;
+    for (int s = 1; s <= k; ++s)
+    {
+        sign = -sign;
+        ncomb = ncomb * (k - s + 1) / s;
+        uint32_t sub = ((1u << s) - 1u) << (k - s);
+        for (int c = 0; c < ncomb; ++c)
+        {
+            double base = subset_base(sub, qs, qstride);
+            double r = (double)sign;
+            int mc = n;
+            while (mc > 0)
+            {
+                if (mc & 1) r = __dmul_rn(r, base);
+                base = __dmul_rn(base, base);
+                mc >>= 1;
+            }
+            prob = __dadd_rn(prob, r);
+            if (c + 1 < ncomb) sub = next_subset_lex(sub, full);
+        }
+    }
+    return prob;
+}
+
+// ---- a5: EGF coverage recurrence, k > 10 (src/prob_any_missing.cpp:57-97) -------------------
+// a[n] = coverage probability of n draws for n = 0..max_n.  q_e = prow[allele_e] / total.
+__device__ __noinline__ void egf_coverage(uint64_t latent, const double *prow, double total,
+                                          int max_n, double *a)
+{
+    double b[kMaxCoi + 1];
+    double ppow[kMaxCoi + 1];
+    for (int m = 0; m <= max_n; ++m) a[m] = 0.0;
+    a[0] = 1.0;
+    uint64_t rest = latent;
+    while (rest)
+    {
+        const int al = __ffsll((long long)rest) - 1;
+        rest &= rest - 1;
+        const double p = __ddiv_rn(prow[al], total);
+        ppow[0] = 0.0;
+        if (max_n >= 1) ppow[1] = p;
+        for (int j = 2; j <= max_n; ++j) ppow[j] = __dmul_rn(ppow[j - 1], p);
+        b[0] = 0.0;
+        for (int m = 1; m <= max_n; ++m)
+        {
+            double comb = (double)m;
+            double sum = 0.0;
+            for (int j = 1; j <= m; ++j)
+            {
+                sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(comb, a[m - j]), ppow[j]));
+                comb = __dmul_rn(comb, __ddiv_rn((double)(m - j), (double)(j + 1)));
+            }
+            b[m] = sum;
+        }
+        for (int m = 0; m <= max_n; ++m) a[m] = b[m];
+    }
+}
+
+// Sampler::dbinom (src/sampler.cpp:44-50); lgam[i] = lgamma(i + 1).
+__device__ __forceinline__ double dbinom_log(int x, int size, double log_p, double log_1mp,
+                                             const double *lgam)
+{
+    const double lp = __dadd_rn(__dmul_rn((double)x, log_p), __dmul_rn((double)(size - x), log_1mp));
+    const double lc = __dsub_rn(__dsub_rn(lgam[size], lgam[x]), lgam[size - x]);
+    return __dadd_rn(lp, lc);
+}
+
+// Relatedness mixture + log-sum-exp (src/chain.cpp:903-920, src/mcmc_utils.h:382-397).
+// On entry acc[t] = PAM(n = k + t); term i = 0..cnt-1 uses n = m - i, i.e. t = cnt - 1 - i.
+template <int NACC>
+__device__ __forceinline__ double relatedness_mixture(double (&acc)[NACC], int k, int m, int cnt,
+                                                      double log_total, double log_r,
+                                                      double log_1mr, const double *lgam)
+{
+    double mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < NACC; ++t)
+    {
+        if (t < cnt)
+        {
+            const int i = cnt - 1 - t;
+            const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
+            const double pam = clamp_pam(acc[t]);
+            const double i_res = __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
+            const double v = __dadd_rn(pr, i_res);
+            acc[t] = v;
+            mx = (mx < v) ? v : mx;  // std::max_element semantics
+        }
+    }
+    if (mx == -INFINITY) return -INFINITY;
+    double sum = 0.0;
+#pragma unroll
+    for (int t = NACC - 1; t >= 0; --t)  // i ascending, as the reference sums
+    {
+        if (t < cnt) sum = __dadd_rn(sum, exp(__dsub_rn(acc[t], mx)));
+    }
+    return __dadd_rn(mx, log(sum));
+}
+
+template <int NACC>
+__device__ __noinline__ double transmission_rel_ie(const double *qs, int qstride, int k, int m,
+                                                   double log_total, double log_r, double log_1mr,
+                                                   const double *lgam)
+{
+    double acc[NACC];
+    const int cnt = m - k + 1;
+    ie_vectorized<NACC>(qs, qstride, k, cnt, acc);
+    return relatedness_mixture<NACC>(acc, k, m, cnt, log_total, log_r, log_1mr, lgam);
+}
+
+// EGF branch of the relatedness path; a[] lives in local memory (k > 10 only).
+__device__ __noinline__ double transmission_rel_egf(uint64_t latent, const double *prow,
+                                                    double total, int k, int m, double log_total,
+                                                    double log_r, double log_1mr,
+                                                    const double *lgam)
+{
+    double a[kMaxCoi + 1];
+    egf_coverage(latent, prow, total, m, a);
+    const int cnt = m - k + 1;
+    double mx = -INFINITY;
+    for (int i = 0; i < cnt; ++i)
+    {
+        const int n = m - i;
+        const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
+        const double pam = clamp_pam(pam_from_coverage(a[n]));
+        const double i_res = __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)n));
+        const double v = __dadd_rn(pr, i_res);
+        a[n] = v;
+        mx = (mx < v) ? v : mx;
+    }
+    if (mx == -INFINITY) return -INFINITY;
+    double sum = 0.0;
+    for (int i = 0; i < cnt; ++i) sum = __dadd_rn(sum, exp(__dsub_rn(a[m - i], mx)));
+    return __dadd_rn(mx, log(sum));
+}
+
+// ---- a2: transmission process of one cell ----------------------------------------------------
+// prow: allele frequencies of the locus; qs: per-thread scratch for up to 10 normalised
+// frequencies, element stride qstride (shared memory, conflict-free when qstride = blockDim.x);
+// lgam: lgamma(i + 1), i < 128.
+__device__ __forceinline__ double transmission_ll(uint64_t latent, const double *prow, int m,
+                                                  double log_r, double log_1mr,
+                                                  bool allow_relatedness, double *qs, int qstride,
+                                                  const double *lgam)
+{
+    const int k = __popcll(latent);
+    if (k == 0 || k > m) return NAN;  // unreachable for states the sampler produces
+    double total = 0.0;
+    {
+        uint64_t rest = latent;
+        while (rest)
+        {
+            const int al = __ffsll((long long)rest) - 1;
+            rest &= rest - 1;
+            total = __dadd_rn(total, prow[al]);
+        }
+    }
+    const double log_total = log(total);
+    if (k <= kIeMax)
+    {
+        uint64_t rest = latent;
+        int e = 0;
+        while (rest)
+        {
+            const int al = __ffsll((long long)rest) - 1;
+            rest &= rest - 1;
+            qs[(k - 1 - e) * qstride] = __ddiv_rn(prow[al], total);
+            ++e;
+        }
+    }
+    if (!allow_relatedness)
+    {
+        // src/chain.cpp:895-899 with probAnyMissingFunctor::operator() (prob_any_missing.cpp:131-154)
+        double pam;
+        if (m == k)
+        {
+            double cov = 1.0;
+            uint64_t rest = latent;
+            while (rest)
+            {
+                const int al = __ffsll((long long)rest) - 1;
+                rest &= rest - 1;
+                cov = __dmul_rn(cov, __ddiv_rn(prow[al], total));
+            }
+            for (int i = 2; i <= k; ++i) cov = __dmul_rn(cov, (double)i);
+            pam = pam_from_coverage(cov);
+        }
+        else if (k <= kIeMax)
+        {
+            pam = ie_scalar(qs, qstride, k, m);
+        }
+        else
+        {
+            double a[kMaxCoi + 1];
+            egf_coverage(latent, prow, total, m, a);
+            pam = pam_from_coverage(a[m]);
+        }
+        pam = clamp_pam(pam);
+        return __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)m));
+    }
+    if (k > kIeMax)
+        return transmission_rel_egf(latent, prow, total, k, m, log_total, log_r, log_1mr, lgam);
+    const int cnt = m - k + 1;
+    if (cnt <= 4) return transmission_rel_ie<4>(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
+    if (cnt <= 8) return transmission_rel_ie<8>(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
+    if (cnt <= 16)
+        return transmission_rel_ie<16>(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
+    if (cnt <= 32)
+        return transmission_rel_ie<32>(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
+    return transmission_rel_ie<64>(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
+}
+
+// ---- a8: latent-genotype proposal ------------------------------------------------------------
+// Uniform choice of `need` of the `n` set bits of `set` (selection sampling; consumes one
+// uniform per visited bit while the outcome is still open).  Distributionally what the
+// reference's shuffle + prefix does (src/sampler.cpp:312-322).
+__device__ __forceinline__ uint64_t choose_bits(Stream &rng, uint64_t set, int n, int need)
+{
+    if (need <= 0) return 0;
+    if (need >= n) return set;
+    uint64_t out = 0;
+    int remaining = n;
+    while (need > 0)
+    {
+        if (need == remaining)
+        {
+            out |= set;
+            break;
+        }
+        const uint64_t low = set & (0ull - set);
+        set ^= low;
+        const double u = rng.next_uniform();
+        if (u * (double)remaining < (double)need)
+        {
+            out |= low;
+            --need;
+        }
+        --remaining;
+    }
+    return out;
+}
+
+// Draws the proposal and returns its mask; *log_prob gets the log proposal density.
+// logC[n * 65 + k] = log(C(n, k)).
+__device__ __forceinline__ uint64_t sample_latent_genotype(Stream &rng, uint64_t obs, int A,
+                                                           int coi, const EpsLogs &e,
+                                                           const double *__restrict__ logC,
+                                                           double *log_prob)
+{
+    const uint64_t all = A >= 64 ? ~0ull : ((1ull << A) - 1ull);
+    const int obs_pos = __popcll(obs);
+    const int obs_neg = A - obs_pos;
+    const int min_fn = obs_pos == 0;
+    const int max_fn = max(min_fn, min(coi, obs_neg));
+    int fn = min_fn;
+    for (int ii = min_fn; ii < max_fn; ++ii) fn += (rng.next_uniform() < e.pr_en);
+    const int tn = obs_neg - fn;
+    const double lp_fn =
+        __dadd_rn(__dadd_rn(logC[obs_neg * kLogCDim + (fn - min_fn)],
+                            __dmul_rn((double)(fn - min_fn), e.l_en)),
+                  __dmul_rn((double)tn, e.l_1men));
+    const int min_fp = max(0, obs_pos + fn - coi);
+    const int max_fp = min(obs_pos, obs_pos + fn - 1);
+    if (max_fp < min_fp)
+    {
+        *log_prob = -INFINITY;
+        return 0;
+    }
+    int fp = min_fp;
+    for (int ii = min_fp; ii < max_fp; ++ii) fp += (rng.next_uniform() < e.pr_ep);
+    const int tp = obs_pos - fp;
+    const double lp_fp =
+        __dadd_rn(__dadd_rn(logC[obs_pos * kLogCDim + (fp - min_fp)],
+                            __dmul_rn((double)(fp - min_fp), e.l_ep)),
+                  __dmul_rn((double)tp, e.l_1mep));
+    const uint64_t pos = choose_bits(rng, obs, obs_pos, tp);
+    const uint64_t neg = choose_bits(rng, ~obs & all, obs_neg, fn);
+    const double lp_pos_idx = -logC[obs_pos * kLogCDim + tp];
+    const double lp_neg_idx = -logC[obs_neg * kLogCDim + fn];
+    *log_prob = __dadd_rn(__dadd_rn(__dadd_rn(lp_pos_idx, lp_neg_idx), lp_fp), lp_fn);
+    return pos | neg;
+}
+
+// ---- proposals and priors --------------------------------------------------------------------
+// Standard normal from two words (Box-Muller, cosine branch).
+__device__ __forceinline__ double next_normal(Stream &rng)
+{
+    const double u1 = rng.next_uniform();
+    const double u2 = rng.next_uniform();
+    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586477 * u2);
+}
+
+// Sampler::sample_coi_delta(mean) (src/sampler.cpp:152-156): +-Geometric(1/(1+mean)) on {0,1,..}.
+__device__ __forceinline__ int next_coi_delta(Stream &rng, double log_1mp)
+{
+    const int sign = (rng.next_u32() & 1u) ? 1 : -1;
+    const double u = rng.next_uniform();
+    const int g = (int)floor(log(u) / log_1mp);
+    return sign * g;
+}
+
+// Sampler::sample_constrained given its N(0, sd) draw eps (src/sampler.cpp:176-190).
+__device__ __forceinline__ void constrained_proposal(double eps, double curr, double lo, double hi,
+                                                     double *prop_out, double *adj_out)
+{
+    const double l_cl = log(__dsub_rn(curr, lo));
+    const double l_hc = log(__dsub_rn(hi, curr));
+    const double unconstrained = __dsub_rn(l_cl, l_hc);
+    const double exp_prop = exp(__dadd_rn(eps, unconstrained));
+    double prop = __ddiv_rn(__dadd_rn(__dmul_rn(hi, exp_prop), lo), __dadd_rn(exp_prop, 1.0));
+    prop = prop < lo ? lo : (prop > hi ? hi : prop);
+    const double adj = __dsub_rn(
+        __dsub_rn(__dadd_rn(log(__dsub_rn(prop, lo)), log(__dsub_rn(hi, prop))), l_cl), l_hc);
+    *prop_out = prop;
+    *adj_out = adj;
+}
+
+// R::dbeta(x, a, b, log = TRUE) incl. R's edge cases at 0 and 1; lbeta = log B(a, b) from host.
+__device__ __forceinline__ double dbeta_log(double x, double a, double b, double lbeta)
+{
+    if (isnan(x)) return x;
+    if (x < 0.0 || x > 1.0) return -INFINITY;
+    if (x == 0.0)
+    {
+        if (a > 1.0) return -INFINITY;
+        if (a < 1.0) return INFINITY;
+        return log(b);
+    }
+    if (x == 1.0)
+    {
+        if (b > 1.0) return -INFINITY;
+        if (b < 1.0) return INFINITY;
+        return log(a);
+    }
+    return (a - 1.0) * log(x) + (b - 1.0) * log1p(-x) - lbeta;
+}
+
+// R::dgamma(x, shape, scale, log = TRUE); lg_shape = lgamma(shape), l_scale = log(scale).
+__device__ __forceinline__ double dgamma_log(double x, double shape, double scale, double lg_shape,
+                                             double l_scale)
+{
+    if (isnan(x)) return x;
+    if (x < 0.0) return -INFINITY;
+    if (x == 0.0)
+    {
+        if (shape < 1.0) return INFINITY;
+        if (shape > 1.0) return -INFINITY;
+        return -l_scale;
+    }
+    return (shape - 1.0) * log(x) - x / scale - lg_shape - shape * l_scale;
+}
+
+// Sampler::dztpois (src/sampler.cpp:38-42).
+__device__ __forceinline__ double dztpois_log(int x, double log_lambda, double log_expm1_lambda,
+                                              const double *lgam)
+{
+    return __dsub_rn(__dsub_rn(__dmul_rn((double)x, log_lambda), log_expm1_lambda), lgam[x]);
+}
+}  // namespace moire

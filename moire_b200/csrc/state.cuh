@@ -1,0 +1,63 @@
+// Device-resident state of a block of tempered chains, as a POD view handed to kernels by value.
+//
+// Replaces the public members of the reference's Chain (src/chain.h:84-142) for ALL chains of one
+// GPU at once.  Per-cell arrays are [T][N][L] (sample-major rows, like
+// genotyping_llik_new[sample * L + locus], src/chain.cpp:1116), per-sample arrays [T][N], allele
+// frequencies [T][L][AP].  Only the accepted ("old") state is stored: proposals live in
+// registers / shared memory of the kernel that makes the accept decision, so the reference's
+// new/old double buffering and its save_* / restore_* copies (src/chain.cpp:1225-1286) vanish.
+// The cell log-likelihood is kept as its two addends (transmission, observation) because two of
+// the eight updates change only one of them.
+#pragma once
+#include <cstdint>
+
+namespace moire
+{
+struct View
+{
+    int N, L, T, AP, nA;
+    int allow_rel, burnin, max_coi, chain_offset;
+    unsigned long long seed;
+
+    // data (read-only)
+    const unsigned long long *obs;  // [N][L]
+    const unsigned char *missing;   // [N][L]
+    const int *nall;                // [L]
+    const int *aclass;              // [L] index into avals
+    const int *avals;               // [nA] distinct allele counts
+    const int *obs_coi;             // [N]
+    const double *logC;             // [65][65] log C(n, k)
+    const double *lgam;             // [128] lgamma(i + 1)
+
+    // per cell [T][N][L]
+    unsigned long long *latent;
+    double *lgadj;
+    double *cellT;
+    double *cellO;
+
+    // per sample [T][N]
+    int *m;
+    double *r, *log_r, *log_1mr;
+    double *eps_pos, *eps_neg;
+    double *sd_eps_neg, *sd_eps_pos, *sd_r, *sd_mr;
+    int *acc_eps_neg, *acc_eps_pos, *acc_m, *acc_r, *acc_mr, *acc_samples;
+    double *pr_eps_neg, *pr_eps_pos, *pr_coi, *pr_r;
+
+    // per locus [T][L][AP]
+    double *p, *p_sd;
+    int *p_acc, *p_att;
+
+    // per chain [T]
+    double *mean_coi, *mean_coi_sd, *mean_coi_acc, *hyper;
+    double *temp, *llik, *prior;
+    int *active;  // init retry mask
+
+    unsigned long long *evals;  // [1] non-missing cell evaluations
+
+    // parameters (src/parameters.h:31-47) and host-precomputed constants
+    double mean_coi_shape, mean_coi_scale, lg_shape, l_scale;
+    double max_eps_pos, eps_pos_a, eps_pos_b, eps_pos_lbeta;
+    double max_eps_neg, eps_neg_a, eps_neg_b, eps_neg_lbeta;
+    double r_a, r_b, r_lbeta;
+};
+}  // namespace moire

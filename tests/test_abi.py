@@ -1,0 +1,65 @@
+"""The C-ABI library loads and exports every symbol include/moire_engine.h declares; without a
+GPU the product fails loudly instead of falling back to anything."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for fn in os.listdir(os.path.join(ROOT, "include")):
+        if fn.endswith(".h"):
+            src = open(os.path.join(ROOT, "include", fn)).read()
+            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+            names |= set(re.findall(r"\b(moire_[a-z0-9_]+)\s*\(", src))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from moire_b200 import _lib
+    lib = _lib.load()
+    decl = declared_symbols()
+    assert len(decl) >= 20
+    for name in sorted(decl):
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+    assert decl >= set(_lib.ENGINE_SYMBOLS), "binding names a symbol the header does not declare"
+    assert isinstance(lib, ctypes.CDLL)
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors, philox4x32-10."""
+    from moire_b200.engine import philox4x32
+    kat = [([0] * 4, [0] * 2, [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for c, k, want in kat:
+        assert [int(x) for x in philox4x32(c, k)] == want
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from moire_b200.data import pack_data
+    from moire_b200.engine import Engine, MoireError
+    from moire_b200.simulate import simulate_data
+    d = simulate_data(mean_coi=3, num_samples=5, epsilon_pos=.01, epsilon_neg=.1,
+                      locus_freq_alphas=[np.ones(4)] * 3, seed=1)
+    with pytest.raises(MoireError, match="no CPU fallback"):
+        Engine(pack_data(d["data"], d["is_missing"]), [1.0])
+
+
+def test_product_does_not_import_oracle():
+    """Only tests/, smoke() and bench.py's baseline legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "moire_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in src.replace("no oracle", ""), os.path.join(dirpath, fn)
