@@ -303,3 +303,6 @@ void orc_eval_cells(int prec, int N, int L, const int *num_alleles, const uint64
         }
     }
 }
+
+/* ---- the engine-semantics Metropolis stepper (fp64) ------------------------------------------ */
+#include "engine_stepper_impl.h"

@@ -59,6 +59,16 @@ void orc_eval_cells(int prec, int N, int L, const int *num_alleles, const uint64
                     int a_pad, int allow_relatedness, double max_eps_neg, double max_eps_pos,
                     double *t_out, double *o_out);
 
+/* Philox4x32-10 of the stepper (independent of the engine's), for the known-answer test. */
+void orc_philox4x32(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+
+/* Engine-semantics Metropolis stepper, one chain, one update kind per call (see
+ * engine_stepper_impl.h).  `chain` is the struct stp_chain defined there (mirrored field by
+ * field in oracle/pyoracle.py). */
+struct stp_chain_s;
+void orc_step_update(void *chain, int kind, int iteration);
+void orc_eval_priors(void *chain);
+
 #ifdef __cplusplus
 }
 #endif

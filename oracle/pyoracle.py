@@ -475,3 +475,103 @@ class Ref:
         out = np.zeros((self.N, max_draws), np.int32)
         D = self.lib.ref_mcmc_coi_draws(h, _p(out), max_draws)
         return out[:, :D]
+
+
+class _StpChain(C.Structure):
+    _fields_ = ([("N", C.c_int), ("L", C.c_int), ("a_pad", C.c_int),
+                 ("num_alleles", C.c_void_p), ("obs", C.c_void_p), ("is_missing", C.c_void_p),
+                 ("allow_relatedness", C.c_int), ("burnin", C.c_int), ("max_coi", C.c_int)] +
+                [(n, C.c_double) for n in ("mean_coi_shape", "mean_coi_scale", "max_eps_pos",
+                                           "eps_pos_alpha", "eps_pos_beta", "max_eps_neg",
+                                           "eps_neg_alpha", "eps_neg_beta", "r_alpha", "r_beta")] +
+                [("seed", C.c_uint64), ("chain", C.c_int), ("temp", C.c_double)] +
+                [(n, C.c_void_p) for n in ("m", "r", "eps_pos", "eps_neg", "p", "latent", "lg_adj",
+                                           "cell_t", "cell_o", "prior_eps_neg", "prior_eps_pos",
+                                           "prior_coi", "prior_r", "mean_coi", "hyper",
+                                           "sd_eps_neg", "sd_eps_pos", "sd_r", "sd_mr",
+                                           "acc_eps_neg", "acc_eps_pos", "acc_m", "acc_r",
+                                           "acc_mr", "acc_samples", "p_sd", "p_acc", "p_att",
+                                           "mean_coi_sd", "mean_coi_acc")] +
+                [("evals", C.c_ulonglong)])
+
+
+STATE_FIELDS = ("m", "r", "eps_pos", "eps_neg", "p", "latent", "lg_adj", "cell_t", "cell_o",
+                "prior_eps_neg", "prior_eps_pos", "prior_coi", "prior_r")
+TUNING_FIELDS = ("sd_eps_neg", "sd_eps_pos", "sd_r", "sd_mr", "acc_eps_neg", "acc_eps_pos",
+                 "acc_m", "acc_r", "acc_mr", "acc_samples", "p_sd", "p_acc", "p_att")
+
+
+class Stepper:
+    """One chain advanced on the CPU with the engine's stream addressing (fp64).
+
+    ``state``: arrays as returned by ``Engine.dump_state`` (p padded to the engine's a_pad);
+    ``diag``: as returned by ``Engine.diagnostics`` (or None for a fresh chain)."""
+
+    def __init__(self, oracle, packed, model, seed, chain, temp, state, diag=None):
+        self.lib = oracle.lib
+        self.lib.orc_step_update.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self.lib.orc_eval_priors.argtypes = [C.c_void_p]
+        N, L = packed.num_samples, packed.num_loci
+        A = state["p"].shape[1]
+        a = self.a = {}
+        a["num_alleles"] = _i32(packed.num_alleles)
+        a["obs"] = np.ascontiguousarray(packed.obs_mask, dtype=np.uint64)
+        a["is_missing"] = np.ascontiguousarray(packed.is_missing, dtype=np.uint8)
+        a["m"] = _i32(state["m"]).copy()
+        for k in ("r", "eps_pos", "eps_neg", "p", "lg_adj", "cell_t", "cell_o", "prior_eps_neg",
+                  "prior_eps_pos", "prior_coi", "prior_r"):
+            a[k] = _f64(state[k]).copy()
+        a["latent"] = np.ascontiguousarray(state["latent"], dtype=np.uint64).copy()
+        a["mean_coi"] = np.array([state["mean_coi"]], dtype=np.float64)
+        a["hyper"] = np.array([state["mean_coi_hyper_prior"]], dtype=np.float64)
+        if diag is None:
+            diag = dict(eps_neg_var=np.ones(N), eps_pos_var=np.ones(N), r_var=np.ones(N),
+                        m_r_var=np.ones(N), p_prop_var=np.ones((L, A)), mean_coi_var=1.0,
+                        mean_coi_accept=0.0)
+        z = lambda k, shape: _i32(diag[k]).copy() if k in diag else np.zeros(shape, np.int32)
+        a["sd_eps_neg"] = _f64(diag["eps_neg_var"]).copy()
+        a["sd_eps_pos"] = _f64(diag["eps_pos_var"]).copy()
+        a["sd_r"] = _f64(diag["r_var"]).copy()
+        a["sd_mr"] = _f64(diag["m_r_var"]).copy()
+        a["acc_eps_neg"] = z("eps_neg_accept", N)
+        a["acc_eps_pos"] = z("eps_pos_accept", N)
+        a["acc_m"] = z("m_accept", N)
+        a["acc_r"] = z("r_accept", N)
+        a["acc_mr"] = z("m_r_accept", N)
+        a["acc_samples"] = z("sample_accept", N)
+        a["p_sd"] = _f64(diag["p_prop_var"]).copy()
+        a["p_acc"] = z("p_accept", (L, A))
+        a["p_att"] = z("p_attempt", (L, A))
+        a["mean_coi_sd"] = np.array([diag["mean_coi_var"]], dtype=np.float64)
+        a["mean_coi_acc"] = np.array([diag["mean_coi_accept"]], dtype=np.float64)
+        s = self.s = _StpChain()
+        s.N, s.L, s.a_pad = N, L, A
+        s.allow_relatedness = int(bool(model["allow_relatedness"]))
+        s.burnin, s.max_coi = int(model["burnin"]), int(model["max_coi"])
+        for k in ("mean_coi_shape", "mean_coi_scale", "max_eps_pos", "eps_pos_alpha",
+                  "eps_pos_beta", "max_eps_neg", "eps_neg_alpha", "eps_neg_beta", "r_alpha",
+                  "r_beta"):
+            setattr(s, k, float(model[k]))
+        s.seed, s.chain, s.temp = seed, chain, float(temp)
+        for k, v in a.items():
+            setattr(s, k, v.ctypes.data)
+        s.evals = 0
+
+    def update(self, kind, iteration):
+        k = UPDATE_KINDS[kind] if isinstance(kind, str) else int(kind)
+        self.lib.orc_step_update(C.byref(self.s), k, iteration)
+
+    def set_temp(self, t):
+        self.s.temp = float(t)
+
+    @property
+    def evals(self):
+        return int(self.s.evals)
+
+    def llik(self):
+        return float((self.a["cell_t"] + self.a["cell_o"]).sum())
+
+    def prior(self):
+        a = self.a
+        return float((a["prior_eps_neg"] + a["prior_eps_pos"] + a["prior_r"]
+                      + a["prior_coi"]).sum() + a["hyper"][0])

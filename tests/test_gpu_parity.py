@@ -117,3 +117,96 @@ def test_runs_are_reproducible_and_sharding_invariant():
         assert np.array_equal(a[k], b[k]), k
     for e in (whole, lo, hi):
         e.close()
+
+
+STATE_KEYS = ("r", "eps_pos", "eps_neg", "p", "lg_adj", "cell_t", "cell_o", "prior_eps_neg",
+              "prior_eps_pos", "prior_coi", "prior_r")
+DIAG_MAP = dict(eps_neg_var="sd_eps_neg", eps_pos_var="sd_eps_pos", r_var="sd_r", m_r_var="sd_mr",
+                eps_neg_accept="acc_eps_neg", eps_pos_accept="acc_eps_pos", m_accept="acc_m",
+                r_accept="acc_r", m_r_accept="acc_mr", sample_accept="acc_samples",
+                p_prop_var="p_sd", p_accept="p_acc", p_attempt="p_att")
+
+
+# The engine's SALT proposal sums its simplex terms as a warp tree, the stepper sequentially, and
+# CUDA's libm differs from glibc's by an ulp: allele frequencies agree to ~1e-16 relative.  The
+# inclusion-exclusion sum amplifies that by its condition number in cells whose coverage
+# probability is tiny (the reference's own fp64 variant has the same sensitivity), so the
+# transmission term of a state reached through DIFFERENT last bits of p is compared at 1e-5
+# here; on IDENTICAL inputs it is compared at 1e-9 (tests above and oracle_recheck below).
+CELL_T_TOL = 1e-5
+
+
+def oracle_recheck(oracle, eng, pk, chain, allow, where):
+    st = eng.dump_state(chain)
+    t, o = oracle.eval_cells(64, pk.num_alleles, pk.obs_mask, pk.is_missing, st["latent"], st["m"],
+                             st["r"], st["eps_neg"], st["eps_pos"], st["p"][:, :pk.max_alleles],
+                             allow)
+    assert rel_err(st["cell_t"], t) < RTOL and rel_err(st["cell_o"], o) < RTOL, where
+
+
+def compare_with_stepper(eng, stp, chain, where):
+    st, dg = eng.dump_state(chain), eng.diagnostics(chain)
+    a = stp.a
+    assert np.array_equal(st["m"], a["m"]), where
+    assert np.array_equal(st["latent"], a["latent"]), where   # bit-exact index work
+    for k in STATE_KEYS:
+        assert rel_err(st[k], a[k]) < (CELL_T_TOL if k == "cell_t" else RTOL), (where, k)
+    assert abs(st["mean_coi"] - a["mean_coi"][0]) < RTOL * max(1, abs(st["mean_coi"])), where
+    for k, sk in DIAG_MAP.items():
+        if dg[k].dtype.kind == "i":
+            assert np.array_equal(dg[k], a[sk]), (where, k)
+        else:
+            assert rel_err(dg[k], a[sk]) < RTOL, (where, k)
+    assert abs(dg["mean_coi_var"] - a["mean_coi_sd"][0]) < RTOL, where
+    assert dg["mean_coi_accept"] == a["mean_coi_acc"][0], where
+    # re-synchronise so that every update is compared from bit-identical inputs
+    for k in STATE_KEYS:
+        a[k][...] = st[k]
+    a["mean_coi"][0] = st["mean_coi"]
+    a["hyper"][0] = st["mean_coi_hyper_prior"]
+    for k, sk in DIAG_MAP.items():
+        a[sk][...] = dg[k]
+    a["mean_coi_sd"][0] = dg["mean_coi_var"]
+
+
+@pytest.mark.parametrize("allow", [1, 0])
+def test_metropolis_updates_match_stepper(oracle, allow):
+    """Every one of the eight updates, kind by kind over several sweeps (including ones past
+    iteration 15, where proposal-scale adaptation is live), against the CPU stepper that
+    restates src/chain.cpp:165-856 with the engine's stream addressing: accepted proposals,
+    latent genotypes, counters bit-exact; floating state to 1e-9."""
+    from moire_b200.data import pack_data
+    from moire_b200.engine import DEFAULT_MODEL
+    from moire_b200.simulate import simulate_data
+    from oracle.pyoracle import Stepper
+    d = simulate_data(mean_coi=4, num_samples=37, epsilon_pos=.03, epsilon_neg=.1,
+                      locus_freq_alphas=[np.ones(5)] * 4 + [np.ones(13)] * 5 + [np.ones(2)] * 2,
+                      internal_relatedness_alpha=.3, internal_relatedness_beta=1,
+                      missingness=.06, seed=23)
+    pk = pack_data(d["data"], d["is_missing"])
+    temps = (1.0, 0.37, 0.0)
+    seed = 77
+    eng, _ = engine_for(pk, temps=temps, allow=allow, seed=seed, burnin=30, max_coi=25)
+    assert not eng.init_chains()["still_ill"].any()
+    model = dict(DEFAULT_MODEL, allow_relatedness=bool(allow), burnin=30, max_coi=25)
+    steppers = [Stepper(oracle, pk, model, seed, c, temps[c], eng.dump_state(c),
+                        eng.diagnostics(c)) for c in range(3)]
+    kinds = ["eps_neg", "eps_pos", "p", "m"] + (["r", "eff_coi"] if allow else []) + \
+            ["samples", "mean_coi"]
+    ev0, _ = eng.counters()
+    for it in list(range(0, 3)) + list(range(16, 21)) + [30, 31]:
+        for kind in kinds:
+            eng.update(kind, it)
+            for c, stp in enumerate(steppers):
+                stp.update(kind, it)
+                compare_with_stepper(eng, stp, c, (it, kind, c))
+        for c in range(3):
+            oracle_recheck(oracle, eng, pk, c, allow, (it, c))
+    eng.reduce()
+    llik, prior = eng.scalars()
+    for c, stp in enumerate(steppers):
+        assert abs(llik[c] - stp.llik()) < 1e-9 * abs(llik[c])
+        assert abs(prior[c] - stp.prior()) < 1e-9 * max(1.0, abs(prior[c]))
+    ev1, _ = eng.counters()
+    assert ev1 - ev0 == sum(s.evals for s in steppers)  # same count of cell evaluations
+    eng.close()
