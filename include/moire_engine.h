@@ -134,6 +134,13 @@ int moire_engine_init_chains(moire_engine *e, int32_t max_tries, int32_t *ill_co
                              int32_t *still_ill, int32_t *first_bad_sample,
                              int32_t *first_bad_locus, int32_t *prior_nonfinite);
 
+/* Every ill-conditioned start seen by the last moire_engine_init_chains, in attempt order:
+ * records of (local chain, 1-based sample, 1-based locus), (chain, 0, 0) when no genotyping term
+ * was non-finite (record_ill_conditioned_start, src/mcmc.cpp:25-39).  *count gets the number of
+ * records; at most max_records are copied. */
+int moire_engine_read_init_log(moire_engine *e, int32_t *records, int32_t max_records,
+                               int32_t *count);
+
 /* One sweep of all updates on every chain of the engine, in the reference's order, followed by
  * the per-chain log-likelihood / prior reduction: the body of the OpenMP loops in
  * MCMC::burnin / MCMC::sample (src/mcmc.cpp:159-174, 308-323).  `iteration` is what the

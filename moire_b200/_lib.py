@@ -42,6 +42,49 @@ class MoireChainDiagnostics(C.Structure):
                                   "mean_coi_accept", "mean_coi_var")]
 
 
+class MoireMcmcParams(C.Structure):
+    _fields_ = [("thin", i32), ("burnin", i32), ("samples", i32), ("adapt_temp", i32),
+                ("pre_adapt_steps", i32), ("temp_adapt_steps", i32),
+                ("max_initialization_tries", i32), ("record_latent_genotypes", i32),
+                ("max_runtime", dbl)]
+
+
+class MoireMcmcSizes(C.Structure):
+    _fields_ = [(n, i32) for n in ("num_chains", "first_chain", "local_chains", "burnin_steps",
+                                   "sample_steps", "num_draws", "num_swap_store", "a_pad")]
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, vp, C.POINTER(dbl), i32, C.POINTER(dbl))
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, vp, i32, i32, dbl, i32)
+
+# every symbol include/moire_mcmc.h declares
+MCMC_SYMBOLS = {
+    "moire_mcmc_create": (C.c_int, [C.POINTER(MoireData), C.POINTER(MoireParams),
+                                    C.POINTER(MoireMcmcParams), vp, i32, i32, i32, i32, u64,
+                                    C.POINTER(vp)]),
+    "moire_mcmc_destroy": (C.c_int, [vp]),
+    "moire_mcmc_last_error": (C.c_char_p, [vp]),
+    "moire_mcmc_partition": (None, [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]),
+    "moire_mcmc_set_allgather": (C.c_int, [vp, ALLGATHER_FN, vp]),
+    "moire_mcmc_engine": (vp, [vp]),
+    "moire_mcmc_init": (C.c_int, [vp, C.POINTER(i32)]),
+    "moire_mcmc_burnin": (C.c_int, [vp, i32]),
+    "moire_mcmc_sample": (C.c_int, [vp, i32]),
+    "moire_mcmc_finalize": (C.c_int, [vp]),
+    "moire_mcmc_run": (C.c_int, [vp, PROGRESS_FN, vp, C.POINTER(i32), C.POINTER(dbl)]),
+    "moire_mcmc_get_sizes": (C.c_int, [vp, C.POINTER(MoireMcmcSizes)]),
+    "moire_mcmc_get_traces": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "moire_mcmc_get_ladder": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "moire_mcmc_get_hot": (C.c_int, [vp, vp]),
+    "moire_mcmc_get_draws": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "moire_mcmc_swap_pass": (C.c_int, [vp, vp, i32, i32]),
+    "moire_mcmc_set_swap_uniforms": (C.c_int, [vp, vp, i32]),
+    "moire_mcmc_set_ladder": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, i32]),
+    "moire_mcmc_adapt_temp": (C.c_int, [vp]),
+    "moire_mcmc_set_local_scalars": (C.c_int, [vp, vp, vp]),
+    "moire_monotone_spline_solve": (dbl, [vp, vp, i32, dbl]),
+}
+
 # every symbol include/moire_engine.h declares: (restype, argtypes)
 ENGINE_SYMBOLS = {
     "moire_last_error": (C.c_char_p, []),
@@ -52,6 +95,7 @@ ENGINE_SYMBOLS = {
     "moire_engine_a_pad": (i32, [vp]),
     "moire_engine_num_chains": (i32, [vp]),
     "moire_engine_init_chains": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
+    "moire_engine_read_init_log": (C.c_int, [vp, vp, i32, vp]),
     "moire_engine_step": (C.c_int, [vp, i32]),
     "moire_engine_update": (C.c_int, [vp, i32, i32]),
     "moire_engine_eval_all": (C.c_int, [vp]),
@@ -85,7 +129,7 @@ def load():
             f"{LIB_PATH} is missing: build the CUDA engine first "
             "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in ENGINE_SYMBOLS.items():
+    for name, (res, args) in list(ENGINE_SYMBOLS.items()) + list(MCMC_SYMBOLS.items()):
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args

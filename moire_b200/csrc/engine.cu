@@ -100,6 +100,7 @@ struct moire_engine
         int kind;
     };
     std::vector<TimedLaunch> pending;
+    std::vector<int32_t> init_log;  // (chain, sample, locus) per ill-conditioned start
     double kind_ms[9] = {0};
     uint64_t kind_launches[9] = {0};
 
@@ -404,6 +405,7 @@ struct moire_engine
         const int T = v.T, N = v.N, L = v.L;
         std::vector<int> act(T, 1), ill(T, 0);
         std::vector<double> llik(T);
+        init_log.clear();
         if (bad_sample) std::fill(bad_sample, bad_sample + T, 0);
         if (bad_locus) std::fill(bad_locus, bad_locus + T, 0);
         if (prior_nonfinite) std::fill(prior_nonfinite, prior_nonfinite + 5 * T, 0);
@@ -429,8 +431,13 @@ struct moire_engine
                 }
                 ++ill[t];
                 any = true;
-                diagnose(t, bad_sample ? &bad_sample[t] : nullptr, bad_locus ? &bad_locus[t] : nullptr,
-                         prior_nonfinite ? &prior_nonfinite[5 * t] : nullptr);
+                int32_t bs = 0, bl = 0;
+                diagnose(t, &bs, &bl, prior_nonfinite ? &prior_nonfinite[5 * t] : nullptr);
+                if (bad_sample) bad_sample[t] = bs;
+                if (bad_locus) bad_locus[t] = bl;
+                init_log.push_back(t);
+                init_log.push_back(bs);
+                init_log.push_back(bl);
             }
             if (!any) break;
         }
@@ -648,6 +655,19 @@ int moire_engine_init_chains(moire_engine *e, int32_t max_tries, int32_t *ill_co
         if (!e) throw InvalidArg{"null engine"};
         e->init_chains(max_tries, ill_count, still_ill, first_bad_sample, first_bad_locus,
                        prior_nonfinite);
+    });
+}
+
+int moire_engine_read_init_log(moire_engine *e, int32_t *records, int32_t max_records,
+                               int32_t *count)
+{
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        const int32_t n = (int32_t)(e->init_log.size() / 3);
+        if (count) *count = n;
+        if (records)
+            std::copy(e->init_log.begin(), e->init_log.begin() + 3 * (size_t)std::min(n, std::max(max_records, 0)),
+                      records);
     });
 }
 

@@ -460,6 +460,35 @@ class Ref:
     def mcmc_free(self, h):
         self.lib.ref_mcmc_free(h)
 
+    def seed_runif(self, seed):
+        self.lib.ref_seed_runif(seed)
+
+    def draw_log_runif(self):
+        return float(self.lib.ref_draw_log_runif())
+
+    def mcmc_swap_pass(self, h, chain_llik, chain_temp, swap_indices, even_swap, step, burnin,
+                       swap_barriers, swap_acceptances, num_swaps):
+        """MCMC::swap_chains (src/mcmc.cpp:190-240) on explicit inputs; returns the new ladder."""
+        T = len(chain_llik)
+        ll, tp = _f64(chain_llik), _f64(chain_temp)
+        si = np.ascontiguousarray(swap_indices, dtype=np.int64)
+        so, to, hot = np.zeros(T, np.int64), np.zeros(T), np.zeros(T, np.int32)
+        sb = _f64(swap_barriers).copy()
+        sa = np.ascontiguousarray(swap_acceptances, dtype=np.int64).copy()
+        ns = C.c_long(int(num_swaps))
+        self.lib.ref_mcmc_swap_pass(h, _p(ll), _p(tp), _p(si), int(even_swap), int(step),
+                                    int(burnin), _p(so), _p(to), _p(hot), _p(sb), _p(sa),
+                                    C.byref(ns))
+        return dict(swap_indices=so, chain_temps=to, hot=hot, swap_barriers=sb,
+                    swap_acceptances=sa, num_swaps=ns.value)
+
+    def mcmc_adapt_temp(self, h, temp_gradient, swap_barriers, num_swaps):
+        """MCMC::adapt_temp (src/mcmc.cpp:244-304) on explicit inputs; returns the new gradient."""
+        out = np.zeros(len(temp_gradient))
+        self.lib.ref_mcmc_adapt_temp(h, _p(_f64(temp_gradient)), _p(_f64(swap_barriers)),
+                                     int(num_swaps), _p(out))
+        return out
+
     def mcmc_summary(self, h):
         N, L, A = self.N, self.L, self.a_pad
         out = dict(m=np.zeros(N), r=np.zeros(N), eps_neg=np.zeros(N), eps_pos=np.zeros(N),
