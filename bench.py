@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: parallel-tempering MCMC steps per second with every temperature of
+the ladder advanced (BASELINE.json's metric), on synthetic `simulate_data` of the named shape.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl reference]
+
+One "step" is everything MCMC::burnin(step) does (src/mcmc.cpp:157-188): the eight Metropolis
+updates on every chain of the ladder, the per-chain log-likelihood reduction, the swap pass and
+(when due) the ladder adaptation.  With N > 1 (launched under torchrun, one rank per GPU) the
+ladder is cut into N contiguous blocks of temperatures and the ranks exchange only the per-chain
+scalar log-likelihoods (NCCL all-gather); total work is fixed, so scaling is "strong".
+
+Our arm prints ONE JSON line: `value` = steps/s with the state resident in HBM (CUDA events on the
+engine's stream around each step, L2 flushed between steps, max over ranks), `e2e` = the same
+metric through the public `run_mcmc` call with host buffers (data packing, upload, chain
+initialisation, every step's scalar read-back, every stored draw's device->host copy, result
+assembly), `roofline` for the dominant kernel, `cpu_baseline` = the reference's own C++ sampler
+(compiled unmodified under oracle/_ref) on this box's host cores.
+
+`--impl reference` times that CPU sampler alone and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mcmc_steps_per_sec_all_temps"
+UNIT = "steps/s"
+B_EVAL = 24  # algorithmic bytes per cell evaluation (obs mask + latent mask + llik)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag = index, threading.Event()
+        self.sm, self.reasons, self.max_mhz, self.err = [], set(), None, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            while not self.stop_flag.is_set():
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.stop_flag.wait(0.05)
+        except Exception as exc:  # no NVML: report that, do not fail the bench
+            self.err = repr(exc)
+
+    def summary(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "error": self.err}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# ---- the reference's CPU sampler (oracle/_ref, built from /root/reference by oracle/Makefile) ----
+def cpu_reference_rate(wl, steps, warmup, budget_s):
+    """MCMC::burnin steps/s (all temperatures) of the unmodified reference C++ on this host, all
+    OpenMP threads.  If the full ladder does not fit the time budget the step is run on a
+    sub-ladder (every k-th temperature) and scaled by chains, and `sample` says so."""
+    from oracle.pyoracle import Ref
+    ref = Ref(32)
+    pk, temps = wl["packed"], np.asarray(wl["temps"], dtype=np.float64)
+    T = len(temps)
+    cores = os.cpu_count() or 1
+    threads = min(cores, T)
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    ref.set_data(pk.num_alleles, pk.obs_mask, pk.is_missing)
+
+    def run(sub_temps, w, k):
+        ref.set_params(pt_chains=sub_temps, pt_num_threads=min(cores, len(sub_temps)),
+                       allow_relatedness=int(wl["model"]["allow_relatedness"]),
+                       max_coi=wl["model"]["max_coi"], burnin=10000)
+        h = ref.mcmc_new(seed=1)
+        t0 = time.time()
+        one = ref.mcmc_time_burnin(h, 0, 0, 1)        # first step, also the estimate
+        if w + k > 1 and one * (w + k) > budget_s:
+            ref.mcmc_free(h)
+            return None, one, time.time() - t0
+        secs = ref.mcmc_time_burnin(h, 1, max(w - 1, 0), k)
+        ref.mcmc_free(h)
+        return secs, one, time.time() - t0
+
+    secs, one, _ = run(temps, warmup, steps)
+    used_T = T
+    if secs is None:
+        # sub-ladder sized to the budget: chains cost about the same, threads <= chains
+        per_chain_round = one / math.ceil(T / threads)
+        rounds = max(1, int(budget_s / ((warmup + steps) * per_chain_round)))
+        used_T = max(2, min(T, rounds * threads))
+        idx = np.unique(np.round(np.linspace(0, T - 1, used_T)).astype(int))
+        used_T = len(idx)
+        secs, one, _ = run(temps[idx], warmup, steps)
+        if secs is None:   # still too slow: one timed step after the estimate step
+            secs, steps = one, 1
+    chain_steps_per_s = used_T * steps / secs
+    value = chain_steps_per_s / T
+    sample = (f"{steps} MCMC::burnin steps after {warmup} warm-up, "
+              f"{used_T} of {T} temperatures" + ("" if used_T == T else " (every k-th; scaled by chains)") +
+              f", {min(cores, used_T)} OpenMP threads, reference C++ (-O2 -fopenmp) via oracle/_ref/libmoire_ref32.so")
+    return dict(value=value, unit=UNIT, cores=min(cores, used_T), kind="reference", sample=sample,
+                host_cores=cores, seconds=secs)
+
+
+def reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_reference_rate(wl, args.steps, args.warmup, budget_s=240.0)
+    line = dict(impl="reference", metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 / base["value"],
+                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
+                data="synthetic", config=config_of(wl, args),
+                cpu_baseline=dict(value=base["value"], unit=UNIT, cores=base["cores"],
+                                  kind=base["kind"], sample=base["sample"]),
+                e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def config_of(wl, args):
+    pk = wl["packed"]
+    return dict(workload=f"{wl['name']}: simulate_data {pk.num_samples} samples x {pk.num_loci} loci, "
+                         f"A_j {int(pk.num_alleles.min())}..{int(pk.num_alleles.max())}, "
+                         f"{len(wl['temps'])} temperatures, relatedness on, max_coi {wl['model']['max_coi']}",
+                samples=pk.num_samples, loci=pk.num_loci, temperatures=len(wl["temps"]),
+                parallelism=f"temperature ladder sharded over {args.gpus} GPU(s)",
+                cache="L2 flushed (256 MiB memset) before every timed step")
+
+
+# ---- our arm ---------------------------------------------------------------------------------------
+def our_arm(args, wl):
+    import torch
+    import torch.distributed as dist
+    from moire_b200.mcmc import MCMC, run_mcmc, torch_allgather
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk, temps, model = wl["packed"], np.asarray(wl["temps"], dtype=np.float64), wl["model"]
+    T = len(temps)
+    if world > T:
+        raise SystemExit(f"{world} ranks for a ladder of {T} temperatures")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gather = torch_allgather(world, dev) if world > 1 else None
+    burnin_total = args.warmup + args.steps + 8
+    mc = MCMC(pk, temps, burnin=burnin_total, samples=0, seed=args.seed, device=local, rank=rank,
+              world_size=world, allgather=gather, **model)
+    if not mc.init():
+        raise SystemExit("chain initialisation failed")
+    eng = mc.engine
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    step = 0
+    for _ in range(args.warmup):
+        mc.burnin(step)
+        step += 1
+    ev0, l0 = eng.counters()
+    ke0 = eng.kind_evals()
+    eng.set_timing(True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        eng.timer_start()
+        mc.burnin(step)
+        dev_ms += eng.timer_stop()
+        step += 1
+    barrier()
+    wall = time.perf_counter() - wall0
+    sampler.stop_flag.set()
+    sampler.join(2.0)
+    kinds = eng.timing()
+    eng.set_timing(False)
+    ev1, l1 = eng.counters()
+    ke1 = eng.kind_evals()
+    stats = torch.tensor([dev_ms, float(ev1 - ev0), float(l1 - l0)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        dev_ms_max = float(mx[0])
+    else:
+        dev_ms_max = dev_ms
+    evals_total, launches_total = float(stats[1]), int(stats[2])
+    ms_per_step = dev_ms_max / args.steps
+    value = 1e3 / ms_per_step
+    mc.close()
+
+    # ---- end to end through the public call, host buffers in, result list out
+    e2e_burn, e2e_samp = args.steps, args.steps
+    barrier()
+    t0 = time.perf_counter()
+    res = run_mcmc(wl["sim"], wl["sim"]["is_missing"], burnin=e2e_burn, samples_per_chain=e2e_samp,
+                   pt_chains=temps, verbose=False, seed=args.seed, device=local,
+                   distributed=world > 1, **{k: v for k, v in model.items()})
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    chain = res["chains"][0]
+    n_steps = e2e_burn + e2e_samp
+    N, L, AP = pk.num_samples, pk.num_loci, (int(pk.num_alleles.max()) + 3) // 4 * 4
+    h2d = (pk.obs_mask.nbytes + pk.is_missing.nbytes + pk.num_alleles.nbytes + pk.observed_coi.nbytes
+           + 8 * T) * world / n_steps + 8 * T          # data + ladder once per rank, temps per step
+    draw_bytes = L * AP * 8 + N * (4 + 4 * 8) + 8
+    d2h = 16 * T + draw_bytes * len(chain["lam_coi"]) / n_steps
+    e2e = dict(value=n_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=int(h2d),
+               d2h_bytes_per_step=int(d2h), seconds=e2e_s, steps=n_steps,
+               call=f"moire_b200.mcmc.run_mcmc(burnin={e2e_burn}, samples_per_chain={e2e_samp}, "
+                    f"pt_chains={T}) incl. pack_data, upload, chain init, per-step scalar read-back, "
+                    f"{len(chain['lam_coi'])} stored draws, result assembly")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (this rank's launches, CUDA events on its stream)
+    peak, peak_src = measured_peak()
+    kind_ms = {k: v[0] for k, v in kinds.items()}
+    kind_n = {k: v[1] for k, v in kinds.items()}
+    top = max((k for k in kind_ms if k != "reduce"), key=lambda k: kind_ms[k])
+    top_evals = ke1[top] - ke0[top] if top in ke1 else 0
+    top_s = kind_ms[top] * 1e-3
+    achieved = top_evals * B_EVAL / top_s / 1e9 if top_s > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_inputs.json")) as f:
+            traffic = json.load(f).get("traffic_bytes_per_launch", {}).get(top)
+    except Exception:
+        pass
+    kernel_name = {"p": "k_update_p"}.get(top, f"k_update_sample<{top}>")
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                    traffic=traffic, kernel=kernel_name, peak_source=peak_src,
+                    launches=kind_n[top], ms_per_launch=kind_ms[top] / max(kind_n[top], 1),
+                    algorithmic_bytes_per_launch=top_evals * B_EVAL / max(kind_n[top], 1),
+                    share_of_step=kind_ms[top] / max(sum(kind_ms.values()), 1e-12),
+                    note="algorithmic fraction: 24 B per cell evaluation; the kernel is fp64-pipe/"
+                         "latency bound (SURVEY F11), see DESIGN.md")
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_reference_rate(wl, steps=2, warmup=1, budget_s=30.0)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as exc:
+            cpu = dict(value=None, unit=UNIT, cores=0, kind="reference", sample=f"unavailable: {exc!r}")
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True,
+                scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+                config=config_of(wl, args), clocks=sampler.summary(), e2e=e2e,
+                gpu_launches=launches_total, roofline=roofline, cpu_baseline=cpu,
+                likelihood_evals_per_sec=evals_total / (dev_ms_max * 1e-3),
+                evals_per_step=evals_total / args.steps,
+                wall_ms_per_step_incl_flush=1e3 * wall / args.steps,
+                kernel_ms_per_step={k: round(v / args.steps, 4) for k, v in kind_ms.items()})
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
+        return
+    from moire_b200.workloads import make_workload
+    wl = make_workload(args.workload)
+    if args.impl == "reference":
+        reference_arm(args, wl)
+    else:
+        if args.warmup < 3:
+            print(f"note: --warmup {args.warmup} < 3", file=sys.stderr)
+        our_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -175,6 +175,12 @@ int moire_engine_record_draw(moire_engine *e, int32_t chain, double *p, int32_t 
 
 /* Work counters since create: non-missing cell likelihood evaluations, kernel launches. */
 int moire_engine_counters(moire_engine *e, uint64_t *cell_evals, uint64_t *kernel_launches);
+/* The same evaluation count split by update kind: [8], indexed by moire_update_kind. */
+int moire_engine_kind_evals(moire_engine *e, uint64_t *evals);
+/* A CUDA-event stopwatch on the engine's stream: start records an event, stop records a second
+ * one, waits for it and returns the device time between the two in ms. */
+int moire_engine_timer_start(moire_engine *e);
+int moire_engine_timer_stop(moire_engine *e, double *ms);
 /* Device time (ms) spent in each update kind (CUDA events) since create; [9]: the 8 kinds + the
  * reduction.  Enabled by moire_engine_set_timing(e, 1) (adds event records around each launch). */
 int moire_engine_set_timing(moire_engine *e, int32_t on);

@@ -110,6 +110,9 @@ ENGINE_SYMBOLS = {
     "moire_engine_read_sample_llik": (C.c_int, [vp, i32, vp]),
     "moire_engine_record_draw": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "moire_engine_counters": (C.c_int, [vp, vp, vp]),
+    "moire_engine_kind_evals": (C.c_int, [vp, vp]),
+    "moire_engine_timer_start": (C.c_int, [vp]),
+    "moire_engine_timer_stop": (C.c_int, [vp, C.POINTER(dbl)]),
     "moire_engine_set_timing": (C.c_int, [vp, i32]),
     "moire_engine_read_timing": (C.c_int, [vp, vp, vp]),
     "moire_engine_synchronize": (C.c_int, [vp]),

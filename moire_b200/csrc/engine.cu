@@ -99,6 +99,7 @@ struct moire_engine
         cudaEvent_t a, b;
         int kind;
     };
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     std::vector<TimedLaunch> pending;
     std::vector<int32_t> init_log;  // (chain, sample, locus) per ill-conditioned start
     double kind_ms[9] = {0};
@@ -117,6 +118,8 @@ struct moire_engine
         p_acc.release(); p_att.release(); active.release(); logC.release(); lgam.release();
         lgadj.release(); cellT.release(); cellO.release(); persample.release(); p.release();
         p_sd.release(); perchain.release(); scratchN.release();
+        if (timer_a) cudaEventDestroy(timer_a);
+        if (timer_b) cudaEventDestroy(timer_b);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -201,7 +204,7 @@ struct moire_engine
         latent.alloc(TNL); lgadj.alloc(TNL); cellT.alloc(TNL); cellO.alloc(TNL);
         m.alloc(TN); acc6.alloc(6 * TN); persample.alloc(14 * TN);
         p.alloc(TLA); p_sd.alloc(TLA); p_acc.alloc(TLA); p_att.alloc(TLA);
-        perchain.alloc(7 * (size_t)T); active.alloc(T); evals.alloc(1); scratchN.alloc(N);
+        perchain.alloc(7 * (size_t)T); active.alloc(T); evals.alloc(16); scratchN.alloc(N);
 
         std::vector<double> logC_h(moire::kLogCDim * moire::kLogCDim, -INFINITY), lgam_h(128);
         for (int n = 0; n < moire::kLogCDim; ++n)
@@ -815,12 +818,50 @@ int moire_engine_counters(moire_engine *e, uint64_t *cell_evals, uint64_t *kerne
         if (!e) throw InvalidArg{"null engine"};
         if (cell_evals)
         {
-            unsigned long long ev = 0;
-            CUDA_TRY(cudaMemcpyAsync(&ev, e->v.evals, sizeof(ev), cudaMemcpyDeviceToHost, e->stream));
+            unsigned long long ev[16];
+            CUDA_TRY(cudaMemcpyAsync(ev, e->v.evals, sizeof(ev), cudaMemcpyDeviceToHost, e->stream));
             CUDA_TRY(cudaStreamSynchronize(e->stream));
-            *cell_evals = ev;
+            *cell_evals = 0;
+            for (int k = 0; k < 16; ++k) *cell_evals += ev[k];
         }
         if (kernel_launches) *kernel_launches = e->launches;
+    });
+}
+
+int moire_engine_kind_evals(moire_engine *e, uint64_t *evals)
+{
+    return guarded(e, [&] {
+        if (!e || !evals) throw InvalidArg{"null argument"};
+        unsigned long long ev[16];
+        CUDA_TRY(cudaMemcpyAsync(ev, e->v.evals, sizeof(ev), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        for (int k = 0; k < 8; ++k) evals[k] = ev[k];
+    });
+}
+
+int moire_engine_timer_start(moire_engine *e)
+{
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        if (!e->timer_a)
+        {
+            CUDA_TRY(cudaEventCreate(&e->timer_a));
+            CUDA_TRY(cudaEventCreate(&e->timer_b));
+        }
+        CUDA_TRY(cudaEventRecord(e->timer_a, e->stream));
+    });
+}
+
+int moire_engine_timer_stop(moire_engine *e, double *ms)
+{
+    return guarded(e, [&] {
+        if (!e || !ms) throw InvalidArg{"null argument"};
+        if (!e->timer_a) throw InvalidArg{"timer_stop without timer_start"};
+        CUDA_TRY(cudaEventRecord(e->timer_b, e->stream));
+        CUDA_TRY(cudaEventSynchronize(e->timer_b));
+        float f = 0;
+        CUDA_TRY(cudaEventElapsedTime(&f, e->timer_a, e->timer_b));
+        *ms = f;
     });
 }
 

@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(kThreads)
             }
         }
     }
-    if (tid == 0 && s_evals) atomicAdd(v.evals, (unsigned long long)s_evals);
+    if (tid == 0 && s_evals) atomicAdd(v.evals + KIND, (unsigned long long)s_evals);
 }
 
 // ---- SALT proposal math (src/mcmc_utils.h:150-313) --------------------------------------------
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(kPThreads) k_update_p(const View v, const int 
         unsigned long long e = evals;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-        if (lane == 0 && e) atomicAdd(v.evals, e);
+        if (lane == 0 && e) atomicAdd(v.evals + KIND_P, e);
     }
 }
 

@@ -52,7 +52,7 @@ struct View
     double *temp, *llik, *prior;
     int *active;  // init retry mask
 
-    unsigned long long *evals;  // [1] non-missing cell evaluations
+    unsigned long long *evals;  // [16] non-missing cell evaluations, by update kind
 
     // parameters (src/parameters.h:31-47) and host-precomputed constants
     double mean_coi_shape, mean_coi_scale, lg_shape, l_scale;

@@ -215,6 +215,19 @@ class Engine:
         self._ck(self.lib.moire_engine_counters(self._h, C.byref(a), C.byref(b)), "counters")
         return int(a.value), int(b.value)
 
+    def kind_evals(self):
+        out = np.zeros(8, np.uint64)
+        self._ck(self.lib.moire_engine_kind_evals(self._h, _ptr(out)), "kind_evals")
+        return {k: int(out[i]) for i, k in enumerate(KIND_NAMES[:8])}
+
+    def timer_start(self):
+        self._ck(self.lib.moire_engine_timer_start(self._h), "timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(self.lib.moire_engine_timer_stop(self._h, C.byref(ms)), "timer_stop")
+        return float(ms.value)
+
     def set_timing(self, on=True):
         self._ck(self.lib.moire_engine_set_timing(self._h, int(on)), "set_timing")
 

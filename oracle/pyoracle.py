@@ -460,6 +460,14 @@ class Ref:
     def mcmc_free(self, h):
         self.lib.ref_mcmc_free(h)
 
+    def mcmc_time_burnin(self, h, first_step, warmup, steps):
+        """Wall seconds of `steps` MCMC::burnin steps after `warmup` untimed ones, driven the way
+        src/main.cpp:54-70 drives them."""
+        return float(self.lib.ref_mcmc_time_burnin(h, int(first_step), int(warmup), int(steps)))
+
+    def omp_max_threads(self):
+        return int(self.lib.ref_omp_max_threads())
+
     def seed_runif(self, seed):
         self.lib.ref_seed_runif(seed)
 

@@ -1,0 +1,112 @@
+"""The drop-in call on the GPU: run_mcmc's result list, the engine-backed driver, and
+distributional agreement with the reference's own sampler (compiled under oracle/_ref)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ["llik_burnin", "llik_sample", "prior_burnin", "prior_sample", "posterior_burnin",
+          "posterior_sample", "data_llik", "coi", "lam_coi", "allele_freqs", "eps_neg", "eps_pos",
+          "relatedness", "latent_genotypes", "observed_coi", "swap_store", "swap_acceptances",
+          "swap_barriers", "temp_gradient", "acceptance_rates", "sampling_variances",
+          "max_runtime_reached", "total_runtime"]     # src/main.cpp:164-186
+
+
+def small_data(seed=31, N=60):
+    from moire_b200.simulate import simulate_data
+    return simulate_data(mean_coi=3, num_samples=N, epsilon_pos=.01, epsilon_neg=.08,
+                         locus_freq_alphas=[np.ones(5)] * 8 + [np.ones(9)] * 6,
+                         internal_relatedness_alpha=.1, internal_relatedness_beta=1,
+                         missingness=.03, seed=seed)
+
+
+def test_run_mcmc_result_layout():
+    from moire_b200.mcmc import run_mcmc
+    d = small_data()
+    res = run_mcmc(d, d["is_missing"], burnin=80, samples_per_chain=40, pt_chains=5, thin=2,
+                   record_latent_genotypes=True, verbose=False, seed=4)
+    assert set(res) == {"runtime", "chains", "args"} and len(res["chains"]) == 1
+    ch = res["chains"][0]
+    assert [f for f in FIELDS if f not in ch] == [] and "mean_coi" in ch
+    N, L = 60, 14
+    D = len(ch["lam_coi"])
+    assert 1 <= D <= 20                                   # thin = 2 of 40 sampling steps
+    assert len(ch["llik_burnin"]) == 80 and len(ch["llik_sample"]) == 40
+    assert len(ch["swap_store"]) == 120 and len(ch["temp_gradient"]) == 5
+    assert np.all(np.isfinite(ch["llik_sample"])) and np.all(np.isfinite(ch["posterior_burnin"]))
+    assert len(ch["coi"]) == N and len(ch["coi"][0]) == D and ch["coi"][0].dtype.kind == "i"
+    assert len(ch["allele_freqs"]) == L and len(ch["allele_freqs"][0]) == D
+    assert len(ch["allele_freqs"][0][0]) == 5 and len(ch["allele_freqs"][13][0]) == 9
+    assert abs(ch["allele_freqs"][3][-1].sum() - 1) < 1e-9
+    lg = ch["latent_genotypes"]
+    assert len(lg) == N and len(lg[0]) == L and len(lg[0][0]) == D
+    assert all(1 <= len(lg[i][j][-1]) <= ch["coi"][i][-1] for i in range(N) for j in range(L))
+    assert len(ch["acceptance_rates"]) == 5 and len(ch["sampling_variances"]) == 5
+    assert set(ch["acceptance_rates"][0]) == {"allele_freq_accept", "coi_accept", "eps_neg_accept",
+                                              "eps_pos_accept", "r_accept", "m_r_accept",
+                                              "full_sample_accept", "mean_coi_accept"}
+    assert ch["temp_gradient"][0] == 1.0 and np.all(np.diff(ch["temp_gradient"]) <= 0)
+    assert np.allclose(ch["mean_coi"], ch["lam_coi"] / (1 - np.exp(-ch["lam_coi"])))
+    # per-sample data_llik sums to the trace of the stored steps
+    tot = np.array([x for x in np.sum(ch["data_llik"], axis=0)])
+    assert np.allclose(tot, np.asarray(ch["llik_sample"])[::2][-D:], rtol=1e-9)
+
+
+def test_single_chain_stores_every_draw_and_is_reproducible():
+    from moire_b200.mcmc import run_mcmc
+    d = small_data(N=30)
+    a = run_mcmc(d, d["is_missing"], burnin=30, samples_per_chain=12, verbose=False, seed=9)
+    b = run_mcmc(d, d["is_missing"], burnin=30, samples_per_chain=12, verbose=False, seed=9)
+    c = run_mcmc(d, d["is_missing"], burnin=30, samples_per_chain=12, verbose=False, seed=10)
+    assert len(a["chains"][0]["lam_coi"]) == 12
+    assert np.array_equal(a["chains"][0]["llik_sample"], b["chains"][0]["llik_sample"])
+    assert not np.array_equal(a["chains"][0]["llik_sample"], c["chains"][0]["llik_sample"])
+
+
+def test_posterior_agrees_with_reference_sampler():
+    """Posterior COI / allele-frequency / error-rate summaries from the engine against the
+    reference's own C++ sampler on the same data, two engine seeds: agreement within Monte-Carlo
+    error (thresholds ~4 standard errors of the between-run differences seen in the reference
+    itself)."""
+    from oracle.pyoracle import Ref, ref_available
+    if not ref_available(32):
+        pytest.skip("oracle/_ref not built")
+    from moire_b200.data import pack_data
+    from moire_b200.mcmc import run_mcmc
+    d = small_data(seed=77, N=80)
+    pk = pack_data(d["data"], d["is_missing"])
+    burn, samp = 600, 600
+    ref = Ref(32)
+    ref.set_data(pk.num_alleles, pk.obs_mask, pk.is_missing)
+    ref.set_params(pt_chains=[1.0], burnin=burn, samples=samp)
+    refs = []
+    for seed in (1, 2):
+        h = ref.mcmc_new(seed=seed)
+        for s in range(burn):
+            ref.lib.ref_mcmc_burnin(h, s)
+        for s in range(samp):
+            ref.lib.ref_mcmc_sample(h, s)
+        refs.append(ref.mcmc_summary(h))
+        ref.mcmc_free(h)
+    ours = []
+    for seed in (11, 12):
+        ch = run_mcmc(d, d["is_missing"], burnin=burn, samples_per_chain=samp, verbose=False,
+                      seed=seed)["chains"][0]
+        ours.append(dict(m=np.mean(ch["coi"], axis=1), r=np.mean(ch["relatedness"], axis=1),
+                         eps_neg=np.mean(ch["eps_neg"], axis=1), eps_pos=np.mean(ch["eps_pos"], axis=1),
+                         p0=np.array([np.mean(ch["allele_freqs"][j], axis=0)[0] for j in range(pk.num_loci)]),
+                         mean_coi=float(np.mean(ch["lam_coi"]))))
+    ref_m = np.mean([r["m"] for r in refs], axis=0)
+    our_m = np.mean([o["m"] for o in ours], axis=0)
+    ref_spread = np.abs(refs[0]["m"] - refs[1]["m"]).mean()
+    assert abs(ref_m.mean() - our_m.mean()) < 0.15, (ref_m.mean(), our_m.mean())
+    assert np.abs(ref_m - our_m).mean() < max(4 * ref_spread, 0.25), (np.abs(ref_m - our_m).mean(), ref_spread)
+    assert np.corrcoef(ref_m, our_m)[0, 1] > 0.95
+    ref_p0 = np.mean([r["p"][:, 0] for r in refs], axis=0)
+    our_p0 = np.mean([o["p0"] for o in ours], axis=0)
+    assert np.abs(ref_p0 - our_p0).max() < 0.03, np.abs(ref_p0 - our_p0).max()
+    for k in ("eps_neg", "eps_pos", "r"):
+        a = np.mean([r[k] for r in refs], axis=0).mean()
+        b = np.mean([o[k] for o in ours], axis=0).mean()
+        assert abs(a - b) < 0.03, (k, a, b)
+    assert abs(np.mean([r["mean_coi"] for r in refs]) - np.mean([o["mean_coi"] for o in ours])) < 0.4
