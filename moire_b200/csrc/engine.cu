@@ -87,6 +87,7 @@ struct moire_engine
     uint64_t launches = 0;
     int tile_S = 1, tiles_per_chain = 1;
     size_t sample_smem = 0, p_smem = 0;
+    int p_threads = 256;
 
     // allocations
     DevBuf<unsigned long long> obs, latent, evals;
@@ -239,14 +240,13 @@ struct moire_engine
         v.active = active.ptr; v.evals = evals.ptr;
         CUDA_TRY(cudaMemcpyAsync(v.temp, temps, T * sizeof(double), cudaMemcpyHostToDevice, stream));
 
-        // tile shape of the per-sample kernel: S consecutive samples, S*L <= kThreads*kCpt cells
-        const int max_cells = moire::kThreads * moire::kCpt;
-        if (L > max_cells)
-            throw InvalidArg{"num_loci > " + std::to_string(max_cells) + " unsupported by the sample kernel"};
-        tile_S = std::max(1, std::min({moire::kMaxTileSamples, max_cells / L, N}));
+        // tile shape of the per-sample kernel: S consecutive samples, about kMaxTileCells cells
+        if (N > 65535) throw InvalidArg{"num_samples > 65535 unsupported (16-bit work lists)"};
+        tile_S = std::max(1, std::min({moire::kMaxTileSamples, moire::kMaxTileCells / L, N}));
         tiles_per_chain = (N + tile_S - 1) / tile_S;
         sample_smem = moire::sample_kernel_smem(tile_S, L, v.nA);
-        p_smem = moire::p_kernel_smem(N, v.AP);
+        p_threads = moire::p_kernel_threads(N);
+        p_smem = moire::p_kernel_smem(N, v.AP, p_threads);
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, device));
         const size_t smem_cap = prop.sharedMemPerBlockOptin;
@@ -335,7 +335,7 @@ struct moire_engine
             case MOIRE_UPDATE_P:
             {
                 Timed tm(this, kind);
-                k_update_p<<<v.T * v.L, kPThreads, p_smem, stream>>>(v, iteration);
+                k_update_p<<<v.T * v.L, p_threads, p_smem, stream>>>(v, iteration);
                 tm.done();
                 break;
             }

@@ -22,10 +22,9 @@
 namespace moire
 {
 constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kCpt = 4;             // cells per thread kept in registers by the sample kernel
 constexpr int kMaxTileSamples = 32;
-constexpr int kPThreads = 256;      // update_p block size
+constexpr int kMaxTileCells = 1024;  // cells of one (chain, sample-tile) block
+constexpr int kSortBins = 12 * 64;   // (min(k, 11), m - k + 1) work classes
 
 struct Proposal
 {
@@ -71,20 +70,107 @@ __device__ __forceinline__ double adapt_sd(double sd, double accepts, double den
     return nv > floor_ ? nv : floor_;  // std::max(sd + update, floor)
 }
 
+// ---- work lists: cells sorted by cost class ---------------------------------------------------
+// The cost of one transmission term is ~2^k (k + m - k + 1) (inclusion-exclusion over the subsets
+// of the k latent alleles, vectorised over the m - k + 1 mixture terms), so cells of one block
+// differ by three orders of magnitude.  A thread-per-cell mapping in natural order leaves ~3 of
+// 32 lanes active (ncu, profiles/r01a).  Instead every block counting-sorts its cells by
+// (k, m - k + 1), heaviest first, and its warps walk the sorted list round-robin: the lanes of a
+// warp then run the same subset sequence and the same register tier, and the heavy classes are
+// spread over all warps.  Which thread evaluates a cell does not change the cell's value, and all
+// sums over cells are taken in cell order afterwards, so results do not depend on the
+// (atomics-ordered) position of a cell inside its class.
+__device__ __forceinline__ int work_class(int k, int m)
+{
+    // reversed so that ascending class = heaviest first
+    const int kk = k > kIeMax ? kIeMax + 1 : k;
+    int cnt = m - k + 1;
+    cnt = cnt < 1 ? 1 : (cnt > 64 ? 64 : cnt);
+    return kSortBins - 1 - (kk * 64 + (cnt - 1));
+}
+
+// hist: kSortBins counters; order: out; s_tmp: >= 34 words.  cls(cell) < 0 leaves the cell out.
+// Returns the number of listed cells (same value in every thread).  Ends with a barrier.
+template <class ClassFn>
+__device__ __forceinline__ int block_sort_cells(int ncell, ClassFn cls, unsigned int *hist,
+                                                unsigned short *order, unsigned int *s_tmp)
+{
+    const int tid = threadIdx.x, B = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = (B + 31) >> 5;
+    for (int b = tid; b < kSortBins; b += B) hist[b] = 0;
+    __syncthreads();
+    for (int c = tid; c < ncell; c += B)
+    {
+        const int key = cls(c);
+        if (key >= 0) atomicAdd(&hist[key], 1u);
+    }
+    __syncthreads();
+    const int per = (kSortBins + B - 1) / B, b0 = tid * per;
+    unsigned int local = 0;
+    for (int q = 0; q < per; ++q)
+        if (b0 + q < kSortBins) local += hist[b0 + q];
+    unsigned int x = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_tmp[warp] = x;
+    __syncthreads();
+    if (warp == 0)
+    {
+        const unsigned int mine = lane < nw ? s_tmp[lane] : 0u;
+        unsigned int w = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        s_tmp[lane] = w - mine;
+        if (lane == 31) s_tmp[32] = w;
+    }
+    __syncthreads();
+    unsigned int base = s_tmp[warp] + x - local;
+    for (int q = 0; q < per; ++q)
+    {
+        if (b0 + q < kSortBins)
+        {
+            const unsigned int h = hist[b0 + q];
+            hist[b0 + q] = base;
+            base += h;
+        }
+    }
+    const int total = (int)s_tmp[32];
+    __syncthreads();
+    for (int c = tid; c < ncell; c += B)
+    {
+        const int key = cls(c);
+        if (key >= 0) order[atomicAdd(&hist[key], 1u)] = (unsigned short)c;
+    }
+    __syncthreads();
+    return total;
+}
+
+__host__ __device__ inline size_t align8(size_t b) { return (b + 7) & ~(size_t)7; }
+
 __host__ __device__ inline size_t sample_kernel_smem(int S, int L, int nA)
 {
+    const size_t C = (size_t)S * L;
     size_t b = 0;
-    b += 128 * sizeof(double);                      // lgam
-    b += (size_t)kIeMax * kThreads * sizeof(double); // qs scratch
-    b += (size_t)2 * S * L * sizeof(double);        // delta, adjd
+    b += 128 * sizeof(double);                        // lgam
+    b += (size_t)kIeMax * kThreads * sizeof(double);  // qs scratch
+    b += 4 * C * sizeof(double);                      // proposed latent, its log density, T, O
     b += (size_t)S * nA * sizeof(EpsLogs);
     b += (size_t)S * sizeof(Proposal);
+    b += kSortBins * sizeof(unsigned int) + 40 * sizeof(unsigned int);
+    b += align8(C * sizeof(unsigned short));
     return b;
 }
 
 // ---- per-sample updates: eps_neg, eps_pos, m, r, eff_coi, samples ----------------------------
 template <int KIND>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
     k_update_sample(const View v, const int iteration, const int S, const int tiles_per_chain)
 {
     constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
@@ -92,15 +178,22 @@ __global__ void __launch_bounds__(kThreads)
     constexpr bool NEED_O = RESAMPLE || KIND == KIND_EPS_NEG || KIND == KIND_EPS_POS;
 
     extern __shared__ double smem[];
+    const int C = S * v.L;
     double *s_lgam = smem;
     double *s_qs = s_lgam + 128;
-    double *s_delta = s_qs + kIeMax * kThreads;
-    double *s_adjd = s_delta + S * v.L;
-    EpsLogs *s_elogs = reinterpret_cast<EpsLogs *>(s_adjd + S * v.L);
+    unsigned long long *s_nlat = reinterpret_cast<unsigned long long *>(s_qs + kIeMax * kThreads);
+    double *s_nadj = reinterpret_cast<double *>(s_nlat + C);
+    double *s_T = s_nadj + C;
+    double *s_O = s_T + C;
+    EpsLogs *s_elogs = reinterpret_cast<EpsLogs *>(s_O + C);
     Proposal *s_prop = reinterpret_cast<Proposal *>(s_elogs + S * v.nA);
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(s_prop + S);
+    unsigned int *s_tmp = s_hist + kSortBins;
+    unsigned short *s_order = reinterpret_cast<unsigned short *>(s_tmp + 40);
     __shared__ unsigned int s_evals;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kThreads / 32;
     const int t = blockIdx.x / tiles_per_chain;
     const int s0 = (blockIdx.x - t * tiles_per_chain) * S;
     const int ns = min(S, v.N - s0);
@@ -223,73 +316,87 @@ __global__ void __launch_bounds__(kThreads)
         __syncthreads();
     }
 
-    // ---- phase B: every cell of the tile ------------------------------------------------------
-    unsigned long long nlat[kCpt];
-    double nT[kCpt], nO[kCpt], nadj[kCpt];
-    unsigned my_evals = 0;
+    // ---- phase B1: per cell, natural (coalesced) order: proposed latent genotype, observation
+    // term -----------------------------------------------------------------------------------
     const size_t tile_base = ((size_t)t * N + s0) * L;  // first cell of the tile in [T][N][L]
     const size_t data_base = (size_t)s0 * L;            // same in [N][L]
     const int ncell = ns * L;
-#pragma unroll
-    for (int c = 0; c < kCpt; ++c)
+    unsigned my_evals = 0;
+    for (int cell = tid; cell < ncell; cell += kThreads)
     {
-        const int cell = tid + c * kThreads;
-        nlat[c] = 0;
-        nT[c] = nO[c] = nadj[c] = 0.0;
-        if (cell < ncell)
+        const int sl = cell / L, j = cell - sl * L;
+        const Proposal &P = s_prop[sl];
+        if (!P.valid) continue;
+        const unsigned long long obs = v.obs[data_base + cell];
+        const bool miss = v.missing[data_base + cell] != 0;
+        const int A = v.nall[j];
+        unsigned long long lat;
+        const EpsLogs *el = NEED_O ? &s_elogs[sl * nA + v.aclass[j]] : nullptr;
+        if (RESAMPLE)
         {
-            const int sl = cell / L, j = cell - sl * L;
-            const Proposal &P = s_prop[sl];
-            double delta = 0.0, adjd = 0.0;
-            if (P.valid)
-            {
-                const size_t gi = tile_base + cell;
-                const unsigned long long obs = v.obs[data_base + cell];
-                const bool miss = v.missing[data_base + cell] != 0;
-                const int A = v.nall[j];
-                const double oldT = v.cellT[gi], oldO = v.cellO[gi];
-                unsigned long long lat = v.latent[gi];
-                const EpsLogs *el = NEED_O ? &s_elogs[sl * nA + v.aclass[j]] : nullptr;
-                if (RESAMPLE)
-                {
-                    Stream crng;
-                    crng.open(v.seed, (uint32_t)iteration, KIND, gchain, (uint32_t)(s0 + sl),
-                              (uint32_t)(j + 1));
-                    double lp;
-                    lat = sample_latent_genotype(crng, obs, A, P.m_new, *el, v.logC, &lp);
-                    nlat[c] = lat;
-                    nadj[c] = lp;
-                    adjd = lp - v.lgadj[gi];
-                }
-                if (!miss)
-                {
-                    double T = oldT, O = oldO;
-                    if (NEED_T)
-                        T = transmission_ll(lat, v.p + ((size_t)t * L + j) * v.AP, P.m_new, P.log_r,
-                                            P.log_1mr, v.allow_rel != 0, s_qs + tid, kThreads,
-                                            s_lgam);
-                    if (NEED_O) O = observation_ll(lat, obs, A, *el);
-                    nT[c] = T;
-                    nO[c] = O;
-                    delta = __dadd_rn(T, O) - __dadd_rn(oldT, oldO);
-                    ++my_evals;
-                }
-            }
-            s_delta[cell] = delta;
-            if (RESAMPLE) s_adjd[cell] = adjd;
+            Stream crng;
+            crng.open(v.seed, (uint32_t)iteration, KIND, gchain, (uint32_t)(s0 + sl),
+                      (uint32_t)(j + 1));
+            double lp;
+            lat = sample_latent_genotype(crng, obs, A, P.m_new, *el, v.logC, &lp);
+            s_nadj[cell] = lp;
+        }
+        else
+        {
+            lat = v.latent[tile_base + cell];
+        }
+        s_nlat[cell] = lat;
+        if (!miss)
+        {
+            if (NEED_O) s_O[cell] = observation_ll(lat, obs, A, *el);
+            ++my_evals;
         }
     }
     if (my_evals) atomicAdd(&s_evals, my_evals);
     __syncthreads();
 
-    // ---- phase C: one warp per sample decides -------------------------------------------------
+    // ---- phase B2: transmission terms, heaviest class first -----------------------------------
+    if (NEED_T)
+    {
+        auto cls = [&](int cell) -> int {
+            const int sl = cell / L;
+            const Proposal &P = s_prop[sl];
+            if (!P.valid || v.missing[data_base + cell] != 0) return -1;
+            return work_class(__popcll(s_nlat[cell]), P.m_new);
+        };
+        const int nwork = block_sort_cells(ncell, cls, s_hist, s_order, s_tmp);
+        for (int w = tid; w < nwork; w += kThreads)
+        {
+            const int cell = s_order[w];
+            const int sl = cell / L, j = cell - sl * L;
+            const Proposal &P = s_prop[sl];
+            s_T[cell] = transmission_ll(s_nlat[cell], v.p + ((size_t)t * L + j) * v.AP, P.m_new,
+                                        P.log_r, P.log_1mr, v.allow_rel != 0, s_qs + tid, kThreads,
+                                        s_lgam);
+        }
+        __syncthreads();
+    }
+
+    // ---- phase C: one warp per sample sums its cells (in locus order) and decides -------------
     for (int sl = warp; sl < ns; sl += kWarps)
     {
+        const Proposal &Pc = s_prop[sl];
         double d = 0.0, a = 0.0;
-        for (int j = lane; j < L; j += 32)
+        if (Pc.valid)
         {
-            d += s_delta[sl * L + j];
-            if (RESAMPLE) a += s_adjd[sl * L + j];
+            for (int j = lane; j < L; j += 32)
+            {
+                const int cell = sl * L + j;
+                const size_t gi = tile_base + cell;
+                if (RESAMPLE) a += s_nadj[cell] - v.lgadj[gi];
+                if (v.missing[data_base + cell] == 0)
+                {
+                    const double oldT = v.cellT[gi], oldO = v.cellO[gi];
+                    const double T = NEED_T ? s_T[cell] : oldT;
+                    const double O = NEED_O ? s_O[cell] : oldO;
+                    d += __dadd_rn(T, O) - __dadd_rn(oldT, oldO);
+                }
+            }
         }
         d = warp_sum(d);
         if (RESAMPLE) a = warp_sum(a);
@@ -359,28 +466,20 @@ __global__ void __launch_bounds__(kThreads)
     __syncthreads();
 
     // ---- phase D: commit the accepted samples' cells -----------------------------------------
-#pragma unroll
-    for (int c = 0; c < kCpt; ++c)
+    for (int cell = tid; cell < ncell; cell += kThreads)
     {
-        const int cell = tid + c * kThreads;
-        if (cell < ncell)
+        const int sl = cell / L;
+        if (!s_prop[sl].accept) continue;
+        const size_t gi = tile_base + cell;
+        if (RESAMPLE)
         {
-            const int sl = cell / L;
-            if (s_prop[sl].accept)
-            {
-                const size_t gi = tile_base + cell;
-                const bool miss = v.missing[data_base + cell] != 0;
-                if (RESAMPLE)
-                {
-                    v.latent[gi] = nlat[c];
-                    v.lgadj[gi] = nadj[c];
-                }
-                if (!miss)
-                {
-                    if (NEED_T) v.cellT[gi] = nT[c];
-                    if (NEED_O) v.cellO[gi] = nO[c];
-                }
-            }
+            v.latent[gi] = s_nlat[cell];
+            v.lgadj[gi] = s_nadj[cell];
+        }
+        if (v.missing[data_base + cell] == 0)
+        {
+            if (NEED_T) v.cellT[gi] = s_T[cell];
+            if (NEED_O) v.cellO[gi] = s_O[cell];
         }
     }
     if (tid == 0 && s_evals) atomicAdd(v.evals + KIND, (unsigned long long)s_evals);
@@ -425,26 +524,34 @@ __device__ __forceinline__ double logit_scale_d(double x, double scale)
 
 __device__ __forceinline__ double expit_d(double x) { return 1.0 / (1.0 + exp(-x)); }
 
-__host__ __device__ inline size_t p_kernel_smem(int N, int AP)
+__host__ __device__ inline int p_kernel_threads(int N) { return N > 2048 ? 512 : 256; }
+
+__host__ __device__ inline size_t p_kernel_smem(int N, int AP, int B)
 {
     size_t b = 0;
-    b += 128 * sizeof(double);                       // lgam
-    b += (size_t)kIeMax * kPThreads * sizeof(double); // qs scratch
-    b += (size_t)3 * N * sizeof(double);             // latent, Told, Tnew
-    b += (size_t)3 * AP * sizeof(double);            // p_cur, p_prop, p_sd
-    b += (size_t)2 * AP * sizeof(int);               // acc, att
-    b += 40 * sizeof(double);                        // reductions + scalars
+    b += 128 * sizeof(double);                  // lgam
+    b += (size_t)kIeMax * B * sizeof(double);   // qs scratch
+    b += (size_t)3 * N * sizeof(double);        // latent, Told, Tnew
+    b += (size_t)3 * AP * sizeof(double);       // p_cur, p_prop, p_sd
+    b += 40 * sizeof(double);                   // reductions + scalars
+    b += (size_t)2 * AP * sizeof(int);          // acc, att
+    b += kSortBins * sizeof(unsigned int) + 40 * sizeof(unsigned int);
+    b += align8((size_t)N * sizeof(unsigned short));  // work list
+    b += align8((size_t)N);                     // COI per sample, 0 = cell missing
     return b;
 }
 
 // ---- update_p: SALT sampler, one block per (chain, locus) (src/chain.cpp:466-565) -------------
-__global__ void __launch_bounds__(kPThreads) k_update_p(const View v, const int iteration)
+// The locus' N cells are staged once (latent genotype, current transmission term, COI) and
+// sorted once by cost class; each of the A_j sequential proposals then re-evaluates them from
+// shared memory under the proposed frequencies.
+__global__ void __launch_bounds__(512) k_update_p(const View v, const int iteration)
 {
     extern __shared__ double smem[];
-    const int N = v.N, L = v.L, AP = v.AP;
+    const int N = v.N, L = v.L, AP = v.AP, B = blockDim.x;
     double *s_lgam = smem;
     double *s_qs = s_lgam + 128;
-    unsigned long long *s_lat = reinterpret_cast<unsigned long long *>(s_qs + kIeMax * kPThreads);
+    unsigned long long *s_lat = reinterpret_cast<unsigned long long *>(s_qs + kIeMax * B);
     double *s_Told = reinterpret_cast<double *>(s_lat + N);
     double *s_Tnew = s_Told + N;
     double *s_pcur = s_Tnew + N;
@@ -453,6 +560,10 @@ __global__ void __launch_bounds__(kPThreads) k_update_p(const View v, const int 
     double *s_red = s_psd + AP;  // 40 doubles: [0..32] reduction, 33 logAdj, 34 flag, 35 accept
     int *s_acc = reinterpret_cast<int *>(s_red + 40);
     int *s_att = s_acc + AP;
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(s_att + AP);
+    unsigned int *s_tmp = s_hist + kSortBins;
+    unsigned short *s_order = reinterpret_cast<unsigned short *>(s_tmp + 40);
+    unsigned char *s_m = reinterpret_cast<unsigned char *>(s_order) + align8((size_t)N * 2);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = blockIdx.x / L, j = blockIdx.x - t * L;
@@ -461,23 +572,29 @@ __global__ void __launch_bounds__(kPThreads) k_update_p(const View v, const int 
     const double temp = v.temp[t];
     const size_t prow = ((size_t)t * L + j) * AP;
 
-    for (int i = tid; i < 128; i += kPThreads) s_lgam[i] = v.lgam[i];
-    for (int a = tid; a < AP; a += kPThreads)
+    for (int i = tid; i < 128; i += B) s_lgam[i] = v.lgam[i];
+    for (int a = tid; a < AP; a += B)
     {
         s_pcur[a] = v.p[prow + a];
         s_psd[a] = v.p_sd[prow + a];
         s_acc[a] = v.p_acc[prow + a];
         s_att[a] = v.p_att[prow + a];
     }
-    unsigned nonmissing = 0;
-    for (int i = tid; i < N; i += kPThreads)
+    for (int i = tid; i < N; i += B)
     {
         const size_t gi = ((size_t)t * N + i) * L + j;
+        const bool miss = v.missing[(size_t)i * L + j] != 0;
         s_lat[i] = v.latent[gi];
         s_Told[i] = v.cellT[gi];
-        nonmissing += v.missing[(size_t)i * L + j] == 0;
+        s_Tnew[i] = 0.0;
+        s_m[i] = miss ? 0 : (unsigned char)v.m[(size_t)t * N + i];
     }
     __syncthreads();
+    auto cls = [&](int i) -> int {
+        const int m = s_m[i];
+        return m == 0 ? -1 : work_class(__popcll(s_lat[i]), m);
+    };
+    const int nwork = block_sort_cells(N, cls, s_hist, s_order, s_tmp);
 
     unsigned long long evals = 0;
     for (int rep = 0; rep < A; ++rep)
@@ -558,21 +675,20 @@ __global__ void __launch_bounds__(kPThreads) k_update_p(const View v, const int 
         __syncthreads();
         if (s_red[34] != 0.0) break;  // src/chain.cpp:503-518: leaves the locus
 
-        // -- all N cells of the locus under the proposed frequencies
-        double dsum = 0.0;
-        for (int i = tid; i < N; i += kPThreads)
+        // -- all cells of the locus under the proposed frequencies, heaviest class first
+        for (int w = tid; w < nwork; w += B)
         {
-            double Tn = 0.0;
-            if (v.missing[(size_t)i * L + j] == 0)
-            {
-                const size_t si = (size_t)t * N + i;
-                Tn = transmission_ll(s_lat[i], s_pprop, v.m[si], v.log_r[si], v.log_1mr[si],
-                                     v.allow_rel != 0, s_qs + tid, kPThreads, s_lgam);
-                dsum += Tn - s_Told[i];
-            }
-            s_Tnew[i] = Tn;
+            const int i = s_order[w];
+            const size_t si = (size_t)t * N + i;
+            s_Tnew[i] = transmission_ll(s_lat[i], s_pprop, s_m[i], v.log_r[si], v.log_1mr[si],
+                                        v.allow_rel != 0, s_qs + tid, B, s_lgam);
         }
-        evals += nonmissing;
+        evals += tid == 0 ? (unsigned long long)nwork : 0ull;
+        __syncthreads();
+        // -- the change of the locus' log-likelihood, summed in sample order
+        double dsum = 0.0;
+        for (int i = tid; i < N; i += B)
+            if (s_m[i] != 0) dsum += s_Tnew[i] - s_Told[i];
         const double d = block_sum(dsum, s_red);
         if (tid == 0)
         {
@@ -593,31 +709,26 @@ __global__ void __launch_bounds__(kPThreads) k_update_p(const View v, const int 
         __syncthreads();
         if (s_red[35] != 0.0)
         {
-            for (int i = tid; i < N; i += kPThreads) s_Told[i] = s_Tnew[i];
-            for (int a = tid; a < A; a += kPThreads) s_pcur[a] = s_pprop[a];
+            for (int i = tid; i < N; i += B)
+                if (s_m[i] != 0) s_Told[i] = s_Tnew[i];
+            for (int a = tid; a < A; a += B) s_pcur[a] = s_pprop[a];
         }
         __syncthreads();
     }
     __syncthreads();
 
-    for (int i = tid; i < N; i += kPThreads)
+    for (int i = tid; i < N; i += B)
     {
-        if (v.missing[(size_t)i * L + j] == 0) v.cellT[((size_t)t * N + i) * L + j] = s_Told[i];
+        if (s_m[i] != 0) v.cellT[((size_t)t * N + i) * L + j] = s_Told[i];
     }
-    for (int a = tid; a < AP; a += kPThreads)
+    for (int a = tid; a < AP; a += B)
     {
         v.p[prow + a] = s_pcur[a];
         v.p_sd[prow + a] = s_psd[a];
         v.p_acc[prow + a] = s_acc[a];
         v.p_att[prow + a] = s_att[a];
     }
-    {
-        // per-thread partial counts -> one atomic per warp
-        unsigned long long e = evals;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-        if (lane == 0 && e) atomicAdd(v.evals + KIND_P, e);
-    }
+    if (tid == 0 && evals) atomicAdd(v.evals + KIND_P, evals);
 }
 
 // ---- update_mean_coi: one block per chain (src/chain.cpp:809-856) ----------------------------

@@ -113,15 +113,18 @@ __device__ __forceinline__ double subset_base(uint32_t sub, const double *qs, in
 }
 
 // ---- a4: vectorised inclusion-exclusion, k <= 10 (src/prob_any_missing.cpp:178-216) --------
-// acc[t] accumulates the PAM of n = k + t draws, t < cnt = m - k + 1 (entries n < k are never
-// read by the mixture).  NACC is the register tier (>= cnt).
+// acc[j] accumulates the PAM of n = k + t0 + j draws, j < cnt (entries n < k are never read by
+// the mixture).  NACC is the register tier (>= cnt).  Every accumulator sees the subsets in the
+// reference's order (by size, then lexicographic) and every power is built by the same chain of
+// multiplications, so a cell evaluated in several passes (t0 > 0) gets the same bits.
 template <int NACC>
-__device__ __forceinline__ void ie_vectorized(const double *qs, int qstride, int k, int cnt,
+__device__ __forceinline__ void ie_vectorized(const double *qs, int qstride, int k, int t0, int cnt,
                                               double (&acc)[NACC])
 {
 #pragma unroll
     for (int t = 0; t < NACC; ++t) acc[t] = 0.0;
     const uint32_t full = (1u << k) - 1u;
+    const int lead = k - 1 + t0;
     int sign = -1;
     int ncomb = 1;
     for (int s = 1; s <= k; ++s)
@@ -133,7 +136,7 @@ __device__ __forceinline__ void ie_vectorized(const double *qs, int qstride, int
         {
             const double base = subset_base(sub, qs, qstride);
             double r = (double)sign;
-            for (int j = 0; j < k - 1; ++j) r = __dmul_rn(r, base);
+            for (int j = 0; j < lead; ++j) r = __dmul_rn(r, base);
 #pragma unroll
             for (int t = 0; t < NACC; ++t)
             {
@@ -260,8 +263,43 @@ __device__ __noinline__ double transmission_rel_ie(const double *qs, int qstride
 {
     double acc[NACC];
     const int cnt = m - k + 1;
-    ie_vectorized<NACC>(qs, qstride, k, cnt, acc);
+    ie_vectorized<NACC>(qs, qstride, k, 0, cnt, acc);
     return relatedness_mixture<NACC>(acc, k, m, cnt, log_total, log_r, log_1mr, lgam);
+}
+
+// m - k >= 16 (rare: a COI far above the number of distinct alleles): the accumulators are
+// produced 16 at a time and parked in local memory, so that the common tiers keep the kernel's
+// register budget.
+__device__ __noinline__ double transmission_rel_ie_wide(const double *qs, int qstride, int k, int m,
+                                                        double log_total, double log_r,
+                                                        double log_1mr, const double *lgam)
+{
+    double v[kMaxCoi];
+    const int cnt = m - k + 1;
+    for (int t0 = 0; t0 < cnt; t0 += 16)
+    {
+        double acc[16];
+        const int c = min(16, cnt - t0);
+        ie_vectorized<16>(qs, qstride, k, t0, c, acc);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < c) v[t0 + j] = acc[j];
+    }
+    double mx = -INFINITY;
+    for (int t = 0; t < cnt; ++t)
+    {
+        const int i = cnt - 1 - t;
+        const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
+        const double pam = clamp_pam(v[t]);
+        const double i_res = __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
+        const double val = __dadd_rn(pr, i_res);
+        v[t] = val;
+        mx = (mx < val) ? val : mx;
+    }
+    if (mx == -INFINITY) return -INFINITY;
+    double sum = 0.0;
+    for (int t = cnt - 1; t >= 0; --t) sum = __dadd_rn(sum, exp(__dsub_rn(v[t], mx)));
+    return __dadd_rn(mx, log(sum));
 }
 
 // EGF branch of the relatedness path; a[] lives in local memory (k > 10 only).
@@ -361,9 +399,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
     if (cnt <= 8) return transmission_rel_ie<8>(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
     if (cnt <= 16)
         return transmission_rel_ie<16>(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
-    if (cnt <= 32)
-        return transmission_rel_ie<32>(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
-    return transmission_rel_ie<64>(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
+    return transmission_rel_ie_wide(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
 }
 
 // ---- a8: latent-genotype proposal ------------------------------------------------------------
