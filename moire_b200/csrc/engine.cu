@@ -60,6 +60,44 @@ struct DevBuf
     }
 };
 
+// The reference's subset order for every k <= 10 (CombinationIndicesGenerator driven by
+// src/prob_any_missing.cpp:20-52): by size, then lexicographic index tuples.  See likelihood.cuh.
+void build_subset_tables(std::vector<unsigned short> &tail, std::vector<unsigned short> &mask)
+{
+    tail.assign(moire::kSubsetEntries, 0);
+    mask.assign(moire::kSubsetEntries, 0);
+    for (int k = 1; k <= moire::kIeMax; ++k)
+    {
+        int idx = moire::subset_block(k);
+        for (int s = 1; s <= k; ++s)
+        {
+            std::vector<int> c(s), prev;
+            for (int i = 0; i < s; ++i) c[i] = i;
+            for (;;)
+            {
+                int d = 0;
+                if (!prev.empty())
+                    while (d < s - 1 && c[d] == prev[d]) ++d;
+                unsigned t = 0, full = 0;
+                for (int i = 0; i < s; ++i)
+                {
+                    full |= 1u << c[i];
+                    if (i >= d) t |= 1u << c[i];
+                }
+                tail[idx] = (unsigned short)(t | (unsigned)d << 10 | (s % 2 == 0 ? 0x4000u : 0u));
+                mask[idx] = (unsigned short)full;
+                ++idx;
+                prev = c;
+                int i = s - 1;  // rightmost position that can still move right
+                while (i >= 0 && c[i] == k - s + i) --i;
+                if (i < 0) break;
+                ++c[i];
+                for (int j = i + 1; j < s; ++j) c[j] = c[j - 1] + 1;
+            }
+        }
+    }
+}
+
 double log_binom_exact(unsigned n, unsigned k)
 {
     // boost::math::binomial_coefficient<double> returns C(n,k) as an integer-valued double
@@ -212,6 +250,12 @@ struct moire_engine
             for (int k = 0; k <= n; ++k) logC_h[n * moire::kLogCDim + k] = log_binom_exact(n, k);
         for (int i = 0; i < 128; ++i) lgam_h[i] = std::lgamma((double)(i + 1));  // sampler.cpp:22-25
 
+        {
+            std::vector<unsigned short> tail_h, mask_h;
+            build_subset_tables(tail_h, mask_h);
+            CUDA_TRY(cudaMemcpyToSymbol(moire::c_sub_tail, tail_h.data(), tail_h.size() * sizeof(unsigned short)));
+            CUDA_TRY(cudaMemcpyToSymbol(moire::g_sub_mask, mask_h.data(), mask_h.size() * sizeof(unsigned short)));
+        }
         obs.upload((const unsigned long long *)d->obs_mask, NL, stream);
         missing.upload(d->is_missing, NL, stream);
         nall.upload(d->num_alleles, L, stream);

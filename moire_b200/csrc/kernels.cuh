@@ -89,8 +89,12 @@ __device__ __forceinline__ int work_class(int k, int m)
     return kSortBins - 1 - (kk * 64 + (cnt - 1));
 }
 
-// hist: kSortBins counters; order: out; s_tmp: >= 34 words.  cls(cell) < 0 leaves the cell out.
-// Returns the number of listed cells (same value in every thread).  Ends with a barrier.
+constexpr int kClassCoopBegin = 64;                       // first class with k <= 10
+constexpr int kClassLightBegin = (12 - kCoopMinK) * 64;   // first class with k < kCoopMinK
+
+// hist: kSortBins counters; order: out; s_tmp: >= 40 words.  cls(cell) < 0 leaves the cell out.
+// Returns the number of listed cells (same value in every thread); s_tmp[33] / s_tmp[34] get the
+// list positions where the k <= 10 cells and the k < kCoopMinK cells begin.  Ends with a barrier.
 template <class ClassFn>
 __device__ __forceinline__ int block_sort_cells(int ncell, ClassFn cls, unsigned int *hist,
                                                 unsigned short *order, unsigned int *s_tmp)
@@ -138,6 +142,8 @@ __device__ __forceinline__ int block_sort_cells(int ncell, ClassFn cls, unsigned
         {
             const unsigned int h = hist[b0 + q];
             hist[b0 + q] = base;
+            if (b0 + q == kClassCoopBegin) s_tmp[33] = base;
+            if (b0 + q == kClassLightBegin) s_tmp[34] = base;
             base += h;
         }
     }
@@ -152,14 +158,61 @@ __device__ __forceinline__ int block_sort_cells(int ncell, ClassFn cls, unsigned
     return total;
 }
 
+// Transmission terms of the listed cells.  The list is heaviest first: [0, n_egf) cells with
+// k > 10 (EGF recurrence, one thread each), [n_egf, coop_end) cells with kCoopMinK <= k <= 10
+// (one warp each, subsets across lanes), the rest light cells (one thread each).
+// fetch(cell, lat, prow, m, log_r, log_1mr) supplies a cell's inputs; out[cell] gets the term.
+// scr: kScratchSlots rows of blockDim.x + 1 doubles.  No block barrier inside.
+template <class Fetch>
+__device__ __forceinline__ void block_eval_transmissions(const unsigned short *order, int nwork,
+                                                         int n_egf, int coop_end, Fetch fetch,
+                                                         double *out, double *scr,
+                                                         const double *lgam, bool allow_rel)
+{
+    const int tid = threadIdx.x, B = blockDim.x, ST = B + 1;
+    const int lane = tid & 31, warp = tid >> 5, nw = B >> 5;
+    for (int w = n_egf + warp; w < coop_end; w += nw)
+    {
+        const int cell = order[w];
+        unsigned long long lat;
+        const double *prow;
+        int m;
+        double log_r, log_1mr;
+        fetch(cell, lat, prow, m, log_r, log_1mr);
+        const int k = __popcll(lat);
+        double T;
+        if (k > m)
+            T = NAN;
+        else if (!allow_rel && m == k)  // closed form, src/prob_any_missing.cpp:139-148
+            T = transmission_ll(lat, prow, m, log_r, log_1mr, allow_rel, scr + tid, ST, lgam);
+        else
+            T = transmission_ll_coop(lat, prow, m, log_r, log_1mr, allow_rel, scr + warp * 32, ST,
+                                     lgam);
+        if (lane == 0) out[cell] = T;
+        __syncwarp();
+    }
+    const int nthread = n_egf + (nwork - coop_end);
+    for (int w = tid; w < nthread; w += B)
+    {
+        const int cell = order[w < n_egf ? w : coop_end + (w - n_egf)];
+        unsigned long long lat;
+        const double *prow;
+        int m;
+        double log_r, log_1mr;
+        fetch(cell, lat, prow, m, log_r, log_1mr);
+        out[cell] = transmission_ll(lat, prow, m, log_r, log_1mr, allow_rel, scr + tid, ST, lgam);
+    }
+}
+
 __host__ __device__ inline size_t align8(size_t b) { return (b + 7) & ~(size_t)7; }
+__host__ __device__ inline size_t scratch_doubles(int B) { return (size_t)kScratchSlots * (B + 1); }
 
 __host__ __device__ inline size_t sample_kernel_smem(int S, int L, int nA)
 {
     const size_t C = (size_t)S * L;
     size_t b = 0;
     b += 128 * sizeof(double);                        // lgam
-    b += (size_t)kIeMax * kThreads * sizeof(double);  // qs scratch
+    b += scratch_doubles(kThreads) * sizeof(double);  // per-thread scratch columns
     b += 4 * C * sizeof(double);                      // proposed latent, its log density, T, O
     b += (size_t)S * nA * sizeof(EpsLogs);
     b += (size_t)S * sizeof(Proposal);
@@ -181,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     const int C = S * v.L;
     double *s_lgam = smem;
     double *s_qs = s_lgam + 128;
-    unsigned long long *s_nlat = reinterpret_cast<unsigned long long *>(s_qs + kIeMax * kThreads);
+    unsigned long long *s_nlat = reinterpret_cast<unsigned long long *>(s_qs + scratch_doubles(kThreads));
     double *s_nadj = reinterpret_cast<double *>(s_nlat + C);
     double *s_T = s_nadj + C;
     double *s_O = s_T + C;
@@ -365,15 +418,18 @@ __global__ void __launch_bounds__(kThreads, 2)
             return work_class(__popcll(s_nlat[cell]), P.m_new);
         };
         const int nwork = block_sort_cells(ncell, cls, s_hist, s_order, s_tmp);
-        for (int w = tid; w < nwork; w += kThreads)
-        {
-            const int cell = s_order[w];
+        auto fetch = [&](int cell, unsigned long long &lat, const double *&prow, int &m,
+                         double &log_r, double &log_1mr) {
             const int sl = cell / L, j = cell - sl * L;
             const Proposal &P = s_prop[sl];
-            s_T[cell] = transmission_ll(s_nlat[cell], v.p + ((size_t)t * L + j) * v.AP, P.m_new,
-                                        P.log_r, P.log_1mr, v.allow_rel != 0, s_qs + tid, kThreads,
-                                        s_lgam);
-        }
+            lat = s_nlat[cell];
+            prow = v.p + ((size_t)t * L + j) * v.AP;
+            m = P.m_new;
+            log_r = P.log_r;
+            log_1mr = P.log_1mr;
+        };
+        block_eval_transmissions(s_order, nwork, (int)s_tmp[33], (int)s_tmp[34], fetch, s_T, s_qs,
+                                 s_lgam, v.allow_rel != 0);
         __syncthreads();
     }
 
@@ -530,7 +586,7 @@ __host__ __device__ inline size_t p_kernel_smem(int N, int AP, int B)
 {
     size_t b = 0;
     b += 128 * sizeof(double);                  // lgam
-    b += (size_t)kIeMax * B * sizeof(double);   // qs scratch
+    b += scratch_doubles(B) * sizeof(double);   // per-thread scratch columns
     b += (size_t)3 * N * sizeof(double);        // latent, Told, Tnew
     b += (size_t)3 * AP * sizeof(double);       // p_cur, p_prop, p_sd
     b += 40 * sizeof(double);                   // reductions + scalars
@@ -545,13 +601,13 @@ __host__ __device__ inline size_t p_kernel_smem(int N, int AP, int B)
 // The locus' N cells are staged once (latent genotype, current transmission term, COI) and
 // sorted once by cost class; each of the A_j sequential proposals then re-evaluates them from
 // shared memory under the proposed frequencies.
-__global__ void __launch_bounds__(512) k_update_p(const View v, const int iteration)
+__global__ void __launch_bounds__(512, 1) k_update_p(const View v, const int iteration)
 {
     extern __shared__ double smem[];
     const int N = v.N, L = v.L, AP = v.AP, B = blockDim.x;
     double *s_lgam = smem;
     double *s_qs = s_lgam + 128;
-    unsigned long long *s_lat = reinterpret_cast<unsigned long long *>(s_qs + kIeMax * B);
+    unsigned long long *s_lat = reinterpret_cast<unsigned long long *>(s_qs + scratch_doubles(B));
     double *s_Told = reinterpret_cast<double *>(s_lat + N);
     double *s_Tnew = s_Told + N;
     double *s_pcur = s_Tnew + N;
@@ -595,6 +651,16 @@ __global__ void __launch_bounds__(512) k_update_p(const View v, const int iterat
         return m == 0 ? -1 : work_class(__popcll(s_lat[i]), m);
     };
     const int nwork = block_sort_cells(N, cls, s_hist, s_order, s_tmp);
+    const int n_egf = (int)s_tmp[33], coop_end = (int)s_tmp[34];
+    auto fetch = [&](int i, unsigned long long &lat, const double *&prow_, int &m, double &log_r,
+                     double &log_1mr) {
+        const size_t si = (size_t)t * N + i;
+        lat = s_lat[i];
+        prow_ = s_pprop;
+        m = s_m[i];
+        log_r = v.log_r[si];
+        log_1mr = v.log_1mr[si];
+    };
 
     unsigned long long evals = 0;
     for (int rep = 0; rep < A; ++rep)
@@ -676,13 +742,8 @@ __global__ void __launch_bounds__(512) k_update_p(const View v, const int iterat
         if (s_red[34] != 0.0) break;  // src/chain.cpp:503-518: leaves the locus
 
         // -- all cells of the locus under the proposed frequencies, heaviest class first
-        for (int w = tid; w < nwork; w += B)
-        {
-            const int i = s_order[w];
-            const size_t si = (size_t)t * N + i;
-            s_Tnew[i] = transmission_ll(s_lat[i], s_pprop, s_m[i], v.log_r[si], v.log_1mr[si],
-                                        v.allow_rel != 0, s_qs + tid, B, s_lgam);
-        }
+        block_eval_transmissions(s_order, nwork, n_egf, coop_end, fetch, s_Tnew, s_qs, s_lgam,
+                                 v.allow_rel != 0);
         evals += tid == 0 ? (unsigned long long)nwork : 0ull;
         __syncthreads();
         // -- the change of the locus' log-likelihood, summed in sample order
@@ -832,7 +893,7 @@ __global__ void __launch_bounds__(kThreads)
     k_eval_cells(const View v, const int chain_sel, const int use_active)
 {
     __shared__ double s_lgam[128];
-    __shared__ double s_qs[kIeMax * kThreads];
+    __shared__ double s_qs[kScratchSlots * (kThreads + 1)];
     const int tid = threadIdx.x;
     for (int i = tid; i < 128; i += kThreads) s_lgam[i] = v.lgam[i];
     __syncthreads();
@@ -852,7 +913,7 @@ __global__ void __launch_bounds__(kThreads)
         EpsLogs el;
         build_eps_logs(el, v.eps_neg[si], v.eps_pos[si], v.max_eps_neg, v.max_eps_pos, v.nall[j]);
         T = transmission_ll(v.latent[gi], v.p + ((size_t)t * v.L + j) * v.AP, v.m[si], v.log_r[si],
-                            v.log_1mr[si], v.allow_rel != 0, s_qs + tid, kThreads, s_lgam);
+                            v.log_1mr[si], v.allow_rel != 0, s_qs + tid, kThreads + 1, s_lgam);
         O = observation_ll(v.latent[gi], v.obs[cell], v.nall[j], el);
     }
     v.cellT[gi] = T;

@@ -87,96 +87,101 @@ __device__ __forceinline__ double pam_from_coverage(double cov)
     return pam;
 }
 
-// Subsets of {0..k-1} of one size in the reference's lexicographic order.  Element e lives at
-// bit (k-1-e), so lexicographic-ascending == numerically descending; the successor is Gosper's
-// hack applied to the complement.
-__device__ __forceinline__ uint32_t next_subset_lex(uint32_t sub, uint32_t full)
-{
-    const uint32_t v = ~sub & full;
-    const uint32_t t = v | (v - 1u);
-    const uint32_t w = (t + 1u) | (((~t & (0u - ~t)) - 1u) >> __ffs(v));
-    return ~w & full;
-}
+// ---- a6: subset enumeration as a table ----------------------------------------------------------
+// The reference walks the non-empty subsets of the k latent alleles by size, then in
+// lexicographic order of their index tuples (CombinationIndicesGenerator,
+// src/combination_indices_generator.cpp:5-76; src/prob_any_missing.cpp:20-52, 186-214).  The
+// order depends on k only, so it is tabulated once on the host (engine.cu: build_subset_tables)
+// for k <= 10: entry idx of block k (offset 2^k - k - 1) describes the idx-th subset as
+//   bits 0..9   "tail": the elements that differ from the previous subset of the same size
+//   bits 10..13 "depth": how many leading elements it shares with that previous subset
+//   bit  14     set when the subset has even size (its term enters with a minus sign)
+// The running differences 1 - q[c0] - q[c1] - ... of the shared leading elements are kept on a
+// small per-thread stack, so a subset costs ~1 subtraction instead of |S|; the value of every
+// base is still produced by exactly the reference's chain of subtractions.  A second table holds
+// the full element masks for the warp-cooperative evaluator.
+constexpr int kSubsetEntries = 2048;  // 2^11 - 11 - 1 = 2036 used
+__constant__ unsigned short c_sub_tail[kSubsetEntries];
+__device__ unsigned short g_sub_mask[kSubsetEntries];
 
-// base = 1 - q[c0] - q[c1] - ... in ascending element order (src/prob_any_missing.cpp:27-31).
-// qs[b * qstride] holds q of the element at bit b.
-__device__ __forceinline__ double subset_base(uint32_t sub, const double *qs, int qstride)
-{
-    double base = 1.0;
-    while (sub)
-    {
-        const int b = 31 - __clz(sub);
-        base = __dsub_rn(base, qs[b * qstride]);
-        sub ^= 1u << b;
-    }
-    return base;
-}
+__host__ __device__ inline int subset_block(int k) { return (1 << k) - k - 1; }
+
+// Per-thread scratch column: slot s of the thread lives at scr[s * ST].  Slots 0..9 hold q (the
+// normalised frequencies of the latent alleles, ascending allele order), slots 10..19 the stack
+// of partial differences; slots 0..15 are reused for the mixture terms once the sums are done.
+constexpr int kScratchSlots = 20;
+constexpr int kPartBase = 10;
 
 // ---- a4: vectorised inclusion-exclusion, k <= 10 (src/prob_any_missing.cpp:178-216) --------
-// acc[j] accumulates the PAM of n = k + t0 + j draws, j < cnt (entries n < k are never read by
-// the mixture).  NACC is the register tier (>= cnt).  Every accumulator sees the subsets in the
-// reference's order (by size, then lexicographic) and every power is built by the same chain of
-// multiplications, so a cell evaluated in several passes (t0 > 0) gets the same bits.
+// acc[j] accumulates the PAM of n = k + t0 + j draws, j < NACC.  Every accumulator sees the
+// subsets in the reference's order and every power is built by the same chain of
+// multiplications (sign, then base k-1 times, then once per n), so the bits do not depend on
+// NACC or t0.
 template <int NACC>
-__device__ __forceinline__ void ie_vectorized(const double *qs, int qstride, int k, int t0, int cnt,
+__device__ __forceinline__ void ie_vectorized(double *scr, int ST, int k, int t0,
                                               double (&acc)[NACC])
 {
 #pragma unroll
     for (int t = 0; t < NACC; ++t) acc[t] = 0.0;
-    const uint32_t full = (1u << k) - 1u;
+    const unsigned short *tab = c_sub_tail + subset_block(k);
+    const int nsub = (1 << k) - 1;
     const int lead = k - 1 + t0;
-    int sign = -1;
-    int ncomb = 1;
-    for (int s = 1; s <= k; ++s)
+    for (int idx = 0; idx < nsub; ++idx)
     {
-        sign = -sign;
-        ncomb = ncomb * (k - s + 1) / s;  // C(k, s), exact
-        uint32_t sub = ((1u << s) - 1u) << (k - s);
-        for (int c = 0; c < ncomb; ++c)
+        const unsigned int e = tab[idx];
+        unsigned int tail = e & 1023u;
+        int pos = (e >> 10) & 15;
+        double base = pos ? scr[(kPartBase + pos - 1) * ST] : 1.0;
+        for (;;)
         {
-            const double base = subset_base(sub, qs, qstride);
-            double r = (double)sign;
-            for (int j = 0; j < lead; ++j) r = __dmul_rn(r, base);
+            const int el = __ffs(tail) - 1;
+            tail &= tail - 1u;
+            base = __dsub_rn(base, scr[el * ST]);
+            if (!tail) break;
+            scr[(kPartBase + pos) * ST] = base;
+            ++pos;
+        }
+        double r = (e & 0x4000u) ? -1.0 : 1.0;
+        for (int j = 0; j < lead; ++j) r = __dmul_rn(r, base);
 #pragma unroll
-            for (int t = 0; t < NACC; ++t)
-            {
-                if (t < cnt)
-                {
-                    r = __dmul_rn(r, base);
-                    acc[t] = __dadd_rn(acc[t], r);
-                }
-            }
-            if (c + 1 < ncomb) sub = next_subset_lex(sub, full);
+        for (int t = 0; t < NACC; ++t)
+        {
+            r = __dmul_rn(r, base);
+            acc[t] = __dadd_rn(acc[t], r);
         }
     }
 }
 
 // ---- a3: scalar inclusion-exclusion, k <= 10 (src/prob_any_missing.cpp:13-53) ---------------
-__device__ __forceinline__ double ie_scalar(const double *qs, int qstride, int k, int n)
+__device__ __forceinline__ double ie_scalar(double *scr, int ST, int k, int n)
 {
-    const uint32_t full = (1u << k) - 1u;
+    const unsigned short *tab = c_sub_tail + subset_block(k);
+    const int nsub = (1 << k) - 1;
     double prob = 0.0;
-    int sign = -1;
-    int ncomb = 1;
-    for (int s = 1; s <= k; ++s)
+    for (int idx = 0; idx < nsub; ++idx)
     {
-        sign = -sign;
-        ncomb = ncomb * (k - s + 1) / s;
-        uint32_t sub = ((1u << s) - 1u) << (k - s);
-        for (int c = 0; c < ncomb; ++c)
+        const unsigned int e = tab[idx];
+        unsigned int tail = e & 1023u;
+        int pos = (e >> 10) & 15;
+        double base = pos ? scr[(kPartBase + pos - 1) * ST] : 1.0;
+        for (;;)
         {
-            double base = subset_base(sub, qs, qstride);
-            double r = (double)sign;
-            int mc = n;
-            while (mc > 0)
-            {
-                if (mc & 1) r = __dmul_rn(r, base);
-                base = __dmul_rn(base, base);
-                mc >>= 1;
-            }
-            prob = __dadd_rn(prob, r);
-            if (c + 1 < ncomb) sub = next_subset_lex(sub, full);
+            const int el = __ffs(tail) - 1;
+            tail &= tail - 1u;
+            base = __dsub_rn(base, scr[el * ST]);
+            if (!tail) break;
+            scr[(kPartBase + pos) * ST] = base;
+            ++pos;
         }
+        double r = (e & 0x4000u) ? -1.0 : 1.0;
+        int mc = n;
+        while (mc > 0)
+        {
+            if (mc & 1) r = __dmul_rn(r, base);
+            base = __dmul_rn(base, base);
+            mc >>= 1;
+        }
+        prob = __dadd_rn(prob, r);
     }
     return prob;
 }
@@ -224,53 +229,83 @@ __device__ __forceinline__ double dbinom_log(int x, int size, double log_p, doub
     return __dadd_rn(lp, lc);
 }
 
-// Relatedness mixture + log-sum-exp (src/chain.cpp:903-920, src/mcmc_utils.h:382-397).
-// On entry acc[t] = PAM(n = k + t); term i = 0..cnt-1 uses n = m - i, i.e. t = cnt - 1 - i.
-template <int NACC>
-__device__ __forceinline__ double relatedness_mixture(double (&acc)[NACC], int k, int m, int cnt,
+// Relatedness mixture + log-sum-exp (src/chain.cpp:903-920, src/mcmc_utils.h:382-397), rolled.
+// On entry val[t * ST] = PAM(n = k + t), t < cnt; term i = 0..cnt-1 uses n = m - i, i.e.
+// t = cnt - 1 - i.  The terms are overwritten in place.
+__device__ __forceinline__ double relatedness_mixture(double *val, int ST, int m, int cnt,
                                                       double log_total, double log_r,
                                                       double log_1mr, const double *lgam)
 {
     double mx = -INFINITY;
-#pragma unroll
-    for (int t = 0; t < NACC; ++t)
+    for (int t = 0; t < cnt; ++t)
     {
-        if (t < cnt)
-        {
-            const int i = cnt - 1 - t;
-            const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
-            const double pam = clamp_pam(acc[t]);
-            const double i_res = __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
-            const double v = __dadd_rn(pr, i_res);
-            acc[t] = v;
-            mx = (mx < v) ? v : mx;  // std::max_element semantics
-        }
+        const int i = cnt - 1 - t;
+        const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
+        const double pam = clamp_pam(val[t * ST]);
+        const double i_res = __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
+        const double v = __dadd_rn(pr, i_res);
+        val[t * ST] = v;
+        mx = (mx < v) ? v : mx;  // std::max_element semantics
     }
     if (mx == -INFINITY) return -INFINITY;
+    if (cnt == 1) return mx;  // exp(0) = 1, log(1) = 0: the sum is the term itself
     double sum = 0.0;
-#pragma unroll
-    for (int t = NACC - 1; t >= 0; --t)  // i ascending, as the reference sums
+    for (int t = cnt - 1; t >= 0; --t)  // i ascending, as the reference sums
     {
-        if (t < cnt) sum = __dadd_rn(sum, exp(__dsub_rn(acc[t], mx)));
+        const double dv = __dsub_rn(val[t * ST], mx);
+        sum = __dadd_rn(sum, dv == 0.0 ? 1.0 : exp(dv));
     }
     return __dadd_rn(mx, log(sum));
 }
 
-template <int NACC>
-__device__ __noinline__ double transmission_rel_ie(const double *qs, int qstride, int k, int m,
+// One instantiation per number of mixture terms (1..16): the accumulators stay in registers
+// without predication; the sorted work lists make the choice uniform across a warp.
+__device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, int m,
                                                    double log_total, double log_r, double log_1mr,
                                                    const double *lgam)
 {
-    double acc[NACC];
     const int cnt = m - k + 1;
-    ie_vectorized<NACC>(qs, qstride, k, 0, cnt, acc);
-    return relatedness_mixture<NACC>(acc, k, m, cnt, log_total, log_r, log_1mr, lgam);
+#define MOIRE_IE_CASE(NACC)                                     \
+    case NACC:                                                  \
+    {                                                           \
+        double acc[NACC];                                       \
+        ie_vectorized<NACC>(scr, ST, k, 0, acc);                \
+        _Pragma("unroll") for (int t = 0; t < NACC; ++t) scr[t * ST] = acc[t]; \
+        break;                                                  \
+    }
+    switch (cnt)
+    {
+        MOIRE_IE_CASE(1)
+        MOIRE_IE_CASE(2)
+        MOIRE_IE_CASE(3)
+        MOIRE_IE_CASE(4)
+        MOIRE_IE_CASE(5)
+        MOIRE_IE_CASE(6)
+        MOIRE_IE_CASE(7)
+        MOIRE_IE_CASE(8)
+        MOIRE_IE_CASE(9)
+        MOIRE_IE_CASE(10)
+        MOIRE_IE_CASE(11)
+        MOIRE_IE_CASE(12)
+        MOIRE_IE_CASE(13)
+        MOIRE_IE_CASE(14)
+        MOIRE_IE_CASE(15)
+        default:
+        {
+            double acc[16];
+            ie_vectorized<16>(scr, ST, k, 0, acc);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) scr[t * ST] = acc[t];
+            break;
+        }
+    }
+#undef MOIRE_IE_CASE
+    return relatedness_mixture(scr, ST, m, cnt, log_total, log_r, log_1mr, lgam);
 }
 
 // m - k >= 16 (rare: a COI far above the number of distinct alleles): the accumulators are
-// produced 16 at a time and parked in local memory, so that the common tiers keep the kernel's
-// register budget.
-__device__ __noinline__ double transmission_rel_ie_wide(const double *qs, int qstride, int k, int m,
+// produced 16 at a time and parked in local memory.
+__device__ __noinline__ double transmission_rel_ie_wide(double *scr, int ST, int k, int m,
                                                         double log_total, double log_r,
                                                         double log_1mr, const double *lgam)
 {
@@ -279,27 +314,12 @@ __device__ __noinline__ double transmission_rel_ie_wide(const double *qs, int qs
     for (int t0 = 0; t0 < cnt; t0 += 16)
     {
         double acc[16];
-        const int c = min(16, cnt - t0);
-        ie_vectorized<16>(qs, qstride, k, t0, c, acc);
+        ie_vectorized<16>(scr, ST, k, t0, acc);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-            if (j < c) v[t0 + j] = acc[j];
+            if (t0 + j < cnt) v[t0 + j] = acc[j];
     }
-    double mx = -INFINITY;
-    for (int t = 0; t < cnt; ++t)
-    {
-        const int i = cnt - 1 - t;
-        const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
-        const double pam = clamp_pam(v[t]);
-        const double i_res = __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
-        const double val = __dadd_rn(pr, i_res);
-        v[t] = val;
-        mx = (mx < val) ? val : mx;
-    }
-    if (mx == -INFINITY) return -INFINITY;
-    double sum = 0.0;
-    for (int t = cnt - 1; t >= 0; --t) sum = __dadd_rn(sum, exp(__dsub_rn(v[t], mx)));
-    return __dadd_rn(mx, log(sum));
+    return relatedness_mixture(v, 1, m, cnt, log_total, log_r, log_1mr, lgam);
 }
 
 // EGF branch of the relatedness path; a[] lives in local memory (k > 10 only).
@@ -328,13 +348,12 @@ __device__ __noinline__ double transmission_rel_egf(uint64_t latent, const doubl
     return __dadd_rn(mx, log(sum));
 }
 
-// ---- a2: transmission process of one cell ----------------------------------------------------
-// prow: allele frequencies of the locus; qs: per-thread scratch for up to 10 normalised
-// frequencies, element stride qstride (shared memory, conflict-free when qstride = blockDim.x);
-// lgam: lgamma(i + 1), i < 128.
+// ---- a2: transmission process of one cell, one thread -------------------------------------------
+// prow: allele frequencies of the locus; scr: the thread's scratch column (kScratchSlots slots,
+// stride ST); lgam: lgamma(i + 1), i < 128.
 __device__ __forceinline__ double transmission_ll(uint64_t latent, const double *prow, int m,
                                                   double log_r, double log_1mr,
-                                                  bool allow_relatedness, double *qs, int qstride,
+                                                  bool allow_relatedness, double *scr, int ST,
                                                   const double *lgam)
 {
     const int k = __popcll(latent);
@@ -358,7 +377,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
         {
             const int al = __ffsll((long long)rest) - 1;
             rest &= rest - 1;
-            qs[(k - 1 - e) * qstride] = __ddiv_rn(prow[al], total);
+            scr[e * ST] = __ddiv_rn(prow[al], total);
             ++e;
         }
     }
@@ -381,7 +400,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
         }
         else if (k <= kIeMax)
         {
-            pam = ie_scalar(qs, qstride, k, m);
+            pam = ie_scalar(scr, ST, k, m);
         }
         else
         {
@@ -394,12 +413,161 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
     }
     if (k > kIeMax)
         return transmission_rel_egf(latent, prow, total, k, m, log_total, log_r, log_1mr, lgam);
-    const int cnt = m - k + 1;
-    if (cnt <= 4) return transmission_rel_ie<4>(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
-    if (cnt <= 8) return transmission_rel_ie<8>(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
-    if (cnt <= 16)
-        return transmission_rel_ie<16>(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
-    return transmission_rel_ie_wide(qs, qstride, k, m, log_total, log_r, log_1mr, lgam);
+    if (m - k + 1 <= 16)
+        return transmission_rel_ie(scr, ST, k, m, log_total, log_r, log_1mr, lgam);
+    return transmission_rel_ie_wide(scr, ST, k, m, log_total, log_r, log_1mr, lgam);
+}
+
+// ---- a2, warp-cooperative: one cell, 32 lanes ---------------------------------------------------
+// For a heavy cell (2^k - 1 subsets, k >= kCoopMinK) the subsets are dealt 32 at a time to the
+// lanes of a warp.  Each lane builds its subset's terms base^(k+t), t < cnt, with the same chain
+// of operations as the one-thread path and parks them in shared memory; lane t then adds the 32
+// terms of accumulator t in subset order.  Floating-point addition is not associative, so this
+// ordered second phase (not a tree reduction) is what keeps the result bit-identical to the
+// one-thread path and to the reference's summation order.  The mixture terms are evaluated one
+// per lane; their log-sum-exp is again summed in the reference's order.
+// All lanes must call with identical arguments; every lane returns the value.
+// wscr: the warp's 32 scratch columns (slot s, column c at wscr[s * ST + c]); slot 16 holds q.
+constexpr int kCoopMinK = 6;
+__device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const double *prow, int m,
+                                                       double log_r, double log_1mr,
+                                                       bool allow_relatedness, double *wscr, int ST,
+                                                       const double *lgam)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int k = __popcll(latent);  // kCoopMinK <= k <= kIeMax <= m guaranteed by the caller
+    double total = 0.0;
+    {
+        uint64_t rest = latent;
+        while (rest)
+        {
+            const int al = __ffsll((long long)rest) - 1;
+            rest &= rest - 1;
+            total = __dadd_rn(total, prow[al]);
+        }
+    }
+    const double log_total = log(total);
+    double *q = wscr + 16 * ST;
+    {
+        // lane e normalises element e
+        uint64_t rest = latent;
+        for (int e = 0; e < lane && rest; ++e) rest &= rest - 1;
+        if (lane < k) q[lane] = __ddiv_rn(prow[__ffsll((long long)rest) - 1], total);
+    }
+    __syncwarp();
+    const unsigned short *masks = g_sub_mask + subset_block(k);
+    const int nsub = (1 << k) - 1;
+    const int cnt = allow_relatedness ? m - k + 1 : 1;
+    double result_mx = -INFINITY, sum_tail = 0.0;
+    // accumulators of up to 4 chunks of 16 mixture terms (cnt <= 64); chunk c, lane t: n = k + 16c + t
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+    {
+        const int t0 = 16 * ch;
+        if (t0 < cnt)  // uniform
+        {
+            const int cc = min(16, cnt - t0);
+            for (int b0 = 0; b0 < nsub; b0 += 32)
+            {
+                const int idx = b0 + lane;
+                if (idx < nsub)
+                {
+                    unsigned int msk = masks[idx];
+                    const bool neg = (__popc(msk) & 1) == 0;
+                    double base = 1.0;
+                    while (msk)
+                    {
+                        const int el = __ffs(msk) - 1;
+                        msk &= msk - 1u;
+                        base = __dsub_rn(base, q[el]);
+                    }
+                    double r = neg ? -1.0 : 1.0;
+                    if (allow_relatedness)
+                    {
+                        const int lead = k - 1 + t0;
+                        for (int j = 0; j < lead; ++j) r = __dmul_rn(r, base);
+                        for (int t = 0; t < cc; ++t)
+                        {
+                            r = __dmul_rn(r, base);
+                            wscr[t * ST + lane] = r;
+                        }
+                    }
+                    else
+                    {
+                        int mc = m;  // probAnyMissingFunctor::operator(): square and multiply
+                        while (mc > 0)
+                        {
+                            if (mc & 1) r = __dmul_rn(r, base);
+                            base = __dmul_rn(base, base);
+                            mc >>= 1;
+                        }
+                        wscr[lane] = r;
+                    }
+                }
+                __syncwarp();
+                if (lane < cc)
+                {
+                    const int nv = min(32, nsub - b0);
+                    const double *row = wscr + lane * ST;
+                    double a = acc[ch];
+                    for (int l = 0; l < nv; ++l) a = __dadd_rn(a, row[l]);
+                    acc[ch] = a;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    if (!allow_relatedness)
+    {
+        const double pam = clamp_pam(__shfl_sync(FULL, acc[0], 0));
+        return __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)m));
+    }
+    // mixture terms, one per (chunk, lane)
+    double v[4];
+    double mx = -INFINITY;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+    {
+        const int t = 16 * ch + lane;
+        v[ch] = -INFINITY;
+        if (lane < 16 && t < cnt)
+        {
+            const int i = cnt - 1 - t;
+            const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
+            const double pam = clamp_pam(acc[ch]);
+            const double i_res = __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
+            v[ch] = __dadd_rn(pr, i_res);
+            mx = (mx < v[ch]) ? v[ch] : mx;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        const double other = __shfl_xor_sync(FULL, mx, o);
+        mx = (mx < other) ? other : mx;
+    }
+    result_mx = mx;
+    if (result_mx == -INFINITY) return -INFINITY;
+    if (cnt == 1) return result_mx;
+    // sum exp(v - mx) in the reference's order: i ascending = t descending
+#pragma unroll
+    for (int ch = 3; ch >= 0; --ch)
+    {
+        if (16 * ch < cnt)  // uniform
+        {
+            double ev = 0.0;
+            if (lane < 16 && 16 * ch + lane < cnt)
+            {
+                const double dv = __dsub_rn(v[ch], result_mx);
+                ev = dv == 0.0 ? 1.0 : exp(dv);
+            }
+            const int top = min(15, cnt - 1 - 16 * ch);
+            for (int t = top; t >= 0; --t) sum_tail = __dadd_rn(sum_tail, __shfl_sync(FULL, ev, t));
+        }
+    }
+    return __dadd_rn(result_mx, log(sum_tail));
 }
 
 // ---- a8: latent-genotype proposal ------------------------------------------------------------
