@@ -160,47 +160,62 @@ __device__ __forceinline__ int block_sort_cells(int ncell, ClassFn cls, unsigned
 
 // Transmission terms of the listed cells.  The list is heaviest first: [0, n_egf) cells with
 // k > 10 (EGF recurrence, one thread each), [n_egf, coop_end) cells with kCoopMinK <= k <= 10
-// (one warp each, subsets across lanes), the rest light cells (one thread each).
+// (one warp each, subsets across lanes), the rest light cells (one thread each).  Work is handed
+// out dynamically, heaviest first, in units of one cooperative cell or one chunk of 32
+// one-thread cells: `next` is a shared counter the caller has zeroed before its last barrier.
 // fetch(cell, lat, prow, m, log_r, log_1mr) supplies a cell's inputs; out[cell] gets the term.
 // scr: kScratchSlots rows of blockDim.x + 1 doubles.  No block barrier inside.
 template <class Fetch>
 __device__ __forceinline__ void block_eval_transmissions(const unsigned short *order, int nwork,
                                                          int n_egf, int coop_end, Fetch fetch,
                                                          double *out, double *scr,
-                                                         const double *lgam, bool allow_rel)
+                                                         const double *lgam, bool allow_rel,
+                                                         unsigned int *next)
 {
-    const int tid = threadIdx.x, B = blockDim.x, ST = B + 1;
-    const int lane = tid & 31, warp = tid >> 5, nw = B >> 5;
-    for (int w = n_egf + warp; w < coop_end; w += nw)
+    const int tid = threadIdx.x, ST = blockDim.x + 1;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int egf_units = (n_egf + 31) >> 5, coop_units = coop_end - n_egf;
+    const int light_units = (nwork - coop_end + 31) >> 5;
+    const int units = egf_units + coop_units + light_units;
+    for (;;)
     {
-        const int cell = order[w];
+        int u = 0;
+        if (lane == 0) u = (int)atomicAdd(next, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= units) break;
         unsigned long long lat;
         const double *prow;
         int m;
         double log_r, log_1mr;
-        fetch(cell, lat, prow, m, log_r, log_1mr);
-        const int k = __popcll(lat);
-        double T;
-        if (k > m)
-            T = NAN;
-        else if (!allow_rel && m == k)  // closed form, src/prob_any_missing.cpp:139-148
-            T = transmission_ll(lat, prow, m, log_r, log_1mr, allow_rel, scr + tid, ST, lgam);
+        if (u >= egf_units && u < egf_units + coop_units)
+        {
+            const int cell = order[n_egf + (u - egf_units)];
+            fetch(cell, lat, prow, m, log_r, log_1mr);
+            const int k = __popcll(lat);
+            double T;
+            if (k > m)
+                T = NAN;
+            else if (!allow_rel && m == k)  // closed form, src/prob_any_missing.cpp:139-148
+                T = transmission_ll(lat, prow, m, log_r, log_1mr, allow_rel, scr + tid, ST, lgam);
+            else
+                T = transmission_ll_coop(lat, prow, m, log_r, log_1mr, allow_rel, scr + warp * 32,
+                                         ST, lgam);
+            if (lane == 0) out[cell] = T;
+        }
         else
-            T = transmission_ll_coop(lat, prow, m, log_r, log_1mr, allow_rel, scr + warp * 32, ST,
-                                     lgam);
-        if (lane == 0) out[cell] = T;
+        {
+            const int w = u < egf_units ? 32 * u + lane
+                                        : coop_end + 32 * (u - egf_units - coop_units) + lane;
+            const int end = u < egf_units ? n_egf : nwork;
+            if (w < end)
+            {
+                const int cell = order[w];
+                fetch(cell, lat, prow, m, log_r, log_1mr);
+                out[cell] =
+                    transmission_ll(lat, prow, m, log_r, log_1mr, allow_rel, scr + tid, ST, lgam);
+            }
+        }
         __syncwarp();
-    }
-    const int nthread = n_egf + (nwork - coop_end);
-    for (int w = tid; w < nthread; w += B)
-    {
-        const int cell = order[w < n_egf ? w : coop_end + (w - n_egf)];
-        unsigned long long lat;
-        const double *prow;
-        int m;
-        double log_r, log_1mr;
-        fetch(cell, lat, prow, m, log_r, log_1mr);
-        out[cell] = transmission_ll(lat, prow, m, log_r, log_1mr, allow_rel, scr + tid, ST, lgam);
     }
 }
 
@@ -243,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(s_prop + S);
     unsigned int *s_tmp = s_hist + kSortBins;
     unsigned short *s_order = reinterpret_cast<unsigned short *>(s_tmp + 40);
-    __shared__ unsigned int s_evals;
+    __shared__ unsigned int s_evals, s_next;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kThreads / 32;
@@ -255,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     const double temp = v.temp[t];
 
     for (int i = tid; i < 128; i += kThreads) s_lgam[i] = v.lgam[i];
-    if (tid == 0) s_evals = 0;
+    if (tid == 0) s_evals = s_next = 0;
     __syncthreads();
 
     // ---- phase A: one proposal per sample -----------------------------------------------------
@@ -429,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 2)
             log_1mr = P.log_1mr;
         };
         block_eval_transmissions(s_order, nwork, (int)s_tmp[33], (int)s_tmp[34], fetch, s_T, s_qs,
-                                 s_lgam, v.allow_rel != 0);
+                                 s_lgam, v.allow_rel != 0, &s_next);
         __syncthreads();
     }
 
@@ -621,6 +636,7 @@ __global__ void __launch_bounds__(512, 1) k_update_p(const View v, const int ite
     unsigned short *s_order = reinterpret_cast<unsigned short *>(s_tmp + 40);
     unsigned char *s_m = reinterpret_cast<unsigned char *>(s_order) + align8((size_t)N * 2);
 
+    __shared__ unsigned int s_next;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = blockIdx.x / L, j = blockIdx.x - t * L;
     const int A = v.nall[j];
@@ -731,6 +747,7 @@ __global__ void __launch_bounds__(512, 1) k_update_p(const View v, const int ite
             below = __any_sync(0xffffffffu, below);
             if (lane == 0)
             {
+                s_next = 0;
                 ++s_att[idx];
                 s_red[33] = (clp - plp) + (double)(A - 1) * (clq - plq);
                 s_red[34] = below ? 1.0 : 0.0;
@@ -743,7 +760,7 @@ __global__ void __launch_bounds__(512, 1) k_update_p(const View v, const int ite
 
         // -- all cells of the locus under the proposed frequencies, heaviest class first
         block_eval_transmissions(s_order, nwork, n_egf, coop_end, fetch, s_Tnew, s_qs, s_lgam,
-                                 v.allow_rel != 0);
+                                 v.allow_rel != 0, &s_next);
         evals += tid == 0 ? (unsigned long long)nwork : 0ull;
         __syncthreads();
         // -- the change of the locus' log-likelihood, summed in sample order

@@ -258,47 +258,33 @@ __device__ __forceinline__ double relatedness_mixture(double *val, int ST, int m
     return __dadd_rn(mx, log(sum));
 }
 
-// One instantiation per number of mixture terms (1..16): the accumulators stay in registers
-// without predication; the sorted work lists make the choice uniform across a warp.
+// One instantiation per number of accumulators: they stay in registers without predication.
+// All lanes that arrive together run the instantiation of the largest count among them (the
+// extra accumulators of a lane with fewer mixture terms are simply never read), so lanes with
+// different counts -- and different k: the subset loop just ends earlier for them -- share one
+// instruction stream.  The sorted work lists make the counts of a warp nearly equal.
 __device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, int m,
                                                    double log_total, double log_r, double log_1mr,
                                                    const double *lgam)
 {
     const int cnt = m - k + 1;
-#define MOIRE_IE_CASE(NACC)                                     \
-    case NACC:                                                  \
-    {                                                           \
-        double acc[NACC];                                       \
-        ie_vectorized<NACC>(scr, ST, k, 0, acc);                \
-        _Pragma("unroll") for (int t = 0; t < NACC; ++t) scr[t * ST] = acc[t]; \
-        break;                                                  \
+    const int cnt_w = __reduce_max_sync(__activemask(), cnt);
+#define MOIRE_IE_CASE(NACC)                                                      \
+    {                                                                            \
+        double acc[NACC];                                                        \
+        ie_vectorized<NACC>(scr, ST, k, 0, acc);                                 \
+        _Pragma("unroll") for (int t = 0; t < NACC; ++t) scr[t * ST] = acc[t];   \
     }
-    switch (cnt)
-    {
-        MOIRE_IE_CASE(1)
-        MOIRE_IE_CASE(2)
-        MOIRE_IE_CASE(3)
-        MOIRE_IE_CASE(4)
-        MOIRE_IE_CASE(5)
-        MOIRE_IE_CASE(6)
-        MOIRE_IE_CASE(7)
-        MOIRE_IE_CASE(8)
-        MOIRE_IE_CASE(9)
-        MOIRE_IE_CASE(10)
-        MOIRE_IE_CASE(11)
-        MOIRE_IE_CASE(12)
-        MOIRE_IE_CASE(13)
-        MOIRE_IE_CASE(14)
-        MOIRE_IE_CASE(15)
-        default:
-        {
-            double acc[16];
-            ie_vectorized<16>(scr, ST, k, 0, acc);
-#pragma unroll
-            for (int t = 0; t < 16; ++t) scr[t * ST] = acc[t];
-            break;
-        }
-    }
+    if (cnt_w <= 1) MOIRE_IE_CASE(1)
+    else if (cnt_w <= 2) MOIRE_IE_CASE(2)
+    else if (cnt_w <= 3) MOIRE_IE_CASE(3)
+    else if (cnt_w <= 4) MOIRE_IE_CASE(4)
+    else if (cnt_w <= 5) MOIRE_IE_CASE(5)
+    else if (cnt_w <= 6) MOIRE_IE_CASE(6)
+    else if (cnt_w <= 8) MOIRE_IE_CASE(8)
+    else if (cnt_w <= 10) MOIRE_IE_CASE(10)
+    else if (cnt_w <= 12) MOIRE_IE_CASE(12)
+    else MOIRE_IE_CASE(16)
 #undef MOIRE_IE_CASE
     return relatedness_mixture(scr, ST, m, cnt, log_total, log_r, log_1mr, lgam);
 }
