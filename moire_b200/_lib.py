@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmoire_b200.so")
+# MOIRE_B200_LIB: an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("MOIRE_B200_LIB") or os.path.join(HERE, "libmoire_b200.so")
 
 vp, i32, u64, dbl = C.c_void_p, C.c_int32, C.c_uint64, C.c_double
 

@@ -311,7 +311,8 @@ struct moire_engine
         CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
         CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EFF_COI>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
         CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_SAMPLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
-        CUDA_TRY(cudaFuncSetAttribute(k_update_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_update_p<MOIRE_P_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_update_p<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
     }
 
     struct Timed
@@ -379,7 +380,10 @@ struct moire_engine
             case MOIRE_UPDATE_P:
             {
                 Timed tm(this, kind);
-                k_update_p<<<v.T * v.L, p_threads, p_smem, stream>>>(v, iteration);
+                if (p_threads == MOIRE_P_THREADS)
+                    k_update_p<MOIRE_P_THREADS><<<v.T * v.L, MOIRE_P_THREADS, p_smem, stream>>>(v, iteration);
+                else
+                    k_update_p<512><<<v.T * v.L, 512, p_smem, stream>>>(v, iteration);
                 tm.done();
                 break;
             }

@@ -21,9 +21,24 @@
 
 namespace moire
 {
-constexpr int kThreads = 256;
+#ifndef MOIRE_MIN_BLOCKS
+#define MOIRE_MIN_BLOCKS 2
+#endif
+#ifndef MOIRE_SORT_CNT_FIRST
+#define MOIRE_SORT_CNT_FIRST 0
+#endif
+#ifndef MOIRE_SAMPLE_THREADS
+#define MOIRE_SAMPLE_THREADS 256
+#endif
+#ifndef MOIRE_P_THREADS
+#define MOIRE_P_THREADS 256
+#endif
+constexpr int kThreads = MOIRE_SAMPLE_THREADS;
 constexpr int kMaxTileSamples = 32;
-constexpr int kMaxTileCells = 1024;  // cells of one (chain, sample-tile) block
+#ifndef MOIRE_TILE_CELLS
+#define MOIRE_TILE_CELLS 1024
+#endif
+constexpr int kMaxTileCells = MOIRE_TILE_CELLS;  // cells of one (chain, sample-tile) block
 constexpr int kSortBins = 12 * 64;   // (min(k, 11), m - k + 1) work classes
 
 struct Proposal
@@ -86,6 +101,11 @@ __device__ __forceinline__ int work_class(int k, int m)
     const int kk = k > kIeMax ? kIeMax + 1 : k;
     int cnt = m - k + 1;
     cnt = cnt < 1 ? 1 : (cnt > 64 ? 64 : cnt);
+#if MOIRE_SORT_CNT_FIRST
+    // light cells: the mixture (cnt terms of log1p + exp) outweighs the subset sums, so equal
+    // counts matter more than equal k inside a warp
+    if (kk < kCoopMinK) return kSortBins - 1 - ((cnt - 1) * kCoopMinK + kk);
+#endif
     return kSortBins - 1 - (kk * 64 + (cnt - 1));
 }
 
@@ -238,7 +258,7 @@ __host__ __device__ inline size_t sample_kernel_smem(int S, int L, int nA)
 
 // ---- per-sample updates: eps_neg, eps_pos, m, r, eff_coi, samples ----------------------------
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, MOIRE_MIN_BLOCKS * (256 / kThreads))
     k_update_sample(const View v, const int iteration, const int S, const int tiles_per_chain)
 {
     constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
@@ -595,7 +615,7 @@ __device__ __forceinline__ double logit_scale_d(double x, double scale)
 
 __device__ __forceinline__ double expit_d(double x) { return 1.0 / (1.0 + exp(-x)); }
 
-__host__ __device__ inline int p_kernel_threads(int N) { return N > 2048 ? 512 : 256; }
+__host__ __device__ inline int p_kernel_threads(int N) { return N > 2048 ? 512 : MOIRE_P_THREADS; }
 
 __host__ __device__ inline size_t p_kernel_smem(int N, int AP, int B)
 {
@@ -616,7 +636,9 @@ __host__ __device__ inline size_t p_kernel_smem(int N, int AP, int B)
 // The locus' N cells are staged once (latent genotype, current transmission term, COI) and
 // sorted once by cost class; each of the A_j sequential proposals then re-evaluates them from
 // shared memory under the proposed frequencies.
-__global__ void __launch_bounds__(512, 1) k_update_p(const View v, const int iteration)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, BLOCK == 512 ? 1 : MOIRE_MIN_BLOCKS * (256 / BLOCK))
+    k_update_p(const View v, const int iteration)
 {
     extern __shared__ double smem[];
     const int N = v.N, L = v.L, AP = v.AP, B = blockDim.x;

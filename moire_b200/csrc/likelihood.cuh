@@ -414,7 +414,10 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
 // per lane; their log-sum-exp is again summed in the reference's order.
 // All lanes must call with identical arguments; every lane returns the value.
 // wscr: the warp's 32 scratch columns (slot s, column c at wscr[s * ST + c]); slot 16 holds q.
-constexpr int kCoopMinK = 6;
+#ifndef MOIRE_COOP_MIN_K
+#define MOIRE_COOP_MIN_K 8
+#endif
+constexpr int kCoopMinK = MOIRE_COOP_MIN_K;
 __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const double *prow, int m,
                                                        double log_r, double log_1mr,
                                                        bool allow_relatedness, double *wscr, int ST,

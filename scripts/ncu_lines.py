@@ -50,3 +50,17 @@ print(f"{'file:line':28s} {'exec%':>7s} {'thr/inst':>8s} {'samp%':>7s} {'barrier
 key = int(os.environ.get("SORTCOL", "0"))
 for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][key])[:top]:
     print(f"{loc[0] + ':' + str(loc[1]):28s} {100 * a[0] / ti:7.2f} {a[1] / max(a[0], 1):8.1f} {100 * a[2] / ts:7.2f} {100 * a[3] / ts:8.2f} {100 * a[4] / ts:8.2f}")
+# ---- thread-instruction share by code region (line ranges of the current sources)
+if os.environ.get("REGIONS"):
+    regs = [tuple(x.split(":")) for x in os.environ["REGIONS"].split(",")]  # name:file:lo:hi
+    tot = sum(a[1] for a in agg.values())
+    out = collections.Counter()
+    for (f, l), a in agg.items():
+        for name, rf, lo, hi in regs:
+            if f == rf and int(lo) <= l <= int(hi):
+                out[name] += a[1]
+                break
+        else:
+            out["other:" + f] += a[1]
+    for k, vv in out.most_common():
+        print(f"  {k:30s} {100 * vv / tot:6.2f}% of thread instructions")
