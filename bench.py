@@ -230,7 +230,9 @@ def our_arm(args, wl):
     mc.close()
 
     # ---- end to end through the public call, host buffers in, result list out
-    e2e_burn, e2e_samp = args.steps, args.steps
+    # long enough that the one-off costs (packing, upload, chain initialisation) are weighed as
+    # in a real run (defaults there: 10000 burn-in + 1000 sampling steps)
+    e2e_burn, e2e_samp = max(3 * args.steps, 30), max(args.steps, 10)
     barrier()
     t0 = time.perf_counter()
     res = run_mcmc(wl["sim"], wl["sim"]["is_missing"], burnin=e2e_burn, samples_per_chain=e2e_samp,
