@@ -21,8 +21,11 @@
 
 namespace moire
 {
-#ifndef MOIRE_MIN_BLOCKS
-#define MOIRE_MIN_BLOCKS 2
+#ifndef MOIRE_MIN_BLOCKS_P
+#define MOIRE_MIN_BLOCKS_P 3
+#endif
+#ifndef MOIRE_MIN_BLOCKS_S
+#define MOIRE_MIN_BLOCKS_S 2
 #endif
 #ifndef MOIRE_SORT_CNT_FIRST
 #define MOIRE_SORT_CNT_FIRST 0
@@ -215,8 +218,6 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
             double T;
             if (k > m)
                 T = NAN;
-            else if (!allow_rel && m == k)  // closed form, src/prob_any_missing.cpp:139-148
-                T = transmission_ll(lat, prow, m, log_r, log_1mr, allow_rel, scr + tid, ST, lgam);
             else
                 T = transmission_ll_coop(lat, prow, m, log_r, log_1mr, allow_rel, scr + warp * 32,
                                          ST, lgam);
@@ -258,7 +259,7 @@ __host__ __device__ inline size_t sample_kernel_smem(int S, int L, int nA)
 
 // ---- per-sample updates: eps_neg, eps_pos, m, r, eff_coi, samples ----------------------------
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, MOIRE_MIN_BLOCKS * (256 / kThreads))
+__global__ void __launch_bounds__(kThreads, MOIRE_MIN_BLOCKS_S * (256 / kThreads))
     k_update_sample(const View v, const int iteration, const int S, const int tiles_per_chain)
 {
     constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
@@ -637,7 +638,7 @@ __host__ __device__ inline size_t p_kernel_smem(int N, int AP, int B)
 // sorted once by cost class; each of the A_j sequential proposals then re-evaluates them from
 // shared memory under the proposed frequencies.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, BLOCK == 512 ? 1 : MOIRE_MIN_BLOCKS * (256 / BLOCK))
+__global__ void __launch_bounds__(BLOCK, BLOCK == 512 ? 1 : MOIRE_MIN_BLOCKS_P * (256 / BLOCK))
     k_update_p(const View v, const int iteration)
 {
     extern __shared__ double smem[];

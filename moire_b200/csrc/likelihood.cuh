@@ -24,6 +24,21 @@
 
 namespace moire
 {
+// libm calls of the per-cell path go through one out-of-line copy each when MOIRE_LIBM_CALLS is
+// set (tuning: smaller hot code, at the price of a call per use)
+#ifndef MOIRE_LIBM_CALLS
+#define MOIRE_LIBM_CALLS 0
+#endif
+#if MOIRE_LIBM_CALLS
+__device__ __noinline__ double cell_log(double x) { return log(x); }
+__device__ __noinline__ double cell_log1p(double x) { return log1p(x); }
+__device__ __noinline__ double cell_exp(double x) { return exp(x); }
+#else
+__device__ __forceinline__ double cell_log(double x) { return log(x); }
+__device__ __forceinline__ double cell_log1p(double x) { return log1p(x); }
+__device__ __forceinline__ double cell_exp(double x) { return exp(x); }
+#endif
+
 constexpr int kIeMax = 10;      // src/prob_any_missing.cpp:11
 constexpr int kMaxCoi = 64;     // MOIRE_MAX_COI
 constexpr int kLogCDim = 65;    // logC[n][k], 0 <= k <= n <= 64
@@ -242,7 +257,7 @@ __device__ __forceinline__ double relatedness_mixture(double *val, int ST, int m
         const int i = cnt - 1 - t;
         const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
         const double pam = clamp_pam(val[t * ST]);
-        const double i_res = __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
+        const double i_res = __dadd_rn(cell_log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
         const double v = __dadd_rn(pr, i_res);
         val[t * ST] = v;
         mx = (mx < v) ? v : mx;  // std::max_element semantics
@@ -253,10 +268,18 @@ __device__ __forceinline__ double relatedness_mixture(double *val, int ST, int m
     for (int t = cnt - 1; t >= 0; --t)  // i ascending, as the reference sums
     {
         const double dv = __dsub_rn(val[t * ST], mx);
-        sum = __dadd_rn(sum, dv == 0.0 ? 1.0 : exp(dv));
+        sum = __dadd_rn(sum, dv == 0.0 ? 1.0 : cell_exp(dv));
     }
-    return __dadd_rn(mx, log(sum));
+    return __dadd_rn(mx, cell_log(sum));
 }
+
+#ifndef MOIRE_MAX_ACC
+#define MOIRE_MAX_ACC 16
+#endif
+#ifndef MOIRE_TIERS
+#define MOIRE_TIERS 3
+#endif
+constexpr int kMaxAcc = 16;  // accumulators kept in registers
 
 // One instantiation per number of accumulators: they stay in registers without predication.
 // All lanes that arrive together run the instantiation of the largest count among them (the
@@ -275,6 +298,8 @@ __device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, i
         ie_vectorized<NACC>(scr, ST, k, 0, acc);                                 \
         _Pragma("unroll") for (int t = 0; t < NACC; ++t) scr[t * ST] = acc[t];   \
     }
+    // MOIRE_TIERS selects the set of accumulator counts compiled (fewer = smaller hot code)
+#if MOIRE_TIERS == 0  // 1 2 3 4 5 6 8 10 12 16
     if (cnt_w <= 1) MOIRE_IE_CASE(1)
     else if (cnt_w <= 2) MOIRE_IE_CASE(2)
     else if (cnt_w <= 3) MOIRE_IE_CASE(3)
@@ -285,24 +310,52 @@ __device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, i
     else if (cnt_w <= 10) MOIRE_IE_CASE(10)
     else if (cnt_w <= 12) MOIRE_IE_CASE(12)
     else MOIRE_IE_CASE(16)
+#elif MOIRE_TIERS == 1  // 2 4 8 16
+    if (cnt_w <= 2) MOIRE_IE_CASE(2)
+    else if (cnt_w <= 4) MOIRE_IE_CASE(4)
+    else if (cnt_w <= 8) MOIRE_IE_CASE(8)
+    else MOIRE_IE_CASE(16)
+#elif MOIRE_TIERS == 2  // 4 8 16
+    if (cnt_w <= 4) MOIRE_IE_CASE(4)
+    else if (cnt_w <= 8) MOIRE_IE_CASE(8)
+    else MOIRE_IE_CASE(16)
+#elif MOIRE_TIERS == 3  // 4 16
+    if (cnt_w <= 4) MOIRE_IE_CASE(4)
+    else MOIRE_IE_CASE(16)
+#elif MOIRE_TIERS == 4  // 3 6 16
+    if (cnt_w <= 3) MOIRE_IE_CASE(3)
+    else if (cnt_w <= 6) MOIRE_IE_CASE(6)
+    else MOIRE_IE_CASE(16)
+#elif MOIRE_TIERS == 5  // 2 4 6 8 16
+    if (cnt_w <= 2) MOIRE_IE_CASE(2)
+    else if (cnt_w <= 4) MOIRE_IE_CASE(4)
+    else if (cnt_w <= 6) MOIRE_IE_CASE(6)
+    else if (cnt_w <= 8) MOIRE_IE_CASE(8)
+    else MOIRE_IE_CASE(16)
+#elif MOIRE_TIERS == 6  // 6 16
+    if (cnt_w <= 6) MOIRE_IE_CASE(6)
+    else MOIRE_IE_CASE(16)
+#else  // 16
+    MOIRE_IE_CASE(16)
+#endif
 #undef MOIRE_IE_CASE
     return relatedness_mixture(scr, ST, m, cnt, log_total, log_r, log_1mr, lgam);
 }
 
-// m - k >= 16 (rare: a COI far above the number of distinct alleles): the accumulators are
-// produced 16 at a time and parked in local memory.
+// m - k >= kMaxAcc (rare: a COI far above the number of distinct alleles): the accumulators are
+// produced kMaxAcc at a time and parked in local memory.
 __device__ __noinline__ double transmission_rel_ie_wide(double *scr, int ST, int k, int m,
                                                         double log_total, double log_r,
                                                         double log_1mr, const double *lgam)
 {
     double v[kMaxCoi];
     const int cnt = m - k + 1;
-    for (int t0 = 0; t0 < cnt; t0 += 16)
+    for (int t0 = 0; t0 < cnt; t0 += kMaxAcc)
     {
-        double acc[16];
-        ie_vectorized<16>(scr, ST, k, t0, acc);
+        double acc[kMaxAcc];
+        ie_vectorized<kMaxAcc>(scr, ST, k, t0, acc);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
+        for (int j = 0; j < kMaxAcc; ++j)
             if (t0 + j < cnt) v[t0 + j] = acc[j];
     }
     return relatedness_mixture(v, 1, m, cnt, log_total, log_r, log_1mr, lgam);
@@ -323,15 +376,32 @@ __device__ __noinline__ double transmission_rel_egf(uint64_t latent, const doubl
         const int n = m - i;
         const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
         const double pam = clamp_pam(pam_from_coverage(a[n]));
-        const double i_res = __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)n));
+        const double i_res = __dadd_rn(cell_log1p(-pam), __dmul_rn(log_total, (double)n));
         const double v = __dadd_rn(pr, i_res);
         a[n] = v;
         mx = (mx < v) ? v : mx;
     }
     if (mx == -INFINITY) return -INFINITY;
     double sum = 0.0;
-    for (int i = 0; i < cnt; ++i) sum = __dadd_rn(sum, exp(__dsub_rn(a[m - i], mx)));
-    return __dadd_rn(mx, log(sum));
+    for (int i = 0; i < cnt; ++i) sum = __dadd_rn(sum, cell_exp(__dsub_rn(a[m - i], mx)));
+    return __dadd_rn(mx, cell_log(sum));
+}
+
+// Relatedness off and n == k: 1 - k! * prod(q) in double (src/prob_any_missing.cpp:139-148).
+__device__ __forceinline__ double transmission_norel_exact_cover(uint64_t latent, const double *prow,
+                                                                 double total, double log_total, int k)
+{
+    double cov = 1.0;
+    uint64_t rest = latent;
+    while (rest)
+    {
+        const int al = __ffsll((long long)rest) - 1;
+        rest &= rest - 1;
+        cov = __dmul_rn(cov, __ddiv_rn(prow[al], total));
+    }
+    for (int i = 2; i <= k; ++i) cov = __dmul_rn(cov, (double)i);
+    const double pam = clamp_pam(pam_from_coverage(cov));
+    return __dadd_rn(cell_log1p(-pam), __dmul_rn(log_total, (double)k));
 }
 
 // ---- a2: transmission process of one cell, one thread -------------------------------------------
@@ -354,7 +424,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
             total = __dadd_rn(total, prow[al]);
         }
     }
-    const double log_total = log(total);
+    const double log_total = cell_log(total);
     if (k <= kIeMax)
     {
         uint64_t rest = latent;
@@ -371,20 +441,8 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
     {
         // src/chain.cpp:895-899 with probAnyMissingFunctor::operator() (prob_any_missing.cpp:131-154)
         double pam;
-        if (m == k)
-        {
-            double cov = 1.0;
-            uint64_t rest = latent;
-            while (rest)
-            {
-                const int al = __ffsll((long long)rest) - 1;
-                rest &= rest - 1;
-                cov = __dmul_rn(cov, __ddiv_rn(prow[al], total));
-            }
-            for (int i = 2; i <= k; ++i) cov = __dmul_rn(cov, (double)i);
-            pam = pam_from_coverage(cov);
-        }
-        else if (k <= kIeMax)
+        if (m == k) return transmission_norel_exact_cover(latent, prow, total, log_total, k);
+        if (k <= kIeMax)
         {
             pam = ie_scalar(scr, ST, k, m);
         }
@@ -395,11 +453,11 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
             pam = pam_from_coverage(a[m]);
         }
         pam = clamp_pam(pam);
-        return __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)m));
+        return __dadd_rn(cell_log1p(-pam), __dmul_rn(log_total, (double)m));
     }
     if (k > kIeMax)
         return transmission_rel_egf(latent, prow, total, k, m, log_total, log_r, log_1mr, lgam);
-    if (m - k + 1 <= 16)
+    if (m - k + 1 <= kMaxAcc)
         return transmission_rel_ie(scr, ST, k, m, log_total, log_r, log_1mr, lgam);
     return transmission_rel_ie_wide(scr, ST, k, m, log_total, log_r, log_1mr, lgam);
 }
@@ -436,7 +494,9 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
             total = __dadd_rn(total, prow[al]);
         }
     }
-    const double log_total = log(total);
+    const double log_total = cell_log(total);
+    if (!allow_relatedness && m == k)
+        return transmission_norel_exact_cover(latent, prow, total, log_total, k);
     double *q = wscr + 16 * ST;
     {
         // lane e normalises element e
@@ -511,7 +571,7 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
     if (!allow_relatedness)
     {
         const double pam = clamp_pam(__shfl_sync(FULL, acc[0], 0));
-        return __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)m));
+        return __dadd_rn(cell_log1p(-pam), __dmul_rn(log_total, (double)m));
     }
     // mixture terms, one per (chunk, lane)
     double v[4];
@@ -526,7 +586,7 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
             const int i = cnt - 1 - t;
             const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
             const double pam = clamp_pam(acc[ch]);
-            const double i_res = __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
+            const double i_res = __dadd_rn(cell_log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
             v[ch] = __dadd_rn(pr, i_res);
             mx = (mx < v[ch]) ? v[ch] : mx;
         }
@@ -550,13 +610,13 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
             if (lane < 16 && 16 * ch + lane < cnt)
             {
                 const double dv = __dsub_rn(v[ch], result_mx);
-                ev = dv == 0.0 ? 1.0 : exp(dv);
+                ev = dv == 0.0 ? 1.0 : cell_exp(dv);
             }
             const int top = min(15, cnt - 1 - 16 * ch);
             for (int t = top; t >= 0; --t) sum_tail = __dadd_rn(sum_tail, __shfl_sync(FULL, ev, t));
         }
     }
-    return __dadd_rn(result_mx, log(sum_tail));
+    return __dadd_rn(result_mx, cell_log(sum_tail));
 }
 
 // ---- a8: latent-genotype proposal ------------------------------------------------------------
