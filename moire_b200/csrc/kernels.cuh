@@ -376,20 +376,20 @@ __global__ void __launch_bounds__(kThreads, MOIRE_MIN_BLOCKS_S * (256 / kThreads
         {
             P.pr_r_new = dbeta_log(P.r_new, v.r_a, v.r_b, v.r_lbeta);
             P.dprior += P.pr_r_new - v.pr_r[si];
-            P.log_r = log(P.r_new);
-            P.log_1mr = log(1.0 - P.r_new);
+            P.log_r = cold_log(P.r_new);
+            P.log_1mr = cold_log(1.0 - P.r_new);
         }
         if (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
         {
             const int mm = P.valid ? P.m_new : 1;  // keep the LUT index in range
-            P.pr_coi_new = dztpois_log(mm, log(lambda), log(exp(lambda) - 1.0), s_lgam);
+            P.pr_coi_new = dztpois_log(mm, cold_log(lambda), cold_log(cold_exp(lambda) - 1.0), s_lgam);
             P.dprior += P.pr_coi_new - v.pr_coi[si];
         }
         // which updates adapt, and when (src/chain.cpp:303-311, 364-372, 618-627, 683-692)
         if (KIND == KIND_EPS_NEG || KIND == KIND_EPS_POS || KIND == KIND_EFF_COI)
             P.adapt = P.valid;
         if (KIND == KIND_R) P.adapt = 1;
-        P.logu = log(rng.next_uniform());
+        P.logu = cold_log(rng.next_uniform());
         s_prop[tid] = P;
     }
     __syncthreads();
@@ -578,43 +578,43 @@ __global__ void __launch_bounds__(kThreads, MOIRE_MIN_BLOCKS_S * (256 / kThreads
 }
 
 // ---- SALT proposal math (src/mcmc_utils.h:150-313) --------------------------------------------
-__device__ __forceinline__ double logit_d(double x)
+__device__ __noinline__ double logit_d(double x)
 {
-    return x < .5 ? log(x) - log1p(-x) : log(x / (1.0 - x));
+    return x < .5 ? cold_log(x) - cold_log1p(-x) : cold_log(x / (1.0 - x));
 }
 
-__device__ __forceinline__ void log_pq_d(double x, double &lp, double &lq)
+__device__ __noinline__ void log_pq_d(double x, double &lp, double &lq)
 {
-    const double ex = exp(x);
+    const double ex = cold_exp(x);
     if (x < 0.0)
     {
-        lq = -log1p(ex);
+        lq = -cold_log1p(ex);
         lp = lq + x;
     }
     else
     {
-        lp = -log1p(1.0 / ex);
+        lp = -cold_log1p(1.0 / ex);
         lq = lp - x;
     }
 }
 
-__device__ __forceinline__ double logit_scale_d(double x, double scale)
+__device__ __noinline__ double logit_scale_d(double x, double scale)
 {
     const bool ok = (scale < 0.69314718055994530942) && (fabs(scale) < fabs(x + scale));
     const double u = -scale - (ok ? 0.0 : x);
     const double w = -scale - (ok ? x : 0.0);
-    const double ev = exp(w);
-    const double eumo = expm1(u);
+    const double ev = cold_exp(w);
+    const double eumo = cold_expm1(u);
     double l2;
     if (isinf(eumo))
-        l2 = fmax(u, w) + log1p(exp(-fabs(u - w)));
+        l2 = fmax(u, w) + cold_log1p(cold_exp(-fabs(u - w)));
     else
-        l2 = log(eumo + ev);
-    if (w > log(2.0 * fabs(eumo))) return -(w + log1p(eumo / ev));
+        l2 = cold_log(eumo + ev);
+    if (w > cold_log(2.0 * fabs(eumo))) return -(w + cold_log1p(eumo / ev));
     return -l2;
 }
 
-__device__ __forceinline__ double expit_d(double x) { return 1.0 / (1.0 + exp(-x)); }
+__device__ __noinline__ double expit_d(double x) { return 1.0 / (1.0 + cold_exp(-x)); }
 
 __host__ __device__ inline int p_kernel_threads(int N) { return N > 2048 ? 512 : MOIRE_P_THREADS; }
 
@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 512 ? 1 : MOIRE_MIN_BLOCKS_P *
             rng.open(v.seed, (uint32_t)iteration, KIND_P, gchain, (uint32_t)j, (uint32_t)rep);
             const int idx = (int)mulhi32(rng.next_u32(), (uint32_t)A);
             const double z = next_normal(rng);
-            const double logu = log(rng.next_uniform());
+            const double logu = cold_log(rng.next_uniform());
             double lg[2], lp[2], lq[2];
             bool rest[2];
 #pragma unroll
@@ -751,9 +751,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 512 ? 1 : MOIRE_MIN_BLOCKS_P *
             double cum = 0.0;
 #pragma unroll
             for (int s = 0; s < 2; ++s)
-                if (rest[s] && (lane + 32 * s) != ba) cum += (bv < 0.0) ? exp(lp[s] - lp1) : exp(lp[s]);
+                if (rest[s] && (lane + 32 * s) != ba) cum += (bv < 0.0) ? cold_exp(lp[s] - lp1) : cold_exp(lp[s]);
             cum = warp_sum(cum);
-            const double lsum = (bv < 0.0) ? lp1 + log1p(cum) : log1p(-exp(lq1) + cum);
+            const double lsum = (bv < 0.0) ? lp1 + cold_log1p(cum) : cold_log1p(-cold_exp(lq1) + cum);
             const double ls = plq - lsum;
             bool below = false;
 #pragma unroll
@@ -848,11 +848,11 @@ __global__ void __launch_bounds__(kThreads) k_update_mean_coi(const View v, cons
         constrained_proposal(z, v.mean_coi[t], 1e-5, (double)v.max_coi, &prop, &adj);
         s_red[33] = prop;
         s_red[34] = adj;
-        s_red[35] = log(rng.next_uniform());
+        s_red[35] = cold_log(rng.next_uniform());
     }
     __syncthreads();
     const double prop = s_red[33];
-    const double ll = log(prop), lem = log(exp(prop) - 1.0);
+    const double ll = cold_log(prop), lem = cold_log(cold_exp(prop) - 1.0);
     double dsum = 0.0;
     for (int i = tid; i < N; i += kThreads)
     {

@@ -24,20 +24,16 @@
 
 namespace moire
 {
-// libm calls of the per-cell path go through one out-of-line copy each when MOIRE_LIBM_CALLS is
-// set (tuning: smaller hot code, at the price of a call per use)
-#ifndef MOIRE_LIBM_CALLS
-#define MOIRE_LIBM_CALLS 0
-#endif
-#if MOIRE_LIBM_CALLS
-__device__ __noinline__ double cell_log(double x) { return log(x); }
-__device__ __noinline__ double cell_log1p(double x) { return log1p(x); }
-__device__ __noinline__ double cell_exp(double x) { return exp(x); }
-#else
-__device__ __forceinline__ double cell_log(double x) { return log(x); }
-__device__ __forceinline__ double cell_log1p(double x) { return log1p(x); }
-__device__ __forceinline__ double cell_exp(double x) { return exp(x); }
-#endif
+// The kernels are instruction-fetch bound (ncu: GPC instruction cache at ~85 % of its request
+// rate, SM instruction-cache hit rate 66 %, profiles/README.md), and CUDA's double-precision
+// log / log1p / exp / expm1 are 100-250 instructions each when inlined.  Only the per-cell hot
+// path (the thread evaluator's log of the frequency sum and the mixture loop) inlines them;
+// every other use -- proposals, priors, SALT, the cooperative and EGF paths -- shares one
+// out-of-line copy per function.
+__device__ __noinline__ double cold_log(double x) { return log(x); }
+__device__ __noinline__ double cold_log1p(double x) { return log1p(x); }
+__device__ __noinline__ double cold_exp(double x) { return exp(x); }
+__device__ __noinline__ double cold_expm1(double x) { return expm1(x); }
 
 constexpr int kIeMax = 10;      // src/prob_any_missing.cpp:11
 constexpr int kMaxCoi = 64;     // MOIRE_MAX_COI
@@ -52,22 +48,22 @@ struct EpsLogs
     double l_en, l_1men, l_ep, l_1mep, pr_en, pr_ep;
 };
 
-__device__ __forceinline__ void build_eps_logs(EpsLogs &e, double eps_neg, double eps_pos,
+__device__ __noinline__ void build_eps_logs(EpsLogs &e, double eps_neg, double eps_pos,
                                                double max_eps_neg, double max_eps_pos, int A)
 {
     const double norm = __ddiv_rn(1.0, (double)A);
     const double xn = __dmul_rn(__dmul_rn(eps_neg, max_eps_neg), norm);
     const double xp = __dmul_rn(__dmul_rn(eps_pos, max_eps_pos), norm);
-    e.o_tp = log(__dsub_rn(1.0, xn));
-    e.o_fn = log(xn);
-    e.o_tn = log(__dsub_rn(1.0, xp));
-    e.o_fp = log(xp);
+    e.o_tp = cold_log(__dsub_rn(1.0, xn));
+    e.o_fn = cold_log(xn);
+    e.o_tn = cold_log(__dsub_rn(1.0, xp));
+    e.o_fp = cold_log(xp);
     e.pr_en = __ddiv_rn(eps_neg, (double)A);
     e.pr_ep = __ddiv_rn(eps_pos, (double)A);
-    e.l_en = log(e.pr_en);
-    e.l_1men = log(__dsub_rn(1.0, e.pr_en));
-    e.l_ep = log(e.pr_ep);
-    e.l_1mep = log(__dsub_rn(1.0, e.pr_ep));
+    e.l_en = cold_log(e.pr_en);
+    e.l_1men = cold_log(__dsub_rn(1.0, e.pr_en));
+    e.l_ep = cold_log(e.pr_ep);
+    e.l_1mep = cold_log(__dsub_rn(1.0, e.pr_ep));
 }
 
 // ---- a7: observation process on masks --------------------------------------------------------
@@ -247,7 +243,7 @@ __device__ __forceinline__ double dbinom_log(int x, int size, double log_p, doub
 // Relatedness mixture + log-sum-exp (src/chain.cpp:903-920, src/mcmc_utils.h:382-397), rolled.
 // On entry val[t * ST] = PAM(n = k + t), t < cnt; term i = 0..cnt-1 uses n = m - i, i.e.
 // t = cnt - 1 - i.  The terms are overwritten in place.
-__device__ __forceinline__ double relatedness_mixture(double *val, int ST, int m, int cnt,
+__device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, int cnt,
                                                       double log_total, double log_r,
                                                       double log_1mr, const double *lgam)
 {
@@ -257,7 +253,7 @@ __device__ __forceinline__ double relatedness_mixture(double *val, int ST, int m
         const int i = cnt - 1 - t;
         const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
         const double pam = clamp_pam(val[t * ST]);
-        const double i_res = __dadd_rn(cell_log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
+        const double i_res = __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
         const double v = __dadd_rn(pr, i_res);
         val[t * ST] = v;
         mx = (mx < v) ? v : mx;  // std::max_element semantics
@@ -268,9 +264,9 @@ __device__ __forceinline__ double relatedness_mixture(double *val, int ST, int m
     for (int t = cnt - 1; t >= 0; --t)  // i ascending, as the reference sums
     {
         const double dv = __dsub_rn(val[t * ST], mx);
-        sum = __dadd_rn(sum, dv == 0.0 ? 1.0 : cell_exp(dv));
+        sum = __dadd_rn(sum, dv == 0.0 ? 1.0 : exp(dv));
     }
-    return __dadd_rn(mx, cell_log(sum));
+    return __dadd_rn(mx, log(sum));
 }
 
 #ifndef MOIRE_MAX_ACC
@@ -376,15 +372,15 @@ __device__ __noinline__ double transmission_rel_egf(uint64_t latent, const doubl
         const int n = m - i;
         const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
         const double pam = clamp_pam(pam_from_coverage(a[n]));
-        const double i_res = __dadd_rn(cell_log1p(-pam), __dmul_rn(log_total, (double)n));
+        const double i_res = __dadd_rn(cold_log1p(-pam), __dmul_rn(log_total, (double)n));
         const double v = __dadd_rn(pr, i_res);
         a[n] = v;
         mx = (mx < v) ? v : mx;
     }
     if (mx == -INFINITY) return -INFINITY;
     double sum = 0.0;
-    for (int i = 0; i < cnt; ++i) sum = __dadd_rn(sum, cell_exp(__dsub_rn(a[m - i], mx)));
-    return __dadd_rn(mx, cell_log(sum));
+    for (int i = 0; i < cnt; ++i) sum = __dadd_rn(sum, cold_exp(__dsub_rn(a[m - i], mx)));
+    return __dadd_rn(mx, cold_log(sum));
 }
 
 // Relatedness off and n == k: 1 - k! * prod(q) in double (src/prob_any_missing.cpp:139-148).
@@ -401,7 +397,7 @@ __device__ __forceinline__ double transmission_norel_exact_cover(uint64_t latent
     }
     for (int i = 2; i <= k; ++i) cov = __dmul_rn(cov, (double)i);
     const double pam = clamp_pam(pam_from_coverage(cov));
-    return __dadd_rn(cell_log1p(-pam), __dmul_rn(log_total, (double)k));
+    return __dadd_rn(cold_log1p(-pam), __dmul_rn(log_total, (double)k));
 }
 
 // ---- a2: transmission process of one cell, one thread -------------------------------------------
@@ -424,7 +420,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
             total = __dadd_rn(total, prow[al]);
         }
     }
-    const double log_total = cell_log(total);
+    const double log_total = log(total);
     if (k <= kIeMax)
     {
         uint64_t rest = latent;
@@ -453,7 +449,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
             pam = pam_from_coverage(a[m]);
         }
         pam = clamp_pam(pam);
-        return __dadd_rn(cell_log1p(-pam), __dmul_rn(log_total, (double)m));
+        return __dadd_rn(cold_log1p(-pam), __dmul_rn(log_total, (double)m));
     }
     if (k > kIeMax)
         return transmission_rel_egf(latent, prow, total, k, m, log_total, log_r, log_1mr, lgam);
@@ -494,7 +490,7 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
             total = __dadd_rn(total, prow[al]);
         }
     }
-    const double log_total = cell_log(total);
+    const double log_total = cold_log(total);
     if (!allow_relatedness && m == k)
         return transmission_norel_exact_cover(latent, prow, total, log_total, k);
     double *q = wscr + 16 * ST;
@@ -571,7 +567,7 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
     if (!allow_relatedness)
     {
         const double pam = clamp_pam(__shfl_sync(FULL, acc[0], 0));
-        return __dadd_rn(cell_log1p(-pam), __dmul_rn(log_total, (double)m));
+        return __dadd_rn(cold_log1p(-pam), __dmul_rn(log_total, (double)m));
     }
     // mixture terms, one per (chunk, lane)
     double v[4];
@@ -586,7 +582,7 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
             const int i = cnt - 1 - t;
             const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
             const double pam = clamp_pam(acc[ch]);
-            const double i_res = __dadd_rn(cell_log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
+            const double i_res = __dadd_rn(cold_log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
             v[ch] = __dadd_rn(pr, i_res);
             mx = (mx < v[ch]) ? v[ch] : mx;
         }
@@ -600,7 +596,7 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
     result_mx = mx;
     if (result_mx == -INFINITY) return -INFINITY;
     if (cnt == 1) return result_mx;
-    // sum exp(v - mx) in the reference's order: i ascending = t descending
+    // sum cold_exp(v - mx) in the reference's order: i ascending = t descending
 #pragma unroll
     for (int ch = 3; ch >= 0; --ch)
     {
@@ -610,13 +606,13 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
             if (lane < 16 && 16 * ch + lane < cnt)
             {
                 const double dv = __dsub_rn(v[ch], result_mx);
-                ev = dv == 0.0 ? 1.0 : cell_exp(dv);
+                ev = dv == 0.0 ? 1.0 : cold_exp(dv);
             }
             const int top = min(15, cnt - 1 - 16 * ch);
             for (int t = top; t >= 0; --t) sum_tail = __dadd_rn(sum_tail, __shfl_sync(FULL, ev, t));
         }
     }
-    return __dadd_rn(result_mx, cell_log(sum_tail));
+    return __dadd_rn(result_mx, cold_log(sum_tail));
 }
 
 // ---- a8: latent-genotype proposal ------------------------------------------------------------
@@ -692,40 +688,40 @@ __device__ __forceinline__ uint64_t sample_latent_genotype(Stream &rng, uint64_t
 
 // ---- proposals and priors --------------------------------------------------------------------
 // Standard normal from two words (Box-Muller, cosine branch).
-__device__ __forceinline__ double next_normal(Stream &rng)
+__device__ __noinline__ double next_normal(Stream &rng)
 {
     const double u1 = rng.next_uniform();
     const double u2 = rng.next_uniform();
-    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586477 * u2);
+    return sqrt(-2.0 * cold_log(u1)) * cos(6.283185307179586477 * u2);
 }
 
 // Sampler::sample_coi_delta(mean) (src/sampler.cpp:152-156): +-Geometric(1/(1+mean)) on {0,1,..}.
-__device__ __forceinline__ int next_coi_delta(Stream &rng, double log_1mp)
+__device__ __noinline__ int next_coi_delta(Stream &rng, double log_1mp)
 {
     const int sign = (rng.next_u32() & 1u) ? 1 : -1;
     const double u = rng.next_uniform();
-    const int g = (int)floor(log(u) / log_1mp);
+    const int g = (int)floor(cold_log(u) / log_1mp);
     return sign * g;
 }
 
 // Sampler::sample_constrained given its N(0, sd) draw eps (src/sampler.cpp:176-190).
-__device__ __forceinline__ void constrained_proposal(double eps, double curr, double lo, double hi,
+__device__ __noinline__ void constrained_proposal(double eps, double curr, double lo, double hi,
                                                      double *prop_out, double *adj_out)
 {
-    const double l_cl = log(__dsub_rn(curr, lo));
-    const double l_hc = log(__dsub_rn(hi, curr));
+    const double l_cl = cold_log(__dsub_rn(curr, lo));
+    const double l_hc = cold_log(__dsub_rn(hi, curr));
     const double unconstrained = __dsub_rn(l_cl, l_hc);
-    const double exp_prop = exp(__dadd_rn(eps, unconstrained));
+    const double exp_prop = cold_exp(__dadd_rn(eps, unconstrained));
     double prop = __ddiv_rn(__dadd_rn(__dmul_rn(hi, exp_prop), lo), __dadd_rn(exp_prop, 1.0));
     prop = prop < lo ? lo : (prop > hi ? hi : prop);
     const double adj = __dsub_rn(
-        __dsub_rn(__dadd_rn(log(__dsub_rn(prop, lo)), log(__dsub_rn(hi, prop))), l_cl), l_hc);
+        __dsub_rn(__dadd_rn(cold_log(__dsub_rn(prop, lo)), cold_log(__dsub_rn(hi, prop))), l_cl), l_hc);
     *prop_out = prop;
     *adj_out = adj;
 }
 
 // R::dbeta(x, a, b, log = TRUE) incl. R's edge cases at 0 and 1; lbeta = log B(a, b) from host.
-__device__ __forceinline__ double dbeta_log(double x, double a, double b, double lbeta)
+__device__ __noinline__ double dbeta_log(double x, double a, double b, double lbeta)
 {
     if (isnan(x)) return x;
     if (x < 0.0 || x > 1.0) return -INFINITY;
@@ -733,19 +729,19 @@ __device__ __forceinline__ double dbeta_log(double x, double a, double b, double
     {
         if (a > 1.0) return -INFINITY;
         if (a < 1.0) return INFINITY;
-        return log(b);
+        return cold_log(b);
     }
     if (x == 1.0)
     {
         if (b > 1.0) return -INFINITY;
         if (b < 1.0) return INFINITY;
-        return log(a);
+        return cold_log(a);
     }
-    return (a - 1.0) * log(x) + (b - 1.0) * log1p(-x) - lbeta;
+    return (a - 1.0) * cold_log(x) + (b - 1.0) * cold_log1p(-x) - lbeta;
 }
 
-// R::dgamma(x, shape, scale, log = TRUE); lg_shape = lgamma(shape), l_scale = log(scale).
-__device__ __forceinline__ double dgamma_log(double x, double shape, double scale, double lg_shape,
+// R::dgamma(x, shape, scale, log = TRUE); lg_shape = lgamma(shape), l_scale = cold_log(scale).
+__device__ __noinline__ double dgamma_log(double x, double shape, double scale, double lg_shape,
                                              double l_scale)
 {
     if (isnan(x)) return x;
@@ -756,7 +752,7 @@ __device__ __forceinline__ double dgamma_log(double x, double shape, double scal
         if (shape > 1.0) return -INFINITY;
         return -l_scale;
     }
-    return (shape - 1.0) * log(x) - x / scale - lg_shape - shape * l_scale;
+    return (shape - 1.0) * cold_log(x) - x / scale - lg_shape - shape * l_scale;
 }
 
 // Sampler::dztpois (src/sampler.cpp:38-42).

@@ -20,8 +20,10 @@
 
 #if defined(__CUDACC__)
 #define MOIRE_HD __host__ __device__ __forceinline__
+#define MOIRE_HD_OUTLINE __host__ __device__ __noinline__
 #else
 #define MOIRE_HD inline
+#define MOIRE_HD_OUTLINE inline
 #endif
 
 namespace moire
@@ -74,6 +76,17 @@ MOIRE_HD void philox4x32_10(const uint32_t ctr[4], uint32_t k0, uint32_t k1, uin
     out[3] = c3;
 }
 
+#if defined(__CUDACC__)
+__device__ __noinline__ uint4 philox_block_device(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  uint32_t k0, uint32_t k1)
+{
+    const uint32_t ctr[4] = {c0, c1, c2, c3};
+    uint32_t out[4];
+    philox4x32_10(ctr, k0, k1, out);
+    return make_uint4(out[0], out[1], out[2], out[3]);
+}
+#endif
+
 // A lazily refilled stream of 32-bit words.
 struct Stream
 {
@@ -94,14 +107,26 @@ struct Stream
         have = 0;
     }
 
+    MOIRE_HD void refill()
+    {
+#if defined(__CUDA_ARCH__)
+        // one out-of-line copy of the ten rounds (the kernels are instruction-fetch bound and a
+        // stream is refilled from dozens of call sites); by value, so the stream stays in registers
+        const uint4 o = philox_block_device(ctr[0], ctr[1], ctr[2], ctr[3], k0, k1);
+        buf[0] = o.x;
+        buf[1] = o.y;
+        buf[2] = o.z;
+        buf[3] = o.w;
+#else
+        philox4x32_10(ctr, k0, k1, buf);
+#endif
+        ctr[3] += 1;
+        have = 4;
+    }
+
     MOIRE_HD uint32_t next_u32()
     {
-        if (have == 0)
-        {
-            philox4x32_10(ctr, k0, k1, buf);
-            ctr[3] += 1;
-            have = 4;
-        }
+        if (have == 0) refill();
         // selects, not an indexed load: keeps buf[] in registers on the device
         const uint32_t v = have == 4 ? buf[0] : have == 3 ? buf[1] : have == 2 ? buf[2] : buf[3];
         --have;
