@@ -469,7 +469,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
 // All lanes must call with identical arguments; every lane returns the value.
 // wscr: the warp's 32 scratch columns (slot s, column c at wscr[s * ST + c]); slot 16 holds q.
 #ifndef MOIRE_COOP_MIN_K
-#define MOIRE_COOP_MIN_K 8
+#define MOIRE_COOP_MIN_K 7
 #endif
 constexpr int kCoopMinK = MOIRE_COOP_MIN_K;
 __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const double *prow, int m,
