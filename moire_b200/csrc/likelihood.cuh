@@ -137,12 +137,14 @@ __device__ __forceinline__ void ie_vectorized(double *scr, int ST, int k, int t0
     const unsigned short *tab = c_sub_tail + subset_block(k);
     const int nsub = (1 << k) - 1;
     const int lead = k - 1 + t0;
+#pragma unroll 1
     for (int idx = 0; idx < nsub; ++idx)
     {
         const unsigned int e = tab[idx];
         unsigned int tail = e & 1023u;
         int pos = (e >> 10) & 15;
         double base = pos ? scr[(kPartBase + pos - 1) * ST] : 1.0;
+#pragma unroll 1
         for (;;)
         {
             const int el = __ffs(tail) - 1;
@@ -153,7 +155,24 @@ __device__ __forceinline__ void ie_vectorized(double *scr, int ST, int k, int t0
             ++pos;
         }
         double r = (e & 0x4000u) ? -1.0 : 1.0;
-        for (int j = 0; j < lead; ++j) r = __dmul_rn(r, base);
+        // r *= base, `lead` times: a jump into a straight run of multiplications (lead <= 9
+        // unless this is a later pass of the wide path)
+        switch (lead)
+        {
+            default:
+#pragma unroll 1
+                for (int j = 9; j < lead; ++j) r = __dmul_rn(r, base);
+            case 9: r = __dmul_rn(r, base);
+            case 8: r = __dmul_rn(r, base);
+            case 7: r = __dmul_rn(r, base);
+            case 6: r = __dmul_rn(r, base);
+            case 5: r = __dmul_rn(r, base);
+            case 4: r = __dmul_rn(r, base);
+            case 3: r = __dmul_rn(r, base);
+            case 2: r = __dmul_rn(r, base);
+            case 1: r = __dmul_rn(r, base);
+            case 0: break;
+        }
 #pragma unroll
         for (int t = 0; t < NACC; ++t)
         {
