@@ -27,8 +27,8 @@ namespace moire
 #ifndef MOIRE_MIN_BLOCKS_S
 #define MOIRE_MIN_BLOCKS_S 2
 #endif
-#ifndef MOIRE_SORT_CNT_FIRST
-#define MOIRE_SORT_CNT_FIRST 0
+#ifndef MOIRE_MERGE_K
+#define MOIRE_MERGE_K 1
 #endif
 #ifndef MOIRE_SAMPLE_THREADS
 #define MOIRE_SAMPLE_THREADS 256
@@ -104,11 +104,10 @@ __device__ __forceinline__ int work_class(int k, int m)
     const int kk = k > kIeMax ? kIeMax + 1 : k;
     int cnt = m - k + 1;
     cnt = cnt < 1 ? 1 : (cnt > 64 ? 64 : cnt);
-#if MOIRE_SORT_CNT_FIRST
-    // light cells: the mixture (cnt terms of log1p + exp) outweighs the subset sums, so equal
+    // cells with at most MOIRE_MERGE_K latent alleles (<= 2^k - 1 cheap subsets) form one class
+    // per mixture count: there the cnt terms of log1p + exp outweigh the subset sums, so equal
     // counts matter more than equal k inside a warp
-    if (kk < kCoopMinK) return kSortBins - 1 - ((cnt - 1) * kCoopMinK + kk);
-#endif
+    if (kk <= MOIRE_MERGE_K) return kSortBins - 1 - (MOIRE_MERGE_K * 64 + (cnt - 1));
     return kSortBins - 1 - (kk * 64 + (cnt - 1));
 }
 

@@ -1,0 +1,149 @@
+"""Full-size shapes and edge cases on the GPU: size-independent properties of the engine state
+(idempotent re-evaluation, per-chain sums, simplex, k <= m, counters) on the BASELINE.json
+configurations, plus spot checks of individual cells against the oracle and degenerate inputs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def popcount(a):
+    return np.vectorize(lambda x: bin(int(x)).count("1"))(a)
+
+
+def check_invariants(eng, pk, chain, oracle=None, allow=1, ncheck=400, seed=0):
+    st = eng.dump_state(chain)
+    cell = st["cell_t"] + st["cell_o"]
+    assert np.all(np.isfinite(cell))
+    assert np.all(cell[pk.is_missing != 0] == 0.0)                 # missing cells contribute nothing
+    k = popcount(st["latent"])
+    assert (k >= 1).all() and (k <= st["m"][:, None]).all()
+    A = pk.num_alleles
+    assert all((int(x) >> int(A[j])) == 0 for j in range(pk.num_loci) for x in st["latent"][:, j][:50])
+    assert np.allclose(st["p"][:, :pk.max_alleles].sum(1), 1.0, atol=1e-9)
+    assert (st["p"][np.arange(pk.num_loci)[:, None], np.arange(st["p"].shape[1])[None, :]]
+            [np.arange(st["p"].shape[1])[None, :] >= A[:, None]] == 0).all()   # padding stays 0
+    assert (st["m"] >= 1).all() and (st["m"] <= eng.model["max_coi"]).all()
+    assert ((st["eps_neg"] > 0) & (st["eps_neg"] < 1) & (st["eps_pos"] > 0) & (st["eps_pos"] < 1)).all()
+    # the per-chain sums are the sums of the cells / priors
+    llik, prior = eng.scalars()
+    assert abs(llik[chain] - cell.sum()) <= 1e-9 * max(1.0, abs(llik[chain]))
+    pri = (st["prior_eps_neg"] + st["prior_eps_pos"] + st["prior_r"] + st["prior_coi"]).sum() + \
+        st["mean_coi_hyper_prior"]
+    assert abs(prior[chain] - pri) < 1e-9 * max(1.0, abs(prior[chain]))
+    assert np.allclose(eng.sample_llik(chain), cell.sum(1), rtol=1e-12, atol=1e-9)
+    if oracle is not None:   # a random subset of samples, every cell, against the CPU restatement
+        rng = np.random.default_rng(seed)
+        rows = np.sort(rng.choice(pk.num_samples, size=min(pk.num_samples, max(1, ncheck // pk.num_loci)),
+                                  replace=False))
+        t, o = oracle.eval_cells(64, pk.num_alleles, pk.obs_mask[rows], pk.is_missing[rows],
+                                 st["latent"][rows], st["m"][rows], st["r"][rows], st["eps_neg"][rows],
+                                 st["eps_pos"][rows], st["p"][:, :pk.max_alleles], allow)
+        err_t = np.abs(st["cell_t"][rows] - t) / np.maximum(1.0, np.abs(t))
+        err_o = np.abs(st["cell_o"][rows] - o) / np.maximum(1.0, np.abs(o))
+        assert err_t.max() < 1e-9 and err_o.max() < 1e-9, (err_t.max(), err_o.max())
+    return st, k
+
+
+@pytest.mark.parametrize("name,chains,steps", [("c2", 3, 3), ("c3", 3, 3), ("c4", 2, 2), ("c5", 3, 3)])
+def test_baseline_shapes_hold_their_invariants(oracle, name, chains, steps):
+    """The named shapes of BASELINE.json (Namibia-like A_j up to 35, 1000x100, 5000x250 with A_j up
+    to 30, COI up to 30): a few chains of the ladder, a few full sweeps, then the properties, and
+    idempotence of a full re-evaluation of the cached terms."""
+    from moire_b200.engine import Engine
+    from moire_b200.workloads import make_workload
+    wl = make_workload(name)
+    pk = wl["packed"]
+    temps = wl["temps"][np.linspace(0, len(wl["temps"]) - 1, chains).astype(int)]
+    eng = Engine(pk, temps, seed=5, burnin=100, **wl["model"])
+    info = eng.init_chains()
+    assert not info["still_ill"].any()
+    ev0, _ = eng.counters()
+    for it in range(steps):
+        eng.step(it)
+    ev1, _ = eng.counters()
+    N, L, nonmiss = pk.num_samples, pk.num_loci, int((pk.is_missing == 0).sum())
+    # upper bound of evaluations per chain-step: 6 N L + N sum_j A_j, missing cells excluded
+    per_locus_nonmiss = (pk.is_missing == 0).sum(0)
+    bound = chains * steps * (6 * nonmiss + int((per_locus_nonmiss * pk.num_alleles).sum()))
+    assert 0.5 * bound < ev1 - ev0 <= bound
+    kmax = 0
+    for c in range(chains):
+        st, k = check_invariants(eng, pk, c, oracle, ncheck=600, seed=c)
+        kmax = max(kmax, int(k.max()))
+        before = (st["cell_t"].copy(), st["cell_o"].copy())
+    if name == "c5":
+        assert kmax > 10          # the EGF branch is live at this shape
+    l0, p0 = eng.scalars()
+    eng.eval_all()                # recompute every cached term from the parameters
+    l1, p1 = eng.scalars()
+    assert np.allclose(l0, l1, rtol=1e-12) and np.allclose(p0, p1, rtol=1e-12)
+    st2 = eng.dump_state(chains - 1)
+    assert np.allclose(st2["cell_t"], before[0], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(st2["cell_o"], before[1])
+    eng.close()
+
+
+def _mini(N, As, seed=3, **kw):
+    from moire_b200.data import pack_data
+    from moire_b200.simulate import simulate_data
+    base = dict(mean_coi=3, num_samples=N, epsilon_pos=.02, epsilon_neg=.1,
+                locus_freq_alphas=[np.ones(a) for a in As], internal_relatedness_alpha=.2,
+                internal_relatedness_beta=1, seed=seed)
+    base.update(kw)
+    d = simulate_data(**base)
+    return pack_data(d["data"], d["is_missing"])
+
+
+@pytest.mark.parametrize("N,As,T,kw", [
+    (1, [2], 1, {}),                                   # one sample, one biallelic locus, one chain
+    (3, [64, 2, 33], 2, {}),                           # the widest mask word
+    (70, [5] * 3, 3, dict(missingness=1.0)),           # every cell missing
+    (33, [7] * 40, 2, dict(missingness=.5)),           # half missing, ragged tile (33 = 32 + 1)
+    (2049, [4, 6], 2, {}),                             # N > 2048: the 512-thread update_p variant
+    (40, [6] * 1100, 1, {}),                           # L > 1024: one sample per tile, long rows
+])
+def test_edge_shapes(oracle, N, As, T, kw):
+    from moire_b200.engine import Engine
+    pk = _mini(N, As, **kw)
+    eng = Engine(pk, np.linspace(1, 0, T) if T > 1 else [1.0], seed=2, burnin=30, max_coi=20)
+    assert not eng.init_chains()["still_ill"].any()
+    for it in range(3):
+        eng.step(it)
+    for c in range(T):
+        check_invariants(eng, pk, c, oracle, ncheck=300)
+    eng.close()
+
+
+def test_high_coi_limits(oracle):
+    """max_coi at the engine's limit (64): wide mixture path (m - k >= 16) and EGF with m = 64."""
+    from moire_b200.engine import Engine
+    pk = _mini(24, [30] * 4 + [3] * 4, sample_cois=np.arange(41, 65), seed=9)
+    eng = Engine(pk, [1.0, 0.2], seed=2, burnin=10, max_coi=64)
+    assert not eng.init_chains()["still_ill"].any()
+    for it in range(2):
+        eng.step(it)
+    wide = 0
+    for c in range(2):
+        st, k = check_invariants(eng, pk, c, oracle, ncheck=10 ** 6)
+        wide += int(((st["m"][:, None] - k + 1 > 16) & (k <= 10)).sum())
+    assert wide > 0
+    eng.close()
+
+
+def test_argument_errors_are_reported_not_fatal():
+    from moire_b200.engine import Engine, MoireError
+    pk = _mini(5, [4, 4])
+    with pytest.raises(MoireError, match="max_coi"):
+        Engine(pk, [1.0], max_coi=65)
+    with pytest.raises(MoireError, match="device_id"):
+        Engine(pk, [1.0], device=99)
+    bad = _mini(5, [4, 4])
+    bad.obs_mask = bad.obs_mask.copy()
+    bad.obs_mask[0, 0] = 1 << 10
+    with pytest.raises(MoireError, match="bits above"):
+        Engine(bad, [1.0])
+    eng = Engine(pk, [1.0])
+    with pytest.raises(MoireError, match="before init"):
+        eng.step(0)
+    eng.close()
