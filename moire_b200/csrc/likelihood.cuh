@@ -30,10 +30,43 @@ namespace moire
 // path (the thread evaluator's log of the frequency sum and the mixture loop) inlines them;
 // every other use -- proposals, priors, SALT, the cooperative and EGF paths -- shares one
 // out-of-line copy per function.
+#ifndef MOIRE_HOT_LOG
+#define MOIRE_HOT_LOG 1
+#endif
+// MOIRE_HOT_LOG: 0 = log / log1p / exp inlined at the hot sites; 1 (default) = log1p(-pam)
+// evaluated as log(1 - pam); 2 = additionally one shared out-of-line log for the hot uses.
+// log(1 - pam): pam is clamped to [0, 1 - eps]; 1 - pam is exact for pam >= 1/2 and carries a
+// relative rounding error <= 2^-53 below, i.e. the term differs from log1p(-pam) by at most
+// ~2e-16 in absolute value -- ulp-level, like the difference between CUDA's and glibc's log1p --
+// while dropping the 250-instruction log1p body from the instruction-fetch-bound hot loop
+// (measured -13 % step time, profiles/variants_o.log).
+#if MOIRE_HOT_LOG == 2
+__device__ __noinline__ double hot_log(double x) { return log(x); }
+#else
+__device__ __forceinline__ double hot_log(double x) { return log(x); }
+#endif
+__device__ __forceinline__ double hot_log1m(double x)
+{
+#if MOIRE_HOT_LOG == 0
+    return log1p(-x);
+#else
+    return hot_log(1.0 - x);
+#endif
+}
 __device__ __noinline__ double cold_log(double x) { return log(x); }
+// log(1 - x) of a clamped PAM, the same formulation on every path
+__device__ __forceinline__ double cold_log1m(double x);
 __device__ __noinline__ double cold_log1p(double x) { return log1p(x); }
 __device__ __noinline__ double cold_exp(double x) { return exp(x); }
 __device__ __noinline__ double cold_expm1(double x) { return expm1(x); }
+__device__ __forceinline__ double cold_log1m(double x)
+{
+#if MOIRE_HOT_LOG == 0
+    return cold_log1p(-x);
+#else
+    return cold_log(1.0 - x);
+#endif
+}
 
 constexpr int kIeMax = 10;      // src/prob_any_missing.cpp:11
 constexpr int kMaxCoi = 64;     // MOIRE_MAX_COI
@@ -272,7 +305,7 @@ __device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, i
         const int i = cnt - 1 - t;
         const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
         const double pam = clamp_pam(val[t * ST]);
-        const double i_res = __dadd_rn(log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
+        const double i_res = __dadd_rn(hot_log1m(pam), __dmul_rn(log_total, (double)(m - i)));
         const double v = __dadd_rn(pr, i_res);
         val[t * ST] = v;
         mx = (mx < v) ? v : mx;  // std::max_element semantics
@@ -285,7 +318,7 @@ __device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, i
         const double dv = __dsub_rn(val[t * ST], mx);
         sum = __dadd_rn(sum, dv == 0.0 ? 1.0 : exp(dv));
     }
-    return __dadd_rn(mx, log(sum));
+    return __dadd_rn(mx, hot_log(sum));
 }
 
 #ifndef MOIRE_MAX_ACC
@@ -294,7 +327,7 @@ __device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, i
 #ifndef MOIRE_TIERS
 #define MOIRE_TIERS 3
 #endif
-constexpr int kMaxAcc = 16;  // accumulators kept in registers
+constexpr int kMaxAcc = MOIRE_MAX_ACC;  // accumulators kept in registers
 
 // One instantiation per number of accumulators: they stay in registers without predication.
 // All lanes that arrive together run the instantiation of the largest count among them (the
@@ -350,8 +383,8 @@ __device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, i
 #elif MOIRE_TIERS == 6  // 6 16
     if (cnt_w <= 6) MOIRE_IE_CASE(6)
     else MOIRE_IE_CASE(16)
-#else  // 16
-    MOIRE_IE_CASE(16)
+#else  // one tier: every cell of the path runs kMaxAcc accumulators
+    MOIRE_IE_CASE(MOIRE_MAX_ACC)
 #endif
 #undef MOIRE_IE_CASE
     return relatedness_mixture(scr, ST, m, cnt, log_total, log_r, log_1mr, lgam);
@@ -391,7 +424,7 @@ __device__ __noinline__ double transmission_rel_egf(uint64_t latent, const doubl
         const int n = m - i;
         const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
         const double pam = clamp_pam(pam_from_coverage(a[n]));
-        const double i_res = __dadd_rn(cold_log1p(-pam), __dmul_rn(log_total, (double)n));
+        const double i_res = __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)n));
         const double v = __dadd_rn(pr, i_res);
         a[n] = v;
         mx = (mx < v) ? v : mx;
@@ -416,7 +449,7 @@ __device__ __forceinline__ double transmission_norel_exact_cover(uint64_t latent
     }
     for (int i = 2; i <= k; ++i) cov = __dmul_rn(cov, (double)i);
     const double pam = clamp_pam(pam_from_coverage(cov));
-    return __dadd_rn(cold_log1p(-pam), __dmul_rn(log_total, (double)k));
+    return __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)k));
 }
 
 // ---- a2: transmission process of one cell, one thread -------------------------------------------
@@ -439,7 +472,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
             total = __dadd_rn(total, prow[al]);
         }
     }
-    const double log_total = log(total);
+    const double log_total = hot_log(total);
     if (k <= kIeMax)
     {
         uint64_t rest = latent;
@@ -468,7 +501,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
             pam = pam_from_coverage(a[m]);
         }
         pam = clamp_pam(pam);
-        return __dadd_rn(cold_log1p(-pam), __dmul_rn(log_total, (double)m));
+        return __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)m));
     }
     if (k > kIeMax)
         return transmission_rel_egf(latent, prow, total, k, m, log_total, log_r, log_1mr, lgam);
@@ -586,7 +619,7 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
     if (!allow_relatedness)
     {
         const double pam = clamp_pam(__shfl_sync(FULL, acc[0], 0));
-        return __dadd_rn(cold_log1p(-pam), __dmul_rn(log_total, (double)m));
+        return __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)m));
     }
     // mixture terms, one per (chunk, lane)
     double v[4];
@@ -601,7 +634,7 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
             const int i = cnt - 1 - t;
             const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
             const double pam = clamp_pam(acc[ch]);
-            const double i_res = __dadd_rn(cold_log1p(-pam), __dmul_rn(log_total, (double)(m - i)));
+            const double i_res = __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)(m - i)));
             v[ch] = __dadd_rn(pr, i_res);
             mx = (mx < v[ch]) ? v[ch] : mx;
         }
