@@ -98,6 +98,24 @@ void build_subset_tables(std::vector<unsigned short> &tail, std::vector<unsigned
     }
 }
 
+// Row m of the EGF recurrence's binomials exactly as the reference produces them
+// (src/prob_any_missing.cpp:81-88): comb = m; comb *= (m - j) / (j + 1).  [j][m] layout.
+void build_egf_binomials(std::vector<double> &tab)
+{
+    const int D = moire::kMaxCoi + 1;
+    tab.assign((size_t)D * D, 0.0);
+    for (int m = 1; m < D; ++m)
+    {
+        volatile double comb = (double)m;
+        for (int j = 1; j <= m; ++j)
+        {
+            tab[(size_t)j * D + m] = comb;
+            const volatile double ratio = (double)(m - j) / (double)(j + 1);
+            comb = comb * ratio;
+        }
+    }
+}
+
 double log_binom_exact(unsigned n, unsigned k)
 {
     // boost::math::binomial_coefficient<double> returns C(n,k) as an integer-valued double
@@ -255,6 +273,9 @@ struct moire_engine
             build_subset_tables(tail_h, mask_h);
             CUDA_TRY(cudaMemcpyToSymbol(moire::c_sub_tail, tail_h.data(), tail_h.size() * sizeof(unsigned short)));
             CUDA_TRY(cudaMemcpyToSymbol(moire::g_sub_mask, mask_h.data(), mask_h.size() * sizeof(unsigned short)));
+            std::vector<double> comb_h;
+            build_egf_binomials(comb_h);
+            CUDA_TRY(cudaMemcpyToSymbol(moire::g_egf_comb, comb_h.data(), comb_h.size() * sizeof(double)));
         }
         obs.upload((const unsigned long long *)d->obs_mask, NL, stream);
         missing.upload(d->is_missing, NL, stream);

@@ -181,10 +181,10 @@ __device__ __forceinline__ int block_sort_cells(int ncell, ClassFn cls, unsigned
 }
 
 // Transmission terms of the listed cells.  The list is heaviest first: [0, n_egf) cells with
-// k > 10 (EGF recurrence, one thread each), [n_egf, coop_end) cells with kCoopMinK <= k <= 10
-// (one warp each, subsets across lanes), the rest light cells (one thread each).  Work is handed
-// out dynamically, heaviest first, in units of one cooperative cell or one chunk of 32
-// one-thread cells: `next` is a shared counter the caller has zeroed before its last barrier.
+// k > 10 (EGF recurrence, one warp each, draws across lanes), [n_egf, coop_end) cells with
+// kCoopMinK <= k <= 10 (one warp each, subsets across lanes), the rest light cells (one thread
+// each).  Work is handed out dynamically, heaviest first, in units of one cooperative cell or one
+// chunk of 32 one-thread cells: `next` is a shared counter the caller has zeroed before its last barrier.
 // fetch(cell, lat, prow, m, log_r, log_1mr) supplies a cell's inputs; out[cell] gets the term.
 // scr: kScratchSlots rows of blockDim.x + 1 doubles.  No block barrier inside.
 template <class Fetch>
@@ -196,7 +196,7 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
 {
     const int tid = threadIdx.x, ST = blockDim.x + 1;
     const int lane = tid & 31, warp = tid >> 5;
-    const int egf_units = (n_egf + 31) >> 5, coop_units = coop_end - n_egf;
+    const int egf_units = n_egf, coop_units = coop_end - n_egf;
     const int light_units = (nwork - coop_end + 31) >> 5;
     const int units = egf_units + coop_units + light_units;
     for (;;)
@@ -209,14 +209,17 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
         const double *prow;
         int m;
         double log_r, log_1mr;
-        if (u >= egf_units && u < egf_units + coop_units)
+        if (u < egf_units + coop_units)
         {
-            const int cell = order[n_egf + (u - egf_units)];
+            const int cell = order[u];
             fetch(cell, lat, prow, m, log_r, log_1mr);
             const int k = __popcll(lat);
             double T;
             if (k > m)
                 T = NAN;
+            else if (u < egf_units)
+                T = transmission_ll_egf_coop(lat, prow, m, log_r, log_1mr, allow_rel, scr + warp * 32,
+                                             ST, lgam);
             else
                 T = transmission_ll_coop(lat, prow, m, log_r, log_1mr, allow_rel, scr + warp * 32,
                                          ST, lgam);
@@ -224,10 +227,8 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
         }
         else
         {
-            const int w = u < egf_units ? 32 * u + lane
-                                        : coop_end + 32 * (u - egf_units - coop_units) + lane;
-            const int end = u < egf_units ? n_egf : nwork;
-            if (w < end)
+            const int w = coop_end + 32 * (u - egf_units - coop_units) + lane;
+            if (w < nwork)
             {
                 const int cell = order[w];
                 fetch(cell, lat, prow, m, log_r, log_1mr);

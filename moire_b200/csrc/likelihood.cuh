@@ -250,6 +250,12 @@ __device__ __forceinline__ double ie_scalar(double *scr, int ST, int k, int n)
 }
 
 // ---- a5: EGF coverage recurrence, k > 10 (src/prob_any_missing.cpp:57-97) -------------------
+// The reference builds the binomials of row m on the fly, comb(m, 1) = m,
+// comb(m, j + 1) = comb(m, j) * ((m - j) / (j + 1)) in double (src/prob_any_missing.cpp:81-88).
+// They depend on (m, j) only, so the host tabulates them with the very same operations
+// (engine.cu: build_egf_binomials) and the device never divides: g_egf_comb[j * 65 + m].
+__device__ double g_egf_comb[(kMaxCoi + 1) * (kMaxCoi + 1)];
+
 // a[n] = coverage probability of n draws for n = 0..max_n.  q_e = prow[allele_e] / total.
 __device__ __noinline__ void egf_coverage(uint64_t latent, const double *prow, double total,
                                           int max_n, double *a)
@@ -270,13 +276,10 @@ __device__ __noinline__ void egf_coverage(uint64_t latent, const double *prow, d
         b[0] = 0.0;
         for (int m = 1; m <= max_n; ++m)
         {
-            double comb = (double)m;
             double sum = 0.0;
             for (int j = 1; j <= m; ++j)
-            {
-                sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(comb, a[m - j]), ppow[j]));
-                comb = __dmul_rn(comb, __ddiv_rn((double)(m - j), (double)(j + 1)));
-            }
+                sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(g_egf_comb[j * (kMaxCoi + 1) + m], a[m - j]),
+                                               ppow[j]));
             b[m] = sum;
         }
         for (int m = 0; m <= max_n; ++m) a[m] = b[m];
@@ -665,6 +668,114 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
         }
     }
     return __dadd_rn(result_mx, cold_log(sum_tail));
+}
+
+// ---- a2 for k > 10, warp-cooperative: the EGF recurrence with the draws across lanes ----------
+// One warp per cell.  For each latent allele the new row b[n] = sum_{j=1..n} C(n,j) a[n-j] q^j is
+// independent across n, so lane l computes n = l + 1 and n = l + 33 (n <= m <= 64), each as the
+// reference's sequential sum over j with the running power q^j built by the same chain of
+// multiplications; a[] lives in the warp's scratch rows.  The mixture terms are one per lane and
+// the log-sum-exp is summed in the reference's order.  All lanes must call with identical
+// arguments; every lane returns the value.
+__device__ __forceinline__ double transmission_ll_egf_coop(uint64_t latent, const double *prow, int m,
+                                                           double log_r, double log_1mr,
+                                                           bool allow_relatedness, double *wscr,
+                                                           int ST, const double *lgam)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int k = __popcll(latent);
+    double total = 0.0;
+    {
+        uint64_t rest = latent;
+        while (rest)
+        {
+            const int al = __ffsll((long long)rest) - 1;
+            rest &= rest - 1;
+            total = __dadd_rn(total, prow[al]);
+        }
+    }
+    const double log_total = cold_log(total);
+    // a[i] at wscr[(i >> 5) * ST + (i & 31)], i <= m <= 64: rows 0..2
+    auto A = [&](int i) -> double & { return wscr[(i >> 5) * ST + (i & 31)]; };
+    for (int i = lane; i <= m; i += 32) A(i) = i == 0 ? 1.0 : 0.0;
+    __syncwarp();
+    uint64_t rest = latent;
+    while (rest)
+    {
+        const int al = __ffsll((long long)rest) - 1;
+        rest &= rest - 1;
+        const double q = __ddiv_rn(prow[al], total);
+        double b[2] = {0.0, 0.0};
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+        {
+            const int n = lane + 1 + 32 * half;
+            if (n <= m)
+            {
+                double sum = 0.0, pw = q;
+                for (int j = 1; j <= n; ++j)
+                {
+                    if (j > 1) pw = __dmul_rn(pw, q);
+                    sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(g_egf_comb[j * (kMaxCoi + 1) + n], A(n - j)), pw));
+                }
+                b[half] = sum;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) A(0) = 0.0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+        {
+            const int n = lane + 1 + 32 * half;
+            if (n <= m) A(n) = b[half];
+        }
+        __syncwarp();
+    }
+    if (!allow_relatedness)
+    {
+        const double pam = clamp_pam(pam_from_coverage(A(m)));
+        return __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)m));
+    }
+    // mixture: term i = 0..cnt-1 uses n = m - i; lanes hold i = lane and i = lane + 32
+    const int cnt = m - k + 1;
+    double v[2];
+    double mx = -INFINITY;
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+    {
+        const int i = lane + 32 * half;
+        v[half] = -INFINITY;
+        if (i < cnt)
+        {
+            const int n = m - i;
+            const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
+            const double pam = clamp_pam(pam_from_coverage(A(n)));
+            const double i_res = __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)n));
+            v[half] = __dadd_rn(pr, i_res);
+            mx = (mx < v[half]) ? v[half] : mx;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        const double other = __shfl_xor_sync(FULL, mx, o);
+        mx = (mx < other) ? other : mx;
+    }
+    if (mx == -INFINITY) return -INFINITY;
+    double sum = 0.0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+    {
+        if (32 * half < cnt)  // uniform
+        {
+            double ev = 0.0;
+            if (lane + 32 * half < cnt) ev = cold_exp(__dsub_rn(v[half], mx));
+            const int top = min(31, cnt - 1 - 32 * half);
+            for (int t = 0; t <= top; ++t) sum = __dadd_rn(sum, __shfl_sync(FULL, ev, t));
+        }
+    }
+    return __dadd_rn(mx, cold_log(sum));
 }
 
 // ---- a8: latent-genotype proposal ------------------------------------------------------------
