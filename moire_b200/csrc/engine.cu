@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -146,7 +147,7 @@ struct moire_engine
     int p_threads = 256;
 
     // allocations
-    DevBuf<unsigned long long> obs, latent, evals;
+    DevBuf<unsigned long long> obs, latent, evals, trace;
     DevBuf<unsigned char> missing;
     DevBuf<int> nall, aclass, avals, obs_coi, m, acc6, p_acc, p_att, active;
     DevBuf<double> logC, lgam, lgadj, cellT, cellO, persample, p, p_sd, perchain, scratchN;
@@ -175,6 +176,17 @@ struct moire_engine
         p_acc.release(); p_att.release(); active.release(); logC.release(); lgam.release();
         lgadj.release(); cellT.release(); cellO.release(); persample.release(); p.release();
         p_sd.release(); perchain.release(); scratchN.release();
+        if (v.trace && std::getenv("MOIRE_B200_TRACE"))
+        {
+            std::vector<unsigned long long> h(64 * 16 * 16 * 2);
+            if (cudaMemcpy(h.data(), v.trace, h.size() * sizeof(h[0]), cudaMemcpyDeviceToHost) == cudaSuccess)
+                if (FILE *f = std::fopen(std::getenv("MOIRE_B200_TRACE"), "wb"))
+                {
+                    std::fwrite(h.data(), sizeof(h[0]), h.size(), f);
+                    std::fclose(f);
+                }
+            trace.release();
+        }
         if (timer_a) cudaEventDestroy(timer_a);
         if (timer_b) cudaEventDestroy(timer_b);
         if (stream) cudaStreamDestroy(stream);
@@ -303,6 +315,12 @@ struct moire_engine
         v.mean_coi = pc + 0 * T; v.mean_coi_sd = pc + 1 * T; v.mean_coi_acc = pc + 2 * T;
         v.hyper = pc + 3 * T; v.temp = pc + 4 * T; v.llik = pc + 5 * T; v.prior = pc + 6 * T;
         v.active = active.ptr; v.evals = evals.ptr;
+        v.trace = nullptr;
+        if (std::getenv("MOIRE_B200_TRACE"))  // tuning aid: per-warp clocks of update_p
+        {
+            trace.alloc(64 * 16 * 16 * 2);
+            v.trace = trace.ptr;
+        }
         CUDA_TRY(cudaMemcpyAsync(v.temp, temps, T * sizeof(double), cudaMemcpyHostToDevice, stream));
 
         // tile shape of the per-sample kernel: S consecutive samples, about kMaxTileCells cells

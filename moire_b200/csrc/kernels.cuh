@@ -782,8 +782,16 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 512 ? 1 : MOIRE_MIN_BLOCKS_P *
         if (s_red[34] != 0.0) break;  // src/chain.cpp:503-518: leaves the locus
 
         // -- all cells of the locus under the proposed frequencies, heaviest class first
+        const long long tr0 = v.trace ? clock64() : 0;
         block_eval_transmissions(s_order, nwork, n_egf, coop_end, fetch, s_Tnew, s_qs, s_lgam,
                                  v.allow_rel != 0, &s_next);
+        if (v.trace && blockIdx.x < 64 && rep < 16 && lane == 0)
+        {
+            // [block][rep][warp] -> (clock at start of the evaluation phase, clock at its end)
+            unsigned long long *tr = v.trace + (((size_t)blockIdx.x * 16 + rep) * 16 + warp) * 2;
+            tr[0] = (unsigned long long)tr0;
+            tr[1] = (unsigned long long)clock64();
+        }
         evals += tid == 0 ? (unsigned long long)nwork : 0ull;
         __syncthreads();
         // -- the change of the locus' log-likelihood, summed in sample order

@@ -612,7 +612,18 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
                     const int nv = min(32, nsub - b0);
                     const double *row = wscr + lane * ST;
                     double a = acc[ch];
-                    for (int l = 0; l < nv; ++l) a = __dadd_rn(a, row[l]);
+                    if (nv == 32)
+                    {
+                        double term[32];
+#pragma unroll
+                        for (int l = 0; l < 32; ++l) term[l] = row[l];  // loads first, then the chain
+#pragma unroll
+                        for (int l = 0; l < 32; ++l) a = __dadd_rn(a, term[l]);
+                    }
+                    else
+                    {
+                        for (int l = 0; l < nv; ++l) a = __dadd_rn(a, row[l]);
+                    }
                     acc[ch] = a;
                 }
                 __syncwarp();

@@ -53,6 +53,7 @@ struct View
     int *active;  // init retry mask
 
     unsigned long long *evals;  // [16] non-missing cell evaluations, by update kind
+    unsigned long long *trace;  // tuning aid (MOIRE_B200_TRACE): per-warp clocks of update_p, or null
 
     // parameters (src/parameters.h:31-47) and host-precomputed constants
     double mean_coi_shape, mean_coi_scale, lg_shape, l_scale;

@@ -36,6 +36,8 @@ class PackedData:
 def pack_data(data, is_missing=False) -> PackedData:
     """``data``: list over loci of [N][A_j] 0/1 arrays (or list of lists of vectors, as R hands
     them over); ``is_missing``: False or a [L][N] boolean matrix (R/mcmc.R:115-125)."""
+    if hasattr(data, "values"):          # a named list keyed by locus (read_rda, R's data$data)
+        data = list(data.values())
     L = len(data)
     if L == 0:
         raise ValueError("no loci")

@@ -110,3 +110,64 @@ def test_posterior_agrees_with_reference_sampler():
         b = np.mean([o[k] for o in ours], axis=0).mean()
         assert abs(a - b) < 0.03, (k, a, b)
     assert abs(np.mean([r["mean_coi"] for r in refs]) - np.mean([o["mean_coi"] for o in ours])) < 0.4
+
+
+def packaged(prefix):
+    from conftest import load_golden
+    from moire_b200.data import PackedData
+    g = load_golden("packaged_data.npz")
+    obs = g[prefix + ".obs_mask"]
+    coi = np.vectorize(lambda x: bin(int(x)).count("1"))(obs).max(axis=1).astype(np.int32)
+    return PackedData(obs.shape[0], obs.shape[1], g[prefix + ".num_alleles"].astype(np.int32), obs,
+                      g[prefix + ".is_missing"].astype(np.uint8), coi), g
+
+
+def test_packaged_demo_run_reproduces_the_reference_authors_posterior():
+    """The reference ships the result of its demo run on `simulated_data` (data/mcmc_results.rda,
+    recipe data-raw/mcmc_results.R: 80 temperatures, 1000 + 1000 steps, eps priors Beta(.1, 9.9)).
+    Same data, same arguments through `run_mcmc` here.  That fixture was produced by an OLDER build
+    of moire, so it is a sanity band, not a pin: the current reference C++ itself
+    (oracle/_ref, same data and priors, 8 temperatures) gives mean COI 6.85, lam 6.85, relatedness
+    0.33 where the fixture has 6.22, 6.21, 0.27 -- and the engine lands on the current reference
+    (6.81 / 6.8 / 0.33).  The log-likelihood at stationarity agrees with the fixture to well
+    within its own trace sd."""
+    from moire_b200.mcmc import run_mcmc
+    pk, g = packaged("sim")
+    a = {k[len("res.arg."):]: float(v) for k, v in g.items() if k.startswith("res.arg.")}
+    res = run_mcmc(pk, burnin=int(a["burnin"]), samples_per_chain=int(a["samples_per_chain"]),
+                   pt_chains=g["res.pt_chains"], eps_pos_alpha=a["eps_pos_alpha"],
+                   eps_pos_beta=a["eps_pos_beta"], eps_neg_alpha=a["eps_neg_alpha"],
+                   eps_neg_beta=a["eps_neg_beta"], r_alpha=a["r_alpha"], r_beta=a["r_beta"],
+                   mean_coi_shape=a["mean_coi_shape"], mean_coi_scale=a["mean_coi_scale"],
+                   max_eps_pos=a["max_eps_pos"], max_eps_neg=a["max_eps_neg"], max_coi=int(a["max_coi"]),
+                   pre_adapt_steps=int(a["pre_adapt_steps"]), temp_adapt_steps=int(a["temp_adapt_steps"]),
+                   verbose=False, seed=17325)
+    ch = res["chains"][0]
+    assert len(ch["temp_gradient"]) == 80 and len(ch["lam_coi"]) > 900
+    ll = np.asarray(ch["llik_sample"])
+    assert abs(ll.mean() - g["res.llik_sample"].mean()) < 60, (ll.mean(), g["res.llik_sample"].mean())
+    m = np.mean(ch["coi"], axis=1)
+    assert abs(m.mean() - g["res.mean_coi_per_sample"].mean()) < 1.0     # older build: 6.22
+    assert abs(m.mean() - 6.85) < 0.35                                   # current reference C++
+    assert np.corrcoef(m, g["res.mean_coi_per_sample"])[0, 1] > 0.97
+    assert abs(np.mean(ch["lam_coi"]) - 6.85) < 0.6
+    assert abs(np.mean(ch["eps_neg"]) - g["res.mean_eps_neg"].mean()) < 0.002
+    assert abs(np.mean(ch["eps_pos"]) - g["res.mean_eps_pos"].mean()) < 0.002
+    assert abs(np.mean(ch["relatedness"]) - 0.326) < 0.05
+    p0 = np.array([np.mean(ch["allele_freqs"][j], axis=0)[0] for j in range(30)])
+    assert np.abs(p0 - g["res.mean_first_allele_freq"]).max() < 0.03
+    # the adapted ladder keeps its end points and stays ordered
+    assert ch["temp_gradient"][0] == 1.0 and ch["temp_gradient"][-1] == 0.0
+    assert np.all(np.diff(ch["temp_gradient"]) <= 0)
+
+
+def test_namibia_data_runs_with_ten_temperatures():
+    """configs[1] of BASELINE.json on the real data shape: 2585 samples x 26 loci, A_j 7..35,
+    11.4 % missing cells, 10 temperatures."""
+    from moire_b200.mcmc import run_mcmc
+    pk, _ = packaged("nam")
+    res = run_mcmc(pk, burnin=30, samples_per_chain=10, pt_chains=10, verbose=False, seed=3)
+    ch = res["chains"][0]
+    assert np.all(np.isfinite(ch["llik_burnin"])) and np.all(np.isfinite(ch["posterior_sample"]))
+    assert ch["llik_burnin"][-1] > ch["llik_burnin"][0]              # burn-in climbs
+    assert len(ch["coi"]) == 2585 and len(ch["allele_freqs"]) == 26 and len(ch["allele_freqs"][22][0]) == 35
