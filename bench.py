@@ -170,6 +170,8 @@ def our_arm(args, wl):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the one JSON line (the image's NCCL_DEBUG=VERSION prints a banner there)
+        os.environ["NCCL_DEBUG"] = os.environ.get("MOIRE_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     pk, temps, model = wl["packed"], np.asarray(wl["temps"], dtype=np.float64), wl["model"]
     T = len(temps)
