@@ -324,72 +324,35 @@ __device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, i
     return __dadd_rn(mx, hot_log(sum));
 }
 
-#ifndef MOIRE_MAX_ACC
-#define MOIRE_MAX_ACC 16
-#endif
-#ifndef MOIRE_TIERS
-#define MOIRE_TIERS 3
-#endif
-constexpr int kMaxAcc = MOIRE_MAX_ACC;  // accumulators kept in registers
+constexpr int kMaxAcc = 16;  // accumulators kept in registers
 
-// One instantiation per number of accumulators: they stay in registers without predication.
-// All lanes that arrive together run the instantiation of the largest count among them (the
+// The subset sums of one cell, accumulators dumped to scr[t * ST], then the mixture.
+// All lanes that arrive together run the accumulator tier of the largest count among them (the
 // extra accumulators of a lane with fewer mixture terms are simply never read), so lanes with
 // different counts -- and different k: the subset loop just ends earlier for them -- share one
-// instruction stream.  The sorted work lists make the counts of a warp nearly equal.
+// instruction stream.  Two tiers are compiled, {4, 16}: measured best on B200
+// (profiles/variants_g.log) -- more tiers mean more distinct hot loops competing for the
+// instruction caches, which costs more than the idle accumulators do.
 __device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, int m,
                                                    double log_total, double log_r, double log_1mr,
                                                    const double *lgam)
 {
     const int cnt = m - k + 1;
     const int cnt_w = __reduce_max_sync(__activemask(), cnt);
-#define MOIRE_IE_CASE(NACC)                                                      \
-    {                                                                            \
-        double acc[NACC];                                                        \
-        ie_vectorized<NACC>(scr, ST, k, 0, acc);                                 \
-        _Pragma("unroll") for (int t = 0; t < NACC; ++t) scr[t * ST] = acc[t];   \
+    if (cnt_w <= 4)
+    {
+        double acc[4];
+        ie_vectorized<4>(scr, ST, k, 0, acc);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) scr[t * ST] = acc[t];
     }
-    // MOIRE_TIERS selects the set of accumulator counts compiled (fewer = smaller hot code)
-#if MOIRE_TIERS == 0  // 1 2 3 4 5 6 8 10 12 16
-    if (cnt_w <= 1) MOIRE_IE_CASE(1)
-    else if (cnt_w <= 2) MOIRE_IE_CASE(2)
-    else if (cnt_w <= 3) MOIRE_IE_CASE(3)
-    else if (cnt_w <= 4) MOIRE_IE_CASE(4)
-    else if (cnt_w <= 5) MOIRE_IE_CASE(5)
-    else if (cnt_w <= 6) MOIRE_IE_CASE(6)
-    else if (cnt_w <= 8) MOIRE_IE_CASE(8)
-    else if (cnt_w <= 10) MOIRE_IE_CASE(10)
-    else if (cnt_w <= 12) MOIRE_IE_CASE(12)
-    else MOIRE_IE_CASE(16)
-#elif MOIRE_TIERS == 1  // 2 4 8 16
-    if (cnt_w <= 2) MOIRE_IE_CASE(2)
-    else if (cnt_w <= 4) MOIRE_IE_CASE(4)
-    else if (cnt_w <= 8) MOIRE_IE_CASE(8)
-    else MOIRE_IE_CASE(16)
-#elif MOIRE_TIERS == 2  // 4 8 16
-    if (cnt_w <= 4) MOIRE_IE_CASE(4)
-    else if (cnt_w <= 8) MOIRE_IE_CASE(8)
-    else MOIRE_IE_CASE(16)
-#elif MOIRE_TIERS == 3  // 4 16
-    if (cnt_w <= 4) MOIRE_IE_CASE(4)
-    else MOIRE_IE_CASE(16)
-#elif MOIRE_TIERS == 4  // 3 6 16
-    if (cnt_w <= 3) MOIRE_IE_CASE(3)
-    else if (cnt_w <= 6) MOIRE_IE_CASE(6)
-    else MOIRE_IE_CASE(16)
-#elif MOIRE_TIERS == 5  // 2 4 6 8 16
-    if (cnt_w <= 2) MOIRE_IE_CASE(2)
-    else if (cnt_w <= 4) MOIRE_IE_CASE(4)
-    else if (cnt_w <= 6) MOIRE_IE_CASE(6)
-    else if (cnt_w <= 8) MOIRE_IE_CASE(8)
-    else MOIRE_IE_CASE(16)
-#elif MOIRE_TIERS == 6  // 6 16
-    if (cnt_w <= 6) MOIRE_IE_CASE(6)
-    else MOIRE_IE_CASE(16)
-#else  // one tier: every cell of the path runs kMaxAcc accumulators
-    MOIRE_IE_CASE(MOIRE_MAX_ACC)
-#endif
-#undef MOIRE_IE_CASE
+    else
+    {
+        double acc[kMaxAcc];
+        ie_vectorized<kMaxAcc>(scr, ST, k, 0, acc);
+#pragma unroll
+        for (int t = 0; t < kMaxAcc; ++t) scr[t * ST] = acc[t];
+    }
     return relatedness_mixture(scr, ST, m, cnt, log_total, log_r, log_1mr, lgam);
 }
 
