@@ -68,6 +68,9 @@ __device__ __forceinline__ double cold_log1m(double x)
 #endif
 }
 
+#ifndef MOIRE_COOP_INLINE
+#define MOIRE_COOP_INLINE __noinline__
+#endif
 constexpr int kIeMax = 10;      // src/prob_any_missing.cpp:11
 constexpr int kMaxCoi = 64;     // MOIRE_MAX_COI
 constexpr int kLogCDim = 65;    // logC[n][k], 0 <= k <= n <= 64
@@ -216,7 +219,7 @@ __device__ __forceinline__ void ie_vectorized(double *scr, int ST, int k, int t0
 }
 
 // ---- a3: scalar inclusion-exclusion, k <= 10 (src/prob_any_missing.cpp:13-53) ---------------
-__device__ __forceinline__ double ie_scalar(double *scr, int ST, int k, int n)
+__device__ MOIRE_COOP_INLINE double ie_scalar(double *scr, int ST, int k, int n)
 {
     const unsigned short *tab = c_sub_tail + subset_block(k);
     const int nsub = (1 << k) - 1;
@@ -490,7 +493,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
 #define MOIRE_COOP_MIN_K 7
 #endif
 constexpr int kCoopMinK = MOIRE_COOP_MIN_K;
-__device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const double *prow, int m,
+__device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const double *prow, int m,
                                                        double log_r, double log_1mr,
                                                        bool allow_relatedness, double *wscr, int ST,
                                                        const double *lgam)
@@ -651,7 +654,7 @@ __device__ __forceinline__ double transmission_ll_coop(uint64_t latent, const do
 // multiplications; a[] lives in the warp's scratch rows.  The mixture terms are one per lane and
 // the log-sum-exp is summed in the reference's order.  All lanes must call with identical
 // arguments; every lane returns the value.
-__device__ __forceinline__ double transmission_ll_egf_coop(uint64_t latent, const double *prow, int m,
+__device__ MOIRE_COOP_INLINE double transmission_ll_egf_coop(uint64_t latent, const double *prow, int m,
                                                            double log_r, double log_1mr,
                                                            bool allow_relatedness, double *wscr,
                                                            int ST, const double *lgam)
