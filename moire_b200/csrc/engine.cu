@@ -143,7 +143,7 @@ struct moire_engine
     std::string last_error;
     uint64_t launches = 0;
     int tile_S = 1, tiles_per_chain = 1;
-    size_t sample_smem = 0, p_smem = 0;
+    size_t sample_smem = 0, sample_smem_o = 0, p_smem = 0;
     int p_threads = 256;
 
     // allocations
@@ -327,7 +327,8 @@ struct moire_engine
         if (N > 65535) throw InvalidArg{"num_samples > 65535 unsupported (16-bit work lists)"};
         tile_S = std::max(1, std::min({moire::kMaxTileSamples, moire::kMaxTileCells / L, N}));
         tiles_per_chain = (N + tile_S - 1) / tile_S;
-        sample_smem = moire::sample_kernel_smem(tile_S, L, v.nA);
+        sample_smem = moire::sample_kernel_smem(tile_S, L, v.nA, true);
+        sample_smem_o = moire::sample_kernel_smem(tile_S, L, v.nA, false);
         p_threads = moire::p_kernel_threads(N);
         p_smem = moire::p_kernel_smem(N, v.AP, p_threads);
         cudaDeviceProp prop;
@@ -344,8 +345,8 @@ struct moire_engine
     {
         using namespace moire;
         const int ss = (int)sample_smem;
-        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EPS_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
-        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EPS_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
+        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EPS_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem_o));
+        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EPS_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem_o));
         CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
         CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
         CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EFF_COI>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
@@ -400,7 +401,8 @@ struct moire_engine
     void launch_sample(int iteration)
     {
         Timed tm(this, KIND);
-        moire::k_update_sample<KIND><<<v.T * tiles_per_chain, moire::kThreads, sample_smem, stream>>>(
+        const size_t smem = (KIND == moire::KIND_EPS_NEG || KIND == moire::KIND_EPS_POS) ? sample_smem_o : sample_smem;
+        moire::k_update_sample<KIND><<<v.T * tiles_per_chain, moire::kThreads, smem, stream>>>(
             v, iteration, tile_S, tiles_per_chain);
         tm.done();
     }

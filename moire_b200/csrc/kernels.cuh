@@ -243,13 +243,16 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
 __host__ __device__ inline size_t align8(size_t b) { return (b + 7) & ~(size_t)7; }
 __host__ __device__ inline size_t scratch_doubles(int B) { return (size_t)kScratchSlots * (B + 1); }
 
-__host__ __device__ inline size_t sample_kernel_smem(int S, int L, int nA)
+// Shared memory of the per-sample kernel.  The two error-rate updates evaluate no transmission
+// term: no scratch columns, no sort, one array per cell -- which lets several of their blocks
+// share an SM (they are plain streaming kernels).
+__host__ __device__ inline size_t sample_kernel_smem(int S, int L, int nA, bool need_t)
 {
     const size_t C = (size_t)S * L;
     size_t b = 0;
-    b += 128 * sizeof(double);                        // lgam
-    b += scratch_doubles(kThreads) * sizeof(double);  // per-thread scratch columns
-    b += 4 * C * sizeof(double);                      // proposed latent, its log density, T, O
+    b += 128 * sizeof(double);                                      // lgam
+    b += (need_t ? scratch_doubles(kThreads) : 0) * sizeof(double);  // per-thread scratch columns
+    b += (need_t ? 4 : 2) * C * sizeof(double);  // proposed latent, [its log density, T,] O
     b += (size_t)S * nA * sizeof(EpsLogs);
     b += (size_t)S * sizeof(Proposal);
     b += kSortBins * sizeof(unsigned int) + 40 * sizeof(unsigned int);
@@ -270,10 +273,11 @@ __global__ void __launch_bounds__(kThreads, MOIRE_MIN_BLOCKS_S * (256 / kThreads
     const int C = S * v.L;
     double *s_lgam = smem;
     double *s_qs = s_lgam + 128;
-    unsigned long long *s_nlat = reinterpret_cast<unsigned long long *>(s_qs + scratch_doubles(kThreads));
+    unsigned long long *s_nlat =
+        reinterpret_cast<unsigned long long *>(s_qs + (NEED_T ? scratch_doubles(kThreads) : 0));
     double *s_nadj = reinterpret_cast<double *>(s_nlat + C);
-    double *s_T = s_nadj + C;
-    double *s_O = s_T + C;
+    double *s_T = s_nadj + (NEED_T ? C : 0);  // the error-rate updates keep only latent and O
+    double *s_O = s_T + (NEED_T ? C : 0);
     EpsLogs *s_elogs = reinterpret_cast<EpsLogs *>(s_O + C);
     Proposal *s_prop = reinterpret_cast<Proposal *>(s_elogs + S * v.nA);
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(s_prop + S);
