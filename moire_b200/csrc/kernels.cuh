@@ -103,6 +103,7 @@ __device__ __forceinline__ int work_class(int k, int m)
     // reversed so that ascending class = heaviest first
     const int kk = k > kIeMax ? kIeMax + 1 : k;
     int cnt = m - k + 1;
+    if (k > kIeMax) cnt = m;  // the EGF recurrence costs ~k m^2: order those cells by m
     cnt = cnt < 1 ? 1 : (cnt > 64 ? 64 : cnt);
     // cells with at most MOIRE_MERGE_K latent alleles (<= 2^k - 1 cheap subsets) form one class
     // per mixture count: there the cnt terms of log1p + exp outweigh the subset sums, so equal
@@ -181,10 +182,10 @@ __device__ __forceinline__ int block_sort_cells(int ncell, ClassFn cls, unsigned
 }
 
 // Transmission terms of the listed cells.  The list is heaviest first: [0, n_egf) cells with
-// k > 10 (EGF recurrence, one warp each, draws across lanes), [n_egf, coop_end) cells with
-// kCoopMinK <= k <= 10 (one warp each, subsets across lanes), the rest light cells (one thread
-// each).  Work is handed out dynamically, heaviest first, in units of one cooperative cell or one
-// chunk of 32 one-thread cells: `next` is a shared counter the caller has zeroed before its last barrier.
+// k > 10 (EGF recurrence), [n_egf, coop_end) cells with kCoopMinK <= k <= 10, the rest light
+// cells.  Work is handed out dynamically, heaviest first, in units of one chunk of 32
+// one-thread cells or one cooperatively evaluated cell (one warp: draws resp. subsets across
+// lanes): `next` is a shared counter the caller has zeroed before its last barrier.
 // fetch(cell, lat, prow, m, log_r, log_1mr) supplies a cell's inputs; out[cell] gets the term.
 // scr: kScratchSlots rows of blockDim.x + 1 doubles.  No block barrier inside.
 template <class Fetch>
@@ -196,9 +197,20 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
 {
     const int tid = threadIdx.x, ST = blockDim.x + 1;
     const int lane = tid & 31, warp = tid >> 5;
-    const int egf_units = n_egf, coop_units = coop_end - n_egf;
-    const int light_units = (nwork - coop_end + 31) >> 5;
-    const int units = egf_units + coop_units + light_units;
+    // A cooperative evaluation costs 3-4x the issue slots of a thread-per-cell one, so whole
+    // warps' worth of heavy cells (plentiful on high-COI data) still go one per thread; only
+    // the leftover of each heavy range -- the few cells that would otherwise occupy a warp alone
+    // and gate the block -- is evaluated cooperatively.
+    // ... and only where a heavy range is long enough to give every warp such a
+    // chunk; a lone chunk of 1023-subset cells would gate the block just the same.
+    const int nw = blockDim.x >> 5;
+    const int heavy = coop_end - n_egf;
+    const int egf_chunks = (n_egf >> 5) >= nw ? n_egf >> 5 : 0;
+    const int heavy_chunks = (heavy >> 5) >= nw ? heavy >> 5 : 0;
+    const int egf_left = n_egf - 32 * egf_chunks, heavy_left = heavy - 32 * heavy_chunks;
+    const int light_chunks = (nwork - coop_end + 31) >> 5;
+    const int u1 = egf_chunks, u2 = u1 + egf_left, u3 = u2 + heavy_chunks, u4 = u3 + heavy_left;
+    const int units = u4 + light_chunks;
     for (;;)
     {
         int u = 0;
@@ -209,15 +221,17 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
         const double *prow;
         int m;
         double log_r, log_1mr;
-        if (u < egf_units + coop_units)
+        const bool coop_egf = u >= u1 && u < u2, coop_ie = u >= u3 && u < u4;
+        if (coop_egf || coop_ie)
         {
-            const int cell = order[u];
+            const int cell = order[coop_egf ? 32 * egf_chunks + (u - u1)
+                                            : n_egf + 32 * heavy_chunks + (u - u3)];
             fetch(cell, lat, prow, m, log_r, log_1mr);
             const int k = __popcll(lat);
             double T;
             if (k > m)
                 T = NAN;
-            else if (u < egf_units)
+            else if (coop_egf)
                 T = transmission_ll_egf_coop(lat, prow, m, log_r, log_1mr, allow_rel, scr + warp * 32,
                                              ST, lgam);
             else
@@ -227,8 +241,23 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
         }
         else
         {
-            const int w = coop_end + 32 * (u - egf_units - coop_units) + lane;
-            if (w < nwork)
+            int w, end;
+            if (u < u1)
+            {
+                w = 32 * u + lane;
+                end = 32 * egf_chunks;
+            }
+            else if (u < u3)
+            {
+                w = n_egf + 32 * (u - u2) + lane;
+                end = n_egf + 32 * heavy_chunks;
+            }
+            else
+            {
+                w = coop_end + 32 * (u - u4) + lane;
+                end = nwork;
+            }
+            if (w < end)
             {
                 const int cell = order[w];
                 fetch(cell, lat, prow, m, log_r, log_1mr);
