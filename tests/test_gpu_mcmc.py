@@ -171,3 +171,42 @@ def test_namibia_data_runs_with_ten_temperatures():
     assert np.all(np.isfinite(ch["llik_burnin"])) and np.all(np.isfinite(ch["posterior_sample"]))
     assert ch["llik_burnin"][-1] > ch["llik_burnin"][0]              # burn-in climbs
     assert len(ch["coi"]) == 2585 and len(ch["allele_freqs"]) == 26 and len(ch["allele_freqs"][22][0]) == 35
+
+
+def test_acceptance_rates_and_adapted_scales_track_the_reference():
+    """The Metropolis machinery as a whole (proposal rules, validity checks, adaptation toward
+    0.23): after the same burn-in on the same data, the per-kind acceptance rates and the adapted
+    proposal scales of the engine's chain agree with the reference's own Chain (oracle/_ref, fp32)
+    -- two independent random streams, so the comparison is distributional (means over samples)."""
+    from oracle.pyoracle import Ref, ref_available
+    if not ref_available(32):
+        pytest.skip("oracle/_ref not built")
+    from moire_b200.data import pack_data
+    from moire_b200.engine import Engine
+    d = small_data(seed=5, N=120)
+    pk = pack_data(d["data"], d["is_missing"])
+    steps = 500
+    ref = Ref(32)
+    ref.set_data(pk.num_alleles, pk.obs_mask, pk.is_missing)
+    ref.set_params(burnin=steps)
+    h = ref.chain_new(1.0, seed=3)
+    for it in range(steps):
+        ref.chain_step(h, it)
+    racc, rsd = ref.chain_get_tuning(h)
+    ref.chain_free(h)
+    eng = Engine(pk, [1.0], seed=8, burnin=steps)
+    eng.init_chains()
+    for it in range(steps):
+        eng.step(it)
+    dg = eng.diagnostics(0)
+    eng.close()
+    names = ["eps_neg_accept", "eps_pos_accept", "m_accept", "r_accept", "m_r_accept", "sample_accept"]
+    for row, name in enumerate(names):
+        a, b = racc[row].mean() / steps, dg[name].mean() / steps
+        assert abs(a - b) < 0.04, (name, a, b)
+    for row, name in enumerate(["eps_neg_var", "eps_pos_var", "r_var", "m_r_var"]):
+        a, b = np.median(rsd[row]), np.median(dg[name])
+        assert abs(a - b) < 0.25 * max(a, b) + 0.02, (name, a, b)
+    # the adapted single-parameter updates sit near the 0.23 target on both sides
+    for row in (0, 1, 3):
+        assert 0.15 < dg[names[row]].mean() / steps < 0.35

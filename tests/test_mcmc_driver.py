@@ -217,3 +217,24 @@ def test_sharded_ladder_two_gloo_ranks_agree_with_one(tmp_path):
         assert np.array_equal(r0[k], v) and np.array_equal(r1[k], v), k
     assert np.array_equal(r0["hot"], hot) and np.array_equal(r1["hot"], hot)
     assert int(r0["draws"]) + int(r1["draws"]) == draws1
+
+
+def test_run_loop_progress_and_interrupt():
+    """The two loops of run_mcmc (src/main.cpp:52-93): the progress callback sees every step of
+    both phases; a non-zero return stops the run like Rcpp::checkUserInterrupt unwinding."""
+    from moire_b200.engine import MoireError
+    mc = ladder_only(3, burnin=6, samples=4)
+    assert mc.init()
+    seen = []
+    reached, minutes = mc.run(lambda phase, step, post, hot: seen.append((phase, step)) or False)
+    assert seen == [(0, s) for s in range(1, 7)] + [(1, s) for s in range(1, 5)]
+    assert reached is False and minutes == 0.0
+    s = mc.sizes()
+    assert (s["burnin_steps"], s["sample_steps"], s["num_swap_store"]) == (6, 4, 10)
+    mc.close()
+    mc = ladder_only(3, burnin=6, samples=4)
+    assert mc.init()
+    with pytest.raises(MoireError, match="interrupted"):
+        mc.run(lambda phase, step, post, hot: phase == 0 and step == 3)
+    assert mc.sizes()["burnin_steps"] == 3
+    mc.close()
