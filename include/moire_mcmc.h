@@ -78,6 +78,11 @@ moire_engine *moire_mcmc_engine(moire_mcmc *h);
  * ANY rank has no finite starting log-likelihood (MCMC::initialization_failed).  The per-attempt
  * failure records of this rank's chains are read with moire_engine_read_init_log. */
 int moire_mcmc_init(moire_mcmc *h, int32_t *failed);
+/* Per chain of THIS rank after moire_mcmc_init: number of ill-conditioned starts [local_chains]
+ * (InitializationDiagnostics::ill_conditioned_per_chain) and non-finite prior-term counts
+ * [local_chains][5] in the order eps_neg, eps_pos, relatedness, coi, mean_coi_hyper
+ * (collect_nonfinite_prior_terms, src/chain.cpp:1050-1081).  NULL = skip. */
+int moire_mcmc_get_init_counts(moire_mcmc *h, int32_t *ill_count, int32_t *prior_nonfinite);
 
 /* MCMC::burnin(step) / MCMC::sample(step) (src/mcmc.cpp:157-188, 306-355): every update on every
  * chain, traces, swap pass, ladder adaptation; sample() also stores the draw of the temp = 1

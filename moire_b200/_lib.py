@@ -69,6 +69,7 @@ MCMC_SYMBOLS = {
     "moire_mcmc_set_allgather": (C.c_int, [vp, ALLGATHER_FN, vp]),
     "moire_mcmc_engine": (vp, [vp]),
     "moire_mcmc_init": (C.c_int, [vp, C.POINTER(i32)]),
+    "moire_mcmc_get_init_counts": (C.c_int, [vp, vp, vp]),
     "moire_mcmc_burnin": (C.c_int, [vp, i32]),
     "moire_mcmc_sample": (C.c_int, [vp, i32]),
     "moire_mcmc_finalize": (C.c_int, [vp]),

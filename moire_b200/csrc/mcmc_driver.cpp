@@ -266,6 +266,7 @@ struct moire_mcmc
         mean_coi_store;
     std::vector<uint64_t> latent_store;
 
+    std::vector<int32_t> init_ill_count, init_prior_nonfinite;  // per local chain, [count] / [count][5]
     std::vector<double> send, recv;
     std::chrono::steady_clock::time_point t_start;
     double elapsed_minutes_rank0 = 0.0;
@@ -636,9 +637,12 @@ int moire_mcmc_init(moire_mcmc *h, int32_t *failed)
 {
     return guarded(h, [&] {
         std::vector<int32_t> still(h->count, 0);
+        h->init_ill_count.assign(h->count, 0);
+        h->init_prior_nonfinite.assign((size_t)5 * h->count, 0);
         if (h->engine)
-            h->ck(moire_engine_init_chains(h->engine, h->prm.max_initialization_tries, nullptr,
-                                           still.data(), nullptr, nullptr, nullptr),
+            h->ck(moire_engine_init_chains(h->engine, h->prm.max_initialization_tries,
+                                           h->init_ill_count.data(), still.data(), nullptr, nullptr,
+                                           h->init_prior_nonfinite.data()),
                   "init_chains");
         double bad = 0.0;
         for (int v : still) bad += v != 0;
@@ -659,6 +663,14 @@ int moire_mcmc_init(moire_mcmc *h, int32_t *failed)
         h->initialised = any == 0.0;
         h->t_start = std::chrono::steady_clock::now();
         if (h->initialised) h->exchange_scalars();
+    });
+}
+
+int moire_mcmc_get_init_counts(moire_mcmc *h, int32_t *ill_count, int32_t *prior_nonfinite)
+{
+    return guarded(h, [&] {
+        copy_out(h->init_ill_count, ill_count);
+        copy_out(h->init_prior_nonfinite, prior_nonfinite);
     });
 }
 

@@ -235,6 +235,12 @@ class MCMC:
         self._ck(self.lib.moire_mcmc_init(self._h, C.byref(failed)), "init")
         return not bool(failed.value)
 
+    def init_counts(self):
+        n = self.engine.T if self.engine is not None else 0
+        ill, pri = np.zeros(max(n, 1), np.int32), np.zeros((max(n, 1), 5), np.int32)
+        self._ck(self.lib.moire_mcmc_get_init_counts(self._h, _ptr(ill), _ptr(pri)), "init_counts")
+        return ill[:n], pri[:n]
+
     def init_log(self):
         n = C.c_int32()
         eh = self.engine._h
@@ -479,10 +485,8 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
             ok = mc.init()
             if not ok:
                 rec = [tuple(int(x) for x in r) for r in mc.init_log()]
-                # prior-term counts and per-chain retry counts come from a fresh read of the
-                # engine's last init (local chains); merged over ranks below
-                info = dict(records=rec, per_chain=np.bincount(
-                    [r[0] for r in rec], minlength=mc.engine.T).tolist())
+                ill, pri = mc.init_counts()          # this rank's chains; merged over ranks below
+                info = dict(records=rec, per_chain=ill.tolist(), prior=pri.sum(axis=0).tolist())
                 if world > 1:
                     import torch.distributed as dist
                     allinfo = [None] * world
@@ -491,7 +495,8 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
                     allinfo = [info]
                 records = [r for i in allinfo for r in i["records"]]
                 per_chain = [c for i in allinfo for c in i["per_chain"]]
-                diag = classify_initialization(records, {}, int(max_initialization_tries),
+                prior = dict(zip(PRIOR_TERMS, np.sum([i["prior"] for i in allinfo], axis=0).tolist()))
+                diag = classify_initialization(records, prior, int(max_initialization_tries),
                                                len(ladder), per_chain)
                 raise InitializationFailure(
                     format_initialization_failure_message(diag, sample_ids, loci), diag)
