@@ -15,6 +15,7 @@
 
 #include "../../include/moire_engine.h"
 #include "kernels.cuh"
+#include "p_flat.cuh"
 
 namespace
 {
@@ -148,6 +149,14 @@ struct moire_engine
 
     // allocations
     DevBuf<unsigned long long> obs, latent, evals, trace;
+    // flat update_p pipeline (p_flat.cuh)
+    moire::PFlat pf{};
+    DevBuf<uint4> pf_list;
+    DevBuf<unsigned int> pf_hist;
+    DevBuf<double> pf_Tcur, pf_Tnew, pf_pprop, pf_round;
+    DevBuf<int> pf_nonmiss;
+    int amax_alleles = 0;
+    bool p_fused = false;
     DevBuf<unsigned char> missing;
     DevBuf<int> nall, aclass, avals, obs_coi, m, acc6, p_acc, p_att, active;
     DevBuf<double> logC, lgam, lgadj, cellT, cellO, persample, p, p_sd, perchain, scratchN;
@@ -174,6 +183,8 @@ struct moire_engine
         obs.release(); latent.release(); evals.release(); missing.release(); nall.release();
         aclass.release(); avals.release(); obs_coi.release(); m.release(); acc6.release();
         p_acc.release(); p_att.release(); active.release(); logC.release(); lgam.release();
+        pf_list.release(); pf_hist.release(); pf_Tcur.release(); pf_Tnew.release(); pf_pprop.release();
+        pf_round.release(); pf_nonmiss.release();
         lgadj.release(); cellT.release(); cellO.release(); persample.release(); p.release();
         p_sd.release(); perchain.release(); scratchN.release();
         if (v.trace && std::getenv("MOIRE_B200_TRACE"))
@@ -331,6 +342,25 @@ struct moire_engine
         sample_smem_o = moire::sample_kernel_smem(tile_S, L, v.nA, false);
         p_threads = moire::p_kernel_threads(N);
         p_smem = moire::p_kernel_smem(N, v.AP, p_threads);
+        // update_p: the flat pipeline unless MOIRE_B200_P_FUSED is set (A/B runs) or the cell
+        // index does not fit 32 bits
+        amax_alleles = amax;
+        // ... or the problem is tiny (the flat pipeline is 2 A_max + 6 launches; below ~10^5 cells
+        // they cost more than the fused kernel's barriers)
+        p_fused = std::getenv("MOIRE_B200_P_FUSED") != nullptr || TNL >= (1ull << 32) || TNL < 100000;
+        if (!p_fused)
+        {
+            pf_list.alloc(TNL); pf_hist.alloc(2 * moire::kSortBins + 8);
+            pf_Tcur.alloc(TNL); pf_Tnew.alloc(TNL);
+            pf_pprop.alloc(TLA); pf_round.alloc((size_t)T * L * 4); pf_nonmiss.alloc(L);
+            std::vector<int> nm(L, 0);
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < L; ++j) nm[j] += d->is_missing[(size_t)i * L + j] == 0;
+            pf_nonmiss.upload(nm.data(), L, stream);
+            pf.list = pf_list.ptr; pf.hist = pf_hist.ptr; pf.Tcur = pf_Tcur.ptr; pf.Tnew = pf_Tnew.ptr;
+            pf.pprop = pf_pprop.ptr; pf.round = pf_round.ptr; pf.nonmiss = pf_nonmiss.ptr;
+            p_smem = 0;  // the fused kernel's per-block arrays are not needed
+        }
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, device));
         const size_t smem_cap = prop.sharedMemPerBlockOptin;
@@ -351,8 +381,12 @@ struct moire_engine
         CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
         CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EFF_COI>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
         CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_SAMPLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
-        CUDA_TRY(cudaFuncSetAttribute(k_update_p<MOIRE_P_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_update_p<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
+        if (p_fused)
+        {
+            CUDA_TRY(cudaFuncSetAttribute(k_update_p<MOIRE_P_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
+            CUDA_TRY(cudaFuncSetAttribute(k_update_p<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
+        }
+        CUDA_TRY(cudaFuncSetAttribute(k_pf_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
     }
 
     struct Timed
@@ -397,6 +431,41 @@ struct moire_engine
         pending.clear();
     }
 
+    static size_t pf_eval_smem() { return (128 + moire::scratch_doubles(256)) * sizeof(double); }
+
+    // update_p as sort-once + (round, eval) per proposal (p_flat.cuh)
+    void update_p_flat(int iteration)
+    {
+        using namespace moire;
+        const size_t total = (size_t)v.T * v.L * v.N;
+        const unsigned cell_blocks = (unsigned)((total + 255) / 256);
+        CUDA_TRY(cudaMemsetAsync(pf.hist, 0, (2 * kSortBins + 8) * sizeof(unsigned int), stream));
+        k_pf_prepare<<<cell_blocks, 256, 0, stream>>>(v, pf);
+        k_pf_scan<<<1, 256, 0, stream>>>(pf);
+        k_pf_scatter<<<cell_blocks, 256, 0, stream>>>(v, pf);
+        unsigned int sc[3];
+        CUDA_TRY(cudaMemcpyAsync(sc, pf.hist + kPfScalars, sizeof(sc), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        const int n_egf = (int)sc[0], coop_end = (int)sc[1], nwork = (int)sc[2];
+        // heavy cells one per thread only where they are a large share of the work (high-COI
+        // shapes); otherwise a chunk of 1023-subset cells would outlast the whole round
+        const int chunked = (size_t)coop_end * 4 > (size_t)nwork ? 1 : 0;
+        const int blocks = pf_blocks(n_egf, chunked, false) + pf_blocks(coop_end - n_egf, chunked, false) +
+                           pf_blocks(nwork - coop_end, true, true);
+        launches += 4;
+        for (int rep = 0; rep < amax_alleles; ++rep)
+        {
+            k_pf_round<<<v.T * v.L, 256, 0, stream>>>(v, pf, iteration, rep);
+            if (blocks > 0)
+                k_pf_eval<<<blocks, 256, pf_eval_smem(), stream>>>(v, pf, n_egf, coop_end, nwork, chunked);
+            launches += 2;
+        }
+        k_pf_round<<<v.T * v.L, 256, 0, stream>>>(v, pf, iteration, amax_alleles);
+        k_pf_finish<<<cell_blocks, 256, 0, stream>>>(v, pf);
+        launches += 2;
+        CUDA_TRY(cudaGetLastError());
+    }
+
     template <int KIND>
     void launch_sample(int iteration)
     {
@@ -421,7 +490,9 @@ struct moire_engine
             case MOIRE_UPDATE_P:
             {
                 Timed tm(this, kind);
-                if (p_threads == MOIRE_P_THREADS)
+                if (!p_fused)
+                    update_p_flat(iteration);
+                else if (p_threads == MOIRE_P_THREADS)
                     k_update_p<MOIRE_P_THREADS><<<v.T * v.L, MOIRE_P_THREADS, p_smem, stream>>>(v, iteration);
                 else
                     k_update_p<512><<<v.T * v.L, 512, p_smem, stream>>>(v, iteration);

@@ -1,0 +1,356 @@
+// update_p as a flat pipeline (src/chain.cpp:466-565).
+//
+// The fused kernel (k_update_p, kernels.cuh) keeps a (chain, locus) in one block for all A_j
+// proposals.  ncu and a per-warp trace showed what that costs on B200: 38 % of warp time at the
+// barrier after the evaluation (a block's few 63..255-subset cells gate it), 18.7 of 32 lanes per
+// instruction (1000 cells per block are too few to sort into uniform warps) and a 10 K-instruction
+// kernel on an instruction-fetch-bound path (profiles/README.md).  Here the work is cut the other
+// way: the latent genotypes do not change during update_p, so ALL cells of ALL chains are sorted
+// ONCE by cost class (device-wide counting sort), and every proposal round is
+//   k_pf_round  one block per (chain, locus): decide the previous proposal in sample order,
+//               commit, draw the next SALT proposal                       (tiny, serial math)
+//   k_pf_eval   a flat grid over the sorted cell list: warps with identical (k, m - k + 1) in
+//               every lane, no block barrier, only the evaluator's code   (all the arithmetic)
+// Rounds = max_j A_j; loci with fewer alleles (or that hit the 1e-12 floor) sit out.  Streams,
+// proposals, per-cell arithmetic and the order of every sum are those of the fused kernel, so the
+// two produce the same chain.
+#pragma once
+#include "kernels.cuh"
+
+namespace moire
+{
+struct PFlat
+{
+    uint4 *list;         // [cells] {cell in [T][N][L], t * L + j, t * N + i, (t * L + j) * N + i}
+    unsigned int *hist;  // [kSortBins] counts, then [kSortBins] running offsets, then 4 scalars
+    double *Tcur, *Tnew; // [T][L][N] transmission terms, locus-major, for the duration of the update
+    double *pprop;       // [T * L][AP] proposed frequencies
+    double *round;       // [T * L][4] logAdj, log u, allele index, flags
+    const int *nonmiss;  // [L] non-missing cells of a locus
+};
+constexpr unsigned kPfActive = 1u, kPfBroken = 2u;
+constexpr int kPfScalars = 2 * kSortBins;  // hist[kPfScalars + 0..2] = n_egf, coop_end, nwork
+
+// ---- once per update: locus-major copy of the current terms, class histogram, sorted list -----
+__global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
+{
+    __shared__ unsigned int s_hist[kSortBins];
+    for (int b = threadIdx.x; b < kSortBins; b += blockDim.x) s_hist[b] = 0;
+    __syncthreads();
+    const size_t total = (size_t)v.T * v.L * v.N;
+    const size_t loc = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (loc < total)
+    {
+        const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
+        const unsigned t = tl / v.L, j = tl - t * v.L;
+        const size_t cell = ((size_t)t * v.N + i) * v.L + j;
+        f.Tcur[loc] = v.cellT[cell];
+        if (v.missing[(size_t)i * v.L + j] == 0)
+            atomicAdd(&s_hist[work_class(__popcll(v.latent[cell]), v.m[(size_t)t * v.N + i])], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kSortBins; b += blockDim.x)
+        if (s_hist[b]) atomicAdd(&f.hist[b], s_hist[b]);
+}
+
+__global__ void __launch_bounds__(256) k_pf_scan(const PFlat f)
+{
+    __shared__ unsigned int s_part[9];
+    const int tid = threadIdx.x;
+    constexpr int per = kSortBins / 256;  // 3
+    unsigned int local = 0, h[per];
+    for (int q = 0; q < per; ++q)
+    {
+        h[q] = f.hist[tid * per + q];
+        local += h[q];
+    }
+    unsigned int x = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((tid & 31) >= o) x += y;
+    }
+    if ((tid & 31) == 31) s_part[tid >> 5] = x;
+    __syncthreads();
+    if (tid == 0)
+    {
+        unsigned int run = 0;
+        for (int w = 0; w < 8; ++w)
+        {
+            const unsigned int c = s_part[w];
+            s_part[w] = run;
+            run += c;
+        }
+        s_part[8] = run;
+    }
+    __syncthreads();
+    unsigned int base = s_part[tid >> 5] + x - local;
+    for (int q = 0; q < per; ++q)
+    {
+        const int b = tid * per + q;
+        f.hist[kSortBins + b] = base;
+        if (b == kClassCoopBegin) f.hist[kPfScalars + 0] = base;
+        if (b == kClassLightBegin) f.hist[kPfScalars + 1] = base;
+        base += h[q];
+    }
+    if (tid == 0) f.hist[kPfScalars + 2] = s_part[8];
+}
+
+__global__ void __launch_bounds__(256) k_pf_scatter(const View v, const PFlat f)
+{
+    const size_t total = (size_t)v.T * v.L * v.N;
+    const size_t loc = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (loc >= total) return;
+    const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
+    const unsigned t = tl / v.L, j = tl - t * v.L;
+    if (v.missing[(size_t)i * v.L + j] != 0) return;
+    const size_t cell = ((size_t)t * v.N + i) * v.L + j;
+    const unsigned tn = t * v.N + i;
+    const int cls = work_class(__popcll(v.latent[cell]), v.m[tn]);
+    const unsigned pos = atomicAdd(&f.hist[kSortBins + cls], 1u);
+    f.list[pos] = make_uint4((unsigned)cell, tl, tn, (unsigned)loc);
+}
+
+// ---- once per proposal round: decide the previous proposal, draw the next ----------------------
+__global__ void __launch_bounds__(256) k_pf_round(const View v, const PFlat f, const int iteration,
+                                                  const int rep)
+{
+    __shared__ double s_red[40];
+    const int N = v.N, L = v.L, AP = v.AP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tl = blockIdx.x, t = tl / L, j = tl - t * L;
+    const int A = v.nall[j];
+    const size_t prow = (size_t)tl * AP;
+    double *st = f.round + (size_t)tl * 4;
+    unsigned flags = rep == 0 ? 0u : (unsigned)st[3];
+
+    if (flags & kPfActive)
+    {
+        // -- the change of the locus' log-likelihood under proposal rep - 1, summed in sample order
+        double dsum = 0.0;
+        const size_t base = (size_t)tl * N;
+        for (int i = tid; i < N; i += 256)
+            if (v.missing[(size_t)i * L + j] == 0) dsum += f.Tnew[base + i] - f.Tcur[base + i];
+        const double d = block_sum(dsum, s_red);
+        if (tid == 0)
+        {
+            const int idx = (int)st[2];
+            const double dpost = v.temp[t] * d;  // the priors do not depend on p
+            const double ratio = dpost + st[0];
+            const bool accept = !(isnan(dpost) || st[1] > ratio);
+            if (accept) ++v.p_acc[prow + idx];
+            if (iteration < v.burnin && v.p_att[prow + idx] > 15)
+            {
+                // src/chain.cpp:555-562
+                const double att = (double)v.p_att[prow + idx];
+                const double rate = ((double)v.p_acc[prow + idx] + 1.0) / (att + 1.0);
+                const double sd = v.p_sd[prow + idx] + (rate - .23) / sqrt(att + 1.0);
+                v.p_sd[prow + idx] = sd > .01 ? sd : .01;
+            }
+            s_red[35] = accept ? 1.0 : 0.0;
+            atomicAdd(v.evals + KIND_P, (unsigned long long)f.nonmiss[j]);
+        }
+        __syncthreads();
+        if (s_red[35] != 0.0)
+        {
+            for (int i = tid; i < N; i += 256)
+                if (v.missing[(size_t)i * L + j] == 0) f.Tcur[base + i] = f.Tnew[base + i];
+            for (int a = tid; a < A; a += 256) v.p[prow + a] = f.pprop[prow + a];
+        }
+        __syncthreads();
+    }
+    flags &= ~kPfActive;
+    if (rep >= A || (flags & kPfBroken))
+    {
+        if (tid == 0) st[3] = (double)flags;
+        return;
+    }
+    // -- proposal `rep`, warp 0, lanes across alleles (same arithmetic as k_update_p)
+    if (warp == 0)
+    {
+        Stream rng;
+        rng.open(v.seed, (uint32_t)iteration, KIND_P, (unsigned)(v.chain_offset + t), (uint32_t)j,
+                 (uint32_t)rep);
+        const int idx = (int)mulhi32(rng.next_u32(), (uint32_t)A);
+        const double z = next_normal(rng);
+        const double logu = cold_log(rng.next_uniform());
+        double lg[2], lp[2], lq[2];
+        bool rest[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+        {
+            const int a = lane + 32 * s;
+            const bool has = a < A;
+            lg[s] = has ? logit_d(v.p[prow + a]) : 0.0;
+            lp[s] = lq[s] = 0.0;
+            if (has) log_pq_d(lg[s], lp[s], lq[s]);
+            rest[s] = has && a != idx;
+        }
+        const double lg_sel = (idx >> 5) ? lg[1] : lg[0];
+        const double logit_curr = __shfl_sync(0xffffffffu, lg_sel, idx & 31);
+        const double logit_prop = logit_curr + v.p_sd[prow + idx] * z;
+        double clp, clq, plp, plq;
+        log_pq_d(logit_curr, clp, clq);
+        log_pq_d(logit_prop, plp, plq);
+        double bv = -INFINITY;
+        int ba = 1 << 30;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+            if (rest[s] && (lg[s] > bv)) { bv = lg[s]; ba = lane + 32 * s; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, ba, o);
+            if (ov > bv || (ov == bv && oa < ba)) { bv = ov; ba = oa; }
+        }
+        const double lp_sel = (ba >> 5) ? lp[1] : lp[0];
+        const double lq_sel = (ba >> 5) ? lq[1] : lq[0];
+        const double lp1 = __shfl_sync(0xffffffffu, lp_sel, ba & 31);
+        const double lq1 = __shfl_sync(0xffffffffu, lq_sel, ba & 31);
+        double cum = 0.0;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+            if (rest[s] && (lane + 32 * s) != ba) cum += (bv < 0.0) ? cold_exp(lp[s] - lp1) : cold_exp(lp[s]);
+        cum = warp_sum(cum);
+        const double lsum = (bv < 0.0) ? lp1 + cold_log1p(cum) : cold_log1p(-cold_exp(lq1) + cum);
+        const double ls = plq - lsum;
+        bool below = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+        {
+            const int a = lane + 32 * s;
+            if (a < A)
+            {
+                const double np = expit_d(a == idx ? logit_prop : logit_scale_d(lg[s], ls));
+                f.pprop[prow + a] = np;
+                below |= np < 1e-12;
+            }
+        }
+        below = __any_sync(0xffffffffu, below);
+        if (lane == 0)
+        {
+            ++v.p_att[prow + idx];
+            st[0] = (clp - plp) + (double)(A - 1) * (clq - plq);
+            st[1] = logu;
+            st[2] = (double)idx;
+            st[3] = (double)(below ? (flags | kPfBroken) : (flags | kPfActive));  // :503-518
+        }
+    }
+}
+
+// ---- once per proposal round: every cell of every active locus, from the sorted list ----------
+// Sections of the list: [0, n_egf) k > 10, [n_egf, coop_end) kCoopMinK <= k <= 10, the rest light.
+// A block takes a few consecutive units of the list -- cooperative cells or chunks of 32
+// one-thread cells of (nearly) one cost class; the hardware block scheduler does the load
+// balancing, heaviest blocks first.  `chunked_heavy`: the heavy sections go one cell
+// per thread too (set by the host where they hold a large share of all cells).
+// Units per block: one per warp for cooperative cells and for chunks of heavy cells (each is
+// long: up to 1023 subsets), two light chunks per warp.
+#ifndef MOIRE_PF_LIGHT_UPB
+#define MOIRE_PF_LIGHT_UPB 16
+#endif
+#ifndef MOIRE_PF_MIN_BLOCKS
+#define MOIRE_PF_MIN_BLOCKS 3
+#endif
+__host__ __device__ inline int pf_units_per_block(bool light) { return light ? MOIRE_PF_LIGHT_UPB : 8; }
+__host__ __device__ inline int pf_blocks(int cells, bool chunked, bool light)
+{
+    const int units = chunked ? (cells + 31) / 32 : cells;
+    const int upb = pf_units_per_block(light);
+    return (units + upb - 1) / upb;
+}
+
+__global__ void __launch_bounds__(256, MOIRE_PF_MIN_BLOCKS)
+    k_pf_eval(const View v, const PFlat f, const int n_egf, const int coop_end, const int nwork,
+              const int chunked_heavy)
+{
+    extern __shared__ double smem[];
+    double *s_lgam = smem;
+    double *s_scr = smem + 128;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int ST = 256 + 1;
+    for (int i = tid; i < 128; i += 256) s_lgam[i] = v.lgam[i];
+    __syncthreads();
+    const bool allow_rel = v.allow_rel != 0;
+    const int b_egf = pf_blocks(n_egf, chunked_heavy, false);
+    const int b_heavy = pf_blocks(coop_end - n_egf, chunked_heavy, false);
+    int b = blockIdx.x, lo, hi;
+    bool coop, egf = false, light = false;
+    if (b < b_egf)
+    {
+        lo = 0;
+        hi = n_egf;
+        coop = !chunked_heavy;
+        egf = true;
+    }
+    else if (b < b_egf + b_heavy)
+    {
+        b -= b_egf;
+        lo = n_egf;
+        hi = coop_end;
+        coop = !chunked_heavy;
+    }
+    else
+    {
+        b -= b_egf + b_heavy;
+        lo = coop_end;
+        hi = nwork;
+        coop = false;
+        light = true;
+    }
+    const int upb = pf_units_per_block(light);
+    for (int u = warp; u < upb; u += 8)
+    {
+        const int unit = b * upb + u;
+        if (coop)
+        {
+            const int w = lo + unit;
+            if (w >= hi) break;
+            const uint4 e = f.list[w];
+            if (((unsigned)f.round[(size_t)e.y * 4 + 3] & kPfActive) == 0) continue;
+            const unsigned long long lat = v.latent[e.x];
+            const int m = v.m[e.z], k = __popcll(lat);
+            const double *prow = f.pprop + (size_t)e.y * v.AP;
+            double T;
+            if (k > m)
+                T = NAN;
+            else if (egf)
+                T = transmission_ll_egf_coop(lat, prow, m, v.log_r[e.z], v.log_1mr[e.z], allow_rel,
+                                             s_scr + warp * 32, ST, s_lgam);
+            else
+                T = transmission_ll_coop(lat, prow, m, v.log_r[e.z], v.log_1mr[e.z], allow_rel,
+                                         s_scr + warp * 32, ST, s_lgam);
+            if (lane == 0) f.Tnew[e.w] = T;
+            __syncwarp();
+        }
+        else
+        {
+            const int w0 = lo + unit * 32;
+            if (w0 >= hi) break;
+            const int w = w0 + lane;
+            if (w < hi)
+            {
+                const uint4 e = f.list[w];
+                if ((unsigned)f.round[(size_t)e.y * 4 + 3] & kPfActive)
+                    f.Tnew[e.w] = transmission_ll(v.latent[e.x], f.pprop + (size_t)e.y * v.AP, v.m[e.z],
+                                                  v.log_r[e.z], v.log_1mr[e.z], allow_rel, s_scr + tid,
+                                                  ST, s_lgam);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---- once per update: the accepted terms back into the sample-major cache -----------------------
+__global__ void __launch_bounds__(256) k_pf_finish(const View v, const PFlat f)
+{
+    const size_t total = (size_t)v.T * v.L * v.N;
+    const size_t loc = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (loc >= total) return;
+    const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
+    const unsigned t = tl / v.L, j = tl - t * v.L;
+    if (v.missing[(size_t)i * v.L + j] == 0) v.cellT[((size_t)t * v.N + i) * v.L + j] = f.Tcur[loc];
+}
+}  // namespace moire
