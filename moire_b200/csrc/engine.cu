@@ -350,7 +350,7 @@ struct moire_engine
         p_fused = std::getenv("MOIRE_B200_P_FUSED") != nullptr || TNL >= (1ull << 32) || TNL < 100000;
         if (!p_fused)
         {
-            pf_list.alloc(TNL); pf_hist.alloc(2 * moire::kSortBins + 8);
+            pf_list.alloc(TNL); pf_hist.alloc(moire::kPfHistWords);
             pf_Tcur.alloc(TNL); pf_Tnew.alloc(TNL);
             pf_pprop.alloc(TLA); pf_round.alloc((size_t)T * L * 4); pf_nonmiss.alloc(L);
             std::vector<int> nm(L, 0);
@@ -386,7 +386,14 @@ struct moire_engine
             CUDA_TRY(cudaFuncSetAttribute(k_update_p<MOIRE_P_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
             CUDA_TRY(cudaFuncSetAttribute(k_update_p<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
         }
-        CUDA_TRY(cudaFuncSetAttribute(k_pf_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
+        CUDA_TRY(cudaFuncSetAttribute(k_flat_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
+        {
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flat_eval, 256, pf_eval_smem()));
+            cudaDeviceProp prop1;
+            CUDA_TRY(cudaGetDeviceProperties(&prop1, device));
+            flat_grid = std::max(1, per_sm) * prop1.multiProcessorCount;
+        }
     }
 
     struct Timed
@@ -432,32 +439,29 @@ struct moire_engine
     }
 
     static size_t pf_eval_smem() { return (128 + moire::scratch_doubles(256)) * sizeof(double); }
+    int flat_grid = 0;  // persistent evaluator grid: resident blocks of the device
 
-    // update_p as sort-once + (round, eval) per proposal (p_flat.cuh)
+    // update_p as sort-once + (round, eval) per proposal (p_flat.cuh); nothing returns to the host
     void update_p_flat(int iteration)
     {
         using namespace moire;
         const size_t total = (size_t)v.T * v.L * v.N;
         const unsigned cell_blocks = (unsigned)((total + 255) / 256);
-        CUDA_TRY(cudaMemsetAsync(pf.hist, 0, (2 * kSortBins + 8) * sizeof(unsigned int), stream));
+        CUDA_TRY(cudaMemsetAsync(pf.hist, 0, kPfHistWords * sizeof(unsigned int), stream));
         k_pf_prepare<<<cell_blocks, 256, 0, stream>>>(v, pf);
         k_pf_scan<<<1, 256, 0, stream>>>(pf);
         k_pf_scatter<<<cell_blocks, 256, 0, stream>>>(v, pf);
-        unsigned int sc[3];
-        CUDA_TRY(cudaMemcpyAsync(sc, pf.hist + kPfScalars, sizeof(sc), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        const int n_egf = (int)sc[0], coop_end = (int)sc[1], nwork = (int)sc[2];
-        // heavy cells one per thread only where they are a large share of the work (high-COI
-        // shapes); otherwise a chunk of 1023-subset cells would outlast the whole round
-        const int chunked = (size_t)coop_end * 4 > (size_t)nwork ? 1 : 0;
-        const int blocks = pf_blocks(n_egf, chunked, false) + pf_blocks(coop_end - n_egf, chunked, false) +
-                           pf_blocks(nwork - coop_end, true, true);
+        FlatSrc src{};
+        src.list = pf.list; src.bounds = pf.hist + kPfScalars;
+        src.latent = v.latent; src.p = pf.pprop; src.p_stride = v.AP;
+        src.m = v.m; src.log_r = v.log_r; src.log_1mr = v.log_1mr;
+        src.round_flags = pf.round; src.out = pf.Tnew;
         launches += 4;
         for (int rep = 0; rep < amax_alleles; ++rep)
         {
             k_pf_round<<<v.T * v.L, 256, 0, stream>>>(v, pf, iteration, rep);
-            if (blocks > 0)
-                k_pf_eval<<<blocks, 256, pf_eval_smem(), stream>>>(v, pf, n_egf, coop_end, nwork, chunked);
+            src.counter = pf.hist + kPfCounters + rep;
+            k_flat_eval<<<flat_grid, 256, pf_eval_smem(), stream>>>(v, src);
             launches += 2;
         }
         k_pf_round<<<v.T * v.L, 256, 0, stream>>>(v, pf, iteration, amax_alleles);

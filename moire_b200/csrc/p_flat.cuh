@@ -9,7 +9,7 @@
 // ONCE by cost class (device-wide counting sort), and every proposal round is
 //   k_pf_round  one block per (chain, locus): decide the previous proposal in sample order,
 //               commit, draw the next SALT proposal                       (tiny, serial math)
-//   k_pf_eval   a flat grid over the sorted cell list: warps with identical (k, m - k + 1) in
+//   k_flat_eval a persistent grid over the sorted cell list: warps with identical (k, m - k + 1) in
 //               every lane, no block barrier, only the evaluator's code   (all the arithmetic)
 // Rounds = max_j A_j; loci with fewer alleles (or that hit the 1e-12 floor) sit out.  Streams,
 // proposals, per-cell arithmetic and the order of every sum are those of the fused kernel, so the
@@ -22,7 +22,7 @@ namespace moire
 struct PFlat
 {
     uint4 *list;         // [cells] {cell in [T][N][L], t * L + j, t * N + i, (t * L + j) * N + i}
-    unsigned int *hist;  // [kSortBins] counts, then [kSortBins] running offsets, then 4 scalars
+    unsigned int *hist;  // [kSortBins] counts, [kSortBins] running offsets, 4 scalars, task counters
     double *Tcur, *Tnew; // [T][L][N] transmission terms, locus-major, for the duration of the update
     double *pprop;       // [T * L][AP] proposed frequencies
     double *round;       // [T * L][4] logAdj, log u, allele index, flags
@@ -30,6 +30,8 @@ struct PFlat
 };
 constexpr unsigned kPfActive = 1u, kPfBroken = 2u;
 constexpr int kPfScalars = 2 * kSortBins;  // hist[kPfScalars + 0..2] = n_egf, coop_end, nwork
+constexpr int kPfCounters = kPfScalars + 4;  // one task counter per evaluator launch of an update
+constexpr int kPfHistWords = kPfCounters + 72;
 
 // ---- once per update: locus-major copy of the current terms, class histogram, sorted list -----
 __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
@@ -240,105 +242,130 @@ __global__ void __launch_bounds__(256) k_pf_round(const View v, const PFlat f, c
     }
 }
 
-// ---- once per proposal round: every cell of every active locus, from the sorted list ----------
+// ---- the flat evaluator: every listed cell, from the sorted list ---------------------------------
 // Sections of the list: [0, n_egf) k > 10, [n_egf, coop_end) kCoopMinK <= k <= 10, the rest light.
-// A block takes a few consecutive units of the list -- cooperative cells or chunks of 32
-// one-thread cells of (nearly) one cost class; the hardware block scheduler does the load
-// balancing, heaviest blocks first.  `chunked_heavy`: the heavy sections go one cell
-// per thread too (set by the host where they hold a large share of all cells).
-// Units per block: one per warp for cooperative cells and for chunks of heavy cells (each is
-// long: up to 1023 subsets), two light chunks per warp.
+// A task is a few consecutive units of the list -- cooperative cells or chunks of 32 one-thread
+// cells of (nearly) one cost class.  The grid is persistent (a few blocks per SM); blocks draw
+// tasks from a device counter, heaviest first, so the section sizes never travel to the host.
+// Heavy sections go one cell per thread too where they hold a large share of all cells (high-COI
+// shapes); otherwise a chunk of 1023-subset cells would outlast everything else.
+struct FlatSrc
+{
+    const uint4 *list;                  // {latent index, p-row index, sample index, output index}
+    const unsigned int *bounds;         // [3] n_egf, coop_end, nwork
+    unsigned int *counter;              // task counter, zero at launch
+    const unsigned long long *latent;   // [list.x]
+    const double *p;                    // row list.y, p_stride doubles apart
+    int p_stride;
+    const int *m;                       // [list.z]
+    const double *log_r, *log_1mr;      // [list.z]
+    const double *round_flags;          // null, or [list.y * 4 + 3] & kPfActive says "evaluate"
+    double *out;                        // [list.w]
+};
+
 #ifndef MOIRE_PF_LIGHT_UPB
-#define MOIRE_PF_LIGHT_UPB 16
+#define MOIRE_PF_LIGHT_UPB 8
 #endif
 #ifndef MOIRE_PF_MIN_BLOCKS
-#define MOIRE_PF_MIN_BLOCKS 3
+#define MOIRE_PF_MIN_BLOCKS 4
 #endif
-__host__ __device__ inline int pf_units_per_block(bool light) { return light ? MOIRE_PF_LIGHT_UPB : 8; }
-__host__ __device__ inline int pf_blocks(int cells, bool chunked, bool light)
+// Units per task: one per warp for cooperative cells and for chunks of heavy cells (each is long:
+// up to 1023 subsets), MOIRE_PF_LIGHT_UPB / 8 light chunks per warp.
+__host__ __device__ inline int pf_units_per_task(bool light) { return light ? MOIRE_PF_LIGHT_UPB : 8; }
+__host__ __device__ inline int pf_tasks(int cells, bool chunked, bool light)
 {
     const int units = chunked ? (cells + 31) / 32 : cells;
-    const int upb = pf_units_per_block(light);
+    const int upb = pf_units_per_task(light);
     return (units + upb - 1) / upb;
 }
 
-__global__ void __launch_bounds__(256, MOIRE_PF_MIN_BLOCKS)
-    k_pf_eval(const View v, const PFlat f, const int n_egf, const int coop_end, const int nwork,
-              const int chunked_heavy)
+__global__ void __launch_bounds__(256, MOIRE_PF_MIN_BLOCKS) k_flat_eval(const View v, const FlatSrc f)
 {
     extern __shared__ double smem[];
     double *s_lgam = smem;
     double *s_scr = smem + 128;
+    __shared__ int s_task;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int ST = 256 + 1;
     for (int i = tid; i < 128; i += 256) s_lgam[i] = v.lgam[i];
-    __syncthreads();
     const bool allow_rel = v.allow_rel != 0;
-    const int b_egf = pf_blocks(n_egf, chunked_heavy, false);
-    const int b_heavy = pf_blocks(coop_end - n_egf, chunked_heavy, false);
-    int b = blockIdx.x, lo, hi;
-    bool coop, egf = false, light = false;
-    if (b < b_egf)
+    const int n_egf = (int)f.bounds[0], coop_end = (int)f.bounds[1], nwork = (int)f.bounds[2];
+    const bool chunked_heavy = (size_t)coop_end * 4 > (size_t)nwork;
+    const int t_egf = pf_tasks(n_egf, chunked_heavy, false);
+    const int t_heavy = pf_tasks(coop_end - n_egf, chunked_heavy, false);
+    const int tasks = t_egf + t_heavy + pf_tasks(nwork - coop_end, true, true);
+    for (;;)
     {
-        lo = 0;
-        hi = n_egf;
-        coop = !chunked_heavy;
-        egf = true;
-    }
-    else if (b < b_egf + b_heavy)
-    {
-        b -= b_egf;
-        lo = n_egf;
-        hi = coop_end;
-        coop = !chunked_heavy;
-    }
-    else
-    {
-        b -= b_egf + b_heavy;
-        lo = coop_end;
-        hi = nwork;
-        coop = false;
-        light = true;
-    }
-    const int upb = pf_units_per_block(light);
-    for (int u = warp; u < upb; u += 8)
-    {
-        const int unit = b * upb + u;
-        if (coop)
+        __syncthreads();
+        if (tid == 0) s_task = (int)atomicAdd(f.counter, 1u);
+        __syncthreads();
+        int b = s_task;
+        if (b >= tasks) break;
+        int lo, hi;
+        bool coop, egf = false, light = false;
+        if (b < t_egf)
         {
-            const int w = lo + unit;
-            if (w >= hi) break;
-            const uint4 e = f.list[w];
-            if (((unsigned)f.round[(size_t)e.y * 4 + 3] & kPfActive) == 0) continue;
-            const unsigned long long lat = v.latent[e.x];
-            const int m = v.m[e.z], k = __popcll(lat);
-            const double *prow = f.pprop + (size_t)e.y * v.AP;
-            double T;
-            if (k > m)
-                T = NAN;
-            else if (egf)
-                T = transmission_ll_egf_coop(lat, prow, m, v.log_r[e.z], v.log_1mr[e.z], allow_rel,
-                                             s_scr + warp * 32, ST, s_lgam);
-            else
-                T = transmission_ll_coop(lat, prow, m, v.log_r[e.z], v.log_1mr[e.z], allow_rel,
-                                         s_scr + warp * 32, ST, s_lgam);
-            if (lane == 0) f.Tnew[e.w] = T;
-            __syncwarp();
+            lo = 0;
+            hi = n_egf;
+            coop = !chunked_heavy;
+            egf = true;
+        }
+        else if (b < t_egf + t_heavy)
+        {
+            b -= t_egf;
+            lo = n_egf;
+            hi = coop_end;
+            coop = !chunked_heavy;
         }
         else
         {
-            const int w0 = lo + unit * 32;
-            if (w0 >= hi) break;
-            const int w = w0 + lane;
-            if (w < hi)
+            b -= t_egf + t_heavy;
+            lo = coop_end;
+            hi = nwork;
+            coop = false;
+            light = true;
+        }
+        const int upb = pf_units_per_task(light);
+        for (int u = warp; u < upb; u += 8)
+        {
+            const int unit = b * upb + u;
+            if (coop)
             {
+                const int w = lo + unit;
+                if (w >= hi) break;
                 const uint4 e = f.list[w];
-                if ((unsigned)f.round[(size_t)e.y * 4 + 3] & kPfActive)
-                    f.Tnew[e.w] = transmission_ll(v.latent[e.x], f.pprop + (size_t)e.y * v.AP, v.m[e.z],
-                                                  v.log_r[e.z], v.log_1mr[e.z], allow_rel, s_scr + tid,
-                                                  ST, s_lgam);
+                if (f.round_flags && ((unsigned)f.round_flags[(size_t)e.y * 4 + 3] & kPfActive) == 0)
+                    continue;
+                const unsigned long long lat = f.latent[e.x];
+                const int m = f.m[e.z], k = __popcll(lat);
+                const double *prow = f.p + (size_t)e.y * f.p_stride;
+                double T;
+                if (k > m)
+                    T = NAN;
+                else if (egf)
+                    T = transmission_ll_egf_coop(lat, prow, m, f.log_r[e.z], f.log_1mr[e.z], allow_rel,
+                                                 s_scr + warp * 32, ST, s_lgam);
+                else
+                    T = transmission_ll_coop(lat, prow, m, f.log_r[e.z], f.log_1mr[e.z], allow_rel,
+                                             s_scr + warp * 32, ST, s_lgam);
+                if (lane == 0) f.out[e.w] = T;
+                __syncwarp();
             }
-            __syncwarp();
+            else
+            {
+                const int w0 = lo + unit * 32;
+                if (w0 >= hi) break;
+                const int w = w0 + lane;
+                if (w < hi)
+                {
+                    const uint4 e = f.list[w];
+                    if (!f.round_flags || ((unsigned)f.round_flags[(size_t)e.y * 4 + 3] & kPfActive))
+                        f.out[e.w] = transmission_ll(f.latent[e.x], f.p + (size_t)e.y * f.p_stride,
+                                                     f.m[e.z], f.log_r[e.z], f.log_1mr[e.z], allow_rel,
+                                                     s_scr + tid, ST, s_lgam);
+                }
+                __syncwarp();
+            }
         }
     }
 }
