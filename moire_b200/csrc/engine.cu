@@ -16,6 +16,7 @@
 #include "../../include/moire_engine.h"
 #include "kernels.cuh"
 #include "p_flat.cuh"
+#include "s_flat.cuh"
 
 namespace
 {
@@ -157,6 +158,11 @@ struct moire_engine
     DevBuf<int> pf_nonmiss;
     int amax_alleles = 0;
     bool p_fused = false;
+    moire::SFlat sf{};
+    DevBuf<moire::Proposal> sf_prop;
+    DevBuf<int> sf_m;
+    DevBuf<double> sf_logr, sf_log1mr, sf_adj;
+    DevBuf<unsigned long long> sf_lat;
     DevBuf<unsigned char> missing;
     DevBuf<int> nall, aclass, avals, obs_coi, m, acc6, p_acc, p_att, active;
     DevBuf<double> logC, lgam, lgadj, cellT, cellO, persample, p, p_sd, perchain, scratchN;
@@ -185,6 +191,7 @@ struct moire_engine
         p_acc.release(); p_att.release(); active.release(); logC.release(); lgam.release();
         pf_list.release(); pf_hist.release(); pf_Tcur.release(); pf_Tnew.release(); pf_pprop.release();
         pf_round.release(); pf_nonmiss.release();
+        sf_prop.release(); sf_m.release(); sf_logr.release(); sf_log1mr.release(); sf_lat.release(); sf_adj.release();
         lgadj.release(); cellT.release(); cellO.release(); persample.release(); p.release();
         p_sd.release(); perchain.release(); scratchN.release();
         if (v.trace && std::getenv("MOIRE_B200_TRACE"))
@@ -360,6 +367,12 @@ struct moire_engine
             pf.list = pf_list.ptr; pf.hist = pf_hist.ptr; pf.Tcur = pf_Tcur.ptr; pf.Tnew = pf_Tnew.ptr;
             pf.pprop = pf_pprop.ptr; pf.round = pf_round.ptr; pf.nonmiss = pf_nonmiss.ptr;
             p_smem = 0;  // the fused kernel's per-block arrays are not needed
+            // the per-sample updates share the list, the histogram and the two term arrays
+            sf_prop.alloc(TN); sf_m.alloc(TN); sf_logr.alloc(TN); sf_log1mr.alloc(TN);
+            sf_lat.alloc(TNL); sf_adj.alloc(TNL);
+            sf.prop = sf_prop.ptr; sf.m_new = sf_m.ptr; sf.log_r_new = sf_logr.ptr;
+            sf.log_1mr_new = sf_log1mr.ptr; sf.lat = sf_lat.ptr; sf.adj = sf_adj.ptr;
+            sf.O = pf_Tcur.ptr; sf.Tn = pf_Tnew.ptr;
         }
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -387,6 +400,13 @@ struct moire_engine
             CUDA_TRY(cudaFuncSetAttribute(k_update_p<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
         }
         CUDA_TRY(cudaFuncSetAttribute(k_flat_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
+        {
+            const int ps = (int)sf_smem(tile_S, v.nA);
+            CUDA_TRY(cudaFuncSetAttribute(k_sf_propose<KIND_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps));
+            CUDA_TRY(cudaFuncSetAttribute(k_sf_propose<KIND_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps));
+            CUDA_TRY(cudaFuncSetAttribute(k_sf_propose<KIND_EFF_COI>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps));
+            CUDA_TRY(cudaFuncSetAttribute(k_sf_propose<KIND_SAMPLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps));
+        }
         {
             int per_sm = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flat_eval, 256, pf_eval_smem()));
@@ -450,7 +470,7 @@ struct moire_engine
         CUDA_TRY(cudaMemsetAsync(pf.hist, 0, kPfHistWords * sizeof(unsigned int), stream));
         k_pf_prepare<<<cell_blocks, 256, 0, stream>>>(v, pf);
         k_pf_scan<<<1, 256, 0, stream>>>(pf);
-        k_pf_scatter<<<cell_blocks, 256, 0, stream>>>(v, pf);
+        k_pf_scatter<<<scatter_blocks(total), 256, 0, stream>>>(v, pf);
         FlatSrc src{};
         src.list = pf.list; src.bounds = pf.hist + kPfScalars;
         src.latent = v.latent; src.p = pf.pprop; src.p_stride = v.AP;
@@ -470,10 +490,41 @@ struct moire_engine
         CUDA_TRY(cudaGetLastError());
     }
 
+    // update_m / update_r / update_eff_coi / update_samples as a flat pipeline (s_flat.cuh)
+    template <int KIND>
+    void update_sample_flat(int iteration)
+    {
+        using namespace moire;
+        constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
+        const size_t total = (size_t)v.T * v.N * v.L;
+        const unsigned tiles = (unsigned)(v.T * tiles_per_chain);
+        CUDA_TRY(cudaMemsetAsync(pf.hist, 0, kPfHistWords * sizeof(unsigned int), stream));
+        k_sf_propose<KIND><<<tiles, 256, sf_smem(tile_S, v.nA), stream>>>(v, sf, pf, iteration, tile_S,
+                                                                          tiles_per_chain);
+        k_pf_scan<<<1, 256, 0, stream>>>(pf);
+        k_sf_scatter<KIND><<<scatter_blocks(total), 256, 0, stream>>>(v, sf, pf);
+        FlatSrc src{};
+        src.list = pf.list; src.bounds = pf.hist + kPfScalars; src.counter = pf.hist + kPfCounters;
+        src.latent = RESAMPLE ? sf.lat : v.latent; src.p = v.p; src.p_stride = v.AP;
+        src.m = sf.m_new; src.log_r = sf.log_r_new; src.log_1mr = sf.log_1mr_new;
+        src.round_flags = nullptr; src.out = sf.Tn;
+        k_flat_eval<<<flat_grid, 256, pf_eval_smem(), stream>>>(v, src);
+        k_sf_decide<KIND><<<tiles, 256, tile_S * sizeof(Proposal), stream>>>(v, sf, iteration, tile_S,
+                                                                             tiles_per_chain);
+        launches += 5;
+        CUDA_TRY(cudaGetLastError());
+    }
+
     template <int KIND>
     void launch_sample(int iteration)
     {
         Timed tm(this, KIND);
+        if (!p_fused && KIND != moire::KIND_EPS_NEG && KIND != moire::KIND_EPS_POS)
+        {
+            update_sample_flat<KIND>(iteration);
+            tm.done();
+            return;
+        }
         const size_t smem = (KIND == moire::KIND_EPS_NEG || KIND == moire::KIND_EPS_POS) ? sample_smem_o : sample_smem;
         moire::k_update_sample<KIND><<<v.T * tiles_per_chain, moire::kThreads, smem, stream>>>(
             v, iteration, tile_S, tiles_per_chain);

@@ -272,6 +272,177 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
 __host__ __device__ inline size_t align8(size_t b) { return (b + 7) & ~(size_t)7; }
 __host__ __device__ inline size_t scratch_doubles(int B) { return (size_t)kScratchSlots * (B + 1); }
 
+// One proposal for sample i of chain t: the draws, validity checks and prior terms of
+// update_eps_neg / update_eps_pos / update_m / update_r / update_eff_coi / update_samples
+// (src/chain.cpp:165-313, 315-374, 567-807) before any cell is evaluated.
+template <int KIND>
+__device__ __forceinline__ Proposal draw_sample_proposal(const View &v, int t, int i, int iteration,
+                                                         const double *s_lgam)
+{
+    const int N = v.N;
+    const unsigned gchain = (unsigned)(v.chain_offset + t);
+    const size_t si = (size_t)t * N + i;
+    Stream rng;
+    rng.open(v.seed, (uint32_t)iteration, KIND, gchain, (uint32_t)i, 0);
+    Proposal P;
+    P.valid = 1;
+    P.adapt = 0;
+    P.accept = 0;
+    P.m_new = v.m[si];
+    P.r_new = v.r[si];
+    P.en_new = v.eps_neg[si];
+    P.ep_new = v.eps_pos[si];
+    P.log_r = v.log_r[si];
+    P.log_1mr = v.log_1mr[si];
+    P.adj = 0.0;
+    P.dprior = 0.0;
+    P.pr_en_new = P.pr_ep_new = P.pr_coi_new = P.pr_r_new = 0.0;
+    const double min_sampled = DBL_MIN;  // std::numeric_limits<double>::min()
+    const double lambda = v.mean_coi[t];
+    const double log_geom = -0.40546510810816438;  // log(1 - 1/3): sample_coi_delta(2)
+
+    if (KIND == KIND_EPS_NEG || KIND == KIND_SAMPLES)
+    {
+        const double z = v.sd_eps_neg[si] * next_normal(rng);
+        double prop, adj;
+        constrained_proposal(z, P.en_new, min_sampled, 1.0, &prop, &adj);
+        const bool ok = prop < 1.0 && prop > 1e-32;
+        P.valid &= ok;
+        P.en_new = prop;
+        P.adj += adj;
+        P.pr_en_new = dbeta_log(prop, v.eps_neg_a, v.eps_neg_b, v.eps_neg_lbeta);
+        P.dprior += P.pr_en_new - v.pr_eps_neg[si];
+    }
+    if (KIND == KIND_EPS_POS || KIND == KIND_SAMPLES)
+    {
+        const double z = v.sd_eps_pos[si] * next_normal(rng);
+        double prop, adj;
+        constrained_proposal(z, P.ep_new, min_sampled, 1.0, &prop, &adj);
+        const bool ok = prop < 1.0 && prop > 1e-32;
+        P.valid &= ok;
+        P.ep_new = prop;
+        P.adj += adj;
+        P.pr_ep_new = dbeta_log(prop, v.eps_pos_a, v.eps_pos_b, v.eps_pos_lbeta);
+        P.dprior += P.pr_ep_new - v.pr_eps_pos[si];
+    }
+    if (KIND == KIND_R || (KIND == KIND_SAMPLES && v.allow_rel))
+    {
+        const double z = v.sd_r[si] * next_normal(rng);
+        double prop, adj;
+        constrained_proposal(z, P.r_new, min_sampled, .99, &prop, &adj);
+        if (KIND == KIND_SAMPLES) P.valid &= (prop < 1.0 && prop > 1e-32);
+        P.r_new = prop;
+        P.adj += adj;
+    }
+    if (KIND == KIND_SAMPLES && !v.allow_rel) P.r_new = 0.0;  // src/chain.cpp:719
+    if (KIND == KIND_EFF_COI)
+    {
+        const double curr_eff = (double)(P.m_new - 1) * (1.0 - P.r_new) + 1.0;
+        const double z = v.sd_mr[si] * next_normal(rng);
+        double prop_eff, adj;
+        constrained_proposal(z, curr_eff, 1.0, (double)v.max_coi, &prop_eff, &adj);
+        const int prop_m = P.m_new + next_coi_delta(rng, log_geom);
+        const double prop_r = 1.0 - (prop_eff - 1.0) / ((double)prop_m - 1.0);
+        // src/chain.cpp:244-246: skipped proposals neither evaluate nor adapt
+        if (prop_m <= 0 || prop_m > v.max_coi || prop_r > 1.0 || prop_r < 1e-32) P.valid = 0;
+        P.m_new = prop_m;
+        P.r_new = prop_r;
+        P.adj += adj;
+    }
+    if (KIND == KIND_M || KIND == KIND_SAMPLES)
+    {
+        const int prop_m = P.m_new + next_coi_delta(rng, log_geom);
+        P.valid &= (prop_m > 0 && prop_m <= v.max_coi);
+        P.m_new = prop_m;
+    }
+    if (KIND == KIND_R || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
+    {
+        P.pr_r_new = dbeta_log(P.r_new, v.r_a, v.r_b, v.r_lbeta);
+        P.dprior += P.pr_r_new - v.pr_r[si];
+        P.log_r = cold_log(P.r_new);
+        P.log_1mr = cold_log(1.0 - P.r_new);
+    }
+    if (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
+    {
+        const int mm = P.valid ? P.m_new : 1;  // keep the LUT index in range
+        P.pr_coi_new = dztpois_log(mm, cold_log(lambda), cold_log(cold_exp(lambda) - 1.0), s_lgam);
+        P.dprior += P.pr_coi_new - v.pr_coi[si];
+    }
+    // which updates adapt, and when (src/chain.cpp:303-311, 364-372, 618-627, 683-692)
+    if (KIND == KIND_EPS_NEG || KIND == KIND_EPS_POS || KIND == KIND_EFF_COI)
+        P.adapt = P.valid;
+    if (KIND == KIND_R) P.adapt = 1;
+    P.logu = cold_log(rng.next_uniform());
+    return P;
+}
+
+// The Metropolis decision for one sample given the summed change d of its cells' log-likelihood
+// and a of its latent genotypes' log proposal densities: acceptance rule of each update, state
+// and prior caches on acceptance, counters, Robbins-Monro adaptation.  Sets P.accept.
+template <int KIND>
+__device__ __forceinline__ void decide_sample(const View &v, Proposal &P, int t, int i, int iteration,
+                                              double d, double a)
+{
+    const size_t si = (size_t)t * v.N + i;
+    const double temp = v.temp[t];
+    bool accept = false;
+    if (P.valid)
+    {
+        const double dpost = temp * d + P.dprior;  // new_post - old_post
+        const double ratio = dpost + (P.adj + a);
+        if (KIND == KIND_M || KIND == KIND_SAMPLES)
+            accept = !isnan(dpost) && P.logu <= ratio;
+        else if (KIND == KIND_EFF_COI)
+            accept = !(isnan(dpost) || isnan(ratio) || P.logu > ratio);
+        else
+            accept = !(isnan(dpost) || P.logu > ratio);
+    }
+    P.accept = accept;
+    int nacc = 0;
+    if (accept)
+    {
+        if (KIND == KIND_EPS_NEG || KIND == KIND_SAMPLES)
+        {
+            v.eps_neg[si] = P.en_new;
+            v.pr_eps_neg[si] = P.pr_en_new;
+        }
+        if (KIND == KIND_EPS_POS || KIND == KIND_SAMPLES)
+        {
+            v.eps_pos[si] = P.ep_new;
+            v.pr_eps_pos[si] = P.pr_ep_new;
+        }
+        if (KIND == KIND_R || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
+        {
+            v.r[si] = P.r_new;
+            v.log_r[si] = P.log_r;
+            v.log_1mr[si] = P.log_1mr;
+            v.pr_r[si] = P.pr_r_new;
+        }
+        if (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
+        {
+            v.m[si] = P.m_new;
+            v.pr_coi[si] = P.pr_coi_new;
+        }
+    }
+    int *accp = KIND == KIND_EPS_NEG   ? v.acc_eps_neg
+                : KIND == KIND_EPS_POS ? v.acc_eps_pos
+                : KIND == KIND_M       ? v.acc_m
+                : KIND == KIND_R       ? v.acc_r
+                : KIND == KIND_EFF_COI ? v.acc_mr
+                                       : v.acc_samples;
+    nacc = accp[si] + (accept ? 1 : 0);
+    if (accept) accp[si] = nacc;
+    if (P.adapt && iteration < v.burnin && iteration > 15)
+    {
+        double *sdp = KIND == KIND_EPS_NEG   ? v.sd_eps_neg
+                      : KIND == KIND_EPS_POS ? v.sd_eps_pos
+                      : KIND == KIND_R       ? v.sd_r
+                                             : v.sd_mr;
+        sdp[si] = adapt_sd(sdp[si], (double)nacc, (double)iteration,
+                           (double)iteration + 1.0, .01);
+    }
+}
+
 // Shared memory of the per-sample kernel.  The two error-rate updates evaluate no transmission
 // term: no scratch columns, no sort, one array per cell -- which lets several of their blocks
 // share an SM (they are plain streaming kernels).
@@ -321,110 +492,13 @@ __global__ void __launch_bounds__(kThreads, MOIRE_MIN_BLOCKS_S * (256 / kThreads
     const int ns = min(S, v.N - s0);
     const int N = v.N, L = v.L, nA = v.nA;
     const unsigned gchain = (unsigned)(v.chain_offset + t);
-    const double temp = v.temp[t];
 
     for (int i = tid; i < 128; i += kThreads) s_lgam[i] = v.lgam[i];
     if (tid == 0) s_evals = s_next = 0;
     __syncthreads();
 
     // ---- phase A: one proposal per sample -----------------------------------------------------
-    if (tid < ns)
-    {
-        const int i = s0 + tid;
-        const size_t si = (size_t)t * N + i;
-        Stream rng;
-        rng.open(v.seed, (uint32_t)iteration, KIND, gchain, (uint32_t)i, 0);
-        Proposal P;
-        P.valid = 1;
-        P.adapt = 0;
-        P.accept = 0;
-        P.m_new = v.m[si];
-        P.r_new = v.r[si];
-        P.en_new = v.eps_neg[si];
-        P.ep_new = v.eps_pos[si];
-        P.log_r = v.log_r[si];
-        P.log_1mr = v.log_1mr[si];
-        P.adj = 0.0;
-        P.dprior = 0.0;
-        P.pr_en_new = P.pr_ep_new = P.pr_coi_new = P.pr_r_new = 0.0;
-        const double min_sampled = DBL_MIN;  // std::numeric_limits<double>::min()
-        const double lambda = v.mean_coi[t];
-        const double log_geom = -0.40546510810816438;  // log(1 - 1/3): sample_coi_delta(2)
-
-        if (KIND == KIND_EPS_NEG || KIND == KIND_SAMPLES)
-        {
-            const double z = v.sd_eps_neg[si] * next_normal(rng);
-            double prop, adj;
-            constrained_proposal(z, P.en_new, min_sampled, 1.0, &prop, &adj);
-            const bool ok = prop < 1.0 && prop > 1e-32;
-            P.valid &= ok;
-            P.en_new = prop;
-            P.adj += adj;
-            P.pr_en_new = dbeta_log(prop, v.eps_neg_a, v.eps_neg_b, v.eps_neg_lbeta);
-            P.dprior += P.pr_en_new - v.pr_eps_neg[si];
-        }
-        if (KIND == KIND_EPS_POS || KIND == KIND_SAMPLES)
-        {
-            const double z = v.sd_eps_pos[si] * next_normal(rng);
-            double prop, adj;
-            constrained_proposal(z, P.ep_new, min_sampled, 1.0, &prop, &adj);
-            const bool ok = prop < 1.0 && prop > 1e-32;
-            P.valid &= ok;
-            P.ep_new = prop;
-            P.adj += adj;
-            P.pr_ep_new = dbeta_log(prop, v.eps_pos_a, v.eps_pos_b, v.eps_pos_lbeta);
-            P.dprior += P.pr_ep_new - v.pr_eps_pos[si];
-        }
-        if (KIND == KIND_R || (KIND == KIND_SAMPLES && v.allow_rel))
-        {
-            const double z = v.sd_r[si] * next_normal(rng);
-            double prop, adj;
-            constrained_proposal(z, P.r_new, min_sampled, .99, &prop, &adj);
-            if (KIND == KIND_SAMPLES) P.valid &= (prop < 1.0 && prop > 1e-32);
-            P.r_new = prop;
-            P.adj += adj;
-        }
-        if (KIND == KIND_SAMPLES && !v.allow_rel) P.r_new = 0.0;  // src/chain.cpp:719
-        if (KIND == KIND_EFF_COI)
-        {
-            const double curr_eff = (double)(P.m_new - 1) * (1.0 - P.r_new) + 1.0;
-            const double z = v.sd_mr[si] * next_normal(rng);
-            double prop_eff, adj;
-            constrained_proposal(z, curr_eff, 1.0, (double)v.max_coi, &prop_eff, &adj);
-            const int prop_m = P.m_new + next_coi_delta(rng, log_geom);
-            const double prop_r = 1.0 - (prop_eff - 1.0) / ((double)prop_m - 1.0);
-            // src/chain.cpp:244-246: skipped proposals neither evaluate nor adapt
-            if (prop_m <= 0 || prop_m > v.max_coi || prop_r > 1.0 || prop_r < 1e-32) P.valid = 0;
-            P.m_new = prop_m;
-            P.r_new = prop_r;
-            P.adj += adj;
-        }
-        if (KIND == KIND_M || KIND == KIND_SAMPLES)
-        {
-            const int prop_m = P.m_new + next_coi_delta(rng, log_geom);
-            P.valid &= (prop_m > 0 && prop_m <= v.max_coi);
-            P.m_new = prop_m;
-        }
-        if (KIND == KIND_R || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
-        {
-            P.pr_r_new = dbeta_log(P.r_new, v.r_a, v.r_b, v.r_lbeta);
-            P.dprior += P.pr_r_new - v.pr_r[si];
-            P.log_r = cold_log(P.r_new);
-            P.log_1mr = cold_log(1.0 - P.r_new);
-        }
-        if (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
-        {
-            const int mm = P.valid ? P.m_new : 1;  // keep the LUT index in range
-            P.pr_coi_new = dztpois_log(mm, cold_log(lambda), cold_log(cold_exp(lambda) - 1.0), s_lgam);
-            P.dprior += P.pr_coi_new - v.pr_coi[si];
-        }
-        // which updates adapt, and when (src/chain.cpp:303-311, 364-372, 618-627, 683-692)
-        if (KIND == KIND_EPS_NEG || KIND == KIND_EPS_POS || KIND == KIND_EFF_COI)
-            P.adapt = P.valid;
-        if (KIND == KIND_R) P.adapt = 1;
-        P.logu = cold_log(rng.next_uniform());
-        s_prop[tid] = P;
-    }
+    if (tid < ns) s_prop[tid] = draw_sample_proposal<KIND>(v, t, s0 + tid, iteration, s_lgam);
     __syncthreads();
 
     if (NEED_O)
@@ -525,68 +599,7 @@ __global__ void __launch_bounds__(kThreads, MOIRE_MIN_BLOCKS_S * (256 / kThreads
         }
         d = warp_sum(d);
         if (RESAMPLE) a = warp_sum(a);
-        if (lane == 0)
-        {
-            Proposal &P = s_prop[sl];
-            const int i = s0 + sl;
-            const size_t si = (size_t)t * N + i;
-            bool accept = false;
-            if (P.valid)
-            {
-                const double dpost = temp * d + P.dprior;  // new_post - old_post
-                const double ratio = dpost + (P.adj + a);
-                if (KIND == KIND_M || KIND == KIND_SAMPLES)
-                    accept = !isnan(dpost) && P.logu <= ratio;
-                else if (KIND == KIND_EFF_COI)
-                    accept = !(isnan(dpost) || isnan(ratio) || P.logu > ratio);
-                else
-                    accept = !(isnan(dpost) || P.logu > ratio);
-            }
-            P.accept = accept;
-            int nacc = 0;
-            if (accept)
-            {
-                if (KIND == KIND_EPS_NEG || KIND == KIND_SAMPLES)
-                {
-                    v.eps_neg[si] = P.en_new;
-                    v.pr_eps_neg[si] = P.pr_en_new;
-                }
-                if (KIND == KIND_EPS_POS || KIND == KIND_SAMPLES)
-                {
-                    v.eps_pos[si] = P.ep_new;
-                    v.pr_eps_pos[si] = P.pr_ep_new;
-                }
-                if (KIND == KIND_R || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
-                {
-                    v.r[si] = P.r_new;
-                    v.log_r[si] = P.log_r;
-                    v.log_1mr[si] = P.log_1mr;
-                    v.pr_r[si] = P.pr_r_new;
-                }
-                if (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
-                {
-                    v.m[si] = P.m_new;
-                    v.pr_coi[si] = P.pr_coi_new;
-                }
-            }
-            int *accp = KIND == KIND_EPS_NEG   ? v.acc_eps_neg
-                        : KIND == KIND_EPS_POS ? v.acc_eps_pos
-                        : KIND == KIND_M       ? v.acc_m
-                        : KIND == KIND_R       ? v.acc_r
-                        : KIND == KIND_EFF_COI ? v.acc_mr
-                                               : v.acc_samples;
-            nacc = accp[si] + (accept ? 1 : 0);
-            if (accept) accp[si] = nacc;
-            if (P.adapt && iteration < v.burnin && iteration > 15)
-            {
-                double *sdp = KIND == KIND_EPS_NEG   ? v.sd_eps_neg
-                              : KIND == KIND_EPS_POS ? v.sd_eps_pos
-                              : KIND == KIND_R       ? v.sd_r
-                                                     : v.sd_mr;
-                sdp[si] = adapt_sd(sdp[si], (double)nacc, (double)iteration,
-                                   (double)iteration + 1.0, .01);
-            }
-        }
+        if (lane == 0) decide_sample<KIND>(v, s_prop[sl], t, s0 + sl, iteration, d, a);
     }
     __syncthreads();
 
