@@ -327,6 +327,9 @@ __device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, i
     return __dadd_rn(mx, hot_log(sum));
 }
 
+#ifndef MOIRE_TIERS
+#define MOIRE_TIERS 2
+#endif
 constexpr int kMaxAcc = 16;  // accumulators kept in registers
 
 // The subset sums of one cell, accumulators dumped to scr[t * ST], then the mixture.
@@ -342,20 +345,42 @@ __device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, i
 {
     const int cnt = m - k + 1;
     const int cnt_w = __reduce_max_sync(__activemask(), cnt);
-    if (cnt_w <= 4)
-    {
-        double acc[4];
-        ie_vectorized<4>(scr, ST, k, 0, acc);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) scr[t * ST] = acc[t];
+#define MOIRE_IE_TIER(NACC)                                                     \
+    {                                                                           \
+        double acc[NACC];                                                       \
+        ie_vectorized<NACC>(scr, ST, k, 0, acc);                                \
+        _Pragma("unroll") for (int t = 0; t < NACC; ++t) scr[t * ST] = acc[t];  \
     }
-    else
-    {
-        double acc[kMaxAcc];
-        ie_vectorized<kMaxAcc>(scr, ST, k, 0, acc);
-#pragma unroll
-        for (int t = 0; t < kMaxAcc; ++t) scr[t * ST] = acc[t];
-    }
+#if MOIRE_TIERS == 0  // 4 16
+    if (cnt_w <= 4) MOIRE_IE_TIER(4)
+    else MOIRE_IE_TIER(16)
+#elif MOIRE_TIERS == 1  // 2 4 8 16
+    if (cnt_w <= 2) MOIRE_IE_TIER(2)
+    else if (cnt_w <= 4) MOIRE_IE_TIER(4)
+    else if (cnt_w <= 8) MOIRE_IE_TIER(8)
+    else MOIRE_IE_TIER(16)
+#elif MOIRE_TIERS == 2  // 2 4 6 8 12 16
+    if (cnt_w <= 2) MOIRE_IE_TIER(2)
+    else if (cnt_w <= 4) MOIRE_IE_TIER(4)
+    else if (cnt_w <= 6) MOIRE_IE_TIER(6)
+    else if (cnt_w <= 8) MOIRE_IE_TIER(8)
+    else if (cnt_w <= 12) MOIRE_IE_TIER(12)
+    else MOIRE_IE_TIER(16)
+#else  // 1 2 3 4 5 6 7 8 10 12 14 16
+    if (cnt_w <= 1) MOIRE_IE_TIER(1)
+    else if (cnt_w <= 2) MOIRE_IE_TIER(2)
+    else if (cnt_w <= 3) MOIRE_IE_TIER(3)
+    else if (cnt_w <= 4) MOIRE_IE_TIER(4)
+    else if (cnt_w <= 5) MOIRE_IE_TIER(5)
+    else if (cnt_w <= 6) MOIRE_IE_TIER(6)
+    else if (cnt_w <= 7) MOIRE_IE_TIER(7)
+    else if (cnt_w <= 8) MOIRE_IE_TIER(8)
+    else if (cnt_w <= 10) MOIRE_IE_TIER(10)
+    else if (cnt_w <= 12) MOIRE_IE_TIER(12)
+    else if (cnt_w <= 14) MOIRE_IE_TIER(14)
+    else MOIRE_IE_TIER(16)
+#endif
+#undef MOIRE_IE_TIER
     return relatedness_mixture(scr, ST, m, cnt, log_total, log_r, log_1mr, lgam);
 }
 
@@ -490,7 +515,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
 // All lanes must call with identical arguments; every lane returns the value.
 // wscr: the warp's 32 scratch columns (slot s, column c at wscr[s * ST + c]); slot 16 holds q.
 #ifndef MOIRE_COOP_MIN_K
-#define MOIRE_COOP_MIN_K 7
+#define MOIRE_COOP_MIN_K 8
 #endif
 constexpr int kCoopMinK = MOIRE_COOP_MIN_K;
 __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const double *prow, int m,
