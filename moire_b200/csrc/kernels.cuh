@@ -114,6 +114,12 @@ __device__ __forceinline__ int work_class(int k, int m)
 
 constexpr int kClassCoopBegin = 64;                       // first class with k <= 10
 constexpr int kClassLightBegin = (12 - kCoopMinK) * 64;   // first class with k < kCoopMinK
+// The fused kernels serve tiny problems only (a few blocks, one per SM: latency, not throughput,
+// decides), so they hand cells to the cooperative evaluator from a lower k.
+#ifndef MOIRE_FUSED_COOP_MIN_K
+#define MOIRE_FUSED_COOP_MIN_K 6
+#endif
+constexpr int kClassLightBeginFused = (12 - MOIRE_FUSED_COOP_MIN_K) * 64;
 
 // hist: kSortBins counters; order: out; s_tmp: >= 40 words.  cls(cell) < 0 leaves the cell out.
 // Returns the number of listed cells (same value in every thread); s_tmp[33] / s_tmp[34] get the
@@ -166,7 +172,7 @@ __device__ __forceinline__ int block_sort_cells(int ncell, ClassFn cls, unsigned
             const unsigned int h = hist[b0 + q];
             hist[b0 + q] = base;
             if (b0 + q == kClassCoopBegin) s_tmp[33] = base;
-            if (b0 + q == kClassLightBegin) s_tmp[34] = base;
+            if (b0 + q == kClassLightBeginFused) s_tmp[34] = base;
             base += h;
         }
     }
