@@ -185,6 +185,10 @@ int moire_engine_timer_stop(moire_engine *e, double *ms);
  * reduction.  Enabled by moire_engine_set_timing(e, 1) (adds event records around each launch). */
 int moire_engine_set_timing(moire_engine *e, int32_t on);
 int moire_engine_read_timing(moire_engine *e, double *ms, uint64_t *launches);
+/* Device time and launch count of the transmission evaluator kernel alone (k_flat_eval, the
+ * dominant kernel; it runs inside update_p and the four per-sample updates that need
+ * transmission terms), accumulated like moire_engine_read_timing. */
+int moire_engine_read_evaluator_timing(moire_engine *e, double *ms, uint64_t *launches);
 int moire_engine_synchronize(moire_engine *e);
 
 /* Philox4x32-10 block (counter, key) -> 4 words; exported so tests can pin the generator against

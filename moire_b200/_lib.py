@@ -117,6 +117,7 @@ ENGINE_SYMBOLS = {
     "moire_engine_timer_stop": (C.c_int, [vp, C.POINTER(dbl)]),
     "moire_engine_set_timing": (C.c_int, [vp, i32]),
     "moire_engine_read_timing": (C.c_int, [vp, vp, vp]),
+    "moire_engine_read_evaluator_timing": (C.c_int, [vp, C.POINTER(dbl), C.POINTER(u64)]),
     "moire_engine_synchronize": (C.c_int, [vp]),
     "moire_philox4x32": (None, [vp, vp, vp]),
 }

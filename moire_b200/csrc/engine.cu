@@ -175,8 +175,8 @@ struct moire_engine
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     std::vector<TimedLaunch> pending;
     std::vector<int32_t> init_log;  // (chain, sample, locus) per ill-conditioned start
-    double kind_ms[9] = {0};
-    uint64_t kind_launches[9] = {0};
+    double kind_ms[10] = {0};  // 8 update kinds, the reduction, [9] = the flat evaluator alone
+    uint64_t kind_launches[10] = {0};
 
     ~moire_engine()
     {
@@ -306,6 +306,18 @@ struct moire_engine
             std::vector<double> comb_h;
             build_egf_binomials(comb_h);
             CUDA_TRY(cudaMemcpyToSymbol(moire::g_egf_comb, comb_h.data(), comb_h.size() * sizeof(double)));
+            const int D = moire::kMaxCoi + 1;
+            std::vector<double> binom_h((size_t)D * D, 0.0);
+            for (int n = 0; n < D; ++n)
+            {
+                long double c = 1.0L;  // exact: C(n, i) < 2^64 for n <= 64
+                for (int i = 0; i <= n; ++i)
+                {
+                    binom_h[(size_t)n * D + i] = (double)c;
+                    c = c * (long double)(n - i) / (long double)(i + 1);
+                }
+            }
+            CUDA_TRY(cudaMemcpyToSymbol(moire::g_binom, binom_h.data(), binom_h.size() * sizeof(double)));
         }
         obs.upload((const unsigned long long *)d->obs_mask, NL, stream);
         missing.upload(d->is_missing, NL, stream);
@@ -461,6 +473,23 @@ struct moire_engine
     static size_t pf_eval_smem() { return (128 + moire::scratch_doubles(256)) * sizeof(double); }
     int flat_grid = 0;  // persistent evaluator grid: resident blocks of the device
 
+    void launch_flat_eval(const moire::FlatSrc &src)
+    {
+        cudaEvent_t a = nullptr, b = nullptr;
+        if (timing)
+        {
+            CUDA_TRY(cudaEventCreate(&a));
+            CUDA_TRY(cudaEventCreate(&b));
+            CUDA_TRY(cudaEventRecord(a, stream));
+        }
+        moire::k_flat_eval<<<flat_grid, 256, pf_eval_smem(), stream>>>(v, src);
+        if (timing)
+        {
+            CUDA_TRY(cudaEventRecord(b, stream));
+            pending.push_back({a, b, 9});
+        }
+    }
+
     // update_p as sort-once + (round, eval) per proposal (p_flat.cuh); nothing returns to the host
     void update_p_flat(int iteration)
     {
@@ -479,12 +508,12 @@ struct moire_engine
         launches += 4;
         for (int rep = 0; rep < amax_alleles; ++rep)
         {
-            k_pf_round<<<v.T * v.L, 256, 0, stream>>>(v, pf, iteration, rep);
+            k_pf_round<<<v.T * v.L, kPfRoundThreads, 0, stream>>>(v, pf, iteration, rep);
             src.counter = pf.hist + kPfCounters + rep;
-            k_flat_eval<<<flat_grid, 256, pf_eval_smem(), stream>>>(v, src);
+            launch_flat_eval(src);
             launches += 2;
         }
-        k_pf_round<<<v.T * v.L, 256, 0, stream>>>(v, pf, iteration, amax_alleles);
+        k_pf_round<<<v.T * v.L, kPfRoundThreads, 0, stream>>>(v, pf, iteration, amax_alleles);
         k_pf_finish<<<cell_blocks, 256, 0, stream>>>(v, pf);
         launches += 2;
         CUDA_TRY(cudaGetLastError());
@@ -508,7 +537,7 @@ struct moire_engine
         src.latent = RESAMPLE ? sf.lat : v.latent; src.p = v.p; src.p_stride = v.AP;
         src.m = sf.m_new; src.log_r = sf.log_r_new; src.log_1mr = sf.log_1mr_new;
         src.round_flags = nullptr; src.out = sf.Tn;
-        k_flat_eval<<<flat_grid, 256, pf_eval_smem(), stream>>>(v, src);
+        launch_flat_eval(src);
         k_sf_decide<KIND><<<tiles, 256, tile_S * sizeof(Proposal), stream>>>(v, sf, iteration, tile_S,
                                                                              tiles_per_chain);
         launches += 5;
@@ -1099,6 +1128,16 @@ int moire_engine_read_timing(moire_engine *e, double *ms, uint64_t *launches)
             if (ms) ms[k] = e->kind_ms[k];
             if (launches) launches[k] = e->kind_launches[k];
         }
+    });
+}
+
+int moire_engine_read_evaluator_timing(moire_engine *e, double *ms, uint64_t *launches)
+{
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        e->resolve_timing();
+        if (ms) *ms = e->kind_ms[9];
+        if (launches) *launches = e->kind_launches[9];
     });
 }
 

@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(256) k_pf_scatter(const View v, const PFlat f)
 }
 
 // ---- once per proposal round: decide the previous proposal, draw the next ----------------------
-__global__ void __launch_bounds__(256) k_pf_round(const View v, const PFlat f, const int iteration,
+constexpr int kPfRoundThreads = 128;  // the proposal is one warp's serial math: many small blocks
+__global__ void __launch_bounds__(kPfRoundThreads) k_pf_round(const View v, const PFlat f, const int iteration,
                                                   const int rep)
 {
     __shared__ double s_red[40];
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(256) k_pf_round(const View v, const PFlat f, c
         // -- the change of the locus' log-likelihood under proposal rep - 1, summed in sample order
         double dsum = 0.0;
         const size_t base = (size_t)tl * N;
-        for (int i = tid; i < N; i += 256)
+        for (int i = tid; i < N; i += kPfRoundThreads)
             if (v.missing[(size_t)i * L + j] == 0) dsum += f.Tnew[base + i] - f.Tcur[base + i];
         const double d = block_sum(dsum, s_red);
         if (tid == 0)
@@ -195,9 +196,9 @@ __global__ void __launch_bounds__(256) k_pf_round(const View v, const PFlat f, c
         __syncthreads();
         if (s_red[35] != 0.0)
         {
-            for (int i = tid; i < N; i += 256)
+            for (int i = tid; i < N; i += kPfRoundThreads)
                 if (v.missing[(size_t)i * L + j] == 0) f.Tcur[base + i] = f.Tnew[base + i];
-            for (int a = tid; a < A; a += 256) v.p[prow + a] = f.pprop[prow + a];
+            for (int a = tid; a < A; a += kPfRoundThreads) v.p[prow + a] = f.pprop[prow + a];
         }
         __syncthreads();
     }

@@ -238,6 +238,17 @@ class Engine:
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KIND_NAMES)}
 
 
+def _evaluator_timing(self):
+    """(ms, launches) of the transmission evaluator kernel alone since timing was enabled."""
+    ms, n = C.c_double(), C.c_uint64()
+    self._ck(self.lib.moire_engine_read_evaluator_timing(self._h, C.byref(ms), C.byref(n)),
+             "read_evaluator_timing")
+    return float(ms.value), int(n.value)
+
+
+Engine.evaluator_timing = _evaluator_timing
+
+
 def philox4x32(counter, key):
     lib = _lib.load()
     c = np.ascontiguousarray(counter, dtype=np.uint32)
