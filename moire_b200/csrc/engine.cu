@@ -508,12 +508,12 @@ struct moire_engine
         launches += 4;
         for (int rep = 0; rep < amax_alleles; ++rep)
         {
-            k_pf_round<<<v.T * v.L, kPfRoundThreads, 0, stream>>>(v, pf, iteration, rep);
+            k_pf_round<<<(v.T * v.L + kPfRoundThreads / 32 - 1) / (kPfRoundThreads / 32), kPfRoundThreads, 0, stream>>>(v, pf, iteration, rep);
             src.counter = pf.hist + kPfCounters + rep;
             launch_flat_eval(src);
             launches += 2;
         }
-        k_pf_round<<<v.T * v.L, kPfRoundThreads, 0, stream>>>(v, pf, iteration, amax_alleles);
+        k_pf_round<<<(v.T * v.L + kPfRoundThreads / 32 - 1) / (kPfRoundThreads / 32), kPfRoundThreads, 0, stream>>>(v, pf, iteration, amax_alleles);
         k_pf_finish<<<cell_blocks, 256, 0, stream>>>(v, pf);
         launches += 2;
         CUDA_TRY(cudaGetLastError());

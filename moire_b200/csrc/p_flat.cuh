@@ -46,9 +46,16 @@ __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
         const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
         const unsigned t = tl / v.L, j = tl - t * v.L;
         const size_t cell = ((size_t)t * v.N + i) * v.L + j;
-        f.Tcur[loc] = v.cellT[cell];
         if (v.missing[(size_t)i * v.L + j] == 0)
+        {
+            f.Tcur[loc] = v.cellT[cell];
             atomicAdd(&s_hist[work_class(__popcll(v.latent[cell]), v.m[(size_t)t * v.N + i])], 1u);
+        }
+        else
+        {
+            f.Tcur[loc] = 0.0;  // never listed, never evaluated: a zero term on both sides
+            f.Tnew[loc] = 0.0;
+        }
     }
     __syncthreads();
     for (int b = threadIdx.x; b < kSortBins; b += blockDim.x)
@@ -154,14 +161,19 @@ __global__ void __launch_bounds__(256) k_pf_scatter(const View v, const PFlat f)
 }
 
 // ---- once per proposal round: decide the previous proposal, draw the next ----------------------
-constexpr int kPfRoundThreads = 128;  // the proposal is one warp's serial math: many small blocks
+// One warp per (chain, locus), no block barriers: the decision and the proposal are one warp's
+// serial math, so the kernel is latency bound and wants as many independent warps in flight as
+// the SM holds (ncu, block-per-locus version: 51 us per round at 27 % issue, 36 % warps active).
+// Tcur / Tnew hold 0 at missing cells (k_pf_prepare), so the sum needs no mask.
+constexpr int kPfRoundThreads = 128;
 __global__ void __launch_bounds__(kPfRoundThreads) k_pf_round(const View v, const PFlat f, const int iteration,
                                                   const int rep)
 {
-    __shared__ double s_red[40];
     const int N = v.N, L = v.L, AP = v.AP;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tl = blockIdx.x, t = tl / L, j = tl - t * L;
+    const int lane = threadIdx.x & 31;
+    const int tl = blockIdx.x * (kPfRoundThreads / 32) + (threadIdx.x >> 5);
+    if (tl >= v.T * L) return;
+    const int t = tl / L, j = tl - t * L;
     const int A = v.nall[j];
     const size_t prow = (size_t)tl * AP;
     double *st = f.round + (size_t)tl * 4;
@@ -169,18 +181,28 @@ __global__ void __launch_bounds__(kPfRoundThreads) k_pf_round(const View v, cons
 
     if (flags & kPfActive)
     {
-        // -- the change of the locus' log-likelihood under proposal rep - 1, summed in sample order
-        double dsum = 0.0;
-        const size_t base = (size_t)tl * N;
-        for (int i = tid; i < N; i += kPfRoundThreads)
-            if (v.missing[(size_t)i * L + j] == 0) dsum += f.Tnew[base + i] - f.Tcur[base + i];
-        const double d = block_sum(dsum, s_red);
-        if (tid == 0)
+        // -- the change of the locus' log-likelihood under proposal rep - 1
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+        const double *tn = f.Tnew + (size_t)tl * N, *tc = f.Tcur + (size_t)tl * N;
+        int i = lane;
+        for (; i + 96 < N; i += 128)
+        {
+            const double a0 = tn[i], a1 = tn[i + 32], a2 = tn[i + 64], a3 = tn[i + 96];
+            const double b0 = tc[i], b1 = tc[i + 32], b2 = tc[i + 64], b3 = tc[i + 96];
+            d0 += a0 - b0;
+            d1 += a1 - b1;
+            d2 += a2 - b2;
+            d3 += a3 - b3;
+        }
+        for (; i < N; i += 32) d0 += tn[i] - tc[i];
+        const double d = warp_sum((d0 + d1) + (d2 + d3));
+        int accept = 0;
+        if (lane == 0)
         {
             const int idx = (int)st[2];
             const double dpost = v.temp[t] * d;  // the priors do not depend on p
             const double ratio = dpost + st[0];
-            const bool accept = !(isnan(dpost) || st[1] > ratio);
+            accept = !(isnan(dpost) || st[1] > ratio);
             if (accept) ++v.p_acc[prow + idx];
             if (iteration < v.burnin && v.p_att[prow + idx] > 15)
             {
@@ -190,26 +212,24 @@ __global__ void __launch_bounds__(kPfRoundThreads) k_pf_round(const View v, cons
                 const double sd = v.p_sd[prow + idx] + (rate - .23) / sqrt(att + 1.0);
                 v.p_sd[prow + idx] = sd > .01 ? sd : .01;
             }
-            s_red[35] = accept ? 1.0 : 0.0;
             atomicAdd(v.evals + KIND_P, (unsigned long long)f.nonmiss[j]);
         }
-        __syncthreads();
-        if (s_red[35] != 0.0)
+        accept = __shfl_sync(0xffffffffu, accept, 0);
+        if (accept)
         {
-            for (int i = tid; i < N; i += kPfRoundThreads)
-                if (v.missing[(size_t)i * L + j] == 0) f.Tcur[base + i] = f.Tnew[base + i];
-            for (int a = tid; a < A; a += kPfRoundThreads) v.p[prow + a] = f.pprop[prow + a];
+            double *tcw = f.Tcur + (size_t)tl * N;
+            for (int q = lane; q < N; q += 32) tcw[q] = tn[q];
+            for (int a = lane; a < A; a += 32) v.p[prow + a] = f.pprop[prow + a];
         }
-        __syncthreads();
+        __syncwarp();
     }
     flags &= ~kPfActive;
     if (rep >= A || (flags & kPfBroken))
     {
-        if (tid == 0) st[3] = (double)flags;
+        if (lane == 0) st[3] = (double)flags;
         return;
     }
-    // -- proposal `rep`, warp 0, lanes across alleles (same arithmetic as k_update_p)
-    if (warp == 0)
+    // -- proposal `rep`, lanes across alleles (same arithmetic as k_update_p)
     {
         Stream rng;
         rng.open(v.seed, (uint32_t)iteration, KIND_P, (unsigned)(v.chain_offset + t), (uint32_t)j,

@@ -1,6 +1,7 @@
 """Join an ncu SASS profile of one kernel with nvdisasm line info: executed warp instructions,
 thread efficiency and stall samples per source line (inlined-at chains collapsed to the innermost
-line).  usage: ncu_lines.py report.ncu-rep libmoire_b200.so mangled_kernel_substring [top]"""
+line).  usage: ncu_lines.py report.ncu-rep libmoire_b200.so mangled_kernel_substring [top]
+NCU_FILTER="-k regex:name -s N -c 1" picks one result of a multi-kernel report."""
 import collections
 import csv
 import os
@@ -30,11 +31,20 @@ for ln in dis.splitlines():
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
     if m:
         lines.append((int(m.group(1), 16), m.group(2), cur))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + os.environ.get("NCU_FILTER", "").split(), capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[2:] if len(r) == len(hdr)]
+tables, cur_t = [], None
+for r in rows[1:]:
+    if len(r) != len(hdr):
+        continue
+    if r[0] == "Address":
+        cur_t = []
+        tables.append(cur_t)
+    elif cur_t is not None:
+        cur_t.append(r)
+data = tables[int(os.environ.get("NCU_TABLE", "0"))]  # a multi-result report: which table
 base = int(data[0][ix["Address"]], 16)
 byoff = {off: loc for off, _, loc in lines}
 agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0])
