@@ -502,7 +502,7 @@ struct moire_engine
         k_pf_scatter<<<scatter_blocks(total), 256, 0, stream>>>(v, pf);
         FlatSrc src{};
         src.list = pf.list; src.bounds = pf.hist + kPfScalars;
-        src.latent = v.latent; src.p = pf.pprop; src.p_stride = v.AP;
+        src.p = pf.pprop; src.p_stride = v.AP; src.out_locus_major = 1;
         src.m = v.m; src.log_r = v.log_r; src.log_1mr = v.log_1mr;
         src.round_flags = pf.round; src.out = pf.Tnew;
         launches += 4;
@@ -524,7 +524,6 @@ struct moire_engine
     void update_sample_flat(int iteration)
     {
         using namespace moire;
-        constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
         const size_t total = (size_t)v.T * v.N * v.L;
         const unsigned tiles = (unsigned)(v.T * tiles_per_chain);
         CUDA_TRY(cudaMemsetAsync(pf.hist, 0, kPfHistWords * sizeof(unsigned int), stream));
@@ -534,14 +533,31 @@ struct moire_engine
         k_sf_scatter<KIND><<<scatter_blocks(total), 256, 0, stream>>>(v, sf, pf);
         FlatSrc src{};
         src.list = pf.list; src.bounds = pf.hist + kPfScalars; src.counter = pf.hist + kPfCounters;
-        src.latent = RESAMPLE ? sf.lat : v.latent; src.p = v.p; src.p_stride = v.AP;
+        src.p = v.p; src.p_stride = v.AP; src.out_locus_major = 0;
         src.m = sf.m_new; src.log_r = sf.log_r_new; src.log_1mr = sf.log_1mr_new;
         src.round_flags = nullptr; src.out = sf.Tn;
         launch_flat_eval(src);
-        k_sf_decide<KIND><<<tiles, 256, tile_S * sizeof(Proposal), stream>>>(v, sf, iteration, tile_S,
-                                                                             tiles_per_chain);
+        k_sf_decide<KIND><<<(unsigned)(((size_t)v.T * v.N + 7) / 8), 256, 0, stream>>>(v, sf, iteration);
         launches += 5;
         CUDA_TRY(cudaGetLastError());
+    }
+
+    template <int KIND>
+    void launch_fused_or_eps(int iteration)
+    {
+        if constexpr (KIND == moire::KIND_EPS_NEG || KIND == moire::KIND_EPS_POS)
+        {
+            if (!p_fused)
+            {
+                const size_t units = (size_t)v.T * v.N;
+                moire::k_eps_update<KIND><<<(unsigned)((units + moire::kEpsWarps - 1) / moire::kEpsWarps),
+                                            moire::kEpsWarps * 32, moire::eps_smem(v.nA), stream>>>(v, iteration);
+                return;
+            }
+        }
+        const size_t smem = (KIND == moire::KIND_EPS_NEG || KIND == moire::KIND_EPS_POS) ? sample_smem_o : sample_smem;
+        moire::k_update_sample<KIND><<<v.T * tiles_per_chain, moire::kThreads, smem, stream>>>(
+            v, iteration, tile_S, tiles_per_chain);
     }
 
     template <int KIND>
@@ -554,9 +570,7 @@ struct moire_engine
             tm.done();
             return;
         }
-        const size_t smem = (KIND == moire::KIND_EPS_NEG || KIND == moire::KIND_EPS_POS) ? sample_smem_o : sample_smem;
-        moire::k_update_sample<KIND><<<v.T * tiles_per_chain, moire::kThreads, smem, stream>>>(
-            v, iteration, tile_S, tiles_per_chain);
+        launch_fused_or_eps<KIND>(iteration);
         tm.done();
     }
 

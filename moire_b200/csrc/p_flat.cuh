@@ -153,8 +153,9 @@ __global__ void __launch_bounds__(256) k_pf_scatter(const View v, const PFlat f)
         if (v.missing[(size_t)i * v.L + j] != 0) return false;
         const size_t cell = ((size_t)t * v.N + i) * v.L + j;
         const unsigned tn = t * v.N + i;
-        cls = work_class(__popcll(v.latent[cell]), v.m[tn]);
-        entry = make_uint4((unsigned)cell, tl, tn, (unsigned)loc);
+        const unsigned long long lat = v.latent[cell];
+        cls = work_class(__popcll(lat), v.m[tn]);
+        entry = make_uint4((unsigned)lat, (unsigned)(lat >> 32), tl, tn);
         return true;
     };
     block_scatter(total, cell_fn, f.hist + kSortBins, f.list);
@@ -311,16 +312,18 @@ __global__ void __launch_bounds__(kPfRoundThreads) k_pf_round(const View v, cons
 // shapes); otherwise a chunk of 1023-subset cells would outlast everything else.
 struct FlatSrc
 {
-    const uint4 *list;                  // {latent index, p-row index, sample index, output index}
+    const uint4 *list;                  // {latent genotype (two words), p-row index t * L + j,
+                                        //  sample index t * N + i}: the genotype travels in the
+                                        //  list, so a unit's loads are list -> frequencies only
     const unsigned int *bounds;         // [3] n_egf, coop_end, nwork
     unsigned int *counter;              // task counter, zero at launch
-    const unsigned long long *latent;   // [list.x]
-    const double *p;                    // row list.y, p_stride doubles apart
+    const double *p;                    // row list.z, p_stride doubles apart
     int p_stride;
-    const int *m;                       // [list.z]
-    const double *log_r, *log_1mr;      // [list.z]
-    const double *round_flags;          // null, or [list.y * 4 + 3] & kPfActive says "evaluate"
-    double *out;                        // [list.w]
+    const int *m;                       // [list.w]
+    const double *log_r, *log_1mr;      // [list.w]
+    const double *round_flags;          // null, or [list.z * 4 + 3] & kPfActive says "evaluate"
+    double *out;                        // locus-major [t][j][i] (p rounds) or sample-major [t][i][j]
+    int out_locus_major;
 };
 
 #ifndef MOIRE_PF_LIGHT_UPB
@@ -349,6 +352,12 @@ __global__ void __launch_bounds__(256, MOIRE_PF_MIN_BLOCKS) k_flat_eval(const Vi
     constexpr int ST = 256 + 1;
     for (int i = tid; i < 128; i += 256) s_lgam[i] = v.lgam[i];
     const bool allow_rel = v.allow_rel != 0;
+    const unsigned N = (unsigned)v.N, L = (unsigned)v.L;
+    const bool locus_major = f.out_locus_major != 0;
+    auto out_index = [&](unsigned tl, unsigned tn) -> size_t {
+        const unsigned t = tl / L;
+        return locus_major ? (size_t)tl * N + (tn - t * N) : (size_t)tn * L + (tl - t * L);
+    };
     const int n_egf = (int)f.bounds[0], coop_end = (int)f.bounds[1], nwork = (int)f.bounds[2];
     const bool chunked_heavy = (size_t)coop_end * 4 > (size_t)nwork;
     const int t_egf = pf_tasks(n_egf, chunked_heavy, false);
@@ -394,21 +403,21 @@ __global__ void __launch_bounds__(256, MOIRE_PF_MIN_BLOCKS) k_flat_eval(const Vi
                 const int w = lo + unit;
                 if (w >= hi) break;
                 const uint4 e = f.list[w];
-                if (f.round_flags && ((unsigned)f.round_flags[(size_t)e.y * 4 + 3] & kPfActive) == 0)
+                if (f.round_flags && ((unsigned)f.round_flags[(size_t)e.z * 4 + 3] & kPfActive) == 0)
                     continue;
-                const unsigned long long lat = f.latent[e.x];
-                const int m = f.m[e.z], k = __popcll(lat);
-                const double *prow = f.p + (size_t)e.y * f.p_stride;
+                const unsigned long long lat = ((unsigned long long)e.y << 32) | e.x;
+                const int m = f.m[e.w], k = __popcll(lat);
+                const double *prow = f.p + (size_t)e.z * f.p_stride;
                 double T;
                 if (k > m)
                     T = NAN;
                 else if (egf)
-                    T = transmission_ll_egf_coop(lat, prow, m, f.log_r[e.z], f.log_1mr[e.z], allow_rel,
+                    T = transmission_ll_egf_coop(lat, prow, m, f.log_r[e.w], f.log_1mr[e.w], allow_rel,
                                                  s_scr + warp * 32, ST, s_lgam);
                 else
-                    T = transmission_ll_coop(lat, prow, m, f.log_r[e.z], f.log_1mr[e.z], allow_rel,
+                    T = transmission_ll_coop(lat, prow, m, f.log_r[e.w], f.log_1mr[e.w], allow_rel,
                                              s_scr + warp * 32, ST, s_lgam);
-                if (lane == 0) f.out[e.w] = T;
+                if (lane == 0) f.out[out_index(e.z, e.w)] = T;
                 __syncwarp();
             }
             else
@@ -419,10 +428,11 @@ __global__ void __launch_bounds__(256, MOIRE_PF_MIN_BLOCKS) k_flat_eval(const Vi
                 if (w < hi)
                 {
                     const uint4 e = f.list[w];
-                    if (!f.round_flags || ((unsigned)f.round_flags[(size_t)e.y * 4 + 3] & kPfActive))
-                        f.out[e.w] = transmission_ll(f.latent[e.x], f.p + (size_t)e.y * f.p_stride,
-                                                     f.m[e.z], f.log_r[e.z], f.log_1mr[e.z], allow_rel,
-                                                     s_scr + tid, ST, s_lgam);
+                    if (!f.round_flags || ((unsigned)f.round_flags[(size_t)e.z * 4 + 3] & kPfActive))
+                        f.out[out_index(e.z, e.w)] =
+                            transmission_ll(((unsigned long long)e.y << 32) | e.x,
+                                            f.p + (size_t)e.z * f.p_stride, f.m[e.w], f.log_r[e.w],
+                                            f.log_1mr[e.w], allow_rel, s_scr + tid, ST, s_lgam);
                 }
                 __syncwarp();
             }
