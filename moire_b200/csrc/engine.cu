@@ -163,6 +163,7 @@ struct moire_engine
     DevBuf<int> sf_m;
     DevBuf<double> sf_logr, sf_log1mr, sf_adj;
     DevBuf<unsigned long long> sf_lat;
+    DevBuf<moire::EpsLogs> sf_elogs;
     DevBuf<unsigned char> missing;
     DevBuf<int> nall, aclass, avals, obs_coi, m, acc6, p_acc, p_att, active;
     DevBuf<double> logC, lgam, lgadj, cellT, cellO, persample, p, p_sd, perchain, scratchN;
@@ -191,7 +192,7 @@ struct moire_engine
         p_acc.release(); p_att.release(); active.release(); logC.release(); lgam.release();
         pf_list.release(); pf_hist.release(); pf_Tcur.release(); pf_Tnew.release(); pf_pprop.release();
         pf_round.release(); pf_nonmiss.release();
-        sf_prop.release(); sf_m.release(); sf_logr.release(); sf_log1mr.release(); sf_lat.release(); sf_adj.release();
+        sf_prop.release(); sf_m.release(); sf_logr.release(); sf_log1mr.release(); sf_lat.release(); sf_adj.release(); sf_elogs.release();
         lgadj.release(); cellT.release(); cellO.release(); persample.release(); p.release();
         p_sd.release(); perchain.release(); scratchN.release();
         if (v.trace && std::getenv("MOIRE_B200_TRACE"))
@@ -381,9 +382,9 @@ struct moire_engine
             p_smem = 0;  // the fused kernel's per-block arrays are not needed
             // the per-sample updates share the list, the histogram and the two term arrays
             sf_prop.alloc(TN); sf_m.alloc(TN); sf_logr.alloc(TN); sf_log1mr.alloc(TN);
-            sf_lat.alloc(TNL); sf_adj.alloc(TNL);
+            sf_lat.alloc(TNL); sf_adj.alloc(TNL); sf_elogs.alloc(TN * (size_t)v.nA);
             sf.prop = sf_prop.ptr; sf.m_new = sf_m.ptr; sf.log_r_new = sf_logr.ptr;
-            sf.log_1mr_new = sf_log1mr.ptr; sf.lat = sf_lat.ptr; sf.adj = sf_adj.ptr;
+            sf.log_1mr_new = sf_log1mr.ptr; sf.lat = sf_lat.ptr; sf.adj = sf_adj.ptr; sf.elogs = sf_elogs.ptr;
             sf.O = pf_Tcur.ptr; sf.Tn = pf_Tnew.ptr;
         }
         cudaDeviceProp prop;
@@ -412,13 +413,6 @@ struct moire_engine
             CUDA_TRY(cudaFuncSetAttribute(k_update_p<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
         }
         CUDA_TRY(cudaFuncSetAttribute(k_flat_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
-        {
-            const int ps = (int)sf_smem(tile_S, v.nA);
-            CUDA_TRY(cudaFuncSetAttribute(k_sf_propose<KIND_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps));
-            CUDA_TRY(cudaFuncSetAttribute(k_sf_propose<KIND_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps));
-            CUDA_TRY(cudaFuncSetAttribute(k_sf_propose<KIND_EFF_COI>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps));
-            CUDA_TRY(cudaFuncSetAttribute(k_sf_propose<KIND_SAMPLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps));
-        }
         {
             int per_sm = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flat_eval, 256, pf_eval_smem()));
@@ -505,7 +499,7 @@ struct moire_engine
         src.p = pf.pprop; src.p_stride = v.AP; src.out_locus_major = 1;
         src.m = v.m; src.log_r = v.log_r; src.log_1mr = v.log_1mr;
         src.round_flags = pf.round; src.out = pf.Tnew;
-        launches += 4;
+        launches += 2;  // prepare, scan, scatter (the caller counted one)
         for (int rep = 0; rep < amax_alleles; ++rep)
         {
             k_pf_round<<<(v.T * v.L + kPfRoundThreads / 32 - 1) / (kPfRoundThreads / 32), kPfRoundThreads, 0, stream>>>(v, pf, iteration, rep);
@@ -525,10 +519,10 @@ struct moire_engine
     {
         using namespace moire;
         const size_t total = (size_t)v.T * v.N * v.L;
-        const unsigned tiles = (unsigned)(v.T * tiles_per_chain);
+        const unsigned draw_blocks = (unsigned)(((size_t)v.T * v.N + kDrawThreads - 1) / kDrawThreads);
         CUDA_TRY(cudaMemsetAsync(pf.hist, 0, kPfHistWords * sizeof(unsigned int), stream));
-        k_sf_propose<KIND><<<tiles, 256, sf_smem(tile_S, v.nA), stream>>>(v, sf, pf, iteration, tile_S,
-                                                                          tiles_per_chain);
+        k_sf_draw<KIND><<<draw_blocks, kDrawThreads, 0, stream>>>(v, sf, iteration);
+        k_sf_cells<KIND><<<sf_cell_blocks(total), 256, 0, stream>>>(v, sf, pf, iteration);
         k_pf_scan<<<1, 256, 0, stream>>>(pf);
         k_sf_scatter<KIND><<<scatter_blocks(total), 256, 0, stream>>>(v, sf, pf);
         FlatSrc src{};
@@ -538,7 +532,7 @@ struct moire_engine
         src.round_flags = nullptr; src.out = sf.Tn;
         launch_flat_eval(src);
         k_sf_decide<KIND><<<(unsigned)(((size_t)v.T * v.N + 7) / 8), 256, 0, stream>>>(v, sf, iteration);
-        launches += 5;
+        launches += 5;  // draw, cells, scan, scatter, eval, decide (the caller counted one)
         CUDA_TRY(cudaGetLastError());
     }
 
@@ -550,8 +544,10 @@ struct moire_engine
             if (!p_fused)
             {
                 const size_t units = (size_t)v.T * v.N;
-                moire::k_eps_update<KIND><<<(unsigned)((units + moire::kEpsWarps - 1) / moire::kEpsWarps),
-                                            moire::kEpsWarps * 32, moire::eps_smem(v.nA), stream>>>(v, iteration);
+                moire::k_sf_draw<KIND><<<(unsigned)((units + moire::kDrawThreads - 1) / moire::kDrawThreads),
+                                         moire::kDrawThreads, 0, stream>>>(v, sf, iteration);
+                moire::k_eps_cells<KIND><<<(unsigned)((units + 7) / 8), 256, 0, stream>>>(v, sf, iteration);
+                launches += 1;  // two kernels; the caller counts one
                 return;
             }
         }

@@ -1,13 +1,19 @@
-// The per-sample updates that need transmission terms (update_m, update_r, update_eff_coi,
-// update_samples; src/chain.cpp:165-374, 697-807) as a flat pipeline, like update_p (p_flat.cuh):
-//   k_sf_propose  one block per (chain, sample tile): the proposals, the resampled latent
-//                 genotypes (own Philox stream per cell), the observation terms, the cost-class
-//                 histogram
+// The per-sample updates (update_eps_neg, update_eps_pos, update_m, update_r, update_eff_coi,
+// update_samples; src/chain.cpp:165-374, 697-807) as flat pipelines, like update_p (p_flat.cuh):
+//   k_sf_draw     one thread per (chain, sample): the proposal (serial scalar math, so it runs
+//                 lanes-across-samples and all samples at once), then the observation logs of the
+//                 proposed error rates per (sample, distinct allele count)
+//   k_sf_cells    one thread per cell: the resampled latent genotype (own Philox stream per
+//                 cell), the observation term, the cost-class histogram
 //   k_pf_scan / k_sf_scatter   device-wide counting sort of the cells of valid proposals
 //   k_flat_eval   the transmission terms, uniform warps, no barriers            (p_flat.cuh)
 //   k_sf_decide   one warp per (chain, sample): the sample's sums, the Metropolis decision, commit
-// Streams, arithmetic and summation order are those of the fused k_update_sample, which stays in
-// use for the two error-rate updates (no transmission term) and for tiny problems.
+//   k_eps_cells   the error-rate updates have no transmission term: cells, decision and commit in
+//                 one warp-per-sample kernel after k_sf_draw
+// No kernel has a serial phase behind a block barrier (ncu, tile-per-block version: the ten
+// proposal lanes of a 256-thread block kept the other warps at the barrier for ~20 us per tile,
+// 37 % of the stall samples).  Streams, arithmetic and summation order are those of the fused
+// k_update_sample, which stays in use for tiny problems.
 #pragma once
 #include "p_flat.cuh"
 
@@ -18,81 +24,87 @@ struct SFlat
     Proposal *prop;                  // [T * N]
     int *m_new;                      // [T * N] proposed COI
     double *log_r_new, *log_1mr_new; // [T * N]
+    EpsLogs *elogs;                  // [T * N][nA] logs of the proposed error rates
     unsigned long long *lat;         // [T][N][L] proposed latent genotypes
     double *adj;                     // [T][N][L] their log proposal densities
     double *O, *Tn;                  // [T][N][L] observation / transmission terms of the proposal
 };
 
-__host__ __device__ inline size_t sf_smem(int S, int nA)
-{
-    return 128 * sizeof(double) + (size_t)S * nA * sizeof(EpsLogs) + (size_t)S * sizeof(Proposal) +
-           kSortBins * sizeof(unsigned int);
-}
+constexpr int kDrawThreads = 128;
 
 template <int KIND>
-__global__ void __launch_bounds__(256)
-    k_sf_propose(const View v, const SFlat sf, const PFlat pf, const int iteration, const int S,
-                 const int tiles_per_chain)
+__global__ void __launch_bounds__(kDrawThreads) k_sf_draw(const View v, const SFlat sf, const int iteration)
 {
-    constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
-    extern __shared__ double smem[];
-    double *s_lgam = smem;
-    EpsLogs *s_elogs = reinterpret_cast<EpsLogs *>(s_lgam + 128);
-    Proposal *s_prop = reinterpret_cast<Proposal *>(s_elogs + S * v.nA);
-    unsigned int *s_hist = reinterpret_cast<unsigned int *>(s_prop + S);
-    __shared__ unsigned int s_evals;
+    constexpr bool LOGS = KIND != KIND_R;  // the kinds that recompute observation terms
+    __shared__ double s_en[kDrawThreads], s_ep[kDrawThreads];
+    __shared__ int s_valid[kDrawThreads];
     const int tid = threadIdx.x;
-    const int t = blockIdx.x / tiles_per_chain;
-    const int s0 = (blockIdx.x - t * tiles_per_chain) * S;
-    const int ns = min(S, v.N - s0);
-    const int N = v.N, L = v.L, nA = v.nA;
-    const unsigned gchain = (unsigned)(v.chain_offset + t);
-    for (int i = tid; i < 128; i += 256) s_lgam[i] = v.lgam[i];
-    for (int b = tid; b < kSortBins; b += 256) s_hist[b] = 0;
-    if (tid == 0) s_evals = 0;
-    __syncthreads();
-    if (tid < ns)
+    const size_t total = (size_t)v.T * v.N;
+    const size_t si0 = (size_t)blockIdx.x * kDrawThreads, si = si0 + tid;
+    if (si < total)
     {
-        const Proposal P = draw_sample_proposal<KIND>(v, t, s0 + tid, iteration, s_lgam);
-        const size_t si = (size_t)t * N + s0 + tid;
-        s_prop[tid] = P;
+        const int t = (int)(si / v.N), i = (int)(si - (size_t)t * v.N);
+        const Proposal P = draw_sample_proposal<KIND>(v, t, i, iteration, v.lgam);
         sf.prop[si] = P;
         sf.m_new[si] = P.m_new;
         sf.log_r_new[si] = P.log_r;
         sf.log_1mr_new[si] = P.log_1mr;
+        s_en[tid] = P.en_new;
+        s_ep[tid] = P.ep_new;
+        s_valid[tid] = P.valid;
     }
+    if (!LOGS) return;
     __syncthreads();
-    if (RESAMPLE)
+    const int n = (int)min((size_t)kDrawThreads, total - si0), nA = v.nA;
+    for (int e = tid; e < n * nA; e += kDrawThreads)
     {
-        for (int e = tid; e < ns * nA; e += 256)
-        {
-            const int sl = e / nA, a = e - sl * nA;
-            build_eps_logs(s_elogs[e], s_prop[sl].en_new, s_prop[sl].ep_new, v.max_eps_neg,
+        const int sl = e / nA, a = e - sl * nA;
+        if (s_valid[sl])
+            build_eps_logs(sf.elogs[(si0 + sl) * nA + a], s_en[sl], s_ep[sl], v.max_eps_neg,
                            v.max_eps_pos, v.avals[a]);
-        }
-        __syncthreads();
     }
-    const size_t tile_base = ((size_t)t * N + s0) * L;
-    const size_t data_base = (size_t)s0 * L;
-    const int ncell = ns * L;
+}
+
+constexpr int kCellsPerThread = 4;
+__host__ __device__ inline unsigned sf_cell_blocks(size_t total)
+{
+    return (unsigned)((total + 256 * kCellsPerThread - 1) / (256 * kCellsPerThread));
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_sf_cells(const View v, const SFlat sf, const PFlat pf, const int iteration)
+{
+    constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
+    __shared__ unsigned int s_hist[kSortBins];
+    __shared__ unsigned int s_evals;
+    const int tid = threadIdx.x;
+    for (int b = tid; b < kSortBins; b += 256) s_hist[b] = 0;
+    if (tid == 0) s_evals = 0;
+    __syncthreads();
+    const unsigned N = (unsigned)v.N, L = (unsigned)v.L, nA = (unsigned)v.nA;
+    const size_t total = (size_t)v.T * N * L;
     unsigned my_evals = 0;
-    for (int cell = tid; cell < ncell; cell += 256)
+#pragma unroll 1
+    for (int c = 0; c < kCellsPerThread; ++c)
     {
-        const int sl = cell / L, j = cell - sl * L;
-        const Proposal &P = s_prop[sl];
-        if (!P.valid) continue;
-        const size_t gi = tile_base + cell;
-        const bool miss = v.missing[data_base + cell] != 0;
+        const size_t gi = ((size_t)blockIdx.x * kCellsPerThread + c) * 256 + tid;
+        if (gi >= total) break;
+        const unsigned tn = (unsigned)(gi / L), j = (unsigned)(gi - (size_t)tn * L);
+        if (!sf.prop[tn].valid) continue;
+        const unsigned t = tn / N, i = tn - t * N;
+        const size_t di = (size_t)i * L + j;
+        const bool miss = v.missing[di] != 0;
+        const int m_new = sf.m_new[tn];
         unsigned long long lat;
         if (RESAMPLE)
         {
-            const unsigned long long obs = v.obs[data_base + cell];
+            const unsigned long long obs = v.obs[di];
             const int A = v.nall[j];
-            const EpsLogs &el = s_elogs[sl * nA + v.aclass[j]];
+            const EpsLogs el = sf.elogs[(size_t)tn * nA + v.aclass[j]];
             Stream crng;
-            crng.open(v.seed, (uint32_t)iteration, KIND, gchain, (uint32_t)(s0 + sl), (uint32_t)(j + 1));
+            crng.open(v.seed, (uint32_t)iteration, KIND, (unsigned)(v.chain_offset + t), i, j + 1u);
             double lp;
-            lat = sample_latent_genotype(crng, obs, A, P.m_new, el, v.logC, &lp);
+            lat = sample_latent_genotype(crng, obs, A, m_new, el, v.logC, &lp);
             sf.lat[gi] = lat;
             sf.adj[gi] = lp;
             if (!miss) sf.O[gi] = observation_ll(lat, obs, A, el);
@@ -103,7 +115,7 @@ __global__ void __launch_bounds__(256)
         }
         if (!miss)
         {
-            atomicAdd(&s_hist[work_class(__popcll(lat), P.m_new)], 1u);
+            atomicAdd(&s_hist[work_class(__popcll(lat), m_new)], 1u);
             ++my_evals;
         }
     }
@@ -147,16 +159,30 @@ __global__ void __launch_bounds__(256) k_sf_decide(const View v, const SFlat sf,
     double d = 0.0, a = 0.0;
     if (valid)
     {
-        for (int j = lane; j < L; j += 32)
+        // four loci per lane in flight (the loads of a chunk are issued before its sums)
+        for (int j0 = 0; j0 < L; j0 += 128)
         {
-            const size_t gi = base + j;
-            if (RESAMPLE) a += sf.adj[gi] - v.lgadj[gi];
-            if (v.missing[data_base + j] == 0)
+            double vT[4], vO[4], vTn[4], vOn[4], va[4], vb[4];
+            bool use[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
             {
-                const double oldT = v.cellT[gi], oldO = v.cellO[gi];
-                const double T = sf.Tn[gi];
-                const double O = RESAMPLE ? sf.O[gi] : oldO;
-                d += __dadd_rn(T, O) - __dadd_rn(oldT, oldO);
+                const int j = j0 + 32 * u + lane;
+                const bool in = j < L;
+                use[u] = in && v.missing[data_base + (in ? j : 0)] == 0;
+                const size_t gi = base + (in ? j : 0);
+                va[u] = (RESAMPLE && in) ? sf.adj[gi] : 0.0;
+                vb[u] = (RESAMPLE && in) ? v.lgadj[gi] : 0.0;
+                vT[u] = use[u] ? v.cellT[gi] : 0.0;
+                vO[u] = use[u] ? v.cellO[gi] : 0.0;
+                vTn[u] = use[u] ? sf.Tn[gi] : 0.0;
+                vOn[u] = (RESAMPLE && use[u]) ? sf.O[gi] : vO[u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+                if (RESAMPLE && j0 + 32 * u + lane < L) a += va[u] - vb[u];
+                if (use[u]) d += __dadd_rn(vTn[u], vOn[u]) - __dadd_rn(vT[u], vO[u]);
             }
         }
     }
@@ -186,46 +212,52 @@ __global__ void __launch_bounds__(256) k_sf_decide(const View v, const SFlat sf,
         }
     }
 }
-// ---- update_eps_neg / update_eps_pos (src/chain.cpp:267-374): no transmission term, so the whole
-// update is one kernel; one warp per (chain, sample), no block barriers.  Lane 0 draws the
-// proposal, lanes across the distinct allele counts build the observation logs of the proposed
-// rates (per-warp shared memory), lanes across loci recompute the observation terms.  Streams,
-// arithmetic and summation order are those of the fused k_update_sample<KIND>.
-constexpr int kEpsWarps = 4;
-__host__ __device__ inline size_t eps_smem(int nA) { return (size_t)kEpsWarps * nA * sizeof(EpsLogs); }
-
+// ---- update_eps_neg / update_eps_pos (src/chain.cpp:267-374) after k_sf_draw: one warp per
+// (chain, sample) recomputes the observation terms under the proposed rate (lanes across loci, four
+// loci per lane in flight), lane 0 decides, the warp commits.
 template <int KIND>
-__global__ void __launch_bounds__(kEpsWarps * 32) k_eps_update(const View v, const int iteration)
+__global__ void __launch_bounds__(256) k_eps_cells(const View v, const SFlat sf, const int iteration)
 {
     static_assert(KIND == KIND_EPS_NEG || KIND == KIND_EPS_POS, "error-rate updates only");
-    extern __shared__ double smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t si = (size_t)blockIdx.x * kEpsWarps + warp;
+    const int lane = threadIdx.x & 31;
+    const size_t si = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (si >= (size_t)v.T * v.N) return;
     const int N = v.N, L = v.L, nA = v.nA;
     const int t = (int)(si / N), i = (int)(si - (size_t)t * N);
-    EpsLogs *el = reinterpret_cast<EpsLogs *>(smem) + (size_t)warp * nA;
-    Proposal P = {};
-    if (lane == 0) P = draw_sample_proposal<KIND>(v, t, i, iteration, v.lgam);
-    const int valid = __shfl_sync(0xffffffffu, lane == 0 ? P.valid : 0, 0);
-    double d = 0.0;
     const size_t base = si * L, data_base = (size_t)i * L;
+    const bool valid = sf.prop[si].valid != 0;
+    const EpsLogs *el = sf.elogs + si * nA;
+    double d = 0.0;
+    unsigned n_eval = 0;
     if (valid)
     {
-        const double en = __shfl_sync(0xffffffffu, P.en_new, 0);
-        const double ep = __shfl_sync(0xffffffffu, P.ep_new, 0);
-        for (int a = lane; a < nA; a += 32)
-            build_eps_logs(el[a], en, ep, v.max_eps_neg, v.max_eps_pos, v.avals[a]);
-        __syncwarp();
-        unsigned n_eval = 0;
-        for (int j = lane; j < L; j += 32)
+        for (int j0 = 0; j0 < L; j0 += 128)
         {
-            if (v.missing[data_base + j] != 0) continue;
-            const size_t gi = base + j;
-            const double oldT = v.cellT[gi], oldO = v.cellO[gi];
-            const double O = observation_ll(v.latent[gi], v.obs[data_base + j], v.nall[j], el[v.aclass[j]]);
-            d += __dadd_rn(oldT, O) - __dadd_rn(oldT, oldO);
-            ++n_eval;
+            double vT[4], vO[4];
+            unsigned long long vl[4], vo[4];
+            int vA[4], vc[4];
+            bool use[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+                const int j = j0 + 32 * u + lane;
+                use[u] = j < L && v.missing[data_base + (j < L ? j : 0)] == 0;
+                const int jj = use[u] ? j : 0;
+                vT[u] = use[u] ? v.cellT[base + jj] : 0.0;
+                vO[u] = use[u] ? v.cellO[base + jj] : 0.0;
+                vl[u] = use[u] ? v.latent[base + jj] : 0ull;
+                vo[u] = use[u] ? v.obs[data_base + jj] : 0ull;
+                vA[u] = v.nall[jj];
+                vc[u] = v.aclass[jj];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (use[u])
+                {
+                    const double O = observation_ll(vl[u], vo[u], vA[u], el[vc[u]]);
+                    d += __dadd_rn(vT[u], O) - __dadd_rn(vT[u], vO[u]);
+                    ++n_eval;
+                }
         }
         n_eval = __reduce_add_sync(0xffffffffu, n_eval);
         if (lane == 0 && n_eval) atomicAdd(v.evals + KIND, (unsigned long long)n_eval);
@@ -234,6 +266,7 @@ __global__ void __launch_bounds__(kEpsWarps * 32) k_eps_update(const View v, con
     int accept = 0;
     if (lane == 0)
     {
+        Proposal P = sf.prop[si];
         decide_sample<KIND>(v, P, t, i, iteration, d, 0.0);
         accept = P.accept;
     }
