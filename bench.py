@@ -143,7 +143,7 @@ def reference_arm(args, wl):
                 cpu_baseline=dict(value=base["value"], unit=UNIT, cores=base["cores"],
                                   kind=base["kind"], sample=base["sample"]),
                 e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_of(wl, args):
@@ -314,12 +314,31 @@ def our_arm(args, wl):
                 evals_per_step=evals_total / args.steps,
                 wall_ms_per_step_incl_flush=1e3 * wall / args.steps,
                 kernel_ms_per_step={k: round(v / args.steps, 4) for k, v in kind_ms.items()})
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
+    # stdout carries exactly one JSON line: everything else that libraries write to fd 1 (NCCL's
+    # version banner at communicator creation, for one) goes to stderr
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -307,6 +307,11 @@ struct moire_engine
             std::vector<double> comb_h;
             build_egf_binomials(comb_h);
             CUDA_TRY(cudaMemcpyToSymbol(moire::g_egf_comb, comb_h.data(), comb_h.size() * sizeof(double)));
+            std::vector<unsigned short> rank_h;
+            std::vector<float> est_h;
+            moire::build_flat_classes(rank_h, est_h);
+            CUDA_TRY(cudaMemcpyToSymbol(moire::c_flat_class, rank_h.data(), rank_h.size() * sizeof(unsigned short)));
+            CUDA_TRY(cudaMemcpyToSymbol(moire::c_flat_est, est_h.data(), est_h.size() * sizeof(float)));
             const int D = moire::kMaxCoi + 1;
             std::vector<double> binom_h((size_t)D * D, 0.0);
             for (int n = 0; n < D; ++n)
@@ -419,6 +424,7 @@ struct moire_engine
             cudaDeviceProp prop1;
             CUDA_TRY(cudaGetDeviceProperties(&prop1, device));
             flat_grid = std::max(1, per_sm) * prop1.multiProcessorCount;
+            pf.eval_threads = flat_grid * 256;
         }
     }
 

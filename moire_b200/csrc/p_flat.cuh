@@ -15,16 +15,19 @@
 // proposals, per-cell arithmetic and the order of every sum are those of the fused kernel, so the
 // two produce the same chain.
 #pragma once
+#include <algorithm>
+#include <vector>
 #include "kernels.cuh"
 
 namespace moire
 {
 struct PFlat
 {
-    uint4 *list;         // [cells] {cell in [T][N][L], t * L + j, t * N + i, (t * L + j) * N + i}
+    uint4 *list;         // [cells] {latent genotype lo, hi, t * L + j, t * N + i}, sorted by cost class
     unsigned int *hist;  // [kSortBins] counts, [kSortBins] running offsets, 4 scalars, task counters
     double *Tcur, *Tnew; // [T][L][N] transmission terms, locus-major, for the duration of the update
     double *pprop;       // [T * L][AP] proposed frequencies
+    int eval_threads;   // threads of one evaluator launch (sets the cooperative threshold)
     double *round;       // [T * L][4] logAdj, log u, allele index, flags
     const int *nonmiss;  // [L] non-missing cells of a locus
 };
@@ -34,6 +37,75 @@ constexpr int kPfCounters = kPfScalars + 4;  // one task counter per evaluator l
 constexpr int kPfHistWords = kPfCounters + 72;
 
 // ---- once per update: locus-major copy of the current terms, class histogram, sorted list -----
+// ---- cost classes of the flat pipelines, ranked by work ----------------------------------------
+// The persistent evaluator is as slow as its longest single task.  A one-thread cell costs
+// ~(2^k - 1) (k + 2 (m - k + 1)) dependent instructions: 127 subsets x 34 mixture terms (k = 7 in
+// a hot chain that wandered to COI 40) keep one thread busy for ~70 us while a whole launch of
+// the c3 ladder takes ~200 us, and a 5-chain shard of it took 180 us instead of ~35
+// (profiles/README.md, r01n).  So the classes (k, m - k + 1) are ranked by estimated one-thread
+// work, heaviest first (c_flat_class[kk * 64 + cnt - 1] is the rank, c_flat_est[rank] the
+// estimate; ranks < 64 are the EGF classes, k > 10, by m), and every launch splits the list where
+// the estimate falls below a threshold: above it a cell goes to the warp-cooperative evaluator
+// whatever its k.  The threshold follows the launch's work per thread (k_pf_scan): the cooperative
+// path has the shorter critical path but the lower throughput (lanes idle in its sums), so a full
+// ladder wants it for the few heaviest cells only (8000 instructions ~ k >= 8, the tuned optimum
+// at 40 chains) and a small shard for many more.
+#ifndef MOIRE_COOP_WORK_MAX
+#define MOIRE_COOP_WORK_MAX 8000.f
+#endif
+#ifndef MOIRE_COOP_WORK_MIN
+#define MOIRE_COOP_WORK_MIN 3000.f
+#endif
+#ifndef MOIRE_COOP_WORK_SHARE
+#define MOIRE_COOP_WORK_SHARE 1.2f
+#endif
+__constant__ unsigned short c_flat_class[12 * 64];
+__constant__ float c_flat_est[kSortBins];
+
+__device__ __forceinline__ int work_class_flat(int k, int m)
+{
+    int kk = k > kIeMax ? kIeMax + 1 : k;
+    int cnt = k > kIeMax ? m : m - k + 1;
+    cnt = cnt < 1 ? 1 : (cnt > 64 ? 64 : cnt);
+    if (kk < MOIRE_MERGE_K) kk = MOIRE_MERGE_K;
+    return c_flat_class[kk * 64 + cnt - 1];
+}
+
+// host: the ranking.  est = subsets x (loop overhead + leading multiplications + two operations
+// per accumulator of the register tier), summed over the passes of 16 mixture terms.
+inline void build_flat_classes(std::vector<unsigned short> &rank, std::vector<float> &est_of_rank)
+{
+    struct C { int kk, cnt; double est; };
+    std::vector<C> cs;
+    for (int kk = MOIRE_MERGE_K; kk <= kIeMax; ++kk)
+        for (int cnt = 1; cnt <= 64; ++cnt)
+        {
+            const double subsets = (double)((1 << kk) - 1);
+            double est = 0.0;
+            for (int t0 = 0; t0 < cnt; t0 += 16)
+            {
+                const int left = cnt - t0;
+                const int nacc = left <= 2 ? 2 : left <= 4 ? 4 : left <= 6 ? 6 : left <= 8 ? 8 : left <= 12 ? 12 : 16;
+                est += subsets * (24.0 + (kk - 1 + t0) + 2.0 * nacc);
+            }
+            cs.push_back({kk, cnt, est});
+        }
+    std::stable_sort(cs.begin(), cs.end(), [](const C &a, const C &b) { return a.est > b.est; });
+    rank.assign(12 * 64, 0);
+    est_of_rank.assign(kSortBins, 0.f);
+    for (int cnt = 1; cnt <= 64; ++cnt)
+    {
+        // EGF: ~k m^2 with k > 10; always ahead of the inclusion-exclusion classes
+        rank[(kIeMax + 1) * 64 + cnt - 1] = (unsigned short)(64 - cnt);
+        est_of_rank[64 - cnt] = 16.f * (float)cnt * (float)cnt + 1e6f;
+    }
+    for (size_t i = 0; i < cs.size(); ++i)
+    {
+        rank[cs[i].kk * 64 + cs[i].cnt - 1] = (unsigned short)(64 + i);
+        est_of_rank[64 + i] = (float)cs[i].est;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
 {
     __shared__ unsigned int s_hist[kSortBins];
@@ -49,7 +121,7 @@ __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
         if (v.missing[(size_t)i * v.L + j] == 0)
         {
             f.Tcur[loc] = v.cellT[cell];
-            atomicAdd(&s_hist[work_class(__popcll(v.latent[cell]), v.m[(size_t)t * v.N + i])], 1u);
+            atomicAdd(&s_hist[work_class_flat(__popcll(v.latent[cell]), v.m[(size_t)t * v.N + i])], 1u);
         }
         else
         {
@@ -65,13 +137,16 @@ __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
 __global__ void __launch_bounds__(256) k_pf_scan(const PFlat f)
 {
     __shared__ unsigned int s_part[9];
+    __shared__ float s_work[8];
     const int tid = threadIdx.x;
     constexpr int per = kSortBins / 256;  // 3
     unsigned int local = 0, h[per];
+    float work = 0.f;
     for (int q = 0; q < per; ++q)
     {
         h[q] = f.hist[tid * per + q];
         local += h[q];
+        work += (float)h[q] * c_flat_est[tid * per + q];
     }
     unsigned int x = local;
 #pragma unroll
@@ -80,7 +155,10 @@ __global__ void __launch_bounds__(256) k_pf_scan(const PFlat f)
         const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
         if ((tid & 31) >= o) x += y;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) work += __shfl_xor_sync(0xffffffffu, work, o);
     if ((tid & 31) == 31) s_part[tid >> 5] = x;
+    if ((tid & 31) == 0) s_work[tid >> 5] = work;
     __syncthreads();
     if (tid == 0)
     {
@@ -94,13 +172,20 @@ __global__ void __launch_bounds__(256) k_pf_scan(const PFlat f)
         s_part[8] = run;
     }
     __syncthreads();
+    float total_work = 0.f;
+    for (int w = 0; w < 8; ++w) total_work += s_work[w];
+    // cooperative above this much one-thread work: a share of the launch's work per thread
+    const float share = MOIRE_COOP_WORK_SHARE * total_work / (float)f.eval_threads;
+    const float thr = fminf(MOIRE_COOP_WORK_MAX, fmaxf(MOIRE_COOP_WORK_MIN, share));
     unsigned int base = s_part[tid >> 5] + x - local;
     for (int q = 0; q < per; ++q)
     {
         const int b = tid * per + q;
         f.hist[kSortBins + b] = base;
         if (b == kClassCoopBegin) f.hist[kPfScalars + 0] = base;
-        if (b == kClassLightBegin) f.hist[kPfScalars + 1] = base;
+        // ranks >= 64 are sorted by estimate, descending: the first one below the threshold
+        if (b >= kClassCoopBegin && c_flat_est[b] < thr && (b == kClassCoopBegin || c_flat_est[b - 1] >= thr))
+            f.hist[kPfScalars + 1] = base;
         base += h[q];
     }
     if (tid == 0) f.hist[kPfScalars + 2] = s_part[8];
@@ -154,7 +239,7 @@ __global__ void __launch_bounds__(256) k_pf_scatter(const View v, const PFlat f)
         const size_t cell = ((size_t)t * v.N + i) * v.L + j;
         const unsigned tn = t * v.N + i;
         const unsigned long long lat = v.latent[cell];
-        cls = work_class(__popcll(lat), v.m[tn]);
+        cls = work_class_flat(__popcll(lat), v.m[tn]);
         entry = make_uint4((unsigned)lat, (unsigned)(lat >> 32), tl, tn);
         return true;
     };

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) k_sf_cells(const View v, const SFlat sf, 
         }
         if (!miss)
         {
-            atomicAdd(&s_hist[work_class(__popcll(lat), m_new)], 1u);
+            atomicAdd(&s_hist[work_class_flat(__popcll(lat), m_new)], 1u);
             ++my_evals;
         }
     }
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_sf_scatter(const View v, const SFlat sf
         const unsigned t = tn / v.N, i = tn - t * v.N;
         if (!sf.prop[tn].valid || v.missing[(size_t)i * v.L + j] != 0) return false;
         const unsigned long long lat = RESAMPLE ? sf.lat[gi] : v.latent[gi];
-        cls = work_class(__popcll(lat), sf.m_new[tn]);
+        cls = work_class_flat(__popcll(lat), sf.m_new[tn]);
         entry = make_uint4((unsigned)lat, (unsigned)(lat >> 32), t * v.L + j, tn);
         return true;
     };
