@@ -340,15 +340,19 @@ __device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, i
         }
     }
 #endif
-    double mx = -INFINITY;
-    for (int t = 0; t < cnt; ++t)
-    {
+    // the reference's log-sum-exp form; val[] is left untouched (the terms are recomputed for the
+    // sum), so that one set of PAMs can serve several samples
+    auto term = [&](int t) -> double {
         const int i = cnt - 1 - t;
         const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
         const double pam = clamp_pam(val[t * ST]);
-        const double i_res = __dadd_rn(hot_log1m(pam), __dmul_rn(log_total, (double)(m - i)));
-        const double v = __dadd_rn(pr, i_res);
-        val[t * ST] = v;
+        const double i_res = __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)(m - i)));
+        return __dadd_rn(pr, i_res);
+    };
+    double mx = -INFINITY;
+    for (int t = 0; t < cnt; ++t)
+    {
+        const double v = term(t);
         mx = (mx < v) ? v : mx;  // std::max_element semantics
     }
     if (mx == -INFINITY) return -INFINITY;
@@ -356,10 +360,10 @@ __device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, i
     double sum = 0.0;
     for (int t = cnt - 1; t >= 0; --t)  // i ascending, as the reference sums
     {
-        const double dv = __dsub_rn(val[t * ST], mx);
-        sum = __dadd_rn(sum, dv == 0.0 ? 1.0 : exp(dv));
+        const double dv = __dsub_rn(term(t), mx);
+        sum = __dadd_rn(sum, dv == 0.0 ? 1.0 : cold_exp(dv));
     }
-    return __dadd_rn(mx, hot_log(sum));
+    return __dadd_rn(mx, cold_log(sum));
 }
 
 #ifndef MOIRE_TIERS
@@ -374,11 +378,9 @@ constexpr int kMaxAcc = 16;  // accumulators kept in registers
 // instruction stream.  Two tiers are compiled, {4, 16}: measured best on B200
 // (profiles/variants_g.log) -- more tiers mean more distinct hot loops competing for the
 // instruction caches, which costs more than the idle accumulators do.
-__device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, int m,
-                                                   double log_total, double log_r, double log_1mr,
-                                                   const double *lgam)
+// PAM(n = k + t), t < cnt <= kMaxAcc, into scr[t * ST] (q in slots 0..k-1 is consumed).
+__device__ __noinline__ void ie_pams(double *scr, int ST, int k, int cnt)
 {
-    const int cnt = m - k + 1;
     const int cnt_w = __reduce_max_sync(__activemask(), cnt);
 #define MOIRE_IE_TIER(NACC)                                                     \
     {                                                                           \
@@ -416,6 +418,14 @@ __device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, i
     else MOIRE_IE_TIER(16)
 #endif
 #undef MOIRE_IE_TIER
+}
+
+__device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, int m,
+                                                   double log_total, double log_r, double log_1mr,
+                                                   const double *lgam)
+{
+    const int cnt = m - k + 1;
+    ie_pams(scr, ST, k, cnt);
     return relatedness_mixture(scr, ST, m, cnt, log_total, log_r, log_1mr, lgam);
 }
 
@@ -585,7 +595,6 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
     const unsigned short *masks = g_sub_mask + subset_block(k);
     const int nsub = (1 << k) - 1;
     const int cnt = allow_relatedness ? m - k + 1 : 1;
-    double result_mx = -INFINITY, sum_tail = 0.0;
     // accumulators of up to 4 chunks of 16 mixture terms (cnt <= 64); chunk c, lane t: n = k + 16c + t
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -661,50 +670,19 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
         const double pam = clamp_pam(__shfl_sync(FULL, acc[0], 0));
         return __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)m));
     }
-    // mixture terms, one per (chunk, lane)
-    double v[4];
-    double mx = -INFINITY;
+    // The mixture through the same function, in the same order of operations, as the one-thread
+    // path: which evaluator a cell lands in depends on the launch (the cooperative threshold
+    // follows the work per thread, so it changes with the number of chains on the device) and must
+    // not change a bit of the result.  Every lane gathers the sums and computes the same value.
+    double pams[kMaxCoi];
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
-    {
-        const int t = 16 * ch + lane;
-        v[ch] = -INFINITY;
-        if (lane < 16 && t < cnt)
-        {
-            const int i = cnt - 1 - t;
-            const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
-            const double pam = clamp_pam(acc[ch]);
-            const double i_res = __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)(m - i)));
-            v[ch] = __dadd_rn(pr, i_res);
-            mx = (mx < v[ch]) ? v[ch] : mx;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-    {
-        const double other = __shfl_xor_sync(FULL, mx, o);
-        mx = (mx < other) ? other : mx;
-    }
-    result_mx = mx;
-    if (result_mx == -INFINITY) return -INFINITY;
-    if (cnt == 1) return result_mx;
-    // sum cold_exp(v - mx) in the reference's order: i ascending = t descending
-#pragma unroll
-    for (int ch = 3; ch >= 0; --ch)
-    {
         if (16 * ch < cnt)  // uniform
         {
-            double ev = 0.0;
-            if (lane < 16 && 16 * ch + lane < cnt)
-            {
-                const double dv = __dsub_rn(v[ch], result_mx);
-                ev = dv == 0.0 ? 1.0 : cold_exp(dv);
-            }
-            const int top = min(15, cnt - 1 - 16 * ch);
-            for (int t = top; t >= 0; --t) sum_tail = __dadd_rn(sum_tail, __shfl_sync(FULL, ev, t));
+            const int top = min(16, cnt - 16 * ch);
+            for (int t = 0; t < top; ++t) pams[16 * ch + t] = __shfl_sync(FULL, acc[ch], t);
         }
-    }
-    return __dadd_rn(result_mx, cold_log(sum_tail));
+    return relatedness_mixture(pams, 1, m, cnt, log_total, log_r, log_1mr, lgam);
 }
 
 // ---- a2 for k > 10, warp-cooperative: the EGF recurrence with the draws across lanes ----------

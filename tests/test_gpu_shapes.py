@@ -147,3 +147,25 @@ def test_argument_errors_are_reported_not_fatal():
     with pytest.raises(MoireError, match="before init"):
         eng.step(0)
     eng.close()
+
+
+def test_chain_states_do_not_depend_on_the_ladder_size():
+    """Which evaluator a cell lands in (one thread or a cooperating warp) follows the launch's work
+    per thread, i.e. the number of chains on the device; both produce the same bits, so a chain's
+    trajectory is the same in a 2-chain and in a 6-chain engine (what makes sharding invisible)."""
+    from moire_b200.engine import Engine
+    from moire_b200.workloads import make_workload
+    wl = make_workload("c3")
+    pk = wl["packed"]
+    temps = wl["temps"][np.linspace(0, len(wl["temps"]) - 1, 6).astype(int)]
+    states = []
+    for n in (2, 6):
+        eng = Engine(pk, temps[:n], seed=9, burnin=100, **wl["model"])
+        eng.init_chains()
+        for it in range(3):
+            eng.step(it)
+        states.append([eng.dump_state(c) for c in range(2)])
+        eng.close()
+    for sa, sb in zip(*states):
+        for key in sa:
+            assert np.array_equal(np.asarray(sa[key]), np.asarray(sb[key]), equal_nan=True), key
