@@ -164,6 +164,7 @@ int moire_engine_get_temps(moire_engine *e, double *temps);
 
 int moire_engine_dump_state(moire_engine *e, int32_t chain, moire_chain_state *out);
 int moire_engine_load_state(moire_engine *e, int32_t chain, const moire_chain_state *in);
+/* chain < 0: every chain of the engine at once, each field [num_chains] times its per-chain size. */
 int moire_engine_read_diagnostics(moire_engine *e, int32_t chain, moire_chain_diagnostics *out);
 /* Chain::get_llik(sample) for every sample (src/chain.cpp:1083-1097): [N]. */
 int moire_engine_read_sample_llik(moire_engine *e, int32_t chain, double *out);

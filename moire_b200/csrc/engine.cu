@@ -797,24 +797,27 @@ struct moire_engine
         initialised = true;
     }
 
-    void read_diag(int t, moire_chain_diagnostics *o)
+    void read_diag(int chain, moire_chain_diagnostics *o)
     {
-        const size_t N = v.N, LA = (size_t)v.L * v.AP;
-        d2h(o->eps_neg_accept, v.acc_eps_neg + t * N, N);
-        d2h(o->eps_pos_accept, v.acc_eps_pos + t * N, N);
-        d2h(o->m_accept, v.acc_m + t * N, N);
-        d2h(o->r_accept, v.acc_r + t * N, N);
-        d2h(o->m_r_accept, v.acc_mr + t * N, N);
-        d2h(o->sample_accept, v.acc_samples + t * N, N);
-        d2h(o->eps_neg_var, v.sd_eps_neg + t * N, N);
-        d2h(o->eps_pos_var, v.sd_eps_pos + t * N, N);
-        d2h(o->r_var, v.sd_r + t * N, N);
-        d2h(o->m_r_var, v.sd_mr + t * N, N);
-        d2h(o->p_accept, v.p_acc + t * LA, LA);
-        d2h(o->p_attempt, v.p_att + t * LA, LA);
-        d2h(o->p_prop_var, v.p_sd + t * LA, LA);
-        d2h(o->mean_coi_accept, v.mean_coi_acc + t, 1);
-        d2h(o->mean_coi_var, v.mean_coi_sd + t, 1);
+        // chain < 0: every chain of the engine in one pass ([T][...] arrays are contiguous)
+        const size_t nc = chain < 0 ? (size_t)v.T : 1, t = chain < 0 ? 0 : (size_t)chain;
+        const size_t N = v.N * nc, LA = (size_t)v.L * v.AP * nc;
+        const size_t sN = v.N, sLA = (size_t)v.L * v.AP;
+        d2h(o->eps_neg_accept, v.acc_eps_neg + t * sN, N);
+        d2h(o->eps_pos_accept, v.acc_eps_pos + t * sN, N);
+        d2h(o->m_accept, v.acc_m + t * sN, N);
+        d2h(o->r_accept, v.acc_r + t * sN, N);
+        d2h(o->m_r_accept, v.acc_mr + t * sN, N);
+        d2h(o->sample_accept, v.acc_samples + t * sN, N);
+        d2h(o->eps_neg_var, v.sd_eps_neg + t * sN, N);
+        d2h(o->eps_pos_var, v.sd_eps_pos + t * sN, N);
+        d2h(o->r_var, v.sd_r + t * sN, N);
+        d2h(o->m_r_var, v.sd_mr + t * sN, N);
+        d2h(o->p_accept, v.p_acc + t * sLA, LA);
+        d2h(o->p_attempt, v.p_att + t * sLA, LA);
+        d2h(o->p_prop_var, v.p_sd + t * sLA, LA);
+        d2h(o->mean_coi_accept, v.mean_coi_acc + t, nc);
+        d2h(o->mean_coi_var, v.mean_coi_sd + t, nc);
         CUDA_TRY(cudaStreamSynchronize(stream));
     }
 
@@ -1034,7 +1037,8 @@ int moire_engine_load_state(moire_engine *e, int32_t chain, const moire_chain_st
 int moire_engine_read_diagnostics(moire_engine *e, int32_t chain, moire_chain_diagnostics *out)
 {
     return guarded(e, [&] {
-        need_chain(e, chain);
+        if (chain >= 0) need_chain(e, chain);
+        if (!e) throw InvalidArg{"null engine"};
         if (!out) throw InvalidArg{"null diagnostics"};
         e->read_diag(chain, out);
     });

@@ -192,6 +192,24 @@ class Engine:
         d["mean_coi_var"] = float(d["mean_coi_var"][0])
         return d
 
+    def diagnostics_all(self):
+        """``diagnostics`` of every chain in one device read: a list of per-chain dicts (views)."""
+        T, N, L, A = self.T, self.N, self.L, self.a_pad
+        i32, f64 = np.int32, np.float64
+        d = dict(eps_neg_accept=np.zeros((T, N), i32), eps_pos_accept=np.zeros((T, N), i32),
+                 m_accept=np.zeros((T, N), i32), r_accept=np.zeros((T, N), i32),
+                 m_r_accept=np.zeros((T, N), i32), sample_accept=np.zeros((T, N), i32),
+                 eps_neg_var=np.zeros((T, N), f64), eps_pos_var=np.zeros((T, N), f64),
+                 r_var=np.zeros((T, N), f64), m_r_var=np.zeros((T, N), f64),
+                 p_accept=np.zeros((T, L, A), i32), p_attempt=np.zeros((T, L, A), i32),
+                 p_prop_var=np.zeros((T, L, A), f64), mean_coi_accept=np.zeros(T, f64),
+                 mean_coi_var=np.zeros(T, f64))
+        cd = _lib.MoireChainDiagnostics(*[_ptr(d[n]) for n, _ in
+                                          _lib.MoireChainDiagnostics._fields_])
+        self._ck(self.lib.moire_engine_read_diagnostics(self._h, -1, C.byref(cd)),
+                 "read_diagnostics")
+        return [{k: (float(v[c]) if v.ndim == 1 else v[c]) for k, v in d.items()} for c in range(T)]
+
     def sample_llik(self, chain=0):
         out = np.zeros(self.N)
         self._ck(self.lib.moire_engine_read_sample_llik(self._h, chain, _ptr(out)),

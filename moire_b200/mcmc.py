@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import time
 
 import numpy as np
@@ -384,14 +385,14 @@ def _assemble_chain(parts, N, L, num_alleles, args, record_latent):
             dr[k] = v[order]
     D = len(dr["draw_step"])
     res = dict(tr)
-    res["data_llik"] = [dr["data_llik"][:, i].copy() for i in range(N)]
-    res["coi"] = [dr["coi"][:, i].copy() for i in range(N)]
+    res["data_llik"] = list(np.ascontiguousarray(dr["data_llik"].T))
+    res["coi"] = list(np.ascontiguousarray(dr["coi"].T))
     res["lam_coi"] = dr["lam_coi"]
-    res["allele_freqs"] = [[dr["allele_freqs"][d, j, :num_alleles[j]].copy() for d in range(D)]
-                           for j in range(L)]
-    res["eps_neg"] = [dr["eps_neg"][:, i].copy() for i in range(N)]
-    res["eps_pos"] = [dr["eps_pos"][:, i].copy() for i in range(N)]
-    res["relatedness"] = [dr["relatedness"][:, i].copy() for i in range(N)]
+    af = np.ascontiguousarray(dr["allele_freqs"].transpose(1, 0, 2))     # [L][D][A]
+    res["allele_freqs"] = [list(af[j, :, :num_alleles[j]]) for j in range(L)]
+    res["eps_neg"] = list(np.ascontiguousarray(dr["eps_neg"].T))
+    res["eps_pos"] = list(np.ascontiguousarray(dr["eps_pos"].T))
+    res["relatedness"] = list(np.ascontiguousarray(dr["relatedness"].T))
     if record_latent and dr["latent"] is not None:
         res["latent_genotypes"] = [[[[b for b in range(64) if int(dr["latent"][d, i, j]) >> b & 1]
                                      for d in range(D)] for j in range(L)] for i in range(N)]
@@ -473,6 +474,8 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
                  eps_neg_alpha=float(eps_neg_alpha), eps_neg_beta=float(eps_neg_beta),
                  r_alpha=float(r_alpha), r_beta=float(r_beta))
     chains = []
+    prof = os.environ.get("MOIRE_B200_PROFILE")    # phase times of the call, to stderr
+    marks = [("pack", time.time())]
     for chain_number in range(1, int(num_chains) + 1):
         mc = MCMC(pk, ladder, burnin=int(burnin), samples=int(round(samples_per_chain)),
                   thin=int(thin), adapt_temp=adapt_temp, pre_adapt_steps=int(pre_adapt_steps),
@@ -482,7 +485,9 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
                   seed=int(seed) + 7919 * (chain_number - 1), device=device, rank=rank,
                   world_size=world, allgather=gather, **model)
         try:
+            marks.append(("create", time.time()))
             ok = mc.init()
+            marks.append(("init", time.time()))
             if not ok:
                 rec = [tuple(int(x) for x in r) for r in mc.init_log()]
                 ill, pri = mc.init_counts()          # this rank's chains; merged over ranks below
@@ -501,8 +506,9 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
                 raise InitializationFailure(
                     format_initialization_failure_message(diag, sample_ids, loci), diag)
             reached, minutes = mc.run(progress)
+            marks.append(("run", time.time()))
             parts = dict(traces=mc.traces(), ladder=mc.ladder(), draws=mc.draws(),
-                         diagnostics=[mc.engine.diagnostics(c) for c in range(mc.engine.T)],
+                         diagnostics=mc.engine.diagnostics_all(),
                          observed_coi=pk.observed_coi.copy(), max_runtime_reached=reached,
                          total_runtime=minutes)
             if world > 1:
@@ -518,6 +524,13 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
                 parts["diagnostics"] = [g for a in allparts for g in a["diagnostics"]]
             chains.append(_assemble_chain(parts, pk.num_samples, pk.num_loci, pk.num_alleles, args,
                                           record_latent_genotypes))
+            marks.append(("assemble", time.time()))
         finally:
             mc.close()
+    if prof:
+        import sys
+        prev = t_start
+        for name, t in marks + [("close", time.time())]:
+            print(f"run_mcmc phase {name}: {1e3 * (t - prev):.1f} ms", file=sys.stderr)
+            prev = t
     return dict(runtime=time.time() - t_start, chains=chains, args=args)
