@@ -372,7 +372,10 @@ struct moire_engine
         amax_alleles = amax;
         // ... or the problem is tiny (the flat pipeline is 2 A_max + 6 launches; below ~10^5 cells
         // they cost more than the fused kernel's barriers)
-        p_fused = std::getenv("MOIRE_B200_P_FUSED") != nullptr || TNL >= (1ull << 32) || TNL < 100000;
+        // MOIRE_B200_FLAT_MIN_CELLS moves that threshold (tests run both pipelines on one shape)
+        size_t flat_min_cells = 100000;
+        if (const char *env = std::getenv("MOIRE_B200_FLAT_MIN_CELLS")) flat_min_cells = (size_t)std::atoll(env);
+        p_fused = std::getenv("MOIRE_B200_P_FUSED") != nullptr || TNL >= (1ull << 32) || TNL < flat_min_cells;
         if (!p_fused)
         {
             pf_list.alloc(TNL); pf_hist.alloc(moire::kPfHistWords);

@@ -960,7 +960,22 @@ __global__ void __launch_bounds__(1024) k_reduce(const View v)
     const double *cT = v.cellT + (size_t)t * ncell;
     const double *cO = v.cellO + (size_t)t * ncell;
     double s = 0.0;
-    for (size_t c = tid; c < ncell; c += blockDim.x) s += __dadd_rn(cT[c], cO[c]);
+    {
+        // a thread's cells in its fixed order, eight loads in flight (one chain per block: the
+        // kernel is latency bound)
+        const size_t B = blockDim.x;
+        size_t c = tid;
+        for (; c + 3 * B < ncell; c += 4 * B)
+        {
+            const double a0 = cT[c], a1 = cT[c + B], a2 = cT[c + 2 * B], a3 = cT[c + 3 * B];
+            const double b0 = cO[c], b1 = cO[c + B], b2 = cO[c + 2 * B], b3 = cO[c + 3 * B];
+            s += __dadd_rn(a0, b0);
+            s += __dadd_rn(a1, b1);
+            s += __dadd_rn(a2, b2);
+            s += __dadd_rn(a3, b3);
+        }
+        for (; c < ncell; c += B) s += __dadd_rn(cT[c], cO[c]);
+    }
     const double llik = block_sum(s, s_red);
     double q = 0.0;
     for (int i = tid; i < v.N; i += blockDim.x)

@@ -823,6 +823,15 @@ __device__ __forceinline__ uint64_t choose_bits(Stream &rng, uint64_t set, int n
     return out;
 }
 
+// The uniform of a word w is (w + 0.5) 2^-32 (exact in double), so "uniform < pr" is the integer
+// test w < ceil(pr 2^32 - 0.5); pr 2^32 is exact too.  pr >= 1 would accept every word: those
+// proposals are rejected before any cell is drawn (eps in (0, 1), A >= 2).
+__device__ __forceinline__ uint32_t bernoulli_threshold(double pr)
+{
+    const double x = ceil(pr * 4294967296.0 - 0.5);
+    return x <= 0.0 ? 0u : (x >= 4294967295.0 ? 4294967295u : (uint32_t)x);
+}
+
 // Draws the proposal and returns its mask; *log_prob gets the log proposal density.
 // logC[n * 65 + k] = log(C(n, k)).
 __device__ __forceinline__ uint64_t sample_latent_genotype(Stream &rng, uint64_t obs, int A,
@@ -836,7 +845,9 @@ __device__ __forceinline__ uint64_t sample_latent_genotype(Stream &rng, uint64_t
     const int min_fn = obs_pos == 0;
     const int max_fn = max(min_fn, min(coi, obs_neg));
     int fn = min_fn;
-    for (int ii = min_fn; ii < max_fn; ++ii) fn += (rng.next_uniform() < e.pr_en);
+    // (w + 0.5) 2^-32 < pr  <=>  w < ceil(pr 2^32 - 0.5): the same Bernoulli draws on the raw words
+    const uint32_t thr_en = bernoulli_threshold(e.pr_en);
+    for (int ii = min_fn; ii < max_fn; ++ii) fn += (rng.next_u32() < thr_en);
     const int tn = obs_neg - fn;
     const double lp_fn =
         __dadd_rn(__dadd_rn(logC[obs_neg * kLogCDim + (fn - min_fn)],
@@ -850,7 +861,8 @@ __device__ __forceinline__ uint64_t sample_latent_genotype(Stream &rng, uint64_t
         return 0;
     }
     int fp = min_fp;
-    for (int ii = min_fp; ii < max_fp; ++ii) fp += (rng.next_uniform() < e.pr_ep);
+    const uint32_t thr_ep = bernoulli_threshold(e.pr_ep);
+    for (int ii = min_fp; ii < max_fp; ++ii) fp += (rng.next_u32() < thr_ep);
     const int tp = obs_pos - fp;
     const double lp_fp =
         __dadd_rn(__dadd_rn(logC[obs_pos * kLogCDim + (fp - min_fp)],
