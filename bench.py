@@ -187,6 +187,11 @@ def our_arm(args, wl):
     burnin_total = args.warmup + args.steps + 8
     mc = MCMC(pk, temps, burnin=burnin_total, samples=0, seed=args.seed, device=local, rank=rank,
               world_size=world, allgather=gather, **model)
+    exchange = "none (one rank)"
+    if world > 1:
+        native = not os.environ.get("MOIRE_B200_CALLBACK_EXCHANGE") and mc.init_nccl(local)
+        exchange = ("ncclAllGather on the engine stream from device scalars (C++ driver)" if native
+                    else "torch.distributed all_gather through the host callback")
     if not mc.init():
         raise SystemExit("chain initialisation failed")
     eng = mc.engine
@@ -310,7 +315,7 @@ def our_arm(args, wl):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True,
                 scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-                config=config_of(wl, args), clocks=sampler.summary(), e2e=e2e,
+                config=dict(config_of(wl, args), exchange=exchange), clocks=sampler.summary(), e2e=e2e,
                 gpu_launches=launches_total, roofline=roofline, cpu_baseline=cpu,
                 likelihood_evals_per_sec=evals_total / (dev_ms_max * 1e-3),
                 evals_per_step=evals_total / args.steps,

@@ -158,6 +158,9 @@ int moire_engine_get_scalars(moire_engine *e, double *llik, double *prior);
 /* Device addresses of the same [num_chains] arrays, for a collective (NCCL all-gather) that
  * wants no host round trip.  Valid until destroy. */
 int moire_engine_device_scalars(moire_engine *e, void **dev_llik, void **dev_prior);
+/* The CUDA stream (cudaStream_t) every call of this engine is ordered on, for work that must follow
+ * a step without a host round trip (the driver's NCCL all-gather of the scalars). */
+int moire_engine_stream(moire_engine *e, void **stream);
 /* Chain::set_temp / get_temp for every chain. */
 int moire_engine_set_temps(moire_engine *e, const double *temps);
 int moire_engine_get_temps(moire_engine *e, double *temps);

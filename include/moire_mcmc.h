@@ -71,6 +71,14 @@ const char *moire_mcmc_last_error(const moire_mcmc *h);
 void moire_mcmc_partition(int32_t T, int32_t rank, int32_t world_size, int32_t *first,
                           int32_t *count);
 int moire_mcmc_set_allgather(moire_mcmc *h, moire_allgather_fn fn, void *ctx);
+/* The native exchange: an ncclAllGather enqueued on the engine's stream straight from the device
+ * sums (no host staging, no callback in the step loop).  Rank 0 makes the 128-byte id with
+ * moire_mcmc_nccl_unique_id and the embedding code hands it to every rank (any broadcast it has),
+ * then every rank calls moire_mcmc_init_nccl (collective).  `library_path` names libnccl.so.2
+ * (NULL: the one already loaded in the process, else the loader's search path).  Replaces
+ * moire_mcmc_set_allgather; world_size == 1 needs neither. */
+int moire_mcmc_nccl_unique_id(char id[128], const char *library_path);
+int moire_mcmc_init_nccl(moire_mcmc *h, const char id[128], const char *library_path);
 /* The engine of this rank's chains (borrowed; destroyed with the driver). */
 moire_engine *moire_mcmc_engine(moire_mcmc *h);
 

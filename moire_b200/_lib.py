@@ -67,6 +67,8 @@ MCMC_SYMBOLS = {
     "moire_mcmc_last_error": (C.c_char_p, [vp]),
     "moire_mcmc_partition": (None, [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]),
     "moire_mcmc_set_allgather": (C.c_int, [vp, ALLGATHER_FN, vp]),
+    "moire_mcmc_nccl_unique_id": (C.c_int, [vp, C.c_char_p]),
+    "moire_mcmc_init_nccl": (C.c_int, [vp, vp, C.c_char_p]),
     "moire_mcmc_engine": (vp, [vp]),
     "moire_mcmc_init": (C.c_int, [vp, C.POINTER(i32)]),
     "moire_mcmc_get_init_counts": (C.c_int, [vp, vp, vp]),
@@ -116,6 +118,7 @@ ENGINE_SYMBOLS = {
     "moire_engine_timer_start": (C.c_int, [vp]),
     "moire_engine_timer_stop": (C.c_int, [vp, C.POINTER(dbl)]),
     "moire_engine_set_timing": (C.c_int, [vp, i32]),
+    "moire_engine_stream": (C.c_int, [vp, C.POINTER(vp)]),
     "moire_engine_read_timing": (C.c_int, [vp, vp, vp]),
     "moire_engine_read_evaluator_timing": (C.c_int, [vp, C.POINTER(dbl), C.POINTER(u64)]),
     "moire_engine_synchronize": (C.c_int, [vp]),

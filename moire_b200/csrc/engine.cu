@@ -999,6 +999,14 @@ int moire_engine_device_scalars(moire_engine *e, void **dev_llik, void **dev_pri
     });
 }
 
+int moire_engine_stream(moire_engine *e, void **stream)
+{
+    return guarded(e, [&] {
+        if (!e || !stream) throw InvalidArg{"null argument"};
+        *stream = (void *)e->stream;
+    });
+}
+
 int moire_engine_set_temps(moire_engine *e, const double *temps)
 {
     return guarded(e, [&] {

@@ -14,6 +14,9 @@
 #include <string>
 #include <vector>
 
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
 #include "../../include/moire_mcmc.h"
 #include "rng.cuh"
 
@@ -230,6 +233,57 @@ struct DriverError
 thread_local std::string g_mcmc_error;
 }  // namespace
 
+namespace
+{
+// ---- NCCL, bound at run time ---------------------------------------------------------------------
+// The ladder's one exchange (T scalars per step) runs as an ncclAllGather enqueued on the engine's
+// stream straight from the device-resident sums: no host staging and no callback into the
+// embedding language inside the step loop.  The library is the one the process already holds
+// (torch's bundled libnccl.so.2, or the path the caller names); only the four entry points below
+// are used, through their stable C signatures (nccl.h: ncclGetUniqueId, ncclCommInitRank,
+// ncclAllGather, ncclCommDestroy).
+struct NcclApi
+{
+    struct UniqueId { char internal[128]; };
+    void *lib = nullptr;
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    static constexpr int kFloat64 = 8;  // ncclFloat64 / ncclDouble
+
+    bool load(const char *path, std::string &err)
+    {
+        if (lib) return true;
+        const char *names[] = {path && path[0] ? path : nullptr, "libnccl.so.2", "libnccl.so"};
+        for (const char *n : names)
+        {
+            if (!n) continue;
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib)
+        {
+            err = std::string("cannot load NCCL: ") + dlerror();
+            return false;
+        }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllGather || !CommDestroy)
+        {
+            err = "NCCL library lacks an entry point";
+            return false;
+        }
+        return true;
+    }
+};
+NcclApi g_nccl;
+}  // namespace
+
 struct moire_mcmc
 {
     moire_engine *engine = nullptr;
@@ -243,6 +297,11 @@ struct moire_mcmc
 
     moire_allgather_fn gather = nullptr;
     void *gather_ctx = nullptr;
+    // native exchange (moire_mcmc_init_nccl)
+    void *nccl_comm = nullptr;
+    double *send_d = nullptr, *recv_d = nullptr;   // [per], [world * per]
+    double *send_pin = nullptr, *recv_pin = nullptr;
+    cudaStream_t stream = nullptr;
 
     // ladder (src/mcmc.h:47-52) -- identical on every rank
     std::vector<int32_t> swap_indices;     // ladder position -> chain id
@@ -273,7 +332,42 @@ struct moire_mcmc
 
     ~moire_mcmc()
     {
+        if (nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(nccl_comm);
+        if (send_d) cudaFree(send_d);
+        if (recv_d) cudaFree(recv_d);
+        if (send_pin) cudaFreeHost(send_pin);
+        if (recv_pin) cudaFreeHost(recv_pin);
         if (engine) moire_engine_destroy(engine);
+    }
+
+    void cu(cudaError_t rc, const char *what)
+    {
+        if (rc != cudaSuccess)
+            throw DriverError{MOIRE_ECUDA, std::string(what) + ": " + cudaGetErrorString(rc)};
+    }
+    void nc(int rc, const char *what)
+    {
+        if (rc != 0)
+            throw DriverError{MOIRE_ECUDA, std::string(what) + ": " +
+                                               (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error")};
+    }
+
+    // recv[r * per + i] = send_r[i] from host buffers, through whichever exchange is installed
+    void host_allgather(const double *snd, int per, double *rcv)
+    {
+        if (nccl_comm)
+        {
+            std::memcpy(send_pin, snd, sizeof(double) * per);
+            cu(cudaMemcpyAsync(send_d, send_pin, sizeof(double) * per, cudaMemcpyHostToDevice, stream), "h2d");
+            nc(g_nccl.AllGather(send_d, recv_d, (size_t)per, NcclApi::kFloat64, nccl_comm, stream), "ncclAllGather");
+            cu(cudaMemcpyAsync(recv_pin, recv_d, sizeof(double) * per * world, cudaMemcpyDeviceToHost, stream), "d2h");
+            cu(cudaStreamSynchronize(stream), "sync");
+            std::memcpy(rcv, recv_pin, sizeof(double) * per * world);
+            return;
+        }
+        if (!gather) throw DriverError{MOIRE_ESTATE, "world_size > 1 needs moire_mcmc_init_nccl or moire_mcmc_set_allgather"};
+        if (gather(gather_ctx, snd, per, rcv) != 0)
+            throw DriverError{MOIRE_ESTATE, "all-gather callback failed"};
     }
 
     void ck(int rc, const char *what)
@@ -315,21 +409,33 @@ struct moire_mcmc
     // every rank's (llik, prior) of its chains -> chain_llik / chain_prior of all T chains
     void exchange_scalars()
     {
-        std::fill(send.begin(), send.end(), 0.0);
-        local_scalars(send.data(), send.data() + cmax);
         const double minutes =
             std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() / 60.0;
-        send[2 * cmax] = minutes;
         const int per = 2 * cmax + 1;
-        if (world == 1)
+        if (world > 1 && nccl_comm && engine)
         {
-            std::copy(send.begin(), send.end(), recv.begin());
+            // device to device: the sums k_reduce left on the engine's stream, the collective on
+            // the same stream, one read-back of all T pairs
+            void *dl = nullptr, *dp = nullptr;
+            ck(moire_engine_device_scalars(engine, &dl, &dp), "device_scalars");
+            send_pin[0] = minutes;
+            cu(cudaMemcpyAsync(send_d, dl, sizeof(double) * count, cudaMemcpyDeviceToDevice, stream), "d2d");
+            cu(cudaMemcpyAsync(send_d + cmax, dp, sizeof(double) * count, cudaMemcpyDeviceToDevice, stream), "d2d");
+            cu(cudaMemcpyAsync(send_d + 2 * cmax, send_pin, sizeof(double), cudaMemcpyHostToDevice, stream), "h2d");
+            nc(g_nccl.AllGather(send_d, recv_d, (size_t)per, NcclApi::kFloat64, nccl_comm, stream), "ncclAllGather");
+            cu(cudaMemcpyAsync(recv_pin, recv_d, sizeof(double) * per * world, cudaMemcpyDeviceToHost, stream), "d2h");
+            cu(cudaStreamSynchronize(stream), "sync");
+            std::memcpy(recv.data(), recv_pin, sizeof(double) * per * world);
         }
         else
         {
-            if (!gather) throw DriverError{MOIRE_ESTATE, "world_size > 1 needs moire_mcmc_set_allgather"};
-            if (gather(gather_ctx, send.data(), per, recv.data()) != 0)
-                throw DriverError{MOIRE_ESTATE, "all-gather callback failed"};
+            std::fill(send.begin(), send.end(), 0.0);
+            local_scalars(send.data(), send.data() + cmax);
+            send[2 * cmax] = minutes;
+            if (world == 1)
+                std::copy(send.begin(), send.end(), recv.begin());
+            else
+                host_allgather(send.data(), per, recv.data());
         }
         for (int r = 0; r < world; ++r)
         {
@@ -631,6 +737,47 @@ int moire_mcmc_set_allgather(moire_mcmc *h, moire_allgather_fn fn, void *ctx)
     });
 }
 
+int moire_mcmc_nccl_unique_id(char id[128], const char *library_path)
+{
+    std::string err;
+    if (!id || !g_nccl.load(library_path, err))
+    {
+        g_mcmc_error = id ? err : "null id";
+        return MOIRE_EINVAL;
+    }
+    NcclApi::UniqueId u;
+    if (g_nccl.GetUniqueId(&u) != 0)
+    {
+        g_mcmc_error = "ncclGetUniqueId failed";
+        return MOIRE_ECUDA;
+    }
+    std::memcpy(id, u.internal, 128);
+    return MOIRE_OK;
+}
+
+int moire_mcmc_init_nccl(moire_mcmc *h, const char id[128], const char *library_path)
+{
+    return guarded(h, [&] {
+        if (!id) throw DriverError{MOIRE_EINVAL, "null id"};
+        if (!h->engine) throw DriverError{MOIRE_ESTATE, "the NCCL exchange needs an engine (device_id >= 0)"};
+        if (h->world < 2) return;
+        std::string err;
+        if (!g_nccl.load(library_path, err)) throw DriverError{MOIRE_EINVAL, err};
+        void *st = nullptr;
+        h->ck(moire_engine_stream(h->engine, &st), "engine_stream");  // also binds the device
+        h->stream = (cudaStream_t)st;
+        const int per = 2 * h->cmax + 1;
+        h->cu(cudaMalloc(&h->send_d, sizeof(double) * per), "cudaMalloc");
+        h->cu(cudaMalloc(&h->recv_d, sizeof(double) * per * h->world), "cudaMalloc");
+        h->cu(cudaMemset(h->send_d, 0, sizeof(double) * per), "cudaMemset");
+        h->cu(cudaMallocHost(&h->send_pin, sizeof(double) * per), "cudaMallocHost");
+        h->cu(cudaMallocHost(&h->recv_pin, sizeof(double) * per * h->world), "cudaMallocHost");
+        NcclApi::UniqueId u;
+        std::memcpy(u.internal, id, 128);
+        h->nc(g_nccl.CommInitRank(&h->nccl_comm, h->world, u, h->rank), "ncclCommInitRank");
+    });
+}
+
 moire_engine *moire_mcmc_engine(moire_mcmc *h) { return h ? h->engine : nullptr; }
 
 int moire_mcmc_init(moire_mcmc *h, int32_t *failed)
@@ -652,10 +799,8 @@ int moire_mcmc_init(moire_mcmc *h, int32_t *failed)
         double any = bad;
         if (h->world > 1)
         {
-            if (!h->gather) throw DriverError{MOIRE_ESTATE, "world_size > 1 needs moire_mcmc_set_allgather"};
             const int per = 2 * h->cmax + 1;
-            if (h->gather(h->gather_ctx, h->send.data(), per, h->recv.data()) != 0)
-                throw DriverError{MOIRE_ESTATE, "all-gather callback failed"};
+            h->host_allgather(h->send.data(), per, h->recv.data());
             any = 0.0;
             for (int r = 0; r < h->world; ++r) any += h->recv[(size_t)r * per];
         }

@@ -217,6 +217,29 @@ class MCMC:
         except Exception:
             pass
 
+    def init_nccl(self, device):
+        """The native exchange (``moire_mcmc_init_nccl``): rank 0 makes the NCCL id, the process
+        group broadcasts it, every rank joins the communicator.  Collective over the ranks of the
+        initialised ``torch.distributed`` group; returns False (callback exchange stays) when the
+        NCCL library cannot be bound."""
+        import torch
+        import torch.distributed as dist
+        path = nccl_library_path()
+        cpath = path.encode() if path else None
+        idbuf = np.zeros(128, np.uint8)
+        ok = 1
+        if self.rank == 0:
+            ok = int(self.lib.moire_mcmc_nccl_unique_id(_ptr(idbuf), cpath) == 0)
+        t = torch.cat([torch.from_numpy(idbuf.copy()), torch.tensor([ok], dtype=torch.uint8)]).to(
+            torch.device("cuda", device))
+        dist.broadcast(t, 0)
+        t = t.cpu().numpy()
+        if not t[128]:
+            return False
+        idbuf = np.ascontiguousarray(t[:128])
+        self._ck(self.lib.moire_mcmc_init_nccl(self._h, _ptr(idbuf), cpath), "init_nccl")
+        return True
+
     def set_allgather(self, fn):
         """``fn(send: np.ndarray[count]) -> np.ndarray[world * count]``."""
         def tramp(_ctx, send, count, recv):
@@ -348,6 +371,22 @@ def monotone_spline_solve(x, y, target):
     return float(lib.moire_monotone_spline_solve(_ptr(x), _ptr(y), len(x), float(target)))
 
 
+def nccl_library_path():
+    """The libnccl.so.2 that torch itself uses (its bundled wheel), or None to let the loader find
+    the one already in the process."""
+    import importlib.util
+    import os as _os
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations or []) if spec else []:
+            cand = _os.path.join(root, "lib", "libnccl.so.2")
+            if _os.path.exists(cand):
+                return cand
+    except Exception:
+        pass
+    return None
+
+
 def torch_allgather(world_size, device=None):
     """The ladder's one exchange as a ``torch.distributed`` all-gather (NCCL when ``device`` is a
     CUDA device, gloo on CPU).  Buffers are allocated once (pinned on the host for NCCL): a step
@@ -460,13 +499,14 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
     if max_coi < 1:
         raise ValueError("Max COI must be greater than 1")   # R/mcmc.R:135-137
     ladder = _ladder(pt_chains, pt_grad)
-    rank, world, gather = 0, 1, None
+    rank, world, gather, native = 0, 1, None, False
     if distributed:
         import torch
         import torch.distributed as dist
         rank, world = dist.get_rank(), dist.get_world_size()
         dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else None
         gather = torch_allgather(world, dev)
+        native = dev is not None and not os.environ.get("MOIRE_B200_CALLBACK_EXCHANGE")
     model = dict(allow_relatedness=bool(allow_relatedness), max_coi=int(max_coi),
                  mean_coi_shape=float(mean_coi_shape), mean_coi_scale=float(mean_coi_scale),
                  max_eps_pos=float(max_eps_pos), eps_pos_alpha=float(eps_pos_alpha),
@@ -485,6 +525,8 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
                   seed=int(seed) + 7919 * (chain_number - 1), device=device, rank=rank,
                   world_size=world, allgather=gather, **model)
         try:
+            if native:
+                mc.init_nccl(device)     # falls back to the callback if NCCL cannot be bound
             marks.append(("create", time.time()))
             ok = mc.init()
             marks.append(("init", time.time()))
