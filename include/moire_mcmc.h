@@ -76,7 +76,8 @@ int moire_mcmc_set_allgather(moire_mcmc *h, moire_allgather_fn fn, void *ctx);
  * moire_mcmc_nccl_unique_id and the embedding code hands it to every rank (any broadcast it has),
  * then every rank calls moire_mcmc_init_nccl (collective).  `library_path` names libnccl.so.2
  * (NULL: the one already loaded in the process, else the loader's search path).  Replaces
- * moire_mcmc_set_allgather; world_size == 1 needs neither. */
+ * moire_mcmc_set_allgather; world_size == 1 needs neither.  The communicator lives as long as
+ * the process; id == NULL re-uses it for another driver of the same (rank, world_size). */
 int moire_mcmc_nccl_unique_id(char id[128], const char *library_path);
 int moire_mcmc_init_nccl(moire_mcmc *h, const char id[128], const char *library_path);
 /* The engine of this rank's chains (borrowed; destroyed with the driver). */

@@ -282,6 +282,9 @@ struct NcclApi
     }
 };
 NcclApi g_nccl;
+// one communicator per process, kept for its lifetime: creating one costs a few hundred ms
+void *g_nccl_comm = nullptr;
+int g_nccl_world = 0, g_nccl_rank = -1;
 }  // namespace
 
 struct moire_mcmc
@@ -332,7 +335,6 @@ struct moire_mcmc
 
     ~moire_mcmc()
     {
-        if (nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(nccl_comm);
         if (send_d) cudaFree(send_d);
         if (recv_d) cudaFree(recv_d);
         if (send_pin) cudaFreeHost(send_pin);
@@ -758,7 +760,6 @@ int moire_mcmc_nccl_unique_id(char id[128], const char *library_path)
 int moire_mcmc_init_nccl(moire_mcmc *h, const char id[128], const char *library_path)
 {
     return guarded(h, [&] {
-        if (!id) throw DriverError{MOIRE_EINVAL, "null id"};
         if (!h->engine) throw DriverError{MOIRE_ESTATE, "the NCCL exchange needs an engine (device_id >= 0)"};
         if (h->world < 2) return;
         std::string err;
@@ -772,9 +773,22 @@ int moire_mcmc_init_nccl(moire_mcmc *h, const char id[128], const char *library_
         h->cu(cudaMemset(h->send_d, 0, sizeof(double) * per), "cudaMemset");
         h->cu(cudaMallocHost(&h->send_pin, sizeof(double) * per), "cudaMallocHost");
         h->cu(cudaMallocHost(&h->recv_pin, sizeof(double) * per * h->world), "cudaMallocHost");
-        NcclApi::UniqueId u;
-        std::memcpy(u.internal, id, 128);
-        h->nc(g_nccl.CommInitRank(&h->nccl_comm, h->world, u, h->rank), "ncclCommInitRank");
+        if (!id)
+        {
+            if (!g_nccl_comm || g_nccl_world != h->world || g_nccl_rank != h->rank)
+                throw DriverError{MOIRE_ESTATE, "no NCCL communicator of this shape to reuse"};
+        }
+        else
+        {
+            NcclApi::UniqueId u;
+            std::memcpy(u.internal, id, 128);
+            void *comm = nullptr;
+            h->nc(g_nccl.CommInitRank(&comm, h->world, u, h->rank), "ncclCommInitRank");
+            g_nccl_comm = comm;  // an earlier communicator stays alive: it may be in use
+            g_nccl_world = h->world;
+            g_nccl_rank = h->rank;
+        }
+        h->nccl_comm = g_nccl_comm;
     });
 }
 

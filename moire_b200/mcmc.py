@@ -226,6 +226,9 @@ class MCMC:
         import torch.distributed as dist
         path = nccl_library_path()
         cpath = path.encode() if path else None
+        if _NCCL_READY.get((self.world, self.rank)):     # the process keeps its communicator
+            self._ck(self.lib.moire_mcmc_init_nccl(self._h, None, cpath), "init_nccl")
+            return True
         idbuf = np.zeros(128, np.uint8)
         ok = 1
         if self.rank == 0:
@@ -238,6 +241,7 @@ class MCMC:
             return False
         idbuf = np.ascontiguousarray(t[:128])
         self._ck(self.lib.moire_mcmc_init_nccl(self._h, _ptr(idbuf), cpath), "init_nccl")
+        _NCCL_READY[(self.world, self.rank)] = True
         return True
 
     def set_allgather(self, fn):
@@ -369,6 +373,9 @@ def monotone_spline_solve(x, y, target):
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.float64)
     return float(lib.moire_monotone_spline_solve(_ptr(x), _ptr(y), len(x), float(target)))
+
+
+_NCCL_READY = {}
 
 
 def nccl_library_path():
