@@ -184,7 +184,7 @@ def our_arm(args, wl):
         torch.cuda.synchronize()
 
     gather = torch_allgather(world, dev) if world > 1 else None
-    burnin_total = args.warmup + args.steps + 8
+    burnin_total = args.warmup + 2 * args.steps + 8
     mc = MCMC(pk, temps, burnin=burnin_total, samples=0, seed=args.seed, device=local, rank=rank,
               world_size=world, allgather=gather, **model)
     exchange = "none (one rank)"
@@ -200,9 +200,9 @@ def our_arm(args, wl):
     for _ in range(args.warmup):
         mc.burnin(step)
         step += 1
+    # ---- the timed region: K steps exactly as the product runs them (the engine replays its
+    # captured step graph), device time from CUDA events on the engine's stream around each step
     ev0, l0 = eng.counters()
-    ke0 = eng.kind_evals()
-    eng.set_timing(True)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
@@ -219,11 +219,22 @@ def our_arm(args, wl):
     wall = time.perf_counter() - wall0
     sampler.stop_flag.set()
     sampler.join(2.0)
+    ev1, l1 = eng.counters()
+    # ---- breakdown pass: the next K steps with an event pair around every update kind and every
+    # evaluator launch (a graph cannot hold events between its kernels, so these steps go out as
+    # plain launches); feeds `roofline` and `kernel_ms_per_step`, not `value`
+    ke0 = eng.kind_evals()
+    eng.set_timing(True)
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        mc.burnin(step)
+        step += 1
     kinds = eng.timing()
     eval_ms, eval_n = eng.evaluator_timing()
     eng.set_timing(False)
-    ev1, l1 = eng.counters()
     ke1 = eng.kind_evals()
+    barrier()
     stats = torch.tensor([dev_ms, float(ev1 - ev0), float(l1 - l0)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone()
@@ -302,7 +313,9 @@ def our_arm(args, wl):
                     share_of_step=top_ms / step_kernel_ms,
                     note="algorithmic fraction: 24 B per cell evaluation; the kernel is fp64-issue/"
                          "latency bound (SURVEY F11), see DESIGN.md; traffic is the ncu capture of "
-                         "one full-ladder launch of this kernel (profiles/roofline_inputs.json)")
+                         "one full-ladder launch of this kernel (profiles/roofline_inputs.json); "
+                         "launch durations from the breakdown pass (K steps after the timed region, "
+                         "plain launches with an event pair per evaluator launch)")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

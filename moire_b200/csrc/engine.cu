@@ -135,6 +135,8 @@ double log_binom_exact(unsigned n, unsigned k)
 }
 }  // namespace
 
+__global__ void k_set_iteration(int *dst, const int iteration) { *dst = iteration; }
+
 struct moire_engine
 {
     moire::View v{};
@@ -158,6 +160,11 @@ struct moire_engine
     DevBuf<int> pf_nonmiss;
     int amax_alleles = 0;
     bool p_fused = false;
+    // the step as a CUDA graph: ~55 launches replayed with one call, iteration read from iter_dev
+    DevBuf<int> iter_dev;
+    cudaGraphExec_t step_graph = nullptr;
+    uint64_t step_graph_launches = 0;
+    bool use_graph = true;
     moire::SFlat sf{};
     DevBuf<moire::Proposal> sf_prop;
     DevBuf<int> sf_m;
@@ -187,6 +194,8 @@ struct moire_engine
             cudaEventDestroy(t.a);
             cudaEventDestroy(t.b);
         }
+        if (step_graph) cudaGraphExecDestroy(step_graph);
+        iter_dev.release();
         obs.release(); latent.release(); evals.release(); missing.release(); nall.release();
         aclass.release(); avals.release(); obs_coi.release(); m.release(); acc6.release();
         p_acc.release(); p_att.release(); active.release(); logC.release(); lgam.release();
@@ -292,7 +301,7 @@ struct moire_engine
         latent.alloc(TNL); lgadj.alloc(TNL); cellT.alloc(TNL); cellO.alloc(TNL);
         m.alloc(TN); acc6.alloc(6 * TN); persample.alloc(14 * TN);
         p.alloc(TLA); p_sd.alloc(TLA); p_acc.alloc(TLA); p_att.alloc(TLA);
-        perchain.alloc(7 * (size_t)T); active.alloc(T); evals.alloc(16); scratchN.alloc(N);
+        perchain.alloc(7 * (size_t)T); active.alloc(T); evals.alloc(16); iter_dev.alloc(1); scratchN.alloc(N);
 
         std::vector<double> logC_h(moire::kLogCDim * moire::kLogCDim, -INFINITY), lgam_h(128);
         for (int n = 0; n < moire::kLogCDim; ++n)
@@ -350,7 +359,7 @@ struct moire_engine
         double *pc = perchain.ptr;
         v.mean_coi = pc + 0 * T; v.mean_coi_sd = pc + 1 * T; v.mean_coi_acc = pc + 2 * T;
         v.hyper = pc + 3 * T; v.temp = pc + 4 * T; v.llik = pc + 5 * T; v.prior = pc + 6 * T;
-        v.active = active.ptr; v.evals = evals.ptr;
+        v.active = active.ptr; v.evals = evals.ptr; v.iter = iter_dev.ptr;
         v.trace = nullptr;
         if (std::getenv("MOIRE_B200_TRACE"))  // tuning aid: per-warp clocks of update_p
         {
@@ -401,6 +410,7 @@ struct moire_engine
         if (sample_smem > smem_cap || p_smem > smem_cap)
             throw InvalidArg{"problem shape needs " + std::to_string(std::max(sample_smem, p_smem)) +
                              " B of shared memory per block; device allows " + std::to_string(smem_cap)};
+        use_graph = std::getenv("MOIRE_B200_NO_GRAPH") == nullptr;
         set_smem_attr();
         CUDA_TRY(cudaStreamSynchronize(stream));
     }
@@ -621,7 +631,7 @@ struct moire_engine
     }
 
     // MCMC::burnin / MCMC::sample loop body (src/mcmc.cpp:162-173, 311-322)
-    void step(int iteration)
+    void step_launches(int iteration)
     {
         update(MOIRE_UPDATE_EPS_NEG, iteration);
         update(MOIRE_UPDATE_EPS_POS, iteration);
@@ -635,6 +645,45 @@ struct moire_engine
         update(MOIRE_UPDATE_SAMPLES, iteration);
         update(MOIRE_UPDATE_MEAN_COI, iteration);
         reduce();
+    }
+
+    // The launches of a step never change (grids, pointers, round numbers; the list bounds and
+    // task counters live on the device), only the iteration does -- and the kernels read that
+    // from device memory when handed kIterFromDevice.  So the step is captured once and replayed:
+    // one host call per step instead of ~55 launches and a handful of memsets, back-to-back on
+    // the device.  Per-kind timing (events between the kernels) uses the plain launches.
+    void step(int iteration)
+    {
+        if (!use_graph || timing)
+        {
+            step_launches(iteration);
+            return;
+        }
+        if (!step_graph)
+        {
+            const uint64_t before = launches;
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            try
+            {
+                step_launches(moire::kIterFromDevice);
+            }
+            catch (...)
+            {
+                cudaStreamEndCapture(stream, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
+            }
+            CUDA_TRY(cudaStreamEndCapture(stream, &graph));
+            step_graph_launches = launches - before;
+            launches = before;
+            const cudaError_t rc = cudaGraphInstantiate(&step_graph, graph, 0);
+            cudaGraphDestroy(graph);
+            CUDA_TRY(rc);
+        }
+        k_set_iteration<<<1, 1, 0, stream>>>(iter_dev.ptr, iteration);  // by value: steps may queue up
+        CUDA_TRY(cudaGraphLaunch(step_graph, stream));
+        launches += step_graph_launches + 1;
     }
 
     void eval_all(int chain_sel, int use_active)

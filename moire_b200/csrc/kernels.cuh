@@ -469,8 +469,9 @@ __host__ __device__ inline size_t sample_kernel_smem(int S, int L, int nA, bool 
 // ---- per-sample updates: eps_neg, eps_pos, m, r, eff_coi, samples ----------------------------
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, MOIRE_MIN_BLOCKS_S * (256 / kThreads))
-    k_update_sample(const View v, const int iteration, const int S, const int tiles_per_chain)
+    k_update_sample(const View v, const int iteration_arg, const int S, const int tiles_per_chain)
 {
+    const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
     constexpr bool NEED_T = RESAMPLE || KIND == KIND_R;
     constexpr bool NEED_O = RESAMPLE || KIND == KIND_EPS_NEG || KIND == KIND_EPS_POS;
@@ -691,8 +692,9 @@ __host__ __device__ inline size_t p_kernel_smem(int N, int AP, int B)
 // shared memory under the proposed frequencies.
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, BLOCK == 512 ? 1 : MOIRE_MIN_BLOCKS_P * (256 / BLOCK))
-    k_update_p(const View v, const int iteration)
+    k_update_p(const View v, const int iteration_arg)
 {
+    const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     extern __shared__ double smem[];
     const int N = v.N, L = v.L, AP = v.AP, B = blockDim.x;
     double *s_lgam = smem;
@@ -893,8 +895,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 512 ? 1 : MOIRE_MIN_BLOCKS_P *
 }
 
 // ---- update_mean_coi: one block per chain (src/chain.cpp:809-856) ----------------------------
-__global__ void __launch_bounds__(kThreads) k_update_mean_coi(const View v, const int iteration)
+__global__ void __launch_bounds__(kThreads) k_update_mean_coi(const View v, const int iteration_arg)
 {
+    const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     __shared__ double s_lgam[128];
     __shared__ double s_red[40];
     const int tid = threadIdx.x, t = blockIdx.x, N = v.N;

@@ -252,9 +252,10 @@ __global__ void __launch_bounds__(256) k_pf_scatter(const View v, const PFlat f)
 // the SM holds (ncu, block-per-locus version: 51 us per round at 27 % issue, 36 % warps active).
 // Tcur / Tnew hold 0 at missing cells (k_pf_prepare), so the sum needs no mask.
 constexpr int kPfRoundThreads = 128;
-__global__ void __launch_bounds__(kPfRoundThreads) k_pf_round(const View v, const PFlat f, const int iteration,
+__global__ void __launch_bounds__(kPfRoundThreads) k_pf_round(const View v, const PFlat f, const int iteration_arg,
                                                   const int rep)
 {
+    const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     const int N = v.N, L = v.L, AP = v.AP;
     const int lane = threadIdx.x & 31;
     const int tl = blockIdx.x * (kPfRoundThreads / 32) + (threadIdx.x >> 5);

@@ -33,8 +33,9 @@ struct SFlat
 constexpr int kDrawThreads = 128;
 
 template <int KIND>
-__global__ void __launch_bounds__(kDrawThreads) k_sf_draw(const View v, const SFlat sf, const int iteration)
+__global__ void __launch_bounds__(kDrawThreads) k_sf_draw(const View v, const SFlat sf, const int iteration_arg)
 {
+    const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     constexpr bool LOGS = KIND != KIND_R;  // the kinds that recompute observation terms
     __shared__ double s_en[kDrawThreads], s_ep[kDrawThreads];
     __shared__ int s_valid[kDrawThreads];
@@ -72,8 +73,9 @@ __host__ __device__ inline unsigned sf_cell_blocks(size_t total)
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(256) k_sf_cells(const View v, const SFlat sf, const PFlat pf, const int iteration)
+__global__ void __launch_bounds__(256) k_sf_cells(const View v, const SFlat sf, const PFlat pf, const int iteration_arg)
 {
+    const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
     __shared__ unsigned int s_hist[kSortBins];
     __shared__ unsigned int s_evals;
@@ -146,8 +148,9 @@ __global__ void __launch_bounds__(256) k_sf_scatter(const View v, const SFlat sf
 // One warp per (chain, sample), no block barriers: the warp sums the sample's cells (lanes across
 // loci, then the shuffle tree -- the order of the fused kernel), lane 0 decides, the warp commits.
 template <int KIND>
-__global__ void __launch_bounds__(256) k_sf_decide(const View v, const SFlat sf, const int iteration)
+__global__ void __launch_bounds__(256) k_sf_decide(const View v, const SFlat sf, const int iteration_arg)
 {
+    const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
     const int lane = threadIdx.x & 31;
     const size_t si = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -216,8 +219,9 @@ __global__ void __launch_bounds__(256) k_sf_decide(const View v, const SFlat sf,
 // (chain, sample) recomputes the observation terms under the proposed rate (lanes across loci, four
 // loci per lane in flight), lane 0 decides, the warp commits.
 template <int KIND>
-__global__ void __launch_bounds__(256) k_eps_cells(const View v, const SFlat sf, const int iteration)
+__global__ void __launch_bounds__(256) k_eps_cells(const View v, const SFlat sf, const int iteration_arg)
 {
+    const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     static_assert(KIND == KIND_EPS_NEG || KIND == KIND_EPS_POS, "error-rate updates only");
     const int lane = threadIdx.x & 31;
     const size_t si = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);

@@ -13,6 +13,9 @@
 
 namespace moire
 {
+// kernels take the iteration by value, or read it from View::iter when handed this
+constexpr int kIterFromDevice = -1;
+
 struct View
 {
     int N, L, T, AP, nA;
@@ -53,6 +56,8 @@ struct View
     int *active;  // init retry mask
 
     unsigned long long *evals;  // [16] non-missing cell evaluations, by update kind
+    const int *iter;            // [1] the step's iteration for kernels launched with iteration < 0
+                                // (the captured step graph: its launch parameters never change)
     unsigned long long *trace;  // tuning aid (MOIRE_B200_TRACE): per-warp clocks of update_p, or null
 
     // parameters (src/parameters.h:31-47) and host-precomputed constants
