@@ -215,3 +215,56 @@ def test_flat_and_fused_pipelines_agree_on_ragged_data_with_missing_cells(monkey
                 assert np.array_equal(x, y), key
             else:
                 assert np.allclose(x, y, rtol=1e-9, atol=1e-12, equal_nan=True), key
+
+
+def test_step_graph_replays_the_plain_launch_sequence(monkeypatch):
+    """moire_engine_step replays a captured CUDA graph; with MOIRE_B200_NO_GRAPH it issues the same
+    kernels one by one.  Same state, bit for bit, and the same launch count."""
+    from moire_b200.engine import Engine
+    from moire_b200.workloads import make_workload
+    wl = make_workload("c3")
+    temps = wl["temps"][:3]
+    outs = []
+    for plain in (False, True):
+        if plain:
+            monkeypatch.setenv("MOIRE_B200_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("MOIRE_B200_NO_GRAPH", raising=False)
+        eng = Engine(wl["packed"], temps, seed=2, burnin=100, **wl["model"])
+        eng.init_chains()
+        _, l0 = eng.counters()
+        for it in range(4):
+            eng.step(it)
+        _, l1 = eng.counters()
+        outs.append(([eng.dump_state(c) for c in range(3)], eng.scalars(), l1 - l0, eng.diagnostics_all(),
+                     [eng.diagnostics(c) for c in range(3)]))
+        eng.close()
+    (sa, (la, pa), na, da, dsa), (sb, (lb, pb), nb, _, _) = outs
+    assert np.array_equal(la, lb) and np.array_equal(pa, pb)
+    assert na == nb + 4                      # plus the one-thread kernel that stores the iteration
+    for x, y in zip(sa, sb):
+        for key in x:
+            assert np.array_equal(np.asarray(x[key]), np.asarray(y[key]), equal_nan=True), key
+    # the bulk diagnostics read is the per-chain read, chain by chain
+    for bulk, one in zip(da, dsa):
+        for key in one:
+            assert np.array_equal(np.asarray(bulk[key]), np.asarray(one[key])), key
+
+
+def test_many_samples_need_no_shared_memory_budget():
+    """9000 samples per locus: beyond what the fused update_p could stage in shared memory; the flat
+    pipelines have no such bound."""
+    from moire_b200.data import pack_data
+    from moire_b200.engine import DEFAULT_MODEL, Engine
+    from moire_b200.simulate import simulate_data
+    sim = simulate_data(mean_coi=2.5, num_samples=9000, epsilon_pos=.01, epsilon_neg=.05,
+                        locus_freq_alphas=[np.full(6, 1.0)] * 8, seed=8)
+    pk = pack_data(sim["data"], sim["is_missing"])
+    model = dict(DEFAULT_MODEL, max_coi=10, burnin=50)
+    eng = Engine(pk, np.array([1.0, .5]), seed=4, **model)
+    assert not eng.init_chains()["still_ill"].any()
+    for it in range(3):
+        eng.step(it)
+    check_invariants(eng, pk, 0)
+    check_invariants(eng, pk, 1)
+    eng.close()
