@@ -24,53 +24,26 @@
 
 namespace moire
 {
-// The kernels are instruction-fetch bound (ncu: GPC instruction cache at ~85 % of its request
-// rate, SM instruction-cache hit rate 66 %, profiles/README.md), and CUDA's double-precision
-// log / log1p / exp / expm1 are 100-250 instructions each when inlined.  Only the per-cell hot
-// path (the thread evaluator's log of the frequency sum and the mixture loop) inlines them;
-// every other use -- proposals, priors, SALT, the cooperative and EGF paths -- shares one
-// out-of-line copy per function.
-#ifndef MOIRE_HOT_LOG
-#define MOIRE_HOT_LOG 1
-#endif
-// MOIRE_HOT_LOG: 0 = log / log1p / exp inlined at the hot sites; 1 (default) = log1p(-pam)
-// evaluated as log(1 - pam); 2 = additionally one shared out-of-line log for the hot uses.
-// log(1 - pam): pam is clamped to [0, 1 - eps]; 1 - pam is exact for pam >= 1/2 and carries a
-// relative rounding error <= 2^-53 below, i.e. the term differs from log1p(-pam) by at most
-// ~2e-16 in absolute value -- ulp-level, like the difference between CUDA's and glibc's log1p --
-// while dropping the 250-instruction log1p body from the instruction-fetch-bound hot loop
-// (measured -13 % step time, profiles/variants_o.log).
-#if MOIRE_HOT_LOG == 2
-__device__ __noinline__ double hot_log(double x) { return log(x); }
-#else
+// The fused kernels were instruction-fetch bound (ncu: GPC instruction cache at ~85 % of its
+// request rate, SM instruction-cache hit rate 66 %, profiles/README.md), and CUDA's
+// double-precision log / log1p / exp / expm1 are 100-250 instructions each when inlined.  Only
+// the per-cell hot path (the one-thread evaluator's log of the frequency sum and the linear
+// mixture) inlines them; every other use -- proposals, priors, SALT, the cooperative and EGF
+// paths, the mixture's fallback -- shares one out-of-line copy per function.
+//
+// log1p(-pam) of a clamped PAM is evaluated as log(1 - pam) on every path: pam is clamped to
+// [0, 1 - eps]; 1 - pam is exact for pam >= 1/2 and carries a relative rounding error <= 2^-53
+// below, i.e. the term differs from log1p(-pam) by at most ~2e-16 in absolute value -- ulp-level,
+// like the difference between CUDA's and glibc's log1p -- while the 250-instruction log1p body
+// cost 13 % of the step when it sat in the hot loop (profiles/variants_o.log).
 __device__ __forceinline__ double hot_log(double x) { return log(x); }
-#endif
-__device__ __forceinline__ double hot_log1m(double x)
-{
-#if MOIRE_HOT_LOG == 0
-    return log1p(-x);
-#else
-    return hot_log(1.0 - x);
-#endif
-}
 __device__ __noinline__ double cold_log(double x) { return log(x); }
-// log(1 - x) of a clamped PAM, the same formulation on every path
-__device__ __forceinline__ double cold_log1m(double x);
 __device__ __noinline__ double cold_log1p(double x) { return log1p(x); }
 __device__ __noinline__ double cold_exp(double x) { return exp(x); }
 __device__ __noinline__ double cold_expm1(double x) { return expm1(x); }
-__device__ __forceinline__ double cold_log1m(double x)
-{
-#if MOIRE_HOT_LOG == 0
-    return cold_log1p(-x);
-#else
-    return cold_log(1.0 - x);
-#endif
-}
+__device__ __forceinline__ double cold_log1m(double x) { return cold_log(1.0 - x); }
 
-#ifndef MOIRE_COOP_INLINE
 #define MOIRE_COOP_INLINE __noinline__
-#endif
 constexpr int kIeMax = 10;      // src/prob_any_missing.cpp:11
 constexpr int kMaxCoi = 64;     // MOIRE_MAX_COI
 constexpr int kLogCDim = 65;    // logC[n][k], 0 <= k <= n <= 64
@@ -260,9 +233,7 @@ __device__ MOIRE_COOP_INLINE double ie_scalar(double *scr, int ST, int k, int n)
 __device__ double g_egf_comb[(kMaxCoi + 1) * (kMaxCoi + 1)];
 // C(n, i) as the nearest double, [n][i]: the weights of the linear-domain relatedness mixture.
 __device__ double g_binom[(kMaxCoi + 1) * (kMaxCoi + 1)];
-#ifndef MOIRE_LINEAR_MIX
-#define MOIRE_LINEAR_MIX 1
-#endif
+
 
 // a[n] = coverage probability of n draws for n = 0..max_n.  q_e = prow[allele_e] / total.
 __device__ __noinline__ void egf_coverage(uint64_t latent, const double *prow, double total,
@@ -310,7 +281,6 @@ __device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, i
                                                       double log_total, double log_r,
                                                       double log_1mr, const double *lgam)
 {
-#if MOIRE_LINEAR_MIX
     // The same sum with the common factor of term i = 0 taken out instead of the largest term:
     //   sum_i C(m-1,i) r^i (1-r)^(m-1-i) total^(m-i) (1 - pam_i)
     //     = (1-r)^(m-1) total^m * S,   S = sum_i C(m-1,i) q^i (1 - pam_i),  q = r / ((1-r) total)
@@ -339,9 +309,7 @@ __device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, i
             return __dadd_rn(lead, hot_log(S));
         }
     }
-#endif
-    // the reference's log-sum-exp form; val[] is left untouched (the terms are recomputed for the
-    // sum), so that one set of PAMs can serve several samples
+    // the reference's log-sum-exp form (val[] is left untouched: the terms are recomputed for the sum)
     auto term = [&](int t) -> double {
         const int i = cnt - 1 - t;
         const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
@@ -366,18 +334,16 @@ __device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, i
     return __dadd_rn(mx, cold_log(sum));
 }
 
-#ifndef MOIRE_TIERS
-#define MOIRE_TIERS 2
-#endif
 constexpr int kMaxAcc = 16;  // accumulators kept in registers
 
 // The subset sums of one cell, accumulators dumped to scr[t * ST], then the mixture.
 // All lanes that arrive together run the accumulator tier of the largest count among them (the
 // extra accumulators of a lane with fewer mixture terms are simply never read), so lanes with
 // different counts -- and different k: the subset loop just ends earlier for them -- share one
-// instruction stream.  Two tiers are compiled, {4, 16}: measured best on B200
-// (profiles/variants_g.log) -- more tiers mean more distinct hot loops competing for the
-// instruction caches, which costs more than the idle accumulators do.
+// instruction stream.  Six tiers are compiled (2, 4, 6, 8, 12, 16).  The fused kernels, which were
+// instruction-fetch bound, did best with two ({4, 16}: more distinct hot loops cost more than idle
+// accumulators, profiles/variants_g.log); the flat evaluator's code fits the instruction cache
+// and gains from the tighter fit.
 // PAM(n = k + t), t < cnt <= kMaxAcc, into scr[t * ST] (q in slots 0..k-1 is consumed).
 __device__ __noinline__ void ie_pams(double *scr, int ST, int k, int cnt)
 {
@@ -388,35 +354,12 @@ __device__ __noinline__ void ie_pams(double *scr, int ST, int k, int cnt)
         ie_vectorized<NACC>(scr, ST, k, 0, acc);                                \
         _Pragma("unroll") for (int t = 0; t < NACC; ++t) scr[t * ST] = acc[t];  \
     }
-#if MOIRE_TIERS == 0  // 4 16
-    if (cnt_w <= 4) MOIRE_IE_TIER(4)
-    else MOIRE_IE_TIER(16)
-#elif MOIRE_TIERS == 1  // 2 4 8 16
-    if (cnt_w <= 2) MOIRE_IE_TIER(2)
-    else if (cnt_w <= 4) MOIRE_IE_TIER(4)
-    else if (cnt_w <= 8) MOIRE_IE_TIER(8)
-    else MOIRE_IE_TIER(16)
-#elif MOIRE_TIERS == 2  // 2 4 6 8 12 16
     if (cnt_w <= 2) MOIRE_IE_TIER(2)
     else if (cnt_w <= 4) MOIRE_IE_TIER(4)
     else if (cnt_w <= 6) MOIRE_IE_TIER(6)
     else if (cnt_w <= 8) MOIRE_IE_TIER(8)
     else if (cnt_w <= 12) MOIRE_IE_TIER(12)
     else MOIRE_IE_TIER(16)
-#else  // 1 2 3 4 5 6 7 8 10 12 14 16
-    if (cnt_w <= 1) MOIRE_IE_TIER(1)
-    else if (cnt_w <= 2) MOIRE_IE_TIER(2)
-    else if (cnt_w <= 3) MOIRE_IE_TIER(3)
-    else if (cnt_w <= 4) MOIRE_IE_TIER(4)
-    else if (cnt_w <= 5) MOIRE_IE_TIER(5)
-    else if (cnt_w <= 6) MOIRE_IE_TIER(6)
-    else if (cnt_w <= 7) MOIRE_IE_TIER(7)
-    else if (cnt_w <= 8) MOIRE_IE_TIER(8)
-    else if (cnt_w <= 10) MOIRE_IE_TIER(10)
-    else if (cnt_w <= 12) MOIRE_IE_TIER(12)
-    else if (cnt_w <= 14) MOIRE_IE_TIER(14)
-    else MOIRE_IE_TIER(16)
-#endif
 #undef MOIRE_IE_TIER
 }
 
@@ -555,8 +498,8 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
 // of operations as the one-thread path and parks them in shared memory; lane t then adds the 32
 // terms of accumulator t in subset order.  Floating-point addition is not associative, so this
 // ordered second phase (not a tree reduction) is what keeps the result bit-identical to the
-// one-thread path and to the reference's summation order.  The mixture terms are evaluated one
-// per lane; their log-sum-exp is again summed in the reference's order.
+// one-thread path and to the reference's summation order.  The sums are then gathered to every
+// lane and go through relatedness_mixture, the one-thread path's own mixture.
 // All lanes must call with identical arguments; every lane returns the value.
 // wscr: the warp's 32 scratch columns (slot s, column c at wscr[s * ST + c]); slot 16 holds q.
 #ifndef MOIRE_COOP_MIN_K
@@ -570,7 +513,7 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int k = __popcll(latent);  // kCoopMinK <= k <= kIeMax <= m guaranteed by the caller
+    const int k = __popcll(latent);  // 1 <= k <= kIeMax, k <= m guaranteed by the caller
     double total = 0.0;
     {
         uint64_t rest = latent;

@@ -7,13 +7,14 @@
 // kernel on an instruction-fetch-bound path (profiles/README.md).  Here the work is cut the other
 // way: the latent genotypes do not change during update_p, so ALL cells of ALL chains are sorted
 // ONCE by cost class (device-wide counting sort), and every proposal round is
-//   k_pf_round  one block per (chain, locus): decide the previous proposal in sample order,
-//               commit, draw the next SALT proposal                       (tiny, serial math)
+//   k_pf_round  one warp per (chain, locus): decide the previous proposal, commit, draw the next
+//               SALT proposal                                             (tiny, serial math)
 //   k_flat_eval a persistent grid over the sorted cell list: warps with identical (k, m - k + 1) in
 //               every lane, no block barrier, only the evaluator's code   (all the arithmetic)
 // Rounds = max_j A_j; loci with fewer alleles (or that hit the 1e-12 floor) sit out.  Streams,
-// proposals, per-cell arithmetic and the order of every sum are those of the fused kernel, so the
-// two produce the same chain.
+// proposals and per-cell arithmetic are those of the fused kernel (the locus sums are taken in a
+// different fixed order), so the two produce the same chain up to rounding-level ties
+// (tests/test_gpu_shapes.py::test_flat_and_fused_pipelines_agree_...).
 #pragma once
 #include <algorithm>
 #include <vector>
@@ -390,7 +391,8 @@ __global__ void __launch_bounds__(kPfRoundThreads) k_pf_round(const View v, cons
 }
 
 // ---- the flat evaluator: every listed cell, from the sorted list ---------------------------------
-// Sections of the list: [0, n_egf) k > 10, [n_egf, coop_end) kCoopMinK <= k <= 10, the rest light.
+// Sections of the list: [0, n_egf) k > 10, [n_egf, coop_end) the classes above the launch's
+// cooperative threshold (k_pf_scan), the rest light.
 // A task is a few consecutive units of the list -- cooperative cells or chunks of 32 one-thread
 // cells of (nearly) one cost class.  The grid is persistent (a few blocks per SM); blocks draw
 // tasks from a device counter, heaviest first, so the section sizes never travel to the host.
