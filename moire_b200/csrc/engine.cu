@@ -433,11 +433,11 @@ struct moire_engine
         CUDA_TRY(cudaFuncSetAttribute(k_flat_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
         {
             int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flat_eval, 256, pf_eval_smem()));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flat_eval, kEvalThreads, pf_eval_smem()));
             cudaDeviceProp prop1;
             CUDA_TRY(cudaGetDeviceProperties(&prop1, device));
             flat_grid = std::max(1, per_sm) * prop1.multiProcessorCount;
-            pf.eval_threads = flat_grid * 256;
+            pf.eval_threads = flat_grid * kEvalThreads;
         }
     }
 
@@ -483,7 +483,7 @@ struct moire_engine
         pending.clear();
     }
 
-    static size_t pf_eval_smem() { return (128 + moire::scratch_doubles(256)) * sizeof(double); }
+    static size_t pf_eval_smem() { return (128 + moire::scratch_doubles(moire::kEvalThreads)) * sizeof(double); }
     int flat_grid = 0;  // persistent evaluator grid: resident blocks of the device
 
     void launch_flat_eval(const moire::FlatSrc &src)
@@ -495,7 +495,7 @@ struct moire_engine
             CUDA_TRY(cudaEventCreate(&b));
             CUDA_TRY(cudaEventRecord(a, stream));
         }
-        moire::k_flat_eval<<<flat_grid, 256, pf_eval_smem(), stream>>>(v, src);
+        moire::k_flat_eval<<<flat_grid, moire::kEvalThreads, pf_eval_smem(), stream>>>(v, src);
         if (timing)
         {
             CUDA_TRY(cudaEventRecord(b, stream));

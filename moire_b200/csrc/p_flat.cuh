@@ -414,15 +414,19 @@ struct FlatSrc
     int out_locus_major;
 };
 
+#ifndef MOIRE_PF_THREADS
+#define MOIRE_PF_THREADS 256
+#endif
+constexpr int kEvalThreads = MOIRE_PF_THREADS, kEvalWarps = kEvalThreads / 32;
 #ifndef MOIRE_PF_LIGHT_UPB
-#define MOIRE_PF_LIGHT_UPB 8
+#define MOIRE_PF_LIGHT_UPB kEvalWarps
 #endif
 #ifndef MOIRE_PF_MIN_BLOCKS
 #define MOIRE_PF_MIN_BLOCKS 4
 #endif
 // Units per task: one per warp for cooperative cells and for chunks of heavy cells (each is long:
 // up to 1023 subsets), MOIRE_PF_LIGHT_UPB / 8 light chunks per warp.
-__host__ __device__ inline int pf_units_per_task(bool light) { return light ? MOIRE_PF_LIGHT_UPB : 8; }
+__host__ __device__ inline int pf_units_per_task(bool light) { return light ? MOIRE_PF_LIGHT_UPB : kEvalWarps; }
 __host__ __device__ inline int pf_tasks(int cells, bool chunked, bool light)
 {
     const int units = chunked ? (cells + 31) / 32 : cells;
@@ -430,15 +434,15 @@ __host__ __device__ inline int pf_tasks(int cells, bool chunked, bool light)
     return (units + upb - 1) / upb;
 }
 
-__global__ void __launch_bounds__(256, MOIRE_PF_MIN_BLOCKS) k_flat_eval(const View v, const FlatSrc f)
+__global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval(const View v, const FlatSrc f)
 {
     extern __shared__ double smem[];
     double *s_lgam = smem;
     double *s_scr = smem + 128;
     __shared__ int s_task;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int ST = 256 + 1;
-    for (int i = tid; i < 128; i += 256) s_lgam[i] = v.lgam[i];
+    constexpr int ST = kEvalThreads + 1;
+    for (int i = tid; i < 128; i += kEvalThreads) s_lgam[i] = v.lgam[i];
     const bool allow_rel = v.allow_rel != 0;
     const unsigned N = (unsigned)v.N, L = (unsigned)v.L;
     const bool locus_major = f.out_locus_major != 0;
@@ -483,7 +487,7 @@ __global__ void __launch_bounds__(256, MOIRE_PF_MIN_BLOCKS) k_flat_eval(const Vi
             light = true;
         }
         const int upb = pf_units_per_task(light);
-        for (int u = warp; u < upb; u += 8)
+        for (int u = warp; u < upb; u += kEvalWarps)
         {
             const int unit = b * upb + u;
             if (coop)
