@@ -775,6 +775,13 @@ __device__ __forceinline__ uint32_t bernoulli_threshold(double pr)
     return x <= 0.0 ? 0u : (x >= 4294967295.0 ? 4294967295u : (uint32_t)x);
 }
 
+// The three phases of the draw (false negatives, false positives, which alleles) each start on a
+// fresh Philox block (MOIRE_RNG_ALIGN, mirrored by the CPU stepper): the lanes of a warp consume
+// different numbers of words per phase, and without this they refill at different times, each
+// refill running for a fraction of the warp (-20 us per resampling kernel at C3).
+#ifndef MOIRE_RNG_ALIGN
+#define MOIRE_RNG_ALIGN 1
+#endif
 // Draws the proposal and returns its mask; *log_prob gets the log proposal density.
 // logC[n * 65 + k] = log(C(n, k)).
 __device__ __forceinline__ uint64_t sample_latent_genotype(Stream &rng, uint64_t obs, int A,
@@ -791,6 +798,9 @@ __device__ __forceinline__ uint64_t sample_latent_genotype(Stream &rng, uint64_t
     // (w + 0.5) 2^-32 < pr  <=>  w < ceil(pr 2^32 - 0.5): the same Bernoulli draws on the raw words
     const uint32_t thr_en = bernoulli_threshold(e.pr_en);
     for (int ii = min_fn; ii < max_fn; ++ii) fn += (rng.next_u32() < thr_en);
+#if MOIRE_RNG_ALIGN
+    rng.have = 0;  // every phase starts on a fresh block: the lanes of a warp refill together
+#endif
     const int tn = obs_neg - fn;
     const double lp_fn =
         __dadd_rn(__dadd_rn(logC[obs_neg * kLogCDim + (fn - min_fn)],
@@ -806,6 +816,9 @@ __device__ __forceinline__ uint64_t sample_latent_genotype(Stream &rng, uint64_t
     int fp = min_fp;
     const uint32_t thr_ep = bernoulli_threshold(e.pr_ep);
     for (int ii = min_fp; ii < max_fp; ++ii) fp += (rng.next_u32() < thr_ep);
+#if MOIRE_RNG_ALIGN
+    rng.have = 0;
+#endif
     const int tp = obs_pos - fp;
     const double lp_fp =
         __dadd_rn(__dadd_rn(logC[obs_pos * kLogCDim + (fp - min_fp)],

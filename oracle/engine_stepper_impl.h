@@ -128,6 +128,7 @@ static uint64_t stp_sample_latent(stp_stream *s, uint64_t obs, int A, int coi, d
     if (max_fn < min_fn) max_fn = min_fn;
     int fn = min_fn;
     for (int ii = min_fn; ii < max_fn; ++ii) fn += (stp_uniform(s) < eps_neg / (double)A);
+    s->have = 0; /* the engine starts every phase of the draw on a fresh Philox block */
     int min_fp = obs_pos + fn - coi;
     if (min_fp < 0) min_fp = 0;
     int max_fp = obs_pos + fn - 1;
@@ -139,6 +140,7 @@ static uint64_t stp_sample_latent(stp_stream *s, uint64_t obs, int A, int coi, d
     }
     int fp = min_fp;
     for (int ii = min_fp; ii < max_fp; ++ii) fp += (stp_uniform(s) < eps_pos / (double)A);
+    s->have = 0;
     const uint64_t pos = stp_choose_bits(s, obs, obs_pos, obs_pos - fp);
     const uint64_t neg = stp_choose_bits(s, ~obs & all, obs_neg, fn);
     *log_prob = latent_log_prob_f64(A, obs_pos, fn, fp, coi, eps_pos, eps_neg);

@@ -65,9 +65,10 @@ def test_single_chain_stores_every_draw_and_is_reproducible():
 
 def test_posterior_agrees_with_reference_sampler():
     """Posterior COI / allele-frequency / error-rate summaries from the engine against the
-    reference's own C++ sampler on the same data, two engine seeds: agreement within Monte-Carlo
-    error (thresholds ~4 standard errors of the between-run differences seen in the reference
-    itself)."""
+    reference's own C++ sampler on the same data, three reference seeds and six engine seeds: the
+    mean COI must agree within four standard errors of the difference, estimated from the
+    between-seed spread of each sampler (with a floor: three seeds give a rough sd); the other
+    summaries within fixed bands a few times their Monte-Carlo error."""
     from oracle.pyoracle import Ref, ref_available
     if not ref_available(32):
         pytest.skip("oracle/_ref not built")
@@ -80,7 +81,7 @@ def test_posterior_agrees_with_reference_sampler():
     ref.set_data(pk.num_alleles, pk.obs_mask, pk.is_missing)
     ref.set_params(pt_chains=[1.0], burnin=burn, samples=samp)
     refs = []
-    for seed in (1, 2):
+    for seed in (1, 2, 3):
         h = ref.mcmc_new(seed=seed)
         for s in range(burn):
             ref.lib.ref_mcmc_burnin(h, s)
@@ -89,7 +90,7 @@ def test_posterior_agrees_with_reference_sampler():
         refs.append(ref.mcmc_summary(h))
         ref.mcmc_free(h)
     ours = []
-    for seed in (11, 12):
+    for seed in (11, 12, 13, 14, 15, 16):
         ch = run_mcmc(d, d["is_missing"], burnin=burn, samples_per_chain=samp, verbose=False,
                       seed=seed)["chains"][0]
         ours.append(dict(m=np.mean(ch["coi"], axis=1), r=np.mean(ch["relatedness"], axis=1),
@@ -99,7 +100,11 @@ def test_posterior_agrees_with_reference_sampler():
     ref_m = np.mean([r["m"] for r in refs], axis=0)
     our_m = np.mean([o["m"] for o in ours], axis=0)
     ref_spread = np.abs(refs[0]["m"] - refs[1]["m"]).mean()
-    assert abs(ref_m.mean() - our_m.mean()) < 0.15, (ref_m.mean(), our_m.mean())
+    ref_runs = np.array([r["m"].mean() for r in refs])
+    our_runs = np.array([o["m"].mean() for o in ours])
+    se = np.sqrt(max(ref_runs.std(ddof=1), 0.1) ** 2 / len(ref_runs) +
+                 max(our_runs.std(ddof=1), 0.1) ** 2 / len(our_runs))
+    assert abs(ref_m.mean() - our_m.mean()) < 4 * se, (ref_runs, our_runs, se)
     assert np.abs(ref_m - our_m).mean() < max(4 * ref_spread, 0.25), (np.abs(ref_m - our_m).mean(), ref_spread)
     assert np.corrcoef(ref_m, our_m)[0, 1] > 0.95
     ref_p0 = np.mean([r["p"][:, 0] for r in refs], axis=0)
