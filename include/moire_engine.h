@@ -158,6 +158,9 @@ int moire_engine_get_scalars(moire_engine *e, double *llik, double *prior);
 /* Device addresses of the same [num_chains] arrays, for a collective (NCCL all-gather) that
  * wants no host round trip.  Valid until destroy. */
 int moire_engine_device_scalars(moire_engine *e, void **dev_llik, void **dev_prior);
+/* Engines return their device buffers to a per-process free list when destroyed (the next engine
+ * of the same shape re-uses them); this hands the list back to the driver. */
+int moire_engine_trim_memory(void);
 /* The CUDA stream (cudaStream_t) every call of this engine is ordered on, for work that must follow
  * a step without a host round trip (the driver's NCCL all-gather of the scalars). */
 int moire_engine_stream(moire_engine *e, void **stream);

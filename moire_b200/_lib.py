@@ -118,6 +118,7 @@ ENGINE_SYMBOLS = {
     "moire_engine_timer_start": (C.c_int, [vp]),
     "moire_engine_timer_stop": (C.c_int, [vp, C.POINTER(dbl)]),
     "moire_engine_set_timing": (C.c_int, [vp, i32]),
+    "moire_engine_trim_memory": (C.c_int, []),
     "moire_engine_stream": (C.c_int, [vp, C.POINTER(vp)]),
     "moire_engine_read_timing": (C.c_int, [vp, vp, vp]),
     "moire_engine_read_evaluator_timing": (C.c_int, [vp, C.POINTER(dbl), C.POINTER(u64)]),

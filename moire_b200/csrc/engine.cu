@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -41,16 +43,85 @@ struct InvalidArg
     std::string msg;
 };
 
+// Device memory comes from a small caching layer: an engine's ~60 buffers (0.7 GB at C3) are
+// handed back to a per-process free list instead of cudaFree -- which synchronises the device and
+// took 5..300 ms for the lot, inside every run_mcmc call -- and the next engine of the same shape
+// (the next of `num_chains` runs, the next call) takes them from there.  Blocks are matched by
+// (device, exact size); moire_engine_trim_memory() returns the list to the driver.
+struct DeviceBlockCache
+{
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> free_blocks;
+    size_t cached_bytes = 0;
+    static constexpr size_t kMaxCachedBytes = (size_t)32 << 30;
+
+    void *take(size_t bytes)
+    {
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            auto it = free_blocks.find({dev, bytes});
+            if (it != free_blocks.end())
+            {
+                void *p = it->second;
+                free_blocks.erase(it);
+                cached_bytes -= bytes;
+                return p;
+            }
+        }
+        void *p = nullptr;
+        const cudaError_t rc = cudaMalloc(&p, bytes);
+        if (rc == cudaErrorMemoryAllocation)
+        {
+            cudaGetLastError();
+            trim();  // cached blocks of other shapes may be what is in the way
+            CUDA_TRY(cudaMalloc(&p, bytes));
+        }
+        else
+            CUDA_TRY(rc);
+        return p;
+    }
+    void give(void *p, size_t bytes)
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cached_bytes + bytes > kMaxCachedBytes)
+        {
+            cudaFree(p);
+            return;
+        }
+        std::lock_guard<std::mutex> lock(mu);
+        free_blocks.insert({{dev, bytes}, p});
+        cached_bytes += bytes;
+    }
+    void trim()
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto &kv : free_blocks)
+        {
+            cudaSetDevice(kv.first.first);
+            cudaFree(kv.second);
+        }
+        cudaSetDevice(cur);
+        free_blocks.clear();
+        cached_bytes = 0;
+    }
+};
+DeviceBlockCache g_block_cache;
+
 template <class T>
 struct DevBuf
 {
     T *ptr = nullptr;
     size_t n = 0;
+    size_t bytes() const { return std::max<size_t>(n, 1) * sizeof(T); }
     void alloc(size_t count)
     {
         n = count;
-        CUDA_TRY(cudaMalloc(&ptr, std::max<size_t>(count, 1) * sizeof(T)));
-        CUDA_TRY(cudaMemset(ptr, 0, std::max<size_t>(count, 1) * sizeof(T)));
+        ptr = static_cast<T *>(g_block_cache.take(bytes()));
+        CUDA_TRY(cudaMemset(ptr, 0, bytes()));
     }
     void upload(const T *src, size_t count, cudaStream_t s)
     {
@@ -58,7 +129,7 @@ struct DevBuf
     }
     void release()
     {
-        if (ptr) cudaFree(ptr);
+        if (ptr) g_block_cache.give(ptr, bytes());
         ptr = nullptr;
     }
 };
@@ -1046,6 +1117,12 @@ int moire_engine_device_scalars(moire_engine *e, void **dev_llik, void **dev_pri
         if (dev_llik) *dev_llik = e->v.llik;
         if (dev_prior) *dev_prior = e->v.prior;
     });
+}
+
+int moire_engine_trim_memory(void)
+{
+    g_block_cache.trim();
+    return MOIRE_OK;
 }
 
 int moire_engine_stream(moire_engine *e, void **stream)

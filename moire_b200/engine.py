@@ -267,6 +267,11 @@ def _evaluator_timing(self):
 Engine.evaluator_timing = _evaluator_timing
 
 
+def trim_memory():
+    """Hand the device buffers cached from closed engines back to the CUDA driver."""
+    _lib.load().moire_engine_trim_memory()
+
+
 def philox4x32(counter, key):
     lib = _lib.load()
     c = np.ascontiguousarray(counter, dtype=np.uint32)

@@ -443,18 +443,27 @@ def _assemble_chain(parts, N, L, num_alleles, args, record_latent):
         res["latent_genotypes"] = [[[[b for b in range(64) if int(dr["latent"][d, i, j]) >> b & 1]
                                      for d in range(D)] for j in range(L)] for i in range(N)]
     else:
-        res["latent_genotypes"] = [[[] for _ in range(L)] for _ in range(N)]
+        # nothing recorded: every (sample, locus) entry is an empty list, as in the reference's
+        # result; the rows are one shared object (read-only by convention, like an R value)
+        res["latent_genotypes"] = [[[] for _ in range(L)]] * N
     res["observed_coi"] = parts["observed_coi"]
     res["swap_store"] = lad["swap_store"]
     res["swap_acceptances"] = lad["swap_acceptances"]
     res["swap_barriers"] = lad["swap_barriers"]
     res["temp_gradient"] = lad["temp_gradient"]
-    res["acceptance_rates"] = [dict(allele_freq_accept=[g["p_accept"][j, :num_alleles[j]] for j in range(L)],
+    na = np.asarray(num_alleles)
+    if (na == na[0]).all():          # one allele count: slice the matrix once per chain
+        def per_locus(mat):
+            return list(mat[:, :int(na[0])])
+    else:
+        def per_locus(mat):
+            return [mat[j, :na[j]] for j in range(L)]
+    res["acceptance_rates"] = [dict(allele_freq_accept=per_locus(g["p_accept"]),
                                     coi_accept=g["m_accept"], eps_neg_accept=g["eps_neg_accept"],
                                     eps_pos_accept=g["eps_pos_accept"], r_accept=g["r_accept"],
                                     m_r_accept=g["m_r_accept"], full_sample_accept=g["sample_accept"],
                                     mean_coi_accept=g["mean_coi_accept"]) for g in diag]
-    res["sampling_variances"] = [dict(allele_freq_var=[g["p_prop_var"][j, :num_alleles[j]] for j in range(L)],
+    res["sampling_variances"] = [dict(allele_freq_var=per_locus(g["p_prop_var"]),
                                       eps_neg_var=g["eps_neg_var"], eps_pos_var=g["eps_pos_var"],
                                       r_var=g["r_var"], m_r_var=g["m_r_var"],
                                       mean_coi_var=g["mean_coi_var"]) for g in diag]
