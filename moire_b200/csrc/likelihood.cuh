@@ -344,16 +344,126 @@ constexpr int kMaxAcc = 16;  // accumulators kept in registers
 // instruction-fetch bound, did best with two ({4, 16}: more distinct hot loops cost more than idle
 // accumulators, profiles/variants_g.log); the flat evaluator's code fits the instruction cache
 // and gains from the tighter fit.
+// ---- small k, unrolled ---------------------------------------------------------------------------
+// For k <= MOIRE_SMALL_K every lane of a class-uniform warp walks the same handful of subsets, so
+// the walk is unrolled at compile time: q in registers, no table decode, no stack in shared
+// memory, the leading multiplications a fixed run.  Subset i of the reference's order (by size,
+// then lexicographic index tuples) is SmallSubsets<K>::mask[i]; each base is the reference's chain of
+// subtractions 1 - q[e1] - q[e2] ..., each power the same chain of multiplications as in
+// ie_vectorized, so the sums are bit-identical to the table-driven walk (a cell may take either
+// path depending on its neighbours in the sorted list).
+#ifndef MOIRE_SMALL_K
+#define MOIRE_SMALL_K 6
+#endif
+template <int K>
+struct SmallSubsets
+{
+    int mask[(1 << K) - 1];
+    constexpr SmallSubsets() : mask{}
+    {
+        int n = 0;
+        for (int size = 1; size <= K; ++size)
+        {
+            int c[K] = {};
+            for (int i = 0; i < size; ++i) c[i] = i;
+            for (;;)
+            {
+                int m = 0;
+                for (int i = 0; i < size; ++i) m |= 1 << c[i];
+                mask[n++] = m;
+                int i = size - 1;
+                while (i >= 0 && c[i] == K - size + i) --i;
+                if (i < 0) break;
+                ++c[i];
+                for (int j = i + 1; j < size; ++j) c[j] = c[j - 1] + 1;
+            }
+        }
+    }
+};
+
+template <int K, int NACC>
+__device__ __forceinline__ void ie_small(const double *scr, int ST, double (&acc)[NACC])
+{
+    constexpr SmallSubsets<K> ord{};
+    double q[K];
+#pragma unroll
+    for (int e = 0; e < K; ++e) q[e] = scr[e * ST];
+#pragma unroll
+    for (int t = 0; t < NACC; ++t) acc[t] = 0.0;
+#pragma unroll
+    for (int i = 0; i < (1 << K) - 1; ++i)
+    {
+        const int msk = ord.mask[i];
+        double base = 1.0;
+        int size = 0;
+#pragma unroll
+        for (int e = 0; e < K; ++e)
+            if ((msk >> e) & 1)
+            {
+                base = __dsub_rn(base, q[e]);
+                ++size;
+            }
+        double r = (size & 1) ? 1.0 : -1.0;
+#pragma unroll
+        for (int j = 0; j < K - 1; ++j) r = __dmul_rn(r, base);
+#pragma unroll
+        for (int t = 0; t < NACC; ++t)
+        {
+            r = __dmul_rn(r, base);
+            acc[t] = __dadd_rn(acc[t], r);
+        }
+    }
+}
+
 // PAM(n = k + t), t < cnt <= kMaxAcc, into scr[t * ST] (q in slots 0..k-1 is consumed).
 __device__ __noinline__ void ie_pams(double *scr, int ST, int k, int cnt)
 {
-    const int cnt_w = __reduce_max_sync(__activemask(), cnt);
-#define MOIRE_IE_TIER(NACC)                                                     \
-    {                                                                           \
-        double acc[NACC];                                                       \
-        ie_vectorized<NACC>(scr, ST, k, 0, acc);                                \
-        _Pragma("unroll") for (int t = 0; t < NACC; ++t) scr[t * ST] = acc[t];  \
+    const unsigned lanes = __activemask();
+    const int cnt_w = __reduce_max_sync(lanes, cnt);
+#define MOIRE_IE_STORE(NACC) _Pragma("unroll") for (int t = 0; t < NACC; ++t) scr[t * ST] = acc[t];
+#define MOIRE_IE_TIER(NACC)                      \
+    {                                            \
+        double acc[NACC];                        \
+        ie_vectorized<NACC>(scr, ST, k, 0, acc); \
+        MOIRE_IE_STORE(NACC)                     \
     }
+#define MOIRE_IE_SMALL(K, NACC)          \
+    {                                    \
+        double acc[NACC];                \
+        ie_small<K, NACC>(scr, ST, acc); \
+        MOIRE_IE_STORE(NACC)             \
+    }
+#define MOIRE_IE_SMALL_TIERS(K)                    \
+    {                                              \
+        if (cnt_w <= 2) MOIRE_IE_SMALL(K, 2)       \
+        else if (cnt_w <= 4) MOIRE_IE_SMALL(K, 4)  \
+        else if (cnt_w <= 6) MOIRE_IE_SMALL(K, 6)  \
+        else if (cnt_w <= 8) MOIRE_IE_SMALL(K, 8)  \
+        else if (cnt_w <= 12) MOIRE_IE_SMALL(K, 12) \
+        else MOIRE_IE_SMALL(K, 16)                 \
+        return;                                    \
+    }
+#if MOIRE_SMALL_K >= 2
+    {
+        const int k_hi = __reduce_max_sync(lanes, k);
+        if (k_hi <= MOIRE_SMALL_K && k_hi >= 2 && __reduce_min_sync(lanes, k) == k_hi)
+        {
+            if (k_hi == 2) MOIRE_IE_SMALL_TIERS(2)
+#if MOIRE_SMALL_K >= 3
+            if (k_hi == 3) MOIRE_IE_SMALL_TIERS(3)
+#endif
+#if MOIRE_SMALL_K >= 4
+            if (k_hi == 4) MOIRE_IE_SMALL_TIERS(4)
+#endif
+#if MOIRE_SMALL_K >= 5
+            if (k_hi == 5) MOIRE_IE_SMALL_TIERS(5)
+#endif
+#if MOIRE_SMALL_K >= 6
+            if (k_hi == 6) MOIRE_IE_SMALL_TIERS(6)
+#endif
+        }
+    }
+#endif
     if (cnt_w <= 2) MOIRE_IE_TIER(2)
     else if (cnt_w <= 4) MOIRE_IE_TIER(4)
     else if (cnt_w <= 6) MOIRE_IE_TIER(6)
@@ -361,6 +471,9 @@ __device__ __noinline__ void ie_pams(double *scr, int ST, int k, int cnt)
     else if (cnt_w <= 12) MOIRE_IE_TIER(12)
     else MOIRE_IE_TIER(16)
 #undef MOIRE_IE_TIER
+#undef MOIRE_IE_SMALL
+#undef MOIRE_IE_SMALL_TIERS
+#undef MOIRE_IE_STORE
 }
 
 __device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, int m,
