@@ -15,7 +15,11 @@ engine's stream around each step, L2 flushed between steps, max over ranks), `e2
 metric through the public `run_mcmc` call with host buffers (data packing, upload, chain
 initialisation, every step's scalar read-back, every stored draw's device->host copy, result
 assembly), `roofline` for the dominant kernel, `cpu_baseline` = the reference's own C++ sampler
-(compiled unmodified under oracle/_ref) on this box's host cores.
+(compiled unmodified under oracle/_ref) on this box's host cores.  The timed steps run as the
+product runs them (the engine replays its captured step graph); the per-kernel numbers behind
+`roofline` and `kernel_ms_per_step` come from K further steps issued as plain launches with an
+event pair around every update kind and every evaluator launch.  With N > 1 the exchange is the
+C++ driver's own ncclAllGather on the engine's stream (`config.exchange` says which path ran).
 
 `--impl reference` times that CPU sampler alone and prints the same line with "impl": "reference".
 """
