@@ -147,6 +147,19 @@ static uint64_t stp_sample_latent(stp_stream *s, uint64_t obs, int A, int coi, d
     return pos | neg;
 }
 
+/* n latent-genotype draws from the engine's streams (seed, draw number), for distribution tests
+ * against the reference's own sampler: masks[i], log_prob[i]. */
+void orc_stp_sample_latent_many(uint64_t seed, int n, uint64_t obs, int A, int coi, double eps_pos,
+                                double eps_neg, uint64_t *masks, double *log_prob)
+{
+    for (int i = 0; i < n; ++i)
+    {
+        stp_stream s;
+        stp_open(&s, seed, (uint32_t)i, 6u, 0u, (uint32_t)i >> 8, 1u);
+        masks[i] = stp_sample_latent(&s, obs, A, coi, eps_pos, eps_neg, &log_prob[i]);
+    }
+}
+
 typedef struct
 {
     /* shapes, data, model */

@@ -112,6 +112,16 @@ class Oracle:
         return self.lib.orc_observation(prec, _p(idx), len(idx), _p(obs), len(obs), eps_neg,
                                         eps_pos, max_eps_neg, max_eps_pos)
 
+    def stepper_sample_latent(self, seed, n, obs_mask, A, coi, eps_pos, eps_neg):
+        """n draws of the engine-semantics latent-genotype proposal: (masks uint64[n], log_prob[n])."""
+        masks, lp = np.zeros(n, np.uint64), np.zeros(n)
+        f = self.lib.orc_stp_sample_latent_many
+        f.restype = None
+        f.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_double,
+                      C.c_void_p, C.c_void_p]
+        f(seed, n, int(obs_mask), A, coi, eps_pos, eps_neg, _p(masks), _p(lp))
+        return masks, lp
+
     def latent_log_prob(self, prec, A, obs_pos, fn, fp, coi, eps_pos, eps_neg):
         return self.lib.orc_latent_log_prob(prec, A, obs_pos, fn, fp, coi, eps_pos, eps_neg)
 
