@@ -147,6 +147,18 @@ static uint64_t stp_sample_latent(stp_stream *s, uint64_t obs, int A, int coi, d
     return pos | neg;
 }
 
+/* n draws of the engine's +-Geometric COI step (mean 2, as every update uses it). */
+void orc_stp_coi_delta_many(uint64_t seed, int n, int *out)
+{
+    const double log_geom = -0.40546510810816438; /* log(1 - 1/3) */
+    for (int i = 0; i < n; ++i)
+    {
+        stp_stream s;
+        stp_open(&s, seed, (uint32_t)i, 3u, 0u, (uint32_t)i >> 8, 0u);
+        out[i] = stp_coi_delta(&s, log_geom);
+    }
+}
+
 /* n latent-genotype draws from the engine's streams (seed, draw number), for distribution tests
  * against the reference's own sampler: masks[i], log_prob[i]. */
 void orc_stp_sample_latent_many(uint64_t seed, int n, uint64_t obs, int A, int coi, double eps_pos,

@@ -66,6 +66,7 @@ void orc_philox4x32(const uint32_t counter[4], const uint32_t key[2], uint32_t o
  * engine_stepper_impl.h).  `chain` is the struct stp_chain defined there (mirrored field by
  * field in oracle/pyoracle.py). */
 struct stp_chain_s;
+void orc_stp_coi_delta_many(uint64_t seed, int n, int *out);
 void orc_stp_sample_latent_many(uint64_t seed, int n, uint64_t obs, int A, int coi, double eps_pos,
                                 double eps_neg, uint64_t *masks, double *log_prob);
 void orc_step_update(void *chain, int kind, int iteration);

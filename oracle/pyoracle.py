@@ -112,6 +112,14 @@ class Oracle:
         return self.lib.orc_observation(prec, _p(idx), len(idx), _p(obs), len(obs), eps_neg,
                                         eps_pos, max_eps_neg, max_eps_pos)
 
+    def stepper_coi_delta(self, seed, n):
+        out = np.zeros(n, np.int32)
+        f = self.lib.orc_stp_coi_delta_many
+        f.restype = None
+        f.argtypes = [C.c_uint64, C.c_int, C.c_void_p]
+        f(seed, n, _p(out))
+        return out
+
     def stepper_sample_latent(self, seed, n, obs_mask, A, coi, eps_pos, eps_neg):
         """n draws of the engine-semantics latent-genotype proposal: (masks uint64[n], log_prob[n])."""
         masks, lp = np.zeros(n, np.uint64), np.zeros(n)
@@ -318,6 +326,14 @@ class Ref:
         k = self.lib.ref_sample_latent_genotype(seed, _p(obs), len(obs), coi, eps_pos, eps_neg,
                                                 _p(out), C.byref(lp))
         return (out[:max(k, 0)].copy(), lp.value)
+
+    def sample_coi_delta(self, seed, mean, n):
+        out = np.zeros(n, np.int32)
+        f = self.lib.ref_sample_coi_delta_many
+        f.restype = None
+        f.argtypes = [C.c_uint64, C.c_double, C.c_int, C.c_void_p]
+        f(seed, mean, n, _p(out))
+        return out
 
     def sample_constrained(self, seed, curr, sd, lo, hi):
         z, prop, adj = C.c_double(), C.c_double(), C.c_double()

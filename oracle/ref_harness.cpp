@@ -377,6 +377,14 @@ int ref_sample_latent_genotype(std::uint64_t seed, const int *obs, int A, int co
     return lg.value.empty() ? -1 : static_cast<int>(lg.value.size());
 }
 
+// n draws of Sampler::sample_coi_delta(mean) (src/sampler.cpp:152-156) from one seeded sampler.
+void ref_sample_coi_delta_many(std::uint64_t seed, double mean, int n, int *out)
+{
+    Sampler s;
+    s.eng.seed(static_cast<std::uint_fast32_t>(seed));
+    for (int i = 0; i < n; ++i) out[i] = s.sample_coi_delta(static_cast<real>(mean));
+}
+
 // sample_constrained (src/sampler.cpp:176-190) plus the normal draw it consumed, obtained by
 // replaying an identically seeded engine through an identical fresh distribution.
 void ref_sample_constrained(std::uint64_t seed, double curr, double sd, double lo, double hi,

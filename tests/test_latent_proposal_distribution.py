@@ -69,3 +69,27 @@ def test_engine_and_reference_proposals_have_the_same_distribution(obs, coi, eps
             if len(mine) and len(theirs):
                 assert np.ptp(mine) < 1e-9 and np.ptp(theirs) < 1e-9
                 assert abs(mine[0] - theirs[0]) < 1e-9 * max(1.0, abs(theirs[0])), (a, b)
+
+
+def test_coi_step_has_the_reference_distribution():
+    """Sampler::sample_coi_delta(2) (src/sampler.cpp:152-156: a fair sign times a
+    std::geometric_distribution with success probability 1/3) against the engine's draw by
+    inversion: the same law on the integers."""
+    n = 200000
+    mine = Oracle().stepper_coi_delta(99, n)
+    ref = Ref(64)
+    if not hasattr(ref.lib, "ref_sample_coi_delta_many"):
+        pytest.skip("oracle/_ref predates ref_sample_coi_delta_many; rebuild with make -C oracle")
+    theirs = ref.sample_coi_delta(7, 2.0, n)
+    lo, hi = min(mine.min(), theirs.min()), max(mine.max(), theirs.max())
+    for v in range(lo, hi + 1):
+        p, q = (mine == v).mean(), (theirs == v).mean()
+        pooled = (p + q) / 2
+        se = np.sqrt(pooled * (1 - pooled) * 2 / n)
+        assert abs(p - q) <= 4.5 * se + 2e-5, (v, p, q)
+    # and the law itself: P(|X| = k) = (1/3)(2/3)^k, the sign fair (zero keeps its mass)
+    for k in range(0, 8):
+        want = (1 / 3) * (2 / 3) ** k
+        got = (np.abs(mine) == k).mean()
+        assert abs(got - want) < 4.5 * np.sqrt(want * (1 - want) / n), (k, got, want)
+    assert abs((mine > 0).mean() - (mine < 0).mean()) < 4.5 * np.sqrt(0.5 / n)
