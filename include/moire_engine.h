@@ -35,6 +35,13 @@ extern "C" {
 #define MOIRE_MAX_ALLELES 64 /* alleles per locus (one mask word) */
 #define MOIRE_MAX_COI 64     /* max_coi supported by the register tiers (reference LUT bound: 127) */
 
+/* Kernel generation: AUTO picks the flat pipelines (device-wide cost-class sort + persistent
+ * evaluator) unless the problem is tiny (< 1e5 cells), where the fused per-tile kernels win on
+ * latency.  Both produce the same chain; tests force each on one shape. */
+#define MOIRE_PIPELINE_AUTO 0
+#define MOIRE_PIPELINE_FLAT 1
+#define MOIRE_PIPELINE_FUSED 2
+
 /* The 8 Metropolis updates in the order MCMC::burnin runs them (src/mcmc.cpp:162-173). */
 enum moire_update_kind
 {
@@ -65,7 +72,7 @@ typedef struct moire_params
     int32_t allow_relatedness;
     int32_t burnin;  /* proposal-scale adaptation runs while iteration < burnin */
     int32_t max_coi;
-    int32_t reserved0;
+    int32_t pipeline; /* MOIRE_PIPELINE_*: which kernel generation runs the updates (0 = by size) */
     double mean_coi_shape, mean_coi_scale;
     double max_eps_pos, eps_pos_alpha, eps_pos_beta;
     double max_eps_neg, eps_neg_alpha, eps_neg_beta;
@@ -197,6 +204,16 @@ int moire_engine_read_timing(moire_engine *e, double *ms, uint64_t *launches);
  * transmission terms), accumulated like moire_engine_read_timing. */
 int moire_engine_read_evaluator_timing(moire_engine *e, double *ms, uint64_t *launches);
 int moire_engine_synchronize(moire_engine *e);
+
+/* The engine's subset enumeration for k latent alleles -- what replaces
+ * CombinationIndicesGenerator (src/combination_indices_generator.cpp:5-76) as driven by
+ * src/prob_any_missing.cpp:20-52, 186-214: sizes 1..k in turn, each in lexicographic order of the
+ * index tuples.  Decoded ON THE DEVICE from one of the three tables the kernels read:
+ * which = 0 the depth/tail table of the one-thread walk (k <= 10), 1 the full-mask table of the
+ * warp-cooperative evaluator (k <= 10), 2 the compile-time order of the unrolled walks (k <= 6).
+ * out[i], i < 2^k - 1: bits 0..k-1 = elements of the i-th subset, bit 15 = its term is subtracted.
+ * Must match the reference's sequences bit for bit (tests/test_gpu_parity.py). */
+int moire_engine_subset_order(moire_engine *e, int32_t which, int32_t k, uint16_t *out);
 
 /* Philox4x32-10 block (counter, key) -> 4 words; exported so tests can pin the generator against
  * the Random123 known-answer vectors. */

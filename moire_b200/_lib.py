@@ -22,7 +22,7 @@ class MoireData(C.Structure):
 
 
 class MoireParams(C.Structure):
-    _fields_ = [("allow_relatedness", i32), ("burnin", i32), ("max_coi", i32), ("reserved0", i32),
+    _fields_ = [("allow_relatedness", i32), ("burnin", i32), ("max_coi", i32), ("pipeline", i32),
                 ("mean_coi_shape", dbl), ("mean_coi_scale", dbl),
                 ("max_eps_pos", dbl), ("eps_pos_alpha", dbl), ("eps_pos_beta", dbl),
                 ("max_eps_neg", dbl), ("eps_neg_alpha", dbl), ("eps_neg_beta", dbl),
@@ -123,6 +123,7 @@ ENGINE_SYMBOLS = {
     "moire_engine_read_timing": (C.c_int, [vp, vp, vp]),
     "moire_engine_read_evaluator_timing": (C.c_int, [vp, C.POINTER(dbl), C.POINTER(u64)]),
     "moire_engine_synchronize": (C.c_int, [vp]),
+    "moire_engine_subset_order": (C.c_int, [vp, i32, i32, vp]),
     "moire_philox4x32": (None, [vp, vp, vp]),
 }
 

@@ -208,6 +208,75 @@ double log_binom_exact(unsigned n, unsigned k)
 
 __global__ void k_set_iteration(int *dst, const int iteration) { *dst = iteration; }
 
+// The subset order of k latent alleles as the kernels see it, decoded on the device from each of
+// the three places it lives: 0 = c_sub_tail (the one-thread table walk: depth + tail against a
+// stack of prefixes, exactly the control flow of ie_vectorized with element masks in place of the
+// partial differences), 1 = g_sub_mask (the warp-cooperative evaluator), 2 = SmallSubsets<K> (the
+// compile-time order of the unrolled walks, k <= MOIRE_SMALL_K).  out[i] = element mask of the
+// i-th subset, bit 15 set when the table gives its term a minus sign.
+template <int K>
+__device__ void dump_small_subsets(unsigned short *out)
+{
+    constexpr moire::SmallSubsets<K> ord{};
+    for (int i = 0; i < (1 << K) - 1; ++i)
+    {
+        int size = 0;
+        for (int e = 0; e < K; ++e) size += (ord.mask[i] >> e) & 1;
+        out[i] = (unsigned short)(ord.mask[i] | ((size & 1) ? 0 : 0x8000));  // ie_small's sign rule
+    }
+}
+
+__global__ void k_dump_subset_order(const int which, const int k, unsigned short *out)
+{
+    using namespace moire;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nsub = (1 << k) - 1;
+    if (which == 0)
+    {
+        const unsigned short *tab = c_sub_tail + subset_block(k);
+        unsigned int prefix[kIeMax + 1];
+        for (int idx = 0; idx < nsub; ++idx)
+        {
+            const unsigned int e = tab[idx];
+            unsigned int tail = e & 1023u;
+            int pos = (e >> 10) & 15;
+            unsigned int base = pos ? prefix[pos - 1] : 0u;
+            for (;;)
+            {
+                const int el = __ffs(tail) - 1;
+                tail &= tail - 1u;
+                base |= 1u << el;
+                if (!tail) break;
+                prefix[pos] = base;
+                ++pos;
+            }
+            out[idx] = (unsigned short)(base | ((e & 0x4000u) ? 0x8000u : 0u));
+        }
+    }
+    else if (which == 1)
+    {
+        const unsigned short *masks = g_sub_mask + subset_block(k);
+        for (int idx = 0; idx < nsub; ++idx)
+        {
+            const unsigned int msk = masks[idx];
+            out[idx] = (unsigned short)(msk | (((__popc(msk) & 1) == 0) ? 0x8000u : 0u));  // coop's sign rule
+        }
+    }
+    else
+    {
+        switch (k)
+        {
+            case 1: dump_small_subsets<1>(out); break;
+            case 2: dump_small_subsets<2>(out); break;
+            case 3: dump_small_subsets<3>(out); break;
+            case 4: dump_small_subsets<4>(out); break;
+            case 5: dump_small_subsets<5>(out); break;
+            case 6: dump_small_subsets<6>(out); break;
+            default: break;
+        }
+    }
+}
+
 struct moire_engine
 {
     moire::View v{};
@@ -440,7 +509,6 @@ struct moire_engine
         CUDA_TRY(cudaMemcpyAsync(v.temp, temps, T * sizeof(double), cudaMemcpyHostToDevice, stream));
 
         // tile shape of the per-sample kernel: S consecutive samples, about kMaxTileCells cells
-        if (N > 65535) throw InvalidArg{"num_samples > 65535 unsupported (16-bit work lists)"};
         tile_S = std::max(1, std::min({moire::kMaxTileSamples, moire::kMaxTileCells / L, N}));
         tiles_per_chain = (N + tile_S - 1) / tile_S;
         sample_smem = moire::sample_kernel_smem(tile_S, L, v.nA, true);
@@ -455,7 +523,18 @@ struct moire_engine
         // MOIRE_B200_FLAT_MIN_CELLS moves that threshold (tests run both pipelines on one shape)
         size_t flat_min_cells = 100000;
         if (const char *env = std::getenv("MOIRE_B200_FLAT_MIN_CELLS")) flat_min_cells = (size_t)std::atoll(env);
-        p_fused = std::getenv("MOIRE_B200_P_FUSED") != nullptr || TNL >= (1ull << 32) || TNL < flat_min_cells;
+        p_fused = std::getenv("MOIRE_B200_P_FUSED") != nullptr || TNL < flat_min_cells;
+        // moire_params::pipeline overrides the size rule (tests run both generations on one shape)
+        if (prm->pipeline == MOIRE_PIPELINE_FLAT) p_fused = false;
+        if (prm->pipeline == MOIRE_PIPELINE_FUSED) p_fused = true;
+        if (prm->pipeline < 0 || prm->pipeline > MOIRE_PIPELINE_FUSED) throw InvalidArg{"unknown pipeline"};
+        if (!p_fused && TNL >= (1ull << 32))
+            throw InvalidArg{"num_chains * num_samples * num_loci must stay below 2^32 per engine "
+                             "(32-bit cell lists): shard the ladder over more engines"};
+        if (p_fused && N > 65535)
+            throw InvalidArg{"the fused (tiny-problem) kernels keep 16-bit work lists: num_samples > 65535 "
+                             "needs the flat pipeline"};
+        if (!p_fused) sample_smem = sample_smem_o = 0;  // the fused kernels' per-block arrays are not needed
         if (!p_fused)
         {
             pf_list.alloc(TNL); pf_hist.alloc(moire::kPfHistWords);
@@ -490,14 +569,14 @@ struct moire_engine
     {
         using namespace moire;
         const int ss = (int)sample_smem;
-        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EPS_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem_o));
-        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EPS_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem_o));
-        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
-        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
-        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EFF_COI>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
-        CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_SAMPLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
         if (p_fused)
         {
+            CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EPS_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem_o));
+            CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EPS_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem_o));
+            CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
+            CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
+            CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_EFF_COI>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
+            CUDA_TRY(cudaFuncSetAttribute(k_update_sample<KIND_SAMPLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss));
             CUDA_TRY(cudaFuncSetAttribute(k_update_p<MOIRE_P_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
             CUDA_TRY(cudaFuncSetAttribute(k_update_p<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
         }
@@ -1303,6 +1382,24 @@ int moire_engine_synchronize(moire_engine *e)
     return guarded(e, [&] {
         if (!e) throw InvalidArg{"null engine"};
         CUDA_TRY(cudaStreamSynchronize(e->stream));
+    });
+}
+
+int moire_engine_subset_order(moire_engine *e, int32_t which, int32_t k, uint16_t *out)
+{
+    return guarded(e, [&] {
+        if (!e || !out) throw InvalidArg{"null argument"};
+        if (which < 0 || which > 2) throw InvalidArg{"which must be 0 (tail table), 1 (mask table) or 2 (unrolled)"};
+        if (k < 1 || k > (which == 2 ? MOIRE_SMALL_K : moire::kIeMax)) throw InvalidArg{"k out of range for this table"};
+        const size_t n = ((size_t)1 << k) - 1;
+        DevBuf<unsigned short> buf;
+        buf.alloc(n);
+        k_dump_subset_order<<<1, 32, 0, e->stream>>>(which, k, buf.ptr);
+        const cudaError_t rc = cudaMemcpyAsync(out, buf.ptr, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->stream);
+        const cudaError_t rs = cudaStreamSynchronize(e->stream);
+        buf.release();
+        CUDA_TRY(rc);
+        CUDA_TRY(rs);
     });
 }
 

@@ -263,12 +263,13 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
                 w = coop_end + 32 * (u - u4) + lane;
                 end = nwork;
             }
+            const unsigned callers = __ballot_sync(0xffffffffu, w < end);
             if (w < end)
             {
                 const int cell = order[w];
                 fetch(cell, lat, prow, m, log_r, log_1mr);
-                out[cell] =
-                    transmission_ll(lat, prow, m, log_r, log_1mr, allow_rel, scr + tid, ST, lgam);
+                out[cell] = transmission_ll(lat, prow, m, log_r, log_1mr, allow_rel, scr + tid, ST,
+                                            lgam, callers);
             }
         }
         __syncwarp();
@@ -1018,20 +1019,23 @@ __global__ void __launch_bounds__(kThreads)
     const size_t ncell = (size_t)v.N * v.L;
     const size_t total = (chain_sel < 0 ? (size_t)v.T : 1) * ncell;
     const size_t g = (size_t)blockIdx.x * kThreads + tid;
-    if (g >= total) return;
-    const int t = chain_sel < 0 ? (int)(g / ncell) : chain_sel;
-    if (use_active && !v.active[t]) return;
-    const size_t cell = g % ncell;
+    const bool in_range = g < total;
+    const int t = chain_sel < 0 ? (int)((in_range ? g : 0) / ncell) : chain_sel;
+    const bool live = in_range && !(use_active && !v.active[t]);
+    const size_t cell = (in_range ? g : 0) % ncell;
     const int i = (int)(cell / v.L), j = (int)(cell - (size_t)i * v.L);
     const size_t gi = (size_t)t * ncell + cell;
+    const bool eval = live && !v.missing[cell];
+    const unsigned callers = __ballot_sync(0xffffffffu, eval);
+    if (!live) return;
     double T = 0.0, O = 0.0;
-    if (!v.missing[cell])
+    if (eval)
     {
         const size_t si = (size_t)t * v.N + i;
         EpsLogs el;
         build_eps_logs(el, v.eps_neg[si], v.eps_pos[si], v.max_eps_neg, v.max_eps_pos, v.nall[j]);
         T = transmission_ll(v.latent[gi], v.p + ((size_t)t * v.L + j) * v.AP, v.m[si], v.log_r[si],
-                            v.log_1mr[si], v.allow_rel != 0, s_qs + tid, kThreads + 1, s_lgam);
+                            v.log_1mr[si], v.allow_rel != 0, s_qs + tid, kThreads + 1, s_lgam, callers);
         O = observation_ll(v.latent[gi], v.obs[cell], v.nall[j], el);
     }
     v.cellT[gi] = T;
@@ -1161,9 +1165,11 @@ __global__ void k_init_p(const View v, const int attempt)
     }
     const double inv = 1.0 / tot;
     for (int a = 0; a < A; ++a) v.p[row + a] *= inv;
-    if (j == 0)
+    if (j == 0 && attempt == 0)
     {
-        // Chain::Chain: mean_coi = Gamma(shape, scale) + 1 (src/chain.cpp:1300-1304)
+        // Chain::Chain: mean_coi = Gamma(shape, scale) + 1 (src/chain.cpp:1300-1304) -- drawn once
+        // in the constructor; the retries of MCMC::MCMC (src/mcmc.cpp:92) call
+        // initialize_parameters(), which leaves it alone
         Stream rng;
         rng.open(v.seed, 0xFFFF0000u + (uint32_t)attempt, KIND_INIT_MEAN_COI,
                  (unsigned)(v.chain_offset + t), 0, 0);

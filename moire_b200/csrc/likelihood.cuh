@@ -416,9 +416,11 @@ __device__ __forceinline__ void ie_small(const double *scr, int ST, double (&acc
 }
 
 // PAM(n = k + t), t < cnt <= kMaxAcc, into scr[t * ST] (q in slots 0..k-1 is consumed).
-__device__ __noinline__ void ie_pams(double *scr, int ST, int k, int cnt)
+// `lanes`: the lanes of the warp that call together (a ballot taken by transmission_ll before
+// its branches diverge), so the tier and the class-uniform fast path depend on the data of
+// exactly those lanes, never on how the scheduler happened to converge them.
+__device__ __noinline__ void ie_pams(double *scr, int ST, int k, int cnt, unsigned lanes)
 {
-    const unsigned lanes = __activemask();
     const int cnt_w = __reduce_max_sync(lanes, cnt);
 #define MOIRE_IE_STORE(NACC) _Pragma("unroll") for (int t = 0; t < NACC; ++t) scr[t * ST] = acc[t];
 #define MOIRE_IE_TIER(NACC)                      \
@@ -478,10 +480,10 @@ __device__ __noinline__ void ie_pams(double *scr, int ST, int k, int cnt)
 
 __device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, int m,
                                                    double log_total, double log_r, double log_1mr,
-                                                   const double *lgam)
+                                                   const double *lgam, unsigned lanes)
 {
     const int cnt = m - k + 1;
-    ie_pams(scr, ST, k, cnt);
+    ie_pams(scr, ST, k, cnt, lanes);
     return relatedness_mixture(scr, ST, m, cnt, log_total, log_r, log_1mr, lgam);
 }
 
@@ -549,13 +551,18 @@ __device__ __forceinline__ double transmission_norel_exact_cover(uint64_t latent
 
 // ---- a2: transmission process of one cell, one thread -------------------------------------------
 // prow: allele frequencies of the locus; scr: the thread's scratch column (kScratchSlots slots,
-// stride ST); lgam: lgamma(i + 1), i < 128.
+// stride ST); lgam: lgamma(i + 1), i < 128.  `callers`: the lanes of the warp that make this call
+// together (a __ballot_sync the caller takes BEFORE branching into the call).
 __device__ __forceinline__ double transmission_ll(uint64_t latent, const double *prow, int m,
                                                   double log_r, double log_1mr,
                                                   bool allow_relatedness, double *scr, int ST,
-                                                  const double *lgam)
+                                                  const double *lgam, unsigned callers)
 {
     const int k = __popcll(latent);
+    // the lanes that will reach the register-tier inclusion-exclusion sums, agreed on while the
+    // callers are still together (the branches below diverge by k and m)
+    const unsigned ie_lanes = __ballot_sync(
+        callers, allow_relatedness && k >= 1 && k <= m && k <= kIeMax && m - k + 1 <= kMaxAcc);
     if (k == 0 || k > m) return NAN;  // unreachable for states the sampler produces
     double total = 0.0;
     {
@@ -601,7 +608,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
     if (k > kIeMax)
         return transmission_rel_egf(latent, prow, total, k, m, log_total, log_r, log_1mr, lgam);
     if (m - k + 1 <= kMaxAcc)
-        return transmission_rel_ie(scr, ST, k, m, log_total, log_r, log_1mr, lgam);
+        return transmission_rel_ie(scr, ST, k, m, log_total, log_r, log_1mr, lgam, ie_lanes);
     return transmission_rel_ie_wide(scr, ST, k, m, log_total, log_r, log_1mr, lgam);
 }
 

@@ -517,15 +517,19 @@ __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval
                 const int w0 = lo + unit * 32;
                 if (w0 >= hi) break;
                 const int w = w0 + lane;
-                if (w < hi)
+                bool go = w < hi;
+                uint4 e = make_uint4(0u, 0u, 0u, 0u);
+                if (go)
                 {
-                    const uint4 e = f.list[w];
-                    if (!f.round_flags || ((unsigned)f.round_flags[(size_t)e.z * 4 + 3] & kPfActive))
-                        f.out[out_index(e.z, e.w)] =
-                            transmission_ll(((unsigned long long)e.y << 32) | e.x,
-                                            f.p + (size_t)e.z * f.p_stride, f.m[e.w], f.log_r[e.w],
-                                            f.log_1mr[e.w], allow_rel, s_scr + tid, ST, s_lgam);
+                    e = f.list[w];
+                    go = !f.round_flags || ((unsigned)f.round_flags[(size_t)e.z * 4 + 3] & kPfActive);
                 }
+                const unsigned callers = __ballot_sync(0xffffffffu, go);
+                if (go)
+                    f.out[out_index(e.z, e.w)] =
+                        transmission_ll(((unsigned long long)e.y << 32) | e.x,
+                                        f.p + (size_t)e.z * f.p_stride, f.m[e.w], f.log_r[e.w],
+                                        f.log_1mr[e.w], allow_rel, s_scr + tid, ST, s_lgam, callers);
                 __syncwarp();
             }
         }

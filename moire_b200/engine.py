@@ -22,6 +22,10 @@ DEFAULT_MODEL = dict(allow_relatedness=True, burnin=10000, max_coi=40, mean_coi_
                      r_beta=1.0)
 
 
+# moire_params.pipeline (include/moire_engine.h): kernel generation, "auto" = by problem size
+PIPELINES = dict(auto=0, flat=1, fused=2)
+
+
 class MoireError(RuntimeError):
     pass
 
@@ -33,7 +37,8 @@ def _ptr(a):
 class Engine:
     """``num_chains`` tempered chains [chain_offset, chain_offset + num_chains) on one device."""
 
-    def __init__(self, data: PackedData, temps, seed=1, device=0, chain_offset=0, **model):
+    def __init__(self, data: PackedData, temps, seed=1, device=0, chain_offset=0, pipeline="auto",
+                 **model):
         self._h = None
         self.lib = _lib.load()
         prm = dict(DEFAULT_MODEL)
@@ -54,7 +59,7 @@ class Engine:
         d = _lib.MoireData(self.N, self.L, _ptr(self._keep["na"]), _ptr(self._keep["obs"]),
                            _ptr(self._keep["mis"]), _ptr(self._keep["coi"]))
         p = _lib.MoireParams(int(bool(prm["allow_relatedness"])), int(prm["burnin"]),
-                             int(prm["max_coi"]), 0, prm["mean_coi_shape"], prm["mean_coi_scale"],
+                             int(prm["max_coi"]), PIPELINES[pipeline], prm["mean_coi_shape"], prm["mean_coi_scale"],
                              prm["max_eps_pos"], prm["eps_pos_alpha"], prm["eps_pos_beta"],
                              prm["max_eps_neg"], prm["eps_neg_alpha"], prm["eps_neg_beta"],
                              prm["r_alpha"], prm["r_beta"])
@@ -227,6 +232,13 @@ class Engine:
             "record_draw")
         d["mean_coi"] = float(d["mean_coi"][0])
         return d
+
+    def subset_order(self, which, k):
+        """Subset enumeration order for k latent alleles as decoded on the device from table
+        ``which`` (0 tail table, 1 mask table, 2 unrolled): (masks[2^k - 1], negative[2^k - 1])."""
+        out = np.zeros((1 << k) - 1, np.uint16)
+        self._ck(self.lib.moire_engine_subset_order(self._h, which, k, _ptr(out)), "subset_order")
+        return out & 0x7FFF, (out & 0x8000) != 0
 
     def counters(self):
         a, b = C.c_uint64(), C.c_uint64()

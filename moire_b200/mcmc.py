@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib
 from .data import PackedData, pack_data
-from .engine import DEFAULT_MODEL, Engine, MoireError, _ptr
+from .engine import DEFAULT_MODEL, PIPELINES, Engine, MoireError, _ptr
 
 PRIOR_TERMS = ("eps_neg", "eps_pos", "relatedness", "coi", "mean_coi_hyper")
 
@@ -144,7 +144,7 @@ class MCMC:
     def __init__(self, data: PackedData, pt_chains, *, burnin, samples, thin=1, adapt_temp=True,
                  pre_adapt_steps=25, temp_adapt_steps=25, max_initialization_tries=10000,
                  record_latent_genotypes=False, max_runtime=math.inf, seed=1, device=0, rank=0,
-                 world_size=1, allgather=None, **model):
+                 world_size=1, allgather=None, pipeline="auto", **model):
         self._h = None
         self.lib = _lib.load()
         prm = dict(DEFAULT_MODEL)
@@ -168,7 +168,7 @@ class MCMC:
         d = _lib.MoireData(self.N, self.L, _ptr(self._keep["na"]), _ptr(self._keep["obs"]),
                            _ptr(self._keep["mis"]), _ptr(self._keep["coi"]))
         p = _lib.MoireParams(int(bool(prm["allow_relatedness"])), int(burnin), int(prm["max_coi"]),
-                             0, prm["mean_coi_shape"], prm["mean_coi_scale"], prm["max_eps_pos"],
+                             PIPELINES[pipeline], prm["mean_coi_shape"], prm["mean_coi_scale"], prm["max_eps_pos"],
                              prm["eps_pos_alpha"], prm["eps_pos_beta"], prm["max_eps_neg"],
                              prm["eps_neg_alpha"], prm["eps_neg_beta"], prm["r_alpha"],
                              prm["r_beta"])
@@ -481,7 +481,7 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
              record_latent_genotypes=False, num_chains=1, num_cores=1, pt_chains=1, pt_grad=1,
              pt_num_threads=1, adapt_temp=True, pre_adapt_steps=25, temp_adapt_steps=25,
              max_initialization_tries=10000, max_runtime=math.inf, *, seed=1, device=0,
-             distributed=None, progress=None):
+             distributed=None, progress=None, pipeline="auto"):
     """Same arguments and result as ``moire::run_mcmc`` (R/mcmc.R:76-182): returns
     ``dict(runtime, chains=[...], args)`` whose ``chains[i]`` holds the 23 fields of
     src/main.cpp:138-189 plus ``mean_coi``.
@@ -492,7 +492,12 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
     Extra keyword-only arguments the R function has no counterpart for: ``seed`` (the reference
     seeds from ``std::random_device``), ``device``, ``distributed`` -- ``True`` to shard the ladder
     over the ranks of an initialised ``torch.distributed`` group (every rank returns the full
-    result) -- and ``progress(phase, step, posterior, hot_chain)``.
+    result) --, ``progress(phase, step, posterior, hot_chain)`` and ``pipeline`` ("auto", "flat",
+    "fused": the kernel generation, include/moire_engine.h).
+
+    Engine limits the reference does not have (``MoireError`` when exceeded): at most
+    MOIRE_MAX_ALLELES alleles per locus, ``max_coi`` <= MOIRE_MAX_COI, and
+    chains-per-GPU x samples x loci < 2^32.
     """
     t_start = time.time()
     args = dict(is_missing=is_missing, allow_relatedness=allow_relatedness, thin=thin,
@@ -539,7 +544,7 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
                   max_initialization_tries=int(max_initialization_tries),
                   record_latent_genotypes=record_latent_genotypes, max_runtime=max_runtime,
                   seed=int(seed) + 7919 * (chain_number - 1), device=device, rank=rank,
-                  world_size=world, allgather=gather, **model)
+                  world_size=world, allgather=gather, pipeline=pipeline, **model)
         try:
             if native:
                 mc.init_nccl(device)     # falls back to the callback if NCCL cannot be bound

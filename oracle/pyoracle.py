@@ -453,6 +453,14 @@ class Ref:
         self.lib.ref_chain_get_tuning(h, _p(acc), _p(sds))
         return acc, sds
 
+    def chain_get_p_tuning(self, h):
+        """(p_accept, p_attempt, p_prop_var), each [L][A_max], of the SALT sampler."""
+        A = int(self.num_alleles.max())
+        acc, att = np.zeros((self.L, A), np.int32), np.zeros((self.L, A), np.int32)
+        sd = np.zeros((self.L, A))
+        self.lib.ref_chain_get_p_tuning(h, A, _p(acc), _p(att), _p(sd))
+        return acc, att, sd
+
     def chain_update(self, h, kind, iteration):
         self.lib.ref_chain_update(h, UPDATE_KINDS[kind] if isinstance(kind, str) else kind,
                                   iteration)

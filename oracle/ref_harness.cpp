@@ -321,6 +321,20 @@ void ref_chain_get_tuning(void *h, int *accepts, double *sds)
     }
 }
 
+// The SALT sampler's per-allele tuning state (src/chain.h:126-128, src/chain.cpp:479-562):
+// [L][a_pad] each.
+void ref_chain_get_p_tuning(void *h, int a_pad, int *p_accept, int *p_attempt, double *p_prop_var)
+{
+    Chain &c = *static_cast<Chain *>(h);
+    for (std::size_t j = 0; j < c.p_prop_var.size(); ++j)
+        for (std::size_t a = 0; a < c.p_prop_var[j].size() && a < static_cast<std::size_t>(a_pad); ++a)
+        {
+            p_accept[j * a_pad + a] = c.p_accept[j][a];
+            p_attempt[j * a_pad + a] = c.p_attempt[j][a];
+            p_prop_var[j * a_pad + a] = c.p_prop_var[j][a];
+        }
+}
+
 // kind: 0 eps_neg, 1 eps_pos, 2 p, 3 m, 4 r, 5 eff_coi, 6 samples, 7 mean_coi
 // (the order MCMC::burnin runs them, src/mcmc.cpp:162-173).
 void ref_chain_update(void *h, int kind, int iteration)

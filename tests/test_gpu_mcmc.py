@@ -92,7 +92,7 @@ def test_posterior_agrees_with_reference_sampler():
     ours = []
     for seed in (11, 12, 13, 14, 15, 16):
         ch = run_mcmc(d, d["is_missing"], burnin=burn, samples_per_chain=samp, verbose=False,
-                      seed=seed)["chains"][0]
+                      seed=seed, pipeline="flat" if seed % 2 else "fused")["chains"][0]
         ours.append(dict(m=np.mean(ch["coi"], axis=1), r=np.mean(ch["relatedness"], axis=1),
                          eps_neg=np.mean(ch["eps_neg"], axis=1), eps_pos=np.mean(ch["eps_pos"], axis=1),
                          p0=np.array([np.mean(ch["allele_freqs"][j], axis=0)[0] for j in range(pk.num_loci)]),
@@ -199,8 +199,9 @@ def test_acceptance_rates_and_adapted_scales_track_the_reference():
     for it in range(steps):
         ref.chain_step(h, it)
     racc, rsd = ref.chain_get_tuning(h)
+    rp_acc, rp_att, rp_sd = ref.chain_get_p_tuning(h)
     ref.chain_free(h)
-    eng = Engine(pk, [1.0], seed=8, burnin=steps)
+    eng = Engine(pk, [1.0], seed=8, burnin=steps, pipeline="flat")   # the benchmarked kernels
     eng.init_chains()
     for it in range(steps):
         eng.step(it)
@@ -213,6 +214,15 @@ def test_acceptance_rates_and_adapted_scales_track_the_reference():
     for row, name in enumerate(["eps_neg_var", "eps_pos_var", "r_var", "m_r_var"]):
         a, b = np.median(rsd[row]), np.median(dg[name])
         assert abs(a - b) < 0.25 * max(a, b) + 0.02, (name, a, b)
+    # the SALT sampler (update_p): per-allele attempts, acceptance rate and adapted scale
+    A = pk.num_alleles
+    sel = np.arange(rp_att.shape[1])[None, :] < A[:, None]
+    assert rp_att[sel].sum() == dg["p_attempt"][:, :rp_att.shape[1]][sel].sum() == steps * A.sum()
+    ra = rp_acc[sel].sum() / rp_att[sel].sum()
+    ea = dg["p_accept"][:, :rp_att.shape[1]][sel].sum() / dg["p_attempt"][:, :rp_att.shape[1]][sel].sum()
+    assert abs(ra - ea) < 0.03 and 0.15 < ea < 0.35, (ra, ea)
+    rs, es = np.median(rp_sd[sel]), np.median(dg["p_prop_var"][:, :rp_att.shape[1]][sel])
+    assert abs(rs - es) < 0.2 * max(rs, es), (rs, es)
     # the adapted single-parameter updates sit near the 0.23 target on both sides
     for row in (0, 1, 3):
         assert 0.15 < dg[names[row]].mean() / steps < 0.35

@@ -58,8 +58,54 @@ def test_cells_match_reference_golden_states(golden_states):
         eng.close()
 
 
+# Both kernel generations are held to the oracle: "flat" is what every benchmarked shape runs
+# (k_flat_eval, k_pf_round, k_sf_*, k_eps_cells), "fused" what tiny problems run.
+PIPELINES = ["flat", "fused"]
+
+
+def test_subset_order_matches_the_reference_generator_bit_exactly(golden_pure):
+    """Row a6: the three places the engine keeps the subset order (depth/tail table of the
+    one-thread walk, mask table of the cooperative evaluator, compile-time order of the unrolled
+    walks), each decoded ON THE DEVICE, against the sequences dumped from the reference's own
+    CombinationIndicesGenerator (src/combination_indices_generator.cpp:5-76) in the order
+    src/prob_any_missing.cpp:20-52 drives it: sizes 1..k in turn.  Bit-exact, signs included."""
+    from moire_b200.engine import Engine
+    g = golden_pure[64]
+    seqs, row = {}, 0
+    for n, r, nrows, nc, gen in g["combo_meta"]:
+        seqs[(int(n), int(r))] = g["combo_rows"][row:row + nrows, :int(r)].astype(np.int64)
+        assert nrows == nc == gen
+        row += nrows
+    pk = _tiny_data()
+    eng = Engine(pk, [1.0])
+    checked = 0
+    for which, kmax in ((0, 10), (1, 10), (2, 6)):
+        for k in range(1, kmax + 1):
+            want_mask, want_neg = [], []
+            for r in range(1, k + 1):
+                for tup in seqs[(k, r)]:
+                    want_mask.append(sum(1 << int(x) for x in tup))
+                    want_neg.append(r % 2 == 0)      # src/prob_any_missing.cpp:22: sign by size
+            masks, neg = eng.subset_order(which, k)
+            assert len(masks) == 2 ** k - 1
+            assert np.array_equal(masks, np.array(want_mask, np.uint16)), (which, k)
+            assert np.array_equal(neg, np.array(want_neg)), (which, k)
+            checked += len(masks)
+    assert checked == 2 * sum(2 ** k - 1 for k in range(1, 11)) + sum(2 ** k - 1 for k in range(1, 7))
+    eng.close()
+
+
+def _tiny_data():
+    from moire_b200.data import pack_data
+    from moire_b200.simulate import simulate_data
+    d = simulate_data(mean_coi=2, num_samples=4, epsilon_pos=.02, epsilon_neg=.1,
+                      locus_freq_alphas=[np.ones(4)] * 2, seed=1)
+    return pack_data(d["data"], d["is_missing"])
+
+
+@pytest.mark.parametrize("pipeline", PIPELINES)
 @pytest.mark.parametrize("allow", [1, 0])
-def test_cells_match_oracle_on_device_drawn_states(oracle, allow):
+def test_cells_match_oracle_on_device_drawn_states(oracle, allow, pipeline):
     """Starting states drawn on the device, then advanced by full sweeps, recomputed by the
     oracle: covers IE (k<=10), the n==k closed form, EGF (k>10) and the relatedness mixture."""
     from moire_b200.data import pack_data
@@ -70,7 +116,7 @@ def test_cells_match_oracle_on_device_drawn_states(oracle, allow):
                       internal_relatedness_alpha=1, internal_relatedness_beta=1,
                       missingness=.03, seed=41)
     pk = pack_data(d["data"], d["is_missing"])
-    eng, _ = engine_for(pk, temps=(1.0, 0.3, 0.0), allow=allow, burnin=50)
+    eng, _ = engine_for(pk, temps=(1.0, 0.3, 0.0), allow=allow, burnin=50, pipeline=pipeline)
     info = eng.init_chains()
     assert not info["still_ill"].any()
     kmax = 0
@@ -169,8 +215,9 @@ def compare_with_stepper(eng, stp, chain, where):
     a["mean_coi_sd"][0] = dg["mean_coi_var"]
 
 
+@pytest.mark.parametrize("pipeline", PIPELINES)
 @pytest.mark.parametrize("allow", [1, 0])
-def test_metropolis_updates_match_stepper(oracle, allow):
+def test_metropolis_updates_match_stepper(oracle, allow, pipeline):
     """Every one of the eight updates, kind by kind over several sweeps (including ones past
     iteration 15, where proposal-scale adaptation is live), against the CPU stepper that
     restates src/chain.cpp:165-856 with the engine's stream addressing: accepted proposals,
@@ -186,7 +233,8 @@ def test_metropolis_updates_match_stepper(oracle, allow):
     pk = pack_data(d["data"], d["is_missing"])
     temps = (1.0, 0.37, 0.0)
     seed = 77
-    eng, _ = engine_for(pk, temps=temps, allow=allow, seed=seed, burnin=30, max_coi=25)
+    eng, _ = engine_for(pk, temps=temps, allow=allow, seed=seed, burnin=30, max_coi=25,
+                        pipeline=pipeline)
     assert not eng.init_chains()["still_ill"].any()
     model = dict(DEFAULT_MODEL, allow_relatedness=bool(allow), burnin=30, max_coi=25)
     steppers = [Stepper(oracle, pk, model, seed, c, temps[c], eng.dump_state(c),
@@ -209,4 +257,46 @@ def test_metropolis_updates_match_stepper(oracle, allow):
         assert abs(prior[c] - stp.prior()) < 1e-9 * max(1.0, abs(prior[c]))
     ev1, _ = eng.counters()
     assert ev1 - ev0 == sum(s.evals for s in steppers)  # same count of cell evaluations
+    eng.close()
+
+
+@pytest.mark.parametrize("pipeline", PIPELINES)
+def test_update_p_adaptation_matches_stepper(oracle, pipeline):
+    """Row a14 past the point where the SALT sampler adapts: 45 update_p calls inside burn-in, so
+    every allele of the 2- and 5-allele loci collects more than 15 attempts and the
+    `p_attempt > 15` branch (src/chain.cpp:555-562) runs for them; p_prop_var, p_accept, p_attempt,
+    the frequencies and the cached terms against the CPU stepper after every call.  Two further
+    calls after burn-in must leave p_prop_var alone."""
+    from moire_b200.data import pack_data
+    from moire_b200.engine import DEFAULT_MODEL
+    from moire_b200.simulate import simulate_data
+    from oracle.pyoracle import Stepper
+    d = simulate_data(mean_coi=3, num_samples=41, epsilon_pos=.03, epsilon_neg=.1,
+                      locus_freq_alphas=[np.ones(2)] * 3 + [np.ones(5)] * 3 + [np.ones(9)] * 2,
+                      internal_relatedness_alpha=.3, internal_relatedness_beta=1,
+                      missingness=.05, seed=29)
+    pk = pack_data(d["data"], d["is_missing"])
+    temps, seed, burnin = (1.0, 0.25), 5, 45
+    eng, _ = engine_for(pk, temps=temps, seed=seed, burnin=burnin, max_coi=20, pipeline=pipeline)
+    assert not eng.init_chains()["still_ill"].any()
+    model = dict(DEFAULT_MODEL, allow_relatedness=True, burnin=burnin, max_coi=20)
+    steppers = [Stepper(oracle, pk, model, seed, c, temps[c], eng.dump_state(c),
+                        eng.diagnostics(c)) for c in range(2)]
+    for it in range(burnin + 2):
+        if it == burnin:
+            frozen = [eng.diagnostics(c)["p_prop_var"].copy() for c in range(2)]
+        eng.update("p", it)
+        for c, stp in enumerate(steppers):
+            stp.update("p", it)
+            compare_with_stepper(eng, stp, c, (it, "p", c))
+    for c in range(2):
+        dg = eng.diagnostics(c)
+        A = pk.num_alleles
+        small = A <= 5
+        att = np.array([dg["p_attempt"][j, :A[j]].min() for j in range(pk.num_loci)])
+        assert (att[small] > 15).all(), att                      # the branch was live for them
+        sd = np.concatenate([dg["p_prop_var"][j, :A[j]] for j in range(pk.num_loci)])
+        assert (sd != 1.0).mean() > .5 and sd.min() >= .01
+        assert np.array_equal(dg["p_prop_var"], frozen[c])       # no adaptation after burn-in
+        assert (dg["p_accept"] <= dg["p_attempt"]).all()
     eng.close()

@@ -173,12 +173,7 @@ def test_chain_states_do_not_depend_on_the_ladder_size():
 
 def _run_pipeline(flat, pk, temps, model, steps, monkeypatch):
     from moire_b200.engine import Engine
-    if flat:
-        monkeypatch.setenv("MOIRE_B200_FLAT_MIN_CELLS", "0")
-        monkeypatch.delenv("MOIRE_B200_P_FUSED", raising=False)
-    else:
-        monkeypatch.setenv("MOIRE_B200_P_FUSED", "1")
-    eng = Engine(pk, temps, seed=21, **model)
+    eng = Engine(pk, temps, seed=21, pipeline="flat" if flat else "fused", **model)
     eng.init_chains()
     for it in range(steps):
         eng.step(it)
