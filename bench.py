@@ -13,13 +13,15 @@ scalar log-likelihoods (NCCL all-gather); total work is fixed, so scaling is "st
 Our arm prints ONE JSON line: `value` = steps/s with the state resident in HBM (CUDA events on the
 engine's stream around each step, L2 flushed between steps, max over ranks), `e2e` = the same
 metric through the public `run_mcmc` call with host buffers (data packing, upload, chain
-initialisation, every step's scalar read-back, every stored draw's device->host copy, result
-assembly), `roofline` for the dominant kernel, `cpu_baseline` = the reference's own C++ sampler
+initialisation, the batched read-back of traces, ladder and stored draws, result assembly), `roofline` for the dominant kernel, `cpu_baseline` = the reference's own C++ sampler
 (compiled unmodified under oracle/_ref) on this box's host cores.  The timed steps run as the
 product runs them (the engine replays its captured step graph); the per-kernel numbers behind
 `roofline` and `kernel_ms_per_step` come from K further steps issued as plain launches with an
 event pair around every update kind and every evaluator launch.  With N > 1 the exchange is the
-C++ driver's own ncclAllGather on the engine's stream (`config.exchange` says which path ran).
+C++ driver's own ncclAllGather on the engine's stream inside the step graph (`exchange` says which
+path ran), the swap pass runs on the device, every rank's ladder is checked against rank 0's
+(`ladder_consistent`), and the line carries an `other_workloads` block with the multi-GPU shapes of
+BASELINE.json (c4; c5 at 16/32/64 temperatures) timed the same way on the same ranks.
 
 `--impl reference` times that CPU sampler alone and prints the same line with "impl": "reference".
 """
@@ -100,17 +102,25 @@ def cpu_reference_rate(wl, steps, warmup, budget_s):
     os.environ.setdefault("OMP_NUM_THREADS", str(threads))
     ref.set_data(pk.num_alleles, pk.obs_mask, pk.is_missing)
 
+    evals = [0]
+
     def run(sub_temps, w, k):
         ref.set_params(pt_chains=sub_temps, pt_num_threads=min(cores, len(sub_temps)),
                        allow_relatedness=int(wl["model"]["allow_relatedness"]),
                        max_coi=wl["model"]["max_coi"], burnin=10000)
         h = ref.mcmc_new(seed=1)
         t0 = time.time()
+        ref.eval_count_reset()
         one = ref.mcmc_time_burnin(h, 0, 0, 1)        # first step, also the estimate
+        evals[0] = ref.eval_count()
         if w + k > 1 and one * (w + k) > budget_s:
             ref.mcmc_free(h)
             return None, one, time.time() - t0
-        secs = ref.mcmc_time_burnin(h, 1, max(w - 1, 0), k)
+        for i in range(max(w - 1, 0)):
+            ref.mcmc_time_burnin(h, 1 + i, 0, 1)
+        ref.eval_count_reset()
+        secs = ref.mcmc_time_burnin(h, max(w, 1), 0, k)
+        evals[0] = ref.eval_count()
         ref.mcmc_free(h)
         return secs, one, time.time() - t0
 
@@ -131,8 +141,11 @@ def cpu_reference_rate(wl, steps, warmup, budget_s):
     sample = (f"{steps} MCMC::burnin steps after {warmup} warm-up, "
               f"{used_T} of {T} temperatures" + ("" if used_T == T else " (every k-th; scaled by chains)") +
               f", {min(cores, used_T)} OpenMP threads, reference C++ (-O2 -fopenmp) via oracle/_ref/libmoire_ref32.so")
+    # non-missing Chain::calculate_genotype_likelihood calls of the timed steps, counted inside the
+    # reference (oracle/ref_harness.cpp) -- the second half of BASELINE.json's metric
     return dict(value=value, unit=UNIT, cores=min(cores, used_T), kind="reference", sample=sample,
-                host_cores=cores, seconds=secs)
+                host_cores=cores, seconds=secs, likelihood_evals_per_sec=evals[0] / secs,
+                evals_per_step_all_temps=evals[0] / steps * T / used_T)
 
 
 def reference_arm(args, wl):
@@ -144,23 +157,96 @@ def reference_arm(args, wl):
                 steps=args.steps, warmup=args.warmup, ms_per_step=1e3 / base["value"],
                 higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
                 data="synthetic", config=config_of(wl, args),
+                parallelism=f"{base['cores']} OpenMP threads over the chains (host CPU; no GPU)",
                 cpu_baseline=dict(value=base["value"], unit=UNIT, cores=base["cores"],
-                                  kind=base["kind"], sample=base["sample"]),
+                                  kind=base["kind"], sample=base["sample"],
+                                  likelihood_evals_per_sec=base["likelihood_evals_per_sec"]),
+                likelihood_evals_per_sec=base["likelihood_evals_per_sec"],
+                evals_per_step=base["evals_per_step_all_temps"],
                 e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
 
 
 def config_of(wl, args):
     pk = wl["packed"]
+    # the workload only: both arms (ours, --impl reference) print the same dict
     return dict(workload=f"{wl['name']}: simulate_data {pk.num_samples} samples x {pk.num_loci} loci, "
                          f"A_j {int(pk.num_alleles.min())}..{int(pk.num_alleles.max())}, "
                          f"{len(wl['temps'])} temperatures, relatedness on, max_coi {wl['model']['max_coi']}",
-                samples=pk.num_samples, loci=pk.num_loci, temperatures=len(wl["temps"]),
-                parallelism=f"temperature ladder sharded over {args.gpus} GPU(s)",
-                cache="L2 flushed (256 MiB memset) before every timed step")
+                samples=pk.num_samples, loci=pk.num_loci, temperatures=len(wl["temps"]))
 
 
 # ---- our arm ---------------------------------------------------------------------------------------
+def ladder_digest(mc):
+    """What every rank must agree on after the same steps: swap_store, the index map, the
+    temperatures by chain, the adapted gradient, the barrier sums and the traces (bit patterns)."""
+    import hashlib
+    lad, tr = mc.ladder(), mc.traces()
+    h = hashlib.sha256()
+    for k in ("swap_store", "swap_indices", "chain_temps", "temp_gradient", "swap_barriers", "swap_acceptances"):
+        h.update(np.ascontiguousarray(lad[k]).tobytes())
+    for k in ("llik_burnin", "prior_burnin", "posterior_burnin"):
+        h.update(np.ascontiguousarray(tr[k]).tobytes())
+    return int.from_bytes(h.digest()[:6], "little")      # 48 bits: exact in a float64
+
+
+def timed_workload(name, T, steps, warmup, world, rank, local, dev, seed):
+    """steps/s of another BASELINE.json shape on the ranks of this run, timed like the main one
+    (CUDA events on the engine's stream, L2 flush before every timed step, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from moire_b200.mcmc import MCMC
+    from moire_b200.workloads import ladder, make_workload
+    wl = make_workload(name)
+    temps = ladder(T)
+    mc = MCMC(wl["packed"], temps, burnin=warmup + steps + 4, samples=0, seed=seed, device=local, rank=rank,
+              world_size=world, **wl["model"])
+    try:
+        if world > 1 and not mc.init_nccl(local):
+            return dict(error="NCCL exchange unavailable")
+        if not mc.init():
+            return dict(error="chain initialisation failed")
+        eng = mc.engine
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        step = 0
+        for _ in range(warmup):
+            mc.burnin(step)
+            step += 1
+        ev0, _ = eng.counters()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            eng.timer_start()
+            mc.burnin(step)
+            ms += eng.timer_stop()
+            step += 1
+        ev1, _ = eng.counters()
+        digest = ladder_digest(mc)
+        st = torch.tensor([ms, float(ev1 - ev0), float(digest)], dtype=torch.float64, device=dev)
+        consistent = True
+        if world > 1:
+            allst = [torch.empty_like(st) for _ in range(world)]
+            dist.all_gather(allst, st)
+            ms_all = [float(x[0]) for x in allst]
+            evals = sum(float(x[1]) for x in allst)
+            consistent = all(float(x[2]) == float(allst[0][2]) for x in allst)
+        else:
+            ms_all, evals = [ms], float(ev1 - ev0)
+        ms_step = max(ms_all) / steps
+        pk = wl["packed"]
+        return dict(workload=f"{name}: {pk.num_samples} x {pk.num_loci}, A_j {int(pk.num_alleles.min())}.."
+                             f"{int(pk.num_alleles.max())}, {T} temperatures, max_coi {wl['model']['max_coi']}",
+                    n_gpus=world, steps=steps, warmup=warmup, value=1e3 / ms_step, unit=UNIT,
+                    ms_per_step=ms_step, per_rank_ms_per_step=[round(m / steps, 4) for m in ms_all],
+                    likelihood_evals_per_sec=evals / (max(ms_all) * 1e-3), ladder_consistent=consistent)
+    finally:
+        mc.close()
+
+
 def our_arm(args, wl):
     import torch
     import torch.distributed as dist
@@ -174,8 +260,10 @@ def our_arm(args, wl):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the one JSON line (the image's NCCL_DEBUG=VERSION prints a banner there)
-        os.environ["NCCL_DEBUG"] = os.environ.get("MOIRE_NCCL_DEBUG", "WARN")
+        # NCCL reports its communicators (nranks, transports, NVLS) at INFO; fd 1 was re-pointed at
+        # stderr in main(), so none of it can reach the one JSON line on stdout
+        os.environ["NCCL_DEBUG"] = os.environ.get("MOIRE_NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
     pk, temps, model = wl["packed"], np.asarray(wl["temps"], dtype=np.float64), wl["model"]
     T = len(temps)
@@ -224,6 +312,7 @@ def our_arm(args, wl):
     sampler.stop_flag.set()
     sampler.join(2.0)
     ev1, l1 = eng.counters()
+    digest = ladder_digest(mc)          # also the read-back of everything the steps left queued
     # ---- breakdown pass: the next K steps with an event pair around every update kind and every
     # evaluator launch (a graph cannot hold events between its kernels, so these steps go out as
     # plain launches); feeds `roofline` and `kernel_ms_per_step`, not `value`
@@ -240,7 +329,14 @@ def our_arm(args, wl):
     ke1 = eng.kind_evals()
     barrier()
     stats = torch.tensor([dev_ms, float(ev1 - ev0), float(l1 - l0)], dtype=torch.float64, device=dev)
+    ladder_consistent = True
+    per_rank_ms = [dev_ms / args.steps]
     if world > 1:
+        dg = torch.tensor([float(digest), dev_ms / args.steps], dtype=torch.float64, device=dev)
+        alld = [torch.empty_like(dg) for _ in range(world)]
+        dist.all_gather(alld, dg)
+        ladder_consistent = all(float(x[0]) == float(alld[0][0]) for x in alld)
+        per_rank_ms = [float(x[1]) for x in alld]
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
@@ -257,7 +353,7 @@ def our_arm(args, wl):
     # stored draws and the assembly of the result list are all inside the timed region.  200 steps
     # at the default K: still 55x shorter than a default run (10000 burn-in + 1000 sampling steps),
     # so the one-off costs weigh more here than they do for a user
-    e2e_burn, e2e_samp = max(15 * args.steps, 150), max(5 * args.steps, 50)
+    e2e_burn, e2e_samp = min(max(15 * args.steps, 150), 1500), min(max(5 * args.steps, 50), 500)
     barrier()
     t0 = time.perf_counter()
     res = run_mcmc(wl["sim"], wl["sim"]["is_missing"], burnin=e2e_burn, samples_per_chain=e2e_samp,
@@ -272,16 +368,31 @@ def our_arm(args, wl):
     chain = res["chains"][0]
     n_steps = e2e_burn + e2e_samp
     N, L, AP = pk.num_samples, pk.num_loci, (int(pk.num_alleles.max()) + 3) // 4 * 4
+    # host -> device: the data and the ladder once per rank, two flag words per step, the ladder
+    # again after each adaptation; device -> host: per step its trace entry (3 doubles + the
+    # swap_store word), the ladder state once per read-back batch (<= 32 steps), the stored draws
+    ladder_bytes = T * (3 * 8 + 2 * 4 + 8 + 8) + 64
     h2d = (pk.obs_mask.nbytes + pk.is_missing.nbytes + pk.num_alleles.nbytes + pk.observed_coi.nbytes
-           + 8 * T) * world / n_steps + 8 * T          # data + ladder once per rank, temps per step
-    draw_bytes = L * AP * 8 + N * (4 + 4 * 8) + 8
-    d2h = 16 * T + draw_bytes * len(chain["lam_coi"]) / n_steps
+           + ladder_bytes) * world / n_steps + 16 + ladder_bytes / 25
+    draw_bytes = L * AP * 8 + N * (4 + 4 * 8) + 8 + 4
+    d2h = 28 + ladder_bytes / 25 + draw_bytes * len(chain["lam_coi"]) / n_steps
     e2e = dict(value=n_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=int(h2d),
                d2h_bytes_per_step=int(d2h), seconds=e2e_s, steps=n_steps,
                call=f"moire_b200.mcmc.run_mcmc(burnin={e2e_burn}, samples_per_chain={e2e_samp}, "
-                    f"pt_chains={T}) incl. pack_data, upload, chain init, per-step scalar read-back, "
-                    f"{len(chain['lam_coi'])} stored draws, result assembly")
+                    f"pt_chains={T}) incl. pack_data, upload, chain init, batched read-back of traces / "
+                    f"ladder / {len(chain['lam_coi'])} stored draws, host-side ladder adaptation, result assembly")
 
+    # ---- the multi-GPU shapes of BASELINE.json on the same ranks (configs[3], configs[4])
+    other = {}
+    if world > 1 and wl["name"] == "c3" and not args.no_other_workloads:
+        for key, name, T in (("c4", "c4", 64), ("c5_T16", "c5", 16), ("c5_T32", "c5", 32), ("c5_T64", "c5", 64)):
+            if T < world:
+                continue
+            try:
+                other[key] = timed_workload(name, T, steps=5, warmup=3, world=world, rank=rank, local=local,
+                                            dev=dev, seed=args.seed)
+            except Exception as exc:  # a shape that does not fit is reported, not fatal
+                other[key] = dict(error=repr(exc))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -325,19 +436,26 @@ def our_arm(args, wl):
     if world == 1 and not args.no_cpu_baseline:
         try:
             cpu = cpu_reference_rate(wl, steps=2, warmup=1, budget_s=30.0)
-            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "likelihood_evals_per_sec")}
         except Exception as exc:
             cpu = dict(value=None, unit=UNIT, cores=0, kind="reference", sample=f"unavailable: {exc!r}")
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True,
                 scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(config_of(wl, args), exchange=exchange), clocks=sampler.summary(), e2e=e2e,
+                config=config_of(wl, args), exchange=exchange,
+                parallelism=f"temperature ladder sharded over {world} GPU(s); swap pass on the device, "
+                            "one graph launch per step",
+                cache="L2 flushed (256 MiB memset) before every timed step",
+                ladder_consistent=ladder_consistent, per_rank_ms_per_step=[round(x, 4) for x in per_rank_ms],
+                clocks=sampler.summary(), e2e=e2e,
                 gpu_launches=launches_total, roofline=roofline, cpu_baseline=cpu,
                 likelihood_evals_per_sec=evals_total / (dev_ms_max * 1e-3),
                 evals_per_step=evals_total / args.steps,
                 wall_ms_per_step_incl_flush=1e3 * wall / args.steps,
                 kernel_ms_per_step={k: round(v / args.steps, 4) for k, v in kind_ms.items()})
+    if other:
+        line["other_workloads"] = other
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -365,12 +483,14 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true",
+                    help="N > 1: skip the c4 / c5 block timed after the main workload")
     args = ap.parse_args()
     if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
         return

@@ -33,7 +33,7 @@ extern "C" {
 #define MOIRE_ESTATE (-4)   /* call order (e.g. step before init) */
 
 #define MOIRE_MAX_ALLELES 64 /* alleles per locus (one mask word) */
-#define MOIRE_MAX_COI 64     /* max_coi supported by the register tiers (reference LUT bound: 127) */
+#define MOIRE_MAX_COI 127    /* the reference's own bound: its lgamma table (src/sampler.cpp:22-25) */
 
 /* Kernel generation: AUTO picks the flat pipelines (device-wide cost-class sort + persistent
  * evaluator) unless the problem is tiny (< 1e5 cells), where the fused per-tile kernels win on
@@ -153,6 +153,18 @@ int moire_engine_read_init_log(moire_engine *e, int32_t *records, int32_t max_re
  * MCMC::burnin / MCMC::sample (src/mcmc.cpp:159-174, 308-323).  `iteration` is what the
  * reference passes to update_* (step during burn-in, burnin + step while sampling). */
 int moire_engine_step(moire_engine *e, int32_t iteration);
+/* For a caller that replays steps without a host round trip (the driver captures a step together
+ * with its all-gather and device-side swap pass into one CUDA graph): with iteration < 0 the
+ * kernels of moire_engine_step read the iteration from the device word below, which the caller
+ * advances on the device; a step issued while the engine's stream is being captured goes into the
+ * caller's graph; moire_engine_captured_step_launches says how many kernel launches that step
+ * was, and moire_engine_add_launches credits the launch counter for every replay (and for the
+ * caller's own kernels that travel with a step). */
+#define MOIRE_ITERATION_FROM_DEVICE (-1)
+int moire_engine_device_iteration(moire_engine *e, int32_t **dev_iteration);
+int moire_engine_device_temps(moire_engine *e, double **dev_temps); /* Chain::temp, [num_chains] */
+int moire_engine_captured_step_launches(moire_engine *e, int64_t *launches);
+int moire_engine_add_launches(moire_engine *e, int64_t n);
 /* A single update kind on every chain (parity tests, profiling). */
 int moire_engine_update(moire_engine *e, int32_t kind, int32_t iteration);
 /* Recompute every cell and prior from the current parameters, then reduce. */
@@ -187,6 +199,22 @@ int moire_engine_record_draw(moire_engine *e, int32_t chain, double *p, int32_t 
                              double *eps_neg, double *eps_pos, double *r, double *sample_llik,
                              double *mean_coi, uint64_t *latent);
 
+/* The same as an enqueue-only call for a device-resident store of many draws (DEVICE pointers,
+ * draw-major like moire_mcmc_get_draws; `latent` may be NULL), gated and addressed on the device:
+ * dev_sel[0] = chain of this engine to record or -1 for none, dev_sel[1] = slot < capacity.
+ * Nothing is synchronised; the caller reads the store back whenever it likes. */
+typedef struct moire_draw_store
+{
+    double *p;            /* [capacity][L][a_pad] */
+    int32_t *m;           /* [capacity][N] */
+    double *eps_neg, *eps_pos, *r, *sample_llik; /* [capacity][N] */
+    double *mean_coi;     /* [capacity] */
+    uint64_t *latent;     /* [capacity][N][L] or NULL */
+    int32_t capacity;
+} moire_draw_store;
+int moire_engine_enqueue_record_draw(moire_engine *e, const int32_t *dev_sel,
+                                     const moire_draw_store *store);
+
 /* Work counters since create: non-missing cell likelihood evaluations, kernel launches. */
 int moire_engine_counters(moire_engine *e, uint64_t *cell_evals, uint64_t *kernel_launches);
 /* The same evaluation count split by update kind: [8], indexed by moire_update_kind. */
@@ -198,6 +226,7 @@ int moire_engine_timer_stop(moire_engine *e, double *ms);
 /* Device time (ms) spent in each update kind (CUDA events) since create; [9]: the 8 kinds + the
  * reduction.  Enabled by moire_engine_set_timing(e, 1) (adds event records around each launch). */
 int moire_engine_set_timing(moire_engine *e, int32_t on);
+int moire_engine_get_timing(moire_engine *e, int32_t *on);
 int moire_engine_read_timing(moire_engine *e, double *ms, uint64_t *launches);
 /* Device time and launch count of the transmission evaluator kernel alone (k_flat_eval, the
  * dominant kernel; it runs inside update_p and the four per-sample updates that need

@@ -8,6 +8,15 @@
  * (MCMC::adapt_temp, src/mcmc.cpp:244-304), the traces and the stores of the temp = 1 chain
  * (src/mcmc.cpp:175-177, 327-355).
  *
+ * Where the ladder lives.  With an engine and a device-side exchange (world_size == 1, or the
+ * NCCL exchange of moire_mcmc_init_nccl) the swap pass, its accumulators, the traces and the
+ * stored draws live ON THE DEVICE (csrc/ladder.cuh): moire_mcmc_burnin / moire_mcmc_sample only
+ * enqueue -- one CUDA-graph launch per step holding the engine's kernels, the all-gather and the
+ * one-warp swap pass -- and the host reads results back where MCMC::adapt_temp is due (every
+ * temp_adapt_steps steps; the spline stays on the host) or a getter asks.  Otherwise (ladder-only
+ * mode, a callback exchange, MOIRE_B200_HOST_LADDER=1) the pass runs on the host after a per-step
+ * read-back.  Same arithmetic (one swap_pair() for both), same results.
+ *
  * Sharding: the ladder of T chains is cut into `world_size` contiguous blocks, one driver (and
  * one engine, one GPU) per rank.  Chains never move; a swap exchanges TEMPERATURES, as in the
  * reference (src/mcmc.cpp:217-219).  The only exchange per step is an all-gather of every
@@ -40,7 +49,8 @@ typedef struct moire_mcmc_params
     int32_t temp_adapt_steps;
     int32_t max_initialization_tries;
     int32_t record_latent_genotypes;
-    double max_runtime; /* minutes; <= 0 or inf: unlimited */
+    double max_runtime; /* minutes; negative or non-finite: unlimited (0 stops at once, like the
+                           reference's `timer.elapsed() < max_runtime`, src/main.cpp:54) */
 } moire_mcmc_params;
 
 typedef struct moire_mcmc moire_mcmc;
@@ -48,8 +58,12 @@ typedef struct moire_mcmc moire_mcmc;
 /* All-gather of `count` doubles per rank: recv[r * count + i] = send_r[i].  Return 0 on success.
  * With world_size == 1 no function is needed. */
 typedef int (*moire_allgather_fn)(void *ctx, const double *send, int32_t count, double *recv);
-/* Called after every step of moire_mcmc_run (Rcpp::checkUserInterrupt + the progress bar,
- * src/main.cpp:56-69): phase 0 = burn-in, 1 = sampling.  Return non-zero to stop the run. */
+/* Called once for every step of moire_mcmc_run (Rcpp::checkUserInterrupt + the progress bar,
+ * src/main.cpp:56-69): phase 0 = burn-in, 1 = sampling; `posterior` and `hot_chain` are that
+ * step's.  Return non-zero to stop the run.  With the ladder on the device (below) steps are
+ * queued and read back in batches of up to 32, so the calls for a batch arrive together after its
+ * last step, and a stop request (like max_runtime) takes effect at the end of a batch -- on
+ * several ranks, at the end of the batch in which every rank has seen the request. */
 typedef int (*moire_progress_fn)(void *ctx, int32_t phase, int32_t step, double posterior,
                                  int32_t hot_chain);
 

@@ -124,6 +124,12 @@ ENGINE_SYMBOLS = {
     "moire_engine_read_evaluator_timing": (C.c_int, [vp, C.POINTER(dbl), C.POINTER(u64)]),
     "moire_engine_synchronize": (C.c_int, [vp]),
     "moire_engine_subset_order": (C.c_int, [vp, i32, i32, vp]),
+    "moire_engine_device_iteration": (C.c_int, [vp, C.POINTER(vp)]),
+    "moire_engine_device_temps": (C.c_int, [vp, C.POINTER(vp)]),
+    "moire_engine_captured_step_launches": (C.c_int, [vp, C.POINTER(C.c_int64)]),
+    "moire_engine_add_launches": (C.c_int, [vp, C.c_int64]),
+    "moire_engine_get_timing": (C.c_int, [vp, C.POINTER(i32)]),
+    "moire_engine_enqueue_record_draw": (C.c_int, [vp, vp, vp]),
     "moire_philox4x32": (None, [vp, vp, vp]),
 }
 

@@ -214,6 +214,34 @@ __global__ void k_set_iteration(int *dst, const int iteration) { *dst = iteratio
 // partial differences), 1 = g_sub_mask (the warp-cooperative evaluator), 2 = SmallSubsets<K> (the
 // compile-time order of the unrolled walks, k <= MOIRE_SMALL_K).  out[i] = element mask of the
 // i-th subset, bit 15 set when the table gives its term a minus sign.
+// What MCMC::sample stores of the hot chain (src/mcmc.cpp:327-347), gated and addressed by
+// device-resident words so that it can be enqueued every sampling step without the host knowing
+// which chain (if any) is hot: sel[0] = local chain index or -1, sel[1] = slot of the store.
+__global__ void __launch_bounds__(256) k_record_draw(const moire::View v, const int *sel, const moire_draw_store st)
+{
+    const int t = sel[0], slot = sel[1];
+    if (t < 0 || t >= v.T || slot < 0 || slot >= st.capacity) return;
+    const size_t N = v.N, L = v.L, LA = L * v.AP, NL = N * L;
+    const size_t g0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = g0; i < LA; i += stride) st.p[slot * LA + i] = v.p[t * LA + i];
+    for (size_t i = g0; i < N; i += stride)
+    {
+        const size_t si = t * N + i;
+        st.m[slot * N + i] = v.m[si];
+        st.eps_neg[slot * N + i] = v.eps_neg[si];
+        st.eps_pos[slot * N + i] = v.eps_pos[si];
+        st.r[slot * N + i] = v.r[si];
+        // Chain::get_llik(sample), src/chain.cpp:1083-1097: the sample's cells in locus order
+        const size_t base = si * L;
+        double sum = 0.0;
+        for (size_t j = 0; j < L; ++j) sum += __dadd_rn(v.cellT[base + j], v.cellO[base + j]);
+        st.sample_llik[slot * N + i] = sum;
+    }
+    if (g0 == 0) st.mean_coi[slot] = v.mean_coi[t];
+    if (st.latent)
+        for (size_t i = g0; i < NL; i += stride) st.latent[slot * NL + i] = v.latent[t * NL + i];
+}
+
 template <int K>
 __device__ void dump_small_subsets(unsigned short *out)
 {
@@ -802,8 +830,27 @@ struct moire_engine
     // from device memory when handed kIterFromDevice.  So the step is captured once and replayed:
     // one host call per step instead of ~55 launches and a handful of memsets, back-to-back on
     // the device.  Per-kind timing (events between the kernels) uses the plain launches.
+    uint64_t replay_step_launches = 0;  // launches of one step issued into a caller's capture
+
     void step(int iteration)
     {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        CUDA_TRY(cudaStreamIsCapturing(stream, &cap));
+        if (cap != cudaStreamCaptureStatusNone)
+        {
+            // the caller (the driver) is capturing this step together with what follows it: plain
+            // launches into its graph; they execute when it replays (moire_engine_note_replay)
+            const uint64_t before = launches;
+            step_launches(iteration);
+            replay_step_launches = launches - before;
+            launches = before;
+            return;
+        }
+        if (iteration < 0)
+        {
+            step_launches(moire::kIterFromDevice);
+            return;
+        }
         if (!use_graph || timing)
         {
             step_launches(iteration);
@@ -1382,6 +1429,62 @@ int moire_engine_synchronize(moire_engine *e)
     return guarded(e, [&] {
         if (!e) throw InvalidArg{"null engine"};
         CUDA_TRY(cudaStreamSynchronize(e->stream));
+    });
+}
+
+int moire_engine_device_iteration(moire_engine *e, int32_t **dev_iteration)
+{
+    return guarded(e, [&] {
+        if (!e || !dev_iteration) throw InvalidArg{"null argument"};
+        *dev_iteration = e->iter_dev.ptr;
+    });
+}
+
+int moire_engine_device_temps(moire_engine *e, double **dev_temps)
+{
+    return guarded(e, [&] {
+        if (!e || !dev_temps) throw InvalidArg{"null argument"};
+        *dev_temps = e->v.temp;
+    });
+}
+
+int moire_engine_captured_step_launches(moire_engine *e, int64_t *launches)
+{
+    return guarded(e, [&] {
+        if (!e || !launches) throw InvalidArg{"null argument"};
+        *launches = (int64_t)e->replay_step_launches;
+    });
+}
+
+int moire_engine_add_launches(moire_engine *e, int64_t n)
+{
+    return guarded(e, [&] {
+        if (!e) throw InvalidArg{"null engine"};
+        e->launches = (uint64_t)((int64_t)e->launches + n);
+    });
+}
+
+int moire_engine_get_timing(moire_engine *e, int32_t *on)
+{
+    return guarded(e, [&] {
+        if (!e || !on) throw InvalidArg{"null argument"};
+        *on = e->timing ? 1 : 0;
+    });
+}
+
+int moire_engine_enqueue_record_draw(moire_engine *e, const int32_t *dev_sel, const moire_draw_store *store)
+{
+    return guarded(e, [&] {
+        if (!e || !dev_sel || !store) throw InvalidArg{"null argument"};
+        if (!store->p || !store->m || !store->eps_neg || !store->eps_pos || !store->r ||
+            !store->sample_llik || !store->mean_coi)
+            throw InvalidArg{"draw store: only `latent` may be null"};
+        const size_t most = std::max({(size_t)e->v.N, (size_t)e->v.L * e->v.AP,
+                                      store->latent ? (size_t)e->v.N * e->v.L : (size_t)0});
+        const unsigned blocks = (unsigned)std::min<size_t>((most + 255) / 256, 592);
+        ++e->launches;
+        k_record_draw<<<blocks, 256, 0, e->stream>>>(e->v, dev_sel, *store);
+        CUDA_TRY(cudaGetLastError());
     });
 }
 

@@ -45,8 +45,8 @@ __device__ __forceinline__ double cold_log1m(double x) { return cold_log(1.0 - x
 
 #define MOIRE_COOP_INLINE __noinline__
 constexpr int kIeMax = 10;      // src/prob_any_missing.cpp:11
-constexpr int kMaxCoi = 64;     // MOIRE_MAX_COI
-constexpr int kLogCDim = 65;    // logC[n][k], 0 <= k <= n <= 64
+constexpr int kMaxCoi = 127;    // MOIRE_MAX_COI: the reference's lgamma LUT bound (src/sampler.cpp:22-25)
+constexpr int kLogCDim = 65;    // logC[n][k], 0 <= k <= n <= 64 (alleles of a locus)
 
 // Per (sample, distinct allele count) logs, built once per tile.
 struct EpsLogs
@@ -235,33 +235,50 @@ __device__ double g_egf_comb[(kMaxCoi + 1) * (kMaxCoi + 1)];
 __device__ double g_binom[(kMaxCoi + 1) * (kMaxCoi + 1)];
 
 
-// a[n] = coverage probability of n draws for n = 0..max_n.  q_e = prow[allele_e] / total.
-__device__ __noinline__ void egf_coverage(uint64_t latent, const double *prow, double total,
-                                          int max_n, double *a)
+// ---- the recurrence as a band ---------------------------------------------------------------
+// After e of the k alleles have been folded in, a_e[n] is exactly 0 for n < e (n draws cannot
+// cover e alleles), and the result rows n = k .. max_n depend on a_e[n'] only for
+// n' <= max_n - (k - e).  So stage e needs the D + 1 rows n = e + d, d = 0 .. D, D = max_n - k, and
+//   band_e[d] = sum_{j = 1 .. d + 1} C(e + d, j) * band_{e-1}[d + 1 - j] * q^j
+// (the reference's terms j > d + 1 multiply an exact zero and come last in its sum, so leaving
+// them out changes no bit; rows outside the band never reach a result).  The update runs in
+// place, d descending.  Work per cell: k (D + 1)(D + 2) / 2 multiply-adds instead of
+// k max_n (max_n + 1) / 2 -- 3.6 x less at k = 13, COI 25, and almost nothing where k is close to
+// the COI.  Each sum is still the reference's: terms in j order, (comb * a) * q^j, q^j by the
+// running product q^(j-1) * q (src/prob_any_missing.cpp:68-91).
+// band[d * ST], d <= D; on return band[d * ST] = coverage(k + d).
+__device__ __forceinline__ void egf_band(uint64_t latent, const double *prow, double total, int D,
+                                         double *band, int ST)
 {
-    double b[kMaxCoi + 1];
-    double ppow[kMaxCoi + 1];
-    for (int m = 0; m <= max_n; ++m) a[m] = 0.0;
-    a[0] = 1.0;
+    constexpr int CS = kMaxCoi + 1;
+    for (int d = 0; d <= D; ++d) band[d * ST] = d == 0 ? 1.0 : 0.0;
     uint64_t rest = latent;
+    int e = 0;
     while (rest)
     {
         const int al = __ffsll((long long)rest) - 1;
         rest &= rest - 1;
-        const double p = __ddiv_rn(prow[al], total);
-        ppow[0] = 0.0;
-        if (max_n >= 1) ppow[1] = p;
-        for (int j = 2; j <= max_n; ++j) ppow[j] = __dmul_rn(ppow[j - 1], p);
-        b[0] = 0.0;
-        for (int m = 1; m <= max_n; ++m)
+        ++e;
+        const double q = __ddiv_rn(prow[al], total);
+        int d = D;
+        // two rows at a time: their sums are independent chains of additions
+        for (; d >= 1; d -= 2)
         {
-            double sum = 0.0;
-            for (int j = 1; j <= m; ++j)
-                sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(g_egf_comb[j * (kMaxCoi + 1) + m], a[m - j]),
-                                               ppow[j]));
-            b[m] = sum;
+            const double *c0 = g_egf_comb + (e + d), *c1 = g_egf_comb + (e + d - 1);
+            double s0 = 0.0, s1 = 0.0, pw = q;
+#pragma unroll 2
+            for (int j = 1; j <= d; ++j)
+            {
+                const double x0 = band[(d + 1 - j) * ST], x1 = band[(d - j) * ST];
+                s0 = __dadd_rn(s0, __dmul_rn(__dmul_rn(c0[j * CS], x0), pw));
+                s1 = __dadd_rn(s1, __dmul_rn(__dmul_rn(c1[j * CS], x1), pw));
+                pw = __dmul_rn(pw, q);
+            }
+            s0 = __dadd_rn(s0, __dmul_rn(__dmul_rn(c0[(d + 1) * CS], band[0]), pw));  // j = d + 1
+            band[d * ST] = s0;
+            band[(d - 1) * ST] = s1;
         }
-        for (int m = 0; m <= max_n; ++m) a[m] = b[m];
+        if (d == 0) band[0] = __dadd_rn(0.0, __dmul_rn(__dmul_rn(g_egf_comb[CS + e], band[0]), q));
     }
 }
 
@@ -506,30 +523,27 @@ __device__ __noinline__ double transmission_rel_ie_wide(double *scr, int ST, int
     return relatedness_mixture(v, 1, m, cnt, log_total, log_r, log_1mr, lgam);
 }
 
-// EGF branch of the relatedness path; a[] lives in local memory (k > 10 only).
-__device__ __noinline__ double transmission_rel_egf(uint64_t latent, const double *prow,
-                                                    double total, int k, int m, double log_total,
-                                                    double log_r, double log_1mr,
-                                                    const double *lgam)
+// EGF branch (k > 10) of one cell on one thread: the band in the thread's scratch column while it
+// fits (m - k < kScratchSlots: nearly always), else in local memory; then the same mixture as every
+// other path.
+__device__ __noinline__ double transmission_egf(uint64_t latent, const double *prow, double total,
+                                                int k, int m, double log_total, double log_r,
+                                                double log_1mr, bool allow_relatedness, double *scr,
+                                                int ST, const double *lgam)
 {
-    double a[kMaxCoi + 1];
-    egf_coverage(latent, prow, total, m, a);
-    const int cnt = m - k + 1;
-    double mx = -INFINITY;
-    for (int i = 0; i < cnt; ++i)
+    const int D = m - k;
+    double local_band[kMaxCoi + 1];
+    double *band = D < kScratchSlots ? scr : local_band;
+    const int BS = D < kScratchSlots ? ST : 1;
+    egf_band(latent, prow, total, D, band, BS);
+    if (!allow_relatedness)
     {
-        const int n = m - i;
-        const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
-        const double pam = clamp_pam(pam_from_coverage(a[n]));
-        const double i_res = __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)n));
-        const double v = __dadd_rn(pr, i_res);
-        a[n] = v;
-        mx = (mx < v) ? v : mx;
+        // src/chain.cpp:895-899 with probAnyMissingFunctor::operator() (prob_any_missing.cpp:149-153)
+        const double pam = clamp_pam(pam_from_coverage(band[D * BS]));
+        return __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)m));
     }
-    if (mx == -INFINITY) return -INFINITY;
-    double sum = 0.0;
-    for (int i = 0; i < cnt; ++i) sum = __dadd_rn(sum, cold_exp(__dsub_rn(a[m - i], mx)));
-    return __dadd_rn(mx, cold_log(sum));
+    for (int d = 0; d <= D; ++d) band[d * BS] = pam_from_coverage(band[d * BS]);
+    return relatedness_mixture(band, BS, m, D + 1, log_total, log_r, log_1mr, lgam);
 }
 
 // Relatedness off and n == k: 1 - k! * prod(q) in double (src/prob_any_missing.cpp:139-148).
@@ -590,23 +604,14 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
     if (!allow_relatedness)
     {
         // src/chain.cpp:895-899 with probAnyMissingFunctor::operator() (prob_any_missing.cpp:131-154)
-        double pam;
         if (m == k) return transmission_norel_exact_cover(latent, prow, total, log_total, k);
-        if (k <= kIeMax)
-        {
-            pam = ie_scalar(scr, ST, k, m);
-        }
-        else
-        {
-            double a[kMaxCoi + 1];
-            egf_coverage(latent, prow, total, m, a);
-            pam = pam_from_coverage(a[m]);
-        }
-        pam = clamp_pam(pam);
+        if (k > kIeMax)
+            return transmission_egf(latent, prow, total, k, m, log_total, log_r, log_1mr, false, scr, ST, lgam);
+        const double pam = clamp_pam(ie_scalar(scr, ST, k, m));
         return __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)m));
     }
     if (k > kIeMax)
-        return transmission_rel_egf(latent, prow, total, k, m, log_total, log_r, log_1mr, lgam);
+        return transmission_egf(latent, prow, total, k, m, log_total, log_r, log_1mr, true, scr, ST, lgam);
     if (m - k + 1 <= kMaxAcc)
         return transmission_rel_ie(scr, ST, k, m, log_total, log_r, log_1mr, lgam, ie_lanes);
     return transmission_rel_ie_wide(scr, ST, k, m, log_total, log_r, log_1mr, lgam);
@@ -658,10 +663,10 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
     const unsigned short *masks = g_sub_mask + subset_block(k);
     const int nsub = (1 << k) - 1;
     const int cnt = allow_relatedness ? m - k + 1 : 1;
-    // accumulators of up to 4 chunks of 16 mixture terms (cnt <= 64); chunk c, lane t: n = k + 16c + t
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    // accumulators of up to 8 chunks of 16 mixture terms (cnt <= 127); chunk c, lane t: n = k + 16c + t
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch)
+    for (int ch = 0; ch < 8; ++ch)
     {
         const int t0 = 16 * ch;
         if (t0 < cnt)  // uniform
@@ -739,7 +744,7 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
     // not change a bit of the result.  Every lane gathers the sums and computes the same value.
     double pams[kMaxCoi];
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch)
+    for (int ch = 0; ch < 8; ++ch)
         if (16 * ch < cnt)  // uniform
         {
             const int top = min(16, cnt - 16 * ch);
@@ -748,21 +753,20 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
     return relatedness_mixture(pams, 1, m, cnt, log_total, log_r, log_1mr, lgam);
 }
 
-// ---- a2 for k > 10, warp-cooperative: the EGF recurrence with the draws across lanes ----------
-// One warp per cell.  For each latent allele the new row b[n] = sum_{j=1..n} C(n,j) a[n-j] q^j is
-// independent across n, so lane l computes n = l + 1 and n = l + 33 (n <= m <= 64), each as the
-// reference's sequential sum over j with the running power q^j built by the same chain of
-// multiplications; a[] lives in the warp's scratch rows.  The mixture terms are one per lane and
-// the log-sum-exp is summed in the reference's order.  All lanes must call with identical
-// arguments; every lane returns the value.
+// ---- a2 for k > 10, warp-cooperative: the band with its rows across lanes ---------------------
+// One warp per cell.  The rows of a stage are independent, so lane l computes row d = l (and
+// l + 32, ... for bands wider than a warp), each as the sequential sum of egf_band; the band lives
+// in the warp's scratch rows.  Every lane then gathers the band and runs the one mixture function.
+// All lanes must call with identical arguments; every lane returns the value.
 __device__ MOIRE_COOP_INLINE double transmission_ll_egf_coop(uint64_t latent, const double *prow, int m,
                                                            double log_r, double log_1mr,
                                                            bool allow_relatedness, double *wscr,
                                                            int ST, const double *lgam)
 {
-    const unsigned FULL = 0xffffffffu;
+    constexpr int CS = kMaxCoi + 1;
     const int lane = threadIdx.x & 31;
     const int k = __popcll(latent);
+    const int D = m - k;
     double total = 0.0;
     {
         uint64_t rest = latent;
@@ -774,86 +778,53 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_egf_coop(uint64_t latent, co
         }
     }
     const double log_total = cold_log(total);
-    // a[i] at wscr[(i >> 5) * ST + (i & 31)], i <= m <= 64: rows 0..2
-    auto A = [&](int i) -> double & { return wscr[(i >> 5) * ST + (i & 31)]; };
-    for (int i = lane; i <= m; i += 32) A(i) = i == 0 ? 1.0 : 0.0;
+    // band[d] at wscr[(d >> 5) * ST + (d & 31)], d <= D < 128: rows 0..3
+    auto B = [&](int d) -> double & { return wscr[(d >> 5) * ST + (d & 31)]; };
+    for (int d = lane; d <= D; d += 32) B(d) = d == 0 ? 1.0 : 0.0;
     __syncwarp();
     uint64_t rest = latent;
+    int e = 0;
     while (rest)
     {
         const int al = __ffsll((long long)rest) - 1;
         rest &= rest - 1;
+        ++e;
         const double q = __ddiv_rn(prow[al], total);
-        double b[2] = {0.0, 0.0};
+        double nb[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int half = 0; half < 2; ++half)
+        for (int part = 0; part < 4; ++part)
         {
-            const int n = lane + 1 + 32 * half;
-            if (n <= m)
+            const int d = lane + 32 * part;
+            if (d <= D)
             {
+                const double *c = g_egf_comb + (e + d);
                 double sum = 0.0, pw = q;
-                for (int j = 1; j <= n; ++j)
+                for (int j = 1; j <= d + 1; ++j)
                 {
                     if (j > 1) pw = __dmul_rn(pw, q);
-                    sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(g_egf_comb[j * (kMaxCoi + 1) + n], A(n - j)), pw));
+                    sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(c[j * CS], B(d + 1 - j)), pw));
                 }
-                b[half] = sum;
+                nb[part] = sum;
             }
         }
         __syncwarp();
-        if (lane == 0) A(0) = 0.0;
 #pragma unroll
-        for (int half = 0; half < 2; ++half)
+        for (int part = 0; part < 4; ++part)
         {
-            const int n = lane + 1 + 32 * half;
-            if (n <= m) A(n) = b[half];
+            const int d = lane + 32 * part;
+            if (d <= D) B(d) = nb[part];
         }
         __syncwarp();
     }
     if (!allow_relatedness)
     {
-        const double pam = clamp_pam(pam_from_coverage(A(m)));
+        const double pam = clamp_pam(pam_from_coverage(B(D)));
         return __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)m));
     }
-    // mixture: term i = 0..cnt-1 uses n = m - i; lanes hold i = lane and i = lane + 32
-    const int cnt = m - k + 1;
-    double v[2];
-    double mx = -INFINITY;
-#pragma unroll
-    for (int half = 0; half < 2; ++half)
-    {
-        const int i = lane + 32 * half;
-        v[half] = -INFINITY;
-        if (i < cnt)
-        {
-            const int n = m - i;
-            const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
-            const double pam = clamp_pam(pam_from_coverage(A(n)));
-            const double i_res = __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)n));
-            v[half] = __dadd_rn(pr, i_res);
-            mx = (mx < v[half]) ? v[half] : mx;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-    {
-        const double other = __shfl_xor_sync(FULL, mx, o);
-        mx = (mx < other) ? other : mx;
-    }
-    if (mx == -INFINITY) return -INFINITY;
-    double sum = 0.0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half)
-    {
-        if (32 * half < cnt)  // uniform
-        {
-            double ev = 0.0;
-            if (lane + 32 * half < cnt) ev = cold_exp(__dsub_rn(v[half], mx));
-            const int top = min(31, cnt - 1 - 32 * half);
-            for (int t = 0; t <= top; ++t) sum = __dadd_rn(sum, __shfl_sync(FULL, ev, t));
-        }
-    }
-    return __dadd_rn(mx, cold_log(sum));
+    double pams[kMaxCoi];
+    for (int d = 0; d <= D; ++d) pams[d] = pam_from_coverage(B(d));
+    __syncwarp();
+    return relatedness_mixture(pams, 1, m, D + 1, log_total, log_r, log_1mr, lgam);
 }
 
 // ---- a8: latent-genotype proposal ------------------------------------------------------------

@@ -1,14 +1,30 @@
-// Host-side parallel-tempering driver (include/moire_mcmc.h).
+// Parallel-tempering driver (include/moire_mcmc.h).
 //
-// What the reference keeps on its master thread stays here, in double: the even/odd temperature
-// swaps (MCMC::swap_chains, src/mcmc.cpp:190-240), the adaptive ladder (MCMC::adapt_temp,
+// What the reference keeps on its master thread, in double: the even/odd temperature swaps
+// (MCMC::swap_chains, src/mcmc.cpp:190-240), the adaptive ladder (MCMC::adapt_temp,
 // src/mcmc.cpp:244-304, with the monotone cubic spline of src/include/spline/src/spline.h), the
 // traces and the stores of the temp = 1 chain (src/mcmc.cpp:175-177, 327-355) and the two loops
 // of run_mcmc (src/main.cpp:52-93).  Everything per-chain goes through the engine's C ABI; no
 // likelihood arithmetic runs here.
+//
+// Two homes for the ladder.  With an engine and a device-side exchange (one rank, or the NCCL
+// all-gather) the ladder lives ON THE DEVICE (ladder.cuh): a step is one graph launch -- the
+// engine's kernels, the pack, the all-gather, the one-warp swap pass -- and the host neither waits
+// for it nor copies anything; traces, accumulators and draws are read back in batches, where
+// adapt_temp is due or a result is asked for.  Otherwise (ladder-only mode for the CPU tests, a
+// callback exchange such as gloo, MOIRE_B200_HOST_LADDER=1) the same pass runs on the host after a
+// per-step read-back, as in round 1.  Both call the one swap_pair() of ladder.cuh.
+//
+// The spline below restates, in double, the parts of the reference's vendored tk::spline
+// (src/include/spline/src/spline.h, (c) Tino Kluge, GPL-2+; moire itself is GPL-3) that
+// MCMC::adapt_temp exercises -- cspline with natural boundaries, make_monotonic, solve_one and its
+// cubic solver -- closely enough to reproduce the reference's adapted ladders (the golden vectors
+// of tests/golden/make_golden_driver.py): that is third-party arithmetic this file credits, not
+// an original design.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -18,6 +34,7 @@
 #include <dlfcn.h>
 
 #include "../../include/moire_mcmc.h"
+#include "ladder.cuh"
 #include "rng.cuh"
 
 namespace
@@ -285,6 +302,7 @@ NcclApi g_nccl;
 // one communicator per process, kept for its lifetime: creating one costs a few hundred ms
 void *g_nccl_comm = nullptr;
 int g_nccl_world = 0, g_nccl_rank = -1;
+int g_nccl_users = 0;  // live drivers holding g_nccl_comm
 }  // namespace
 
 struct moire_mcmc
@@ -312,7 +330,7 @@ struct moire_mcmc
     std::vector<double> swap_barriers;      // [T-1]
     std::vector<double> temp_gradient;      // [T]
     std::vector<double> chain_temp;         // [T] by chain id (Chain::temp)
-    std::vector<char> chain_hot;            // [T] by chain id (Chain::hot)
+    std::vector<int> chain_hot;             // [T] by chain id (Chain::hot)
     std::vector<double> chain_llik, chain_prior;  // [T] by chain id, after the last step
     int64_t num_swaps = 0;
     bool even_swap = true;
@@ -332,13 +350,33 @@ struct moire_mcmc
     std::vector<double> send, recv;
     std::chrono::steady_clock::time_point t_start;
     double elapsed_minutes_rank0 = 0.0;
+    bool local_stop = false, stop_any = false;  // the progress callback's request, here / on any rank
+
+    // ---- the ladder on the device (ladder.cuh) ----
+    bool dev_mode = false;
+    moire::LadderDev ld{};
+    std::vector<void *> dev_allocs;
+    double *host_flags = nullptr;       // pinned + mapped: minutes, stop
+    moire_draw_store store{};           // device-resident draws since the last read-back
+    cudaGraphExec_t step_graph[2] = {nullptr, nullptr};  // burn-in step, sampling step
+    int64_t graph_launches[2] = {0, 0};  // kernel launches one replay stands for
+    bool graph_ok = true;
+    bool batch_open = false, host_dirty = true;
+    int next_step = -1, next_phase = -1;
+    int pending = 0, pending_phase = 0, draws_bound = 0;
+    static constexpr int kTraceCap = 256;
 
     ~moire_mcmc()
     {
+        for (auto &g : step_graph)
+            if (g) cudaGraphExecDestroy(g);
+        for (void *p : dev_allocs) cudaFree(p);
+        if (host_flags) cudaFreeHost(host_flags);
         if (send_d) cudaFree(send_d);
         if (recv_d) cudaFree(recv_d);
         if (send_pin) cudaFreeHost(send_pin);
         if (recv_pin) cudaFreeHost(recv_pin);
+        if (nccl_comm && nccl_comm == g_nccl_comm) --g_nccl_users;
         if (engine) moire_engine_destroy(engine);
     }
 
@@ -413,7 +451,7 @@ struct moire_mcmc
     {
         const double minutes =
             std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() / 60.0;
-        const int per = 2 * cmax + 1;
+        const int per = 2 * cmax + 2;
         if (world > 1 && nccl_comm && engine)
         {
             // device to device: the sums k_reduce left on the engine's stream, the collective on
@@ -421,9 +459,10 @@ struct moire_mcmc
             void *dl = nullptr, *dp = nullptr;
             ck(moire_engine_device_scalars(engine, &dl, &dp), "device_scalars");
             send_pin[0] = minutes;
+            send_pin[1] = local_stop ? 1.0 : 0.0;
             cu(cudaMemcpyAsync(send_d, dl, sizeof(double) * count, cudaMemcpyDeviceToDevice, stream), "d2d");
             cu(cudaMemcpyAsync(send_d + cmax, dp, sizeof(double) * count, cudaMemcpyDeviceToDevice, stream), "d2d");
-            cu(cudaMemcpyAsync(send_d + 2 * cmax, send_pin, sizeof(double), cudaMemcpyHostToDevice, stream), "h2d");
+            cu(cudaMemcpyAsync(send_d + 2 * cmax, send_pin, 2 * sizeof(double), cudaMemcpyHostToDevice, stream), "h2d");
             nc(g_nccl.AllGather(send_d, recv_d, (size_t)per, NcclApi::kFloat64, nccl_comm, stream), "ncclAllGather");
             cu(cudaMemcpyAsync(recv_pin, recv_d, sizeof(double) * per * world, cudaMemcpyDeviceToHost, stream), "d2h");
             cu(cudaStreamSynchronize(stream), "sync");
@@ -434,6 +473,7 @@ struct moire_mcmc
             std::fill(send.begin(), send.end(), 0.0);
             local_scalars(send.data(), send.data() + cmax);
             send[2 * cmax] = minutes;
+            send[2 * cmax + 1] = local_stop ? 1.0 : 0.0;
             if (world == 1)
                 std::copy(send.begin(), send.end(), recv.begin());
             else
@@ -450,6 +490,9 @@ struct moire_mcmc
             }
         }
         elapsed_minutes_rank0 = recv[2 * cmax];
+        // the stop request of any rank's progress callback reaches every rank with the same step's
+        // exchange, so all ranks leave the loop together (nobody is left waiting in a collective)
+        for (int r = 0; r < world; ++r) stop_any = stop_any || recv[(size_t)r * per + 2 * cmax + 1] != 0.0;
     }
 
     double uniform_for_pair(int step, int pair)
@@ -462,37 +505,20 @@ struct moire_mcmc
         }
         // the reference draws R::runif here (src/mcmc.cpp:212); every rank must draw the same
         // number, so the stream is keyed by (seed, pass counter, pair) only
-        moire::Stream s;
-        s.open(seed, swap_passes, moire::KIND_SWAP, 0xFFFFu, (uint32_t)pair, (uint32_t)(step & 0xFFFF));
-        return s.next_uniform();
+        return moire::swap_uniform(seed, swap_passes, pair, step);
     }
 
     // MCMC::swap_chains (src/mcmc.cpp:190-240)
     bool swap_pass(int step, bool burnin)
     {
         bool moved = false;
+        static_assert(sizeof(long long) == sizeof(int64_t), "swap counters");
         for (int i = even_swap ? 1 : 0; i < T - 1; i += 2)
         {
-            const int a = swap_indices[i], b = swap_indices[i + 1];
-            const double V_a = -chain_llik[a], temp_a = chain_temp[a];
-            const double V_b = -chain_llik[b], temp_b = chain_temp[b];
-            const double ratio = (temp_b - temp_a) * (V_b - V_a);
-            const double rate = std::min(1.0, std::exp(ratio));
-            if (burnin && step > prm.pre_adapt_steps) swap_barriers[i] += 1.0 - rate;
             const double u = std::log(uniform_for_pair(step, i));
-            if ((ratio > 0 || u < ratio) && !std::isnan(ratio))
-            {
-                std::swap(swap_indices[i], swap_indices[i + 1]);
-                chain_temp[a] = temp_b;
-                chain_temp[b] = temp_a;
-                if (i == 0)
-                {
-                    chain_hot[b] = 1;
-                    chain_hot[a] = 0;
-                }
-                if (!burnin) swap_acceptances[i]++;
-                moved = true;
-            }
+            moved |= moire::swap_pair(i, burnin, burnin && step > prm.pre_adapt_steps, u, chain_llik.data(),
+                                      chain_temp.data(), chain_hot.data(), swap_indices.data(),
+                                      swap_barriers.data(), reinterpret_cast<long long *>(swap_acceptances.data()));
         }
         swap_store.push_back(swap_indices[0]);
         if (burnin && step > prm.pre_adapt_steps) num_swaps++;
@@ -569,8 +595,314 @@ struct moire_mcmc
            "record_draw");
     }
 
+    // ================= the ladder on the device =================================================
+    template <class T>
+    T *dev_alloc(size_t n)
+    {
+        void *p = nullptr;
+        cu(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)), "cudaMalloc");
+        cu(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)), "cudaMemset");
+        dev_allocs.push_back(p);
+        return static_cast<T *>(p);
+    }
+
+    // Called at the end of moire_mcmc_init: from here on the steps of this driver run without the
+    // host (see the header comment).  Needs an engine and an exchange that lives on the device.
+    void setup_device_ladder()
+    {
+        if (!engine || (world > 1 && !nccl_comm) || std::getenv("MOIRE_B200_HOST_LADDER")) return;
+        if (!stream)
+        {
+            void *st = nullptr;
+            ck(moire_engine_stream(engine, &st), "engine_stream");
+            stream = (cudaStream_t)st;
+        }
+        graph_ok = std::getenv("MOIRE_B200_NO_GRAPH") == nullptr;
+        ld.T = T; ld.world = world; ld.first = first; ld.count = count; ld.cmax = cmax;
+        ld.per = 2 * cmax + 2;
+        ld.pre_adapt_steps = prm.pre_adapt_steps; ld.thin = prm.thin; ld.burnin = prm.burnin;
+        ld.trace_cap = kTraceCap;
+        ld.seed = seed;
+        void *dl = nullptr, *dp = nullptr;
+        ck(moire_engine_device_scalars(engine, &dl, &dp), "device_scalars");
+        ld.eng_llik = (const double *)dl;
+        ld.eng_prior = (const double *)dp;
+        double *dt = nullptr;
+        int32_t *di = nullptr;
+        ck(moire_engine_device_temps(engine, &dt), "device_temps");
+        ck(moire_engine_device_iteration(engine, &di), "device_iteration");
+        ld.eng_temp = dt;
+        ld.eng_iter = di;
+        if (world > 1)
+        {
+            ld.send = send_d;  // moire_mcmc_init_nccl sized them for `per`
+            ld.recv = recv_d;
+        }
+        else
+        {
+            ld.send = dev_alloc<double>(ld.per);
+            ld.recv = ld.send;
+        }
+        cu(cudaHostAlloc((void **)&host_flags, 2 * sizeof(double), cudaHostAllocMapped), "cudaHostAlloc");
+        host_flags[0] = host_flags[1] = 0.0;
+        double *hf_dev = nullptr;
+        cu(cudaHostGetDevicePointer((void **)&hf_dev, host_flags, 0), "cudaHostGetDevicePointer");
+        ld.host_flags = hf_dev;
+        ld.chain_llik = dev_alloc<double>(T);
+        ld.chain_prior = dev_alloc<double>(T);
+        ld.chain_temp = dev_alloc<double>(T);
+        ld.chain_hot = dev_alloc<int>(T);
+        ld.swap_indices = dev_alloc<int>(T);
+        ld.swap_acc = dev_alloc<long long>(T);
+        ld.swap_barriers = dev_alloc<double>(T);
+        ld.ctl = dev_alloc<long long>(moire::LC_WORDS);
+        ld.minutes = dev_alloc<double>(1);
+        ld.trace = dev_alloc<double>((size_t)3 * kTraceCap);
+        ld.swap_store = dev_alloc<int>(kTraceCap);
+        ld.draw_sel = dev_alloc<int>(2);
+        // the draw store: as many draws as the run can produce, within ~1 GiB (then it is read
+        // back when full)
+        const size_t LA = (size_t)L * AP, NL = (size_t)N * L;
+        const size_t per_draw = LA * 8 + (size_t)N * (4 + 4 * 8) + 8 + (prm.record_latent_genotypes ? NL * 8 : 0);
+        const size_t thin = (size_t)std::max(prm.thin, 1);
+        const size_t want = ((size_t)std::max(prm.samples, 0) + thin - 1) / thin + 1;
+        const size_t cap = std::max<size_t>(1, std::min(want, ((size_t)1 << 30) / std::max<size_t>(per_draw, 1)));
+        ld.draw_cap = (int)cap;
+        ld.draw_step = dev_alloc<int>(cap);
+        store.capacity = (int32_t)cap;
+        store.p = dev_alloc<double>(cap * LA);
+        store.m = dev_alloc<int32_t>(cap * N);
+        store.eps_neg = dev_alloc<double>(cap * N);
+        store.eps_pos = dev_alloc<double>(cap * N);
+        store.r = dev_alloc<double>(cap * N);
+        store.sample_llik = dev_alloc<double>(cap * N);
+        store.mean_coi = dev_alloc<double>(cap);
+        store.latent = prm.record_latent_genotypes ? dev_alloc<uint64_t>(cap * NL) : nullptr;
+        dev_mode = true;
+        host_dirty = true;
+        batch_open = false;
+    }
+
+    template <class T>
+    void h2d(T *dst, const T *src, size_t n)
+    {
+        cu(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, stream), "h2d");
+    }
+    template <class T>
+    void d2h(T *dst, const T *src, size_t n)
+    {
+        cu(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, stream), "d2h");
+    }
+
+    // host ladder -> device, and the control words of the batch that starts at (step, phase)
+    void begin_batch(int step, int phase)
+    {
+        long long ctl[moire::LC_WORDS] = {(long long)num_swaps, even_swap ? 1 : 0, (long long)swap_passes,
+                                          step, phase, 0, 0, stop_any ? 1 : 0};
+        h2d(ld.ctl, ctl, moire::LC_WORDS);
+        if (host_dirty)
+        {
+            h2d(ld.chain_llik, chain_llik.data(), T);
+            h2d(ld.chain_prior, chain_prior.data(), T);
+            h2d(ld.chain_temp, chain_temp.data(), T);
+            h2d(ld.chain_hot, chain_hot.data(), T);
+            h2d(ld.swap_indices, swap_indices.data(), T);
+            if (T > 1)
+            {
+                h2d(ld.swap_acc, reinterpret_cast<const long long *>(swap_acceptances.data()), T - 1);
+                h2d(ld.swap_barriers, swap_barriers.data(), T - 1);
+            }
+            host_dirty = false;
+        }
+        cu(moire::launch_ladder_begin(ld, stream), "k_ladder_begin");
+        // the copies above read pageable host memory: done with it before the caller moves on
+        cu(cudaStreamSynchronize(stream), "sync");
+        batch_open = true;
+        next_step = step;
+        next_phase = phase;
+        pending = 0;
+        pending_phase = phase;
+        draws_bound = 0;
+    }
+
+    // device ladder -> host: the state, the traces of the steps enqueued since the last read-back
+    // and the draws stored since then.  The one place the host waits for the device.
+    void flush()
+    {
+        if (!dev_mode || !batch_open) return;
+        long long ctl[moire::LC_WORDS];
+        std::vector<double> tr((size_t)3 * std::max(pending, 1));
+        std::vector<int> ss(std::max(pending, 1));
+        double minutes = 0.0;
+        d2h(ctl, ld.ctl, moire::LC_WORDS);
+        d2h(&minutes, ld.minutes, 1);
+        d2h(chain_llik.data(), ld.chain_llik, T);
+        d2h(chain_prior.data(), ld.chain_prior, T);
+        d2h(chain_temp.data(), ld.chain_temp, T);
+        d2h(chain_hot.data(), ld.chain_hot, T);
+        d2h(swap_indices.data(), ld.swap_indices, T);
+        if (T > 1)
+        {
+            d2h(reinterpret_cast<long long *>(swap_acceptances.data()), ld.swap_acc, T - 1);
+            d2h(swap_barriers.data(), ld.swap_barriers, T - 1);
+        }
+        if (pending > 0)
+        {
+            d2h(tr.data(), ld.trace, (size_t)3 * pending);
+            d2h(ss.data(), ld.swap_store, pending);
+        }
+        cu(cudaStreamSynchronize(stream), "sync");
+        batch_open = false;
+        if (pending > 0)
+        {
+            if (ctl[moire::LC_TRACE_COUNT] != pending)
+                throw DriverError{MOIRE_ESTATE, "device ladder: step count out of step with the host"};
+            num_swaps = ctl[moire::LC_NUM_SWAPS];
+            even_swap = ctl[moire::LC_EVEN_SWAP] != 0;
+            swap_passes = (uint32_t)ctl[moire::LC_SWAP_PASSES];
+            stop_any = stop_any || ctl[moire::LC_STOP] != 0;
+            elapsed_minutes_rank0 = minutes;
+            auto &vl = pending_phase == 0 ? llik_burnin : llik_sample;
+            auto &vp = pending_phase == 0 ? prior_burnin : prior_sample;
+            auto &vq = pending_phase == 0 ? posterior_burnin : posterior_sample;
+            for (int k = 0; k < pending; ++k)
+            {
+                vl.push_back(tr[3 * k]);
+                vp.push_back(tr[3 * k + 1]);
+                vq.push_back(tr[3 * k + 2]);
+                if (!(pending_phase == 0 && T == 1)) swap_store.push_back(ss[k]);  // src/mcmc.cpp:179
+            }
+        }
+        const int nd = (int)ctl[moire::LC_NDRAWS];
+        if (nd > 0)
+        {
+            const size_t D = draw_step.size(), LA = (size_t)L * AP, NL = (size_t)N * L;
+            draw_step.resize(D + nd);
+            p_store.resize((D + nd) * LA);
+            m_store.resize((D + nd) * N);
+            eps_neg_store.resize((D + nd) * N);
+            eps_pos_store.resize((D + nd) * N);
+            r_store.resize((D + nd) * N);
+            data_llik_store.resize((D + nd) * N);
+            mean_coi_store.resize(D + nd);
+            d2h(draw_step.data() + D, ld.draw_step, nd);
+            d2h(p_store.data() + D * LA, store.p, nd * LA);
+            d2h(m_store.data() + D * N, store.m, (size_t)nd * N);
+            d2h(eps_neg_store.data() + D * N, store.eps_neg, (size_t)nd * N);
+            d2h(eps_pos_store.data() + D * N, store.eps_pos, (size_t)nd * N);
+            d2h(r_store.data() + D * N, store.r, (size_t)nd * N);
+            d2h(data_llik_store.data() + D * N, store.sample_llik, (size_t)nd * N);
+            d2h(mean_coi_store.data() + D, store.mean_coi, nd);
+            if (store.latent)
+            {
+                latent_store.resize((D + nd) * NL);
+                d2h(latent_store.data() + D * NL, store.latent, nd * NL);
+            }
+            cu(cudaStreamSynchronize(stream), "sync");
+        }
+        pending = 0;
+        draws_bound = 0;
+    }
+
+    // the launches of one step on the stream: what a replayed graph holds
+    void step_body(int phase)
+    {
+        ck(moire_engine_step(engine, MOIRE_ITERATION_FROM_DEVICE), "step");
+        if (phase == 1) ck(moire_engine_enqueue_record_draw(engine, ld.draw_sel, &store), "record_draw");
+        cu(moire::launch_ladder_pack(ld, stream), "k_ladder_pack");
+        if (world > 1)
+            nc(g_nccl.AllGather(ld.send, recv_d, (size_t)ld.per, NcclApi::kFloat64, nccl_comm, stream), "ncclAllGather");
+        cu(moire::launch_ladder_step(ld, stream), "k_ladder_step");
+    }
+
+    void enqueue_step(int phase)
+    {
+        host_flags[0] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() / 60.0;
+        host_flags[1] = local_stop ? 1.0 : 0.0;
+        int32_t timing_on = 0;
+        ck(moire_engine_get_timing(engine, &timing_on), "get_timing");
+        if (graph_ok && !timing_on && !step_graph[phase])
+        {
+            // capture the step once; from then on it is one cudaGraphLaunch
+            uint64_t l0 = 0, l1 = 0;
+            ck(moire_engine_counters(engine, nullptr, &l0), "counters");
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            if (ok)
+            {
+                try
+                {
+                    step_body(phase);
+                }
+                catch (const DriverError &)
+                {
+                    ok = false;
+                }
+                ok = cudaStreamEndCapture(stream, &graph) == cudaSuccess && ok && graph;
+            }
+            if (ok) ok = cudaGraphInstantiate(&step_graph[phase], graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (!ok)
+            {
+                // a library in the step that cannot be captured: plain launches from here on
+                cudaGetLastError();
+                step_graph[phase] = nullptr;
+                graph_ok = false;
+            }
+            else
+            {
+                ck(moire_engine_counters(engine, nullptr, &l1), "counters");
+                int64_t captured = 0;
+                ck(moire_engine_captured_step_launches(engine, &captured), "captured_step_launches");
+                graph_launches[phase] = captured + (int64_t)(l1 - l0) + 2;
+                ck(moire_engine_add_launches(engine, -(int64_t)(l1 - l0)), "add_launches");
+            }
+        }
+        if (graph_ok && !timing_on && step_graph[phase])
+        {
+            cu(cudaGraphLaunch(step_graph[phase], stream), "cudaGraphLaunch");
+            ck(moire_engine_add_launches(engine, graph_launches[phase]), "add_launches");
+        }
+        else
+        {
+            step_body(phase);
+            ck(moire_engine_add_launches(engine, 2), "add_launches");
+        }
+        ++pending;
+        ++next_step;
+    }
+
+    void device_step(int step, int phase)
+    {
+        const bool thinned = phase == 1 && (prm.thin == 0 || step % prm.thin == 0);
+        if (batch_open && (next_step != step || next_phase != phase || pending >= kTraceCap ||
+                           (thinned && draws_bound >= ld.draw_cap)))
+            flush();
+        if (!batch_open) begin_batch(step, phase);
+        enqueue_step(phase);
+        if (thinned) ++draws_bound;
+        if (phase == 0 && T > 1)
+        {
+            // MCMC::adapt_temp is due on a schedule the host can follow without reading anything:
+            // num_swaps counts the burn-in steps past pre_adapt_steps since the last adaptation
+            if (step > prm.pre_adapt_steps) ++num_swaps;
+            if (prm.temp_adapt_steps > 0 && num_swaps % prm.temp_adapt_steps == 0 &&
+                step > prm.pre_adapt_steps && prm.adapt_temp)
+            {
+                flush();  // num_swaps, the barriers and the index map as the device left them
+                if (adapt_ladder()) host_dirty = true;
+            }
+        }
+    }
+
+    // ================= the ladder on the host ===================================================
     void burnin_step(int step)
     {
+        if (dev_mode)
+        {
+            device_step(step, 0);
+            return;
+        }
         engine_step(step);
         exchange_scalars();
         push_traces(llik_burnin, prior_burnin, posterior_burnin);
@@ -586,6 +918,11 @@ struct moire_mcmc
 
     void sample_step(int step)
     {
+        if (dev_mode)
+        {
+            device_step(step, 1);
+            return;
+        }
         engine_step(prm.burnin + step);
         if (prm.thin == 0 || step % prm.thin == 0)
         {
@@ -601,6 +938,7 @@ struct moire_mcmc
 
     void finalize()
     {
+        flush();
         const double half = (double)(num_swaps / 2);  // integer division, as the reference
         for (auto &b : swap_barriers) b /= half;
     }
@@ -718,8 +1056,8 @@ int moire_mcmc_create(const moire_data *data, const moire_params *model,
     h->chain_hot.assign(T, 0);
     h->chain_llik.assign(T, 0.0);
     h->chain_prior.assign(T, 0.0);
-    h->send.assign(2 * h->cmax + 1, 0.0);
-    h->recv.assign((size_t)world_size * (2 * h->cmax + 1), 0.0);
+    h->send.assign(2 * h->cmax + 2, 0.0);
+    h->recv.assign((size_t)world_size * (2 * h->cmax + 2), 0.0);
     h->t_start = std::chrono::steady_clock::now();
     *out = h;
     return MOIRE_OK;
@@ -767,7 +1105,7 @@ int moire_mcmc_init_nccl(moire_mcmc *h, const char id[128], const char *library_
         void *st = nullptr;
         h->ck(moire_engine_stream(h->engine, &st), "engine_stream");  // also binds the device
         h->stream = (cudaStream_t)st;
-        const int per = 2 * h->cmax + 1;
+        const int per = 2 * h->cmax + 2;
         h->cu(cudaMalloc(&h->send_d, sizeof(double) * per), "cudaMalloc");
         h->cu(cudaMalloc(&h->recv_d, sizeof(double) * per * h->world), "cudaMalloc");
         h->cu(cudaMemset(h->send_d, 0, sizeof(double) * per), "cudaMemset");
@@ -784,11 +1122,15 @@ int moire_mcmc_init_nccl(moire_mcmc *h, const char id[128], const char *library_
             std::memcpy(u.internal, id, 128);
             void *comm = nullptr;
             h->nc(g_nccl.CommInitRank(&comm, h->world, u, h->rank), "ncclCommInitRank");
-            g_nccl_comm = comm;  // an earlier communicator stays alive: it may be in use
+            // the communicator this replaces goes away unless a live driver still holds it
+            if (g_nccl_comm && g_nccl_users == 0 && g_nccl.CommDestroy) g_nccl.CommDestroy(g_nccl_comm);
+            g_nccl_comm = comm;
             g_nccl_world = h->world;
             g_nccl_rank = h->rank;
+            g_nccl_users = 0;
         }
         h->nccl_comm = g_nccl_comm;
+        ++g_nccl_users;
     });
 }
 
@@ -813,7 +1155,7 @@ int moire_mcmc_init(moire_mcmc *h, int32_t *failed)
         double any = bad;
         if (h->world > 1)
         {
-            const int per = 2 * h->cmax + 1;
+            const int per = 2 * h->cmax + 2;
             h->host_allgather(h->send.data(), per, h->recv.data());
             any = 0.0;
             for (int r = 0; r < h->world; ++r) any += h->recv[(size_t)r * per];
@@ -822,6 +1164,8 @@ int moire_mcmc_init(moire_mcmc *h, int32_t *failed)
         h->initialised = any == 0.0;
         h->t_start = std::chrono::steady_clock::now();
         if (h->initialised) h->exchange_scalars();
+        h->stop_any = false;
+        if (h->initialised && !h->dev_mode) h->setup_device_ladder();
     });
 }
 
@@ -859,41 +1203,63 @@ int moire_mcmc_run(moire_mcmc *h, moire_progress_fn progress, void *ctx,
 {
     return guarded(h, [&] {
         if (!h->initialised) throw DriverError{MOIRE_ESTATE, "run before a successful moire_mcmc_init"};
-        const double limit = (h->prm.max_runtime > 0 && std::isfinite(h->prm.max_runtime))
+        // negative or non-finite: no limit; 0 stops at once, as `timer.elapsed() < 0` would
+        const double limit = (h->prm.max_runtime >= 0 && std::isfinite(h->prm.max_runtime))
                                  ? h->prm.max_runtime
                                  : std::numeric_limits<double>::infinity();
         h->t_start = std::chrono::steady_clock::now();
         h->elapsed_minutes_rank0 = 0.0;
+        h->local_stop = h->stop_any = false;
         // the reference compares whole minutes (Timer<..., std::chrono::minutes>, src/main.cpp:36);
         // rank 0's clock decides for every rank
         auto minutes = [&] { return std::floor(h->elapsed_minutes_rank0); };
-        bool stop = false;
-        int step = 0;
-        while (!stop && step < h->prm.burnin && minutes() < limit)
-        {
-            h->burnin_step(step);
-            ++step;
-            if (progress)
-                stop = progress(ctx, 0, step, h->posterior_burnin.back(), h->swap_indices[0]) != 0;
-        }
-        step = 0;
-        while (!stop && step < h->prm.samples && minutes() < limit)
-        {
-            h->sample_step(step);
-            ++step;
-            if (progress)
-                stop = progress(ctx, 1, step, h->posterior_sample.back(), h->swap_indices[0]) != 0;
-        }
-        if (max_runtime_reached) *max_runtime_reached = minutes() >= limit && step < h->prm.samples;
+        // With the ladder on the device the loop runs in batches: up to kBatch steps are queued,
+        // then one read-back brings their traces, rank 0's clock and every rank's stop word, the
+        // callback is told about each of those steps (with its own posterior and hot chain), and
+        // the stop / max_runtime decisions are taken -- on every rank from the same gathered words,
+        // so all ranks leave after the same step.  On the host ladder a batch is one step.
+        const int kBatch = h->dev_mode ? 32 : 1;
+        auto phase_loop = [&](int phase, int total) {
+            int step = 0;
+            while (!h->stop_any && step < total && minutes() < limit)
+            {
+                const int b0 = step;
+                const size_t s0 = h->swap_store.size();
+                do
+                {
+                    if (phase == 0) h->burnin_step(step);
+                    else h->sample_step(step);
+                    ++step;
+                } while (step < total && step - b0 < kBatch);
+                h->flush();
+                const auto &post = phase == 0 ? h->posterior_burnin : h->posterior_sample;
+                for (int s = b0; s < step && progress; ++s)
+                {
+                    const size_t si = s0 + (size_t)(s - b0);
+                    const int hot = si < h->swap_store.size() ? h->swap_store[si] : h->swap_indices[0];
+                    if (progress(ctx, phase, s + 1, post[post.size() - (size_t)(step - s)], hot) != 0)
+                    {
+                        h->local_stop = true;
+                        if (h->world == 1) h->stop_any = true;  // else: agreed through the next exchange
+                        break;
+                    }
+                }
+            }
+            return step;
+        };
+        phase_loop(0, h->prm.burnin);
+        const int sampled = phase_loop(1, h->prm.samples);
+        if (max_runtime_reached) *max_runtime_reached = minutes() >= limit && sampled < h->prm.samples;
         h->finalize();
         if (runtime_minutes) *runtime_minutes = minutes();
-        if (stop) throw DriverError{MOIRE_ESTATE, "interrupted by the progress callback"};
+        if (h->stop_any) throw DriverError{MOIRE_ESTATE, "interrupted by the progress callback"};
     });
 }
 
 int moire_mcmc_get_sizes(moire_mcmc *h, moire_mcmc_sizes *out)
 {
     return guarded(h, [&] {
+        h->flush();
         if (!out) throw DriverError{MOIRE_EINVAL, "null output"};
         out->num_chains = h->T;
         out->first_chain = h->first;
@@ -911,6 +1277,7 @@ int moire_mcmc_get_traces(moire_mcmc *h, double *llik_burnin, double *prior_burn
                           double *posterior_sample)
 {
     return guarded(h, [&] {
+        h->flush();
         copy_out(h->llik_burnin, llik_burnin);
         copy_out(h->prior_burnin, prior_burnin);
         copy_out(h->posterior_burnin, posterior_burnin);
@@ -925,6 +1292,7 @@ int moire_mcmc_get_ladder(moire_mcmc *h, int32_t *swap_store, int64_t *swap_acce
                           double *chain_temps)
 {
     return guarded(h, [&] {
+        h->flush();
         copy_out(h->swap_store, swap_store);
         copy_out(h->swap_acceptances, swap_acceptances);
         copy_out(h->swap_barriers, swap_barriers);
@@ -937,6 +1305,7 @@ int moire_mcmc_get_ladder(moire_mcmc *h, int32_t *swap_store, int64_t *swap_acce
 int moire_mcmc_get_hot(moire_mcmc *h, int32_t *hot)
 {
     return guarded(h, [&] {
+        h->flush();
         if (!hot) throw DriverError{MOIRE_EINVAL, "null output"};
         for (int c = 0; c < h->T; ++c) hot[c] = h->chain_hot[c];
     });
@@ -947,6 +1316,7 @@ int moire_mcmc_get_draws(moire_mcmc *h, int32_t *draw_step, double *allele_freqs
                          double *data_llik, double *lam_coi, uint64_t *latent)
 {
     return guarded(h, [&] {
+        h->flush();
         copy_out(h->draw_step, draw_step);
         copy_out(h->p_store, allele_freqs);
         copy_out(h->m_store, coi);
@@ -962,6 +1332,8 @@ int moire_mcmc_get_draws(moire_mcmc *h, int32_t *draw_step, double *allele_freqs
 int moire_mcmc_swap_pass(moire_mcmc *h, const double *chain_llik, int32_t step, int32_t is_burnin)
 {
     return guarded(h, [&] {
+        h->flush();
+        h->host_dirty = true;
         if (!chain_llik) throw DriverError{MOIRE_EINVAL, "null llik"};
         h->chain_llik.assign(chain_llik, chain_llik + h->T);
         if (h->swap_pass(step, is_burnin != 0)) h->push_local_temps();
@@ -981,6 +1353,8 @@ int moire_mcmc_set_ladder(moire_mcmc *h, const double *temp_gradient, const doub
                           int64_t num_swaps, int32_t even_swap)
 {
     return guarded(h, [&] {
+        h->flush();
+        h->host_dirty = true;
         const int T = h->T;
         if (temp_gradient) h->temp_gradient.assign(temp_gradient, temp_gradient + T);
         if (swap_barriers) h->swap_barriers.assign(swap_barriers, swap_barriers + (T - 1));
@@ -1007,6 +1381,8 @@ int moire_mcmc_set_local_scalars(moire_mcmc *h, const double *llik, const double
 int moire_mcmc_adapt_temp(moire_mcmc *h)
 {
     return guarded(h, [&] {
+        h->flush();
+        h->host_dirty = true;
         if (h->adapt_ladder()) h->push_local_temps();
     });
 }

@@ -63,10 +63,19 @@ constexpr int kPfHistWords = kPfCounters + 72;
 __constant__ unsigned short c_flat_class[12 * 64];
 __constant__ float c_flat_est[kSortBins];
 
+// EGF cells (k > 10) cost ~k cnt^2 / 2 (the band recurrence, likelihood.cuh): 16 widths x 4 ranges
+// of k share the 64 slots of row 11, so that the lanes of a chunk run (nearly) the same loops.
+__host__ __device__ inline int egf_k_range(int k) { return k <= 13 ? 0 : k <= 17 ? 1 : k <= 23 ? 2 : 3; }
+
 __device__ __forceinline__ int work_class_flat(int k, int m)
 {
-    int kk = k > kIeMax ? kIeMax + 1 : k;
-    int cnt = k > kIeMax ? m : m - k + 1;
+    int cnt = m - k + 1;
+    if (k > kIeMax)
+    {
+        cnt = cnt < 1 ? 1 : (cnt > 16 ? 16 : cnt);
+        return c_flat_class[(kIeMax + 1) * 64 + egf_k_range(k) * 16 + cnt - 1];
+    }
+    int kk = k;
     cnt = cnt < 1 ? 1 : (cnt > 64 ? 64 : cnt);
     if (kk < MOIRE_MERGE_K) kk = MOIRE_MERGE_K;
     return c_flat_class[kk * 64 + cnt - 1];
@@ -94,11 +103,24 @@ inline void build_flat_classes(std::vector<unsigned short> &rank, std::vector<fl
     std::stable_sort(cs.begin(), cs.end(), [](const C &a, const C &b) { return a.est > b.est; });
     rank.assign(12 * 64, 0);
     est_of_rank.assign(kSortBins, 0.f);
-    for (int cnt = 1; cnt <= 64; ++cnt)
     {
-        // EGF: ~k m^2 with k > 10; always ahead of the inclusion-exclusion classes
-        rank[(kIeMax + 1) * 64 + cnt - 1] = (unsigned short)(64 - cnt);
-        est_of_rank[64 - cnt] = 16.f * (float)cnt * (float)cnt + 1e6f;
+        // EGF classes: ranks 0..63 (their own section of the list, ahead of the inclusion-exclusion
+        // classes), heaviest first among themselves
+        struct E { int slot; double est; };
+        std::vector<E> es;
+        const double kmid[4] = {12.0, 15.5, 20.0, 30.0};
+        for (int kr = 0; kr < 4; ++kr)
+            for (int cnt = 1; cnt <= 16; ++cnt)
+            {
+                const double w = cnt < 16 ? cnt : 24.0;  // the last slot also holds everything wider
+                es.push_back({kr * 16 + cnt - 1, kmid[kr] * (w * (w + 1.0) / 2.0 * 7.0 + 20.0) + 40.0 * w + 600.0});
+            }
+        std::stable_sort(es.begin(), es.end(), [](const E &a, const E &b) { return a.est > b.est; });
+        for (size_t i = 0; i < es.size(); ++i)
+        {
+            rank[(kIeMax + 1) * 64 + es[i].slot] = (unsigned short)i;
+            est_of_rank[i] = (float)es[i].est;
+        }
     }
     for (size_t i = 0; i < cs.size(); ++i)
     {

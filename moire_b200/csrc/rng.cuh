@@ -77,7 +77,7 @@ MOIRE_HD void philox4x32_10(const uint32_t ctr[4], uint32_t k0, uint32_t k1, uin
 }
 
 #if defined(__CUDACC__)
-__device__ __noinline__ uint4 philox_block_device(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+static __device__ __noinline__ uint4 philox_block_device(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                   uint32_t k0, uint32_t k1)
 {
     const uint32_t ctr[4] = {c0, c1, c2, c3};

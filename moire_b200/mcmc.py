@@ -175,7 +175,7 @@ class MCMC:
         mr = float(max_runtime)
         mp = _lib.MoireMcmcParams(int(thin), int(burnin), int(samples), int(bool(adapt_temp)),
                                   int(pre_adapt_steps), int(temp_adapt_steps), self.max_tries,
-                                  int(self.record_latent), mr if math.isfinite(mr) else 0.0)
+                                  int(self.record_latent), mr if math.isfinite(mr) else -1.0)
         h = C.c_void_p()
         rc = self.lib.moire_mcmc_create(C.byref(d), C.byref(p), C.byref(mp), _ptr(self.temps0),
                                         self.T, rank, world_size, device, seed, C.byref(h))

@@ -290,6 +290,10 @@ class Ref:
         L.ref_mcmc_prior.argtypes = [vp]
         L.ref_mcmc_time_burnin.restype = d
         L.ref_mcmc_time_burnin.argtypes = [vp, i, i, i]
+        L.ref_eval_count.restype = C.c_ulonglong
+        L.ref_eval_count.argtypes = []
+        L.ref_eval_count_reset.restype = None
+        L.ref_eval_count_reset.argtypes = []
         L.ref_mcmc_summary.restype = i
         L.ref_mcmc_summary.argtypes = [vp, vp, vp, vp, vp, vp, i, vp]
         L.ref_mcmc_coi_draws.restype = i
@@ -498,6 +502,13 @@ class Ref:
         """Wall seconds of `steps` MCMC::burnin steps after `warmup` untimed ones, driven the way
         src/main.cpp:54-70 drives them."""
         return float(self.lib.ref_mcmc_time_burnin(h, int(first_step), int(warmup), int(steps)))
+
+    def eval_count(self):
+        """Non-missing calculate_genotype_likelihood evaluations since eval_count_reset()."""
+        return int(self.lib.ref_eval_count())
+
+    def eval_count_reset(self):
+        self.lib.ref_eval_count_reset()
 
     def omp_max_threads(self):
         return int(self.lib.ref_omp_max_threads())

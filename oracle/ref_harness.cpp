@@ -543,6 +543,43 @@ double ref_mcmc_time_burnin(void *h, int first_step, int warmup, int steps)
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// ---- evaluation counter ("count them exactly on both sides") ----------------------
+// Chain::calculate_genotype_likelihood (src/chain.cpp:1114-1134) asks
+// GenotypingData::is_missing(locus, sample) exactly once per call, nowhere else on the sampler's
+// path, and evaluates the cell iff the answer is false.  The reference sources stay untouched: the
+// linker redirects that one call (-Wl,--wrap, oracle/Makefile) through the function below, which
+// forwards to the real member and counts the non-missing answers per OpenMP thread.
+namespace
+{
+struct alignas(64) EvalSlot { unsigned long long n; };
+EvalSlot g_eval_slots[1024];
+}
+bool __real__ZNK14GenotypingData10is_missingEii(const GenotypingData *, int, int);
+bool __wrap__ZNK14GenotypingData10is_missingEii(const GenotypingData *self, int locus, int sample)
+{
+    const bool missing = __real__ZNK14GenotypingData10is_missingEii(self, locus, sample);
+#ifdef _OPENMP
+    const int slot = omp_get_thread_num() & 1023;
+#else
+    const int slot = 0;
+#endif
+    g_eval_slots[slot].n += missing ? 0ull : 1ull;
+    return missing;
+}
+
+// Non-missing cell likelihood evaluations since the last reset (all threads).
+unsigned long long ref_eval_count()
+{
+    unsigned long long tot = 0;
+    for (const auto &sl : g_eval_slots) tot += sl.n;
+    return tot;
+}
+
+void ref_eval_count_reset()
+{
+    for (auto &sl : g_eval_slots) sl.n = 0;
+}
+
 int ref_omp_max_threads()
 {
 #ifdef _OPENMP

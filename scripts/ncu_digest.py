@@ -26,7 +26,15 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(src.splitlines()))
 hdr, data = rows[1], rows[2:]
 ix = {h: i for i, h in enumerate(hdr)}
-data = [r for r in data if len(r) == len(hdr)]
+data = [r for r in data if len(r) == len(hdr) and r[ix["# Samples"]].isdigit()]
+if "--first" in sys.argv:   # several captured launches: keep the first kernel's rows only
+    seen, keep = set(), []
+    for r in data:
+        if r[ix["Address"]] in seen:
+            break
+        seen.add(r[ix["Address"]])
+        keep.append(r)
+    data = keep
 ts = sum(int(r[ix["# Samples"]]) for r in data)
 ti = sum(int(r[ix["Instructions Executed"]]) for r in data)
 print("SASS instructions", len(data), "samples", ts, "warp instr", ti)

@@ -63,6 +63,55 @@ def test_single_chain_stores_every_draw_and_is_reproducible():
     assert not np.array_equal(a["chains"][0]["llik_sample"], c["chains"][0]["llik_sample"])
 
 
+@pytest.mark.parametrize("T,latent", [(5, True), (1, False)])
+def test_device_ladder_reproduces_host_ladder(monkeypatch, T, latent):
+    """Row f3: swap pass, barrier accumulators, traces, hot flags and the stored draws on the device
+    (csrc/ladder.cu; one graph launch per step, batched read-back) against the same run with the
+    ladder on the host after a per-step read-back (MOIRE_B200_HOST_LADDER=1, round 1's path, itself
+    pinned to the reference's MCMC::swap_chains by tests/test_mcmc_driver.py).  Same streams, one
+    swap_pair() for both: every integer result identical; floating results identical or, where the
+    device's exp/log feed the barrier sums and through them the adapted ladder, equal to rounding."""
+    from moire_b200.mcmc import run_mcmc
+    d = small_data(N=50)
+    kw = dict(burnin=90, samples_per_chain=45, pt_chains=T, thin=2, record_latent_genotypes=latent,
+              pre_adapt_steps=10, temp_adapt_steps=7, verbose=False, seed=6)
+    dev = run_mcmc(d, d["is_missing"], **kw)["chains"][0]
+    monkeypatch.setenv("MOIRE_B200_HOST_LADDER", "1")
+    host = run_mcmc(d, d["is_missing"], **kw)["chains"][0]
+    assert len(dev["swap_store"]) == len(host["swap_store"]) == (135 if T > 1 else 45)
+    for k in ("swap_store", "swap_acceptances", "coi", "observed_coi"):
+        assert np.array_equal(np.asarray(dev[k]), np.asarray(host[k])), k
+    for k in ("llik_burnin", "prior_burnin", "posterior_burnin", "llik_sample", "prior_sample",
+              "posterior_sample", "lam_coi", "temp_gradient", "swap_barriers", "eps_neg", "eps_pos",
+              "relatedness", "data_llik"):
+        a, b = np.asarray(dev[k], float), np.asarray(host[k], float)
+        assert a.shape == b.shape and np.allclose(a, b, rtol=1e-10, atol=1e-12, equal_nan=True), k
+    assert len(dev["lam_coi"]) == len(host["lam_coi"]) and (T > 1 or len(dev["lam_coi"]) == 23)
+    for la, lb in zip(dev["allele_freqs"], host["allele_freqs"]):
+        assert np.allclose(np.asarray(la), np.asarray(lb), rtol=1e-10)
+    if latent:
+        assert dev["latent_genotypes"] == host["latent_genotypes"]
+    assert dev["acceptance_rates"][0]["coi_accept"].tolist() == host["acceptance_rates"][0]["coi_accept"].tolist()
+
+
+def test_progress_and_stop_with_the_ladder_on_the_device():
+    """moire_mcmc_run in batches: the callback still hears about every step, each with that step's
+    own posterior (the trace entry), and a stop request ends the run at the end of its batch."""
+    from moire_b200.engine import MoireError
+    from moire_b200.mcmc import run_mcmc
+    d = small_data(N=30)
+    seen = []
+    res = run_mcmc(d, d["is_missing"], burnin=70, samples_per_chain=10, pt_chains=3, verbose=False,
+                   seed=2, progress=lambda ph, st, post, hot: seen.append((ph, st, post, hot)) and False)
+    ch = res["chains"][0]
+    assert [(p, s) for p, s, _, _ in seen] == [(0, s) for s in range(1, 71)] + [(1, s) for s in range(1, 11)]
+    assert np.array_equal([x[2] for x in seen[:70]], ch["posterior_burnin"])
+    assert np.array_equal([x[3] for x in seen], ch["swap_store"])
+    with pytest.raises(MoireError, match="interrupted"):
+        run_mcmc(d, d["is_missing"], burnin=70, samples_per_chain=10, pt_chains=3, verbose=False, seed=2,
+                 progress=lambda ph, st, post, hot: ph == 0 and st == 40)
+
+
 def test_posterior_agrees_with_reference_sampler():
     """Posterior COI / allele-frequency / error-rate summaries from the engine against the
     reference's own C++ sampler on the same data, three reference seeds and six engine seeds: the
@@ -217,7 +266,10 @@ def test_acceptance_rates_and_adapted_scales_track_the_reference():
     # the SALT sampler (update_p): per-allele attempts, acceptance rate and adapted scale
     A = pk.num_alleles
     sel = np.arange(rp_att.shape[1])[None, :] < A[:, None]
-    assert rp_att[sel].sum() == dg["p_attempt"][:, :rp_att.shape[1]][sel].sum() == steps * A.sum()
+    # A_j proposals per locus and step, fewer where a proposal fell below 1e-12 and the locus was
+    # left early (src/chain.cpp:503-518)
+    for att in (rp_att[sel].sum(), dg["p_attempt"][:, :rp_att.shape[1]][sel].sum()):
+        assert 0.8 * steps * A.sum() < att <= steps * A.sum(), att
     ra = rp_acc[sel].sum() / rp_att[sel].sum()
     ea = dg["p_accept"][:, :rp_att.shape[1]][sel].sum() / dg["p_attempt"][:, :rp_att.shape[1]][sel].sum()
     assert abs(ra - ea) < 0.03 and 0.15 < ea < 0.35, (ra, ea)

