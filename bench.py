@@ -242,7 +242,8 @@ def timed_workload(name, T, steps, warmup, world, rank, local, dev, seed):
                              f"{int(pk.num_alleles.max())}, {T} temperatures, max_coi {wl['model']['max_coi']}",
                     n_gpus=world, steps=steps, warmup=warmup, value=1e3 / ms_step, unit=UNIT,
                     ms_per_step=ms_step, per_rank_ms_per_step=[round(m / steps, 4) for m in ms_all],
-                    likelihood_evals_per_sec=evals / (max(ms_all) * 1e-3), ladder_consistent=consistent)
+                    likelihood_evals_per_sec=evals / (max(ms_all) * 1e-3), ladder=mc.mode(),
+                    ladder_consistent=consistent)
     finally:
         mc.close()
 
@@ -312,6 +313,7 @@ def our_arm(args, wl):
     sampler.stop_flag.set()
     sampler.join(2.0)
     ev1, l1 = eng.counters()
+    ladder_mode = mc.mode()
     digest = ladder_digest(mc)          # also the read-back of everything the steps left queued
     # ---- breakdown pass: the next K steps with an event pair around every update kind and every
     # evaluator launch (a graph cannot hold events between its kernels, so these steps go out as
@@ -444,10 +446,9 @@ def our_arm(args, wl):
                 warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True,
                 scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                 config=config_of(wl, args), exchange=exchange,
-                parallelism=f"temperature ladder sharded over {world} GPU(s); swap pass on the device, "
-                            "one graph launch per step",
+                parallelism=f"temperature ladder sharded over {world} GPU(s)",
                 cache="L2 flushed (256 MiB memset) before every timed step",
-                ladder_consistent=ladder_consistent, per_rank_ms_per_step=[round(x, 4) for x in per_rank_ms],
+                ladder=ladder_mode, ladder_consistent=ladder_consistent, per_rank_ms_per_step=[round(x, 4) for x in per_rank_ms],
                 clocks=sampler.summary(), e2e=e2e,
                 gpu_launches=launches_total, roofline=roofline, cpu_baseline=cpu,
                 likelihood_evals_per_sec=evals_total / (dev_ms_max * 1e-3),

@@ -119,6 +119,11 @@ int moire_mcmc_finalize(moire_mcmc *h);
 int moire_mcmc_run(moire_mcmc *h, moire_progress_fn progress, void *ctx,
                    int32_t *max_runtime_reached, double *runtime_minutes);
 
+/* Where the ladder of this driver lives (1 = on the device, 0 = on the host) and whether its steps
+ * replay a captured CUDA graph (0 before the first step, or when a library in the step -- the
+ * NCCL exchange -- refused capture and the step goes out as plain launches). */
+int moire_mcmc_get_mode(moire_mcmc *h, int32_t *device_ladder, int32_t *step_graph);
+
 /* ---- results (src/main.cpp:138-189) ---------------------------------------------------------- */
 typedef struct moire_mcmc_sizes
 {

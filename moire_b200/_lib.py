@@ -77,6 +77,7 @@ MCMC_SYMBOLS = {
     "moire_mcmc_finalize": (C.c_int, [vp]),
     "moire_mcmc_run": (C.c_int, [vp, PROGRESS_FN, vp, C.POINTER(i32), C.POINTER(dbl)]),
     "moire_mcmc_get_sizes": (C.c_int, [vp, C.POINTER(MoireMcmcSizes)]),
+    "moire_mcmc_get_mode": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32)]),
     "moire_mcmc_get_traces": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "moire_mcmc_get_ladder": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "moire_mcmc_get_hot": (C.c_int, [vp, vp]),

@@ -336,7 +336,8 @@ struct moire_engine
     moire::SFlat sf{};
     DevBuf<moire::Proposal> sf_prop;
     DevBuf<int> sf_m;
-    DevBuf<double> sf_logr, sf_log1mr, sf_adj;
+    DevBuf<double> sf_adj;
+    DevBuf<moire::SampleScal> sf_ss, pf_ss;
     DevBuf<unsigned long long> sf_lat;
     DevBuf<moire::EpsLogs> sf_elogs;
     DevBuf<unsigned char> missing;
@@ -369,7 +370,7 @@ struct moire_engine
         p_acc.release(); p_att.release(); active.release(); logC.release(); lgam.release();
         pf_list.release(); pf_hist.release(); pf_Tcur.release(); pf_Tnew.release(); pf_pprop.release();
         pf_round.release(); pf_nonmiss.release();
-        sf_prop.release(); sf_m.release(); sf_logr.release(); sf_log1mr.release(); sf_lat.release(); sf_adj.release(); sf_elogs.release();
+        sf_prop.release(); sf_m.release(); sf_ss.release(); pf_ss.release(); sf_lat.release(); sf_adj.release(); sf_elogs.release();
         lgadj.release(); cellT.release(); cellO.release(); persample.release(); p.release();
         p_sd.release(); perchain.release(); scratchN.release();
         if (v.trace && std::getenv("MOIRE_B200_TRACE"))
@@ -520,6 +521,7 @@ struct moire_engine
         v.eps_pos = ps + 3 * TN; v.eps_neg = ps + 4 * TN;
         v.sd_eps_neg = ps + 5 * TN; v.sd_eps_pos = ps + 6 * TN; v.sd_r = ps + 7 * TN; v.sd_mr = ps + 8 * TN;
         v.pr_eps_neg = ps + 9 * TN; v.pr_eps_pos = ps + 10 * TN; v.pr_coi = ps + 11 * TN; v.pr_r = ps + 12 * TN;
+        v.odds = ps + 13 * TN;
         int *ac = acc6.ptr;
         v.acc_eps_neg = ac + 0 * TN; v.acc_eps_pos = ac + 1 * TN; v.acc_m = ac + 2 * TN;
         v.acc_r = ac + 3 * TN; v.acc_mr = ac + 4 * TN; v.acc_samples = ac + 5 * TN;
@@ -576,10 +578,11 @@ struct moire_engine
             pf.pprop = pf_pprop.ptr; pf.round = pf_round.ptr; pf.nonmiss = pf_nonmiss.ptr;
             p_smem = 0;  // the fused kernel's per-block arrays are not needed
             // the per-sample updates share the list, the histogram and the two term arrays
-            sf_prop.alloc(TN); sf_m.alloc(TN); sf_logr.alloc(TN); sf_log1mr.alloc(TN);
+            sf_prop.alloc(TN); sf_m.alloc(TN); sf_ss.alloc(TN); pf_ss.alloc(TN);
+            pf.ss = pf_ss.ptr;
             sf_lat.alloc(TNL); sf_adj.alloc(TNL); sf_elogs.alloc(TN * (size_t)v.nA);
-            sf.prop = sf_prop.ptr; sf.m_new = sf_m.ptr; sf.log_r_new = sf_logr.ptr;
-            sf.log_1mr_new = sf_log1mr.ptr; sf.lat = sf_lat.ptr; sf.adj = sf_adj.ptr; sf.elogs = sf_elogs.ptr;
+            sf.prop = sf_prop.ptr; sf.m_new = sf_m.ptr; sf.ss = sf_ss.ptr;
+            sf.lat = sf_lat.ptr; sf.adj = sf_adj.ptr; sf.elogs = sf_elogs.ptr;
             sf.O = pf_Tcur.ptr; sf.Tn = pf_Tnew.ptr;
         }
         cudaDeviceProp prop;
@@ -661,7 +664,7 @@ struct moire_engine
         pending.clear();
     }
 
-    static size_t pf_eval_smem() { return (128 + moire::scratch_doubles(moire::kEvalThreads)) * sizeof(double); }
+    size_t pf_eval_smem() const { return moire::pf_eval_smem_doubles(v.max_coi) * sizeof(double); }
     int flat_grid = 0;  // persistent evaluator grid: resident blocks of the device
 
     void launch_flat_eval(const moire::FlatSrc &src)
@@ -694,7 +697,7 @@ struct moire_engine
         FlatSrc src{};
         src.list = pf.list; src.bounds = pf.hist + kPfScalars;
         src.p = pf.pprop; src.p_stride = v.AP; src.out_locus_major = 1;
-        src.m = v.m; src.log_r = v.log_r; src.log_1mr = v.log_1mr;
+        src.ss = pf.ss; src.binom_rows = v.max_coi;
         src.round_flags = pf.round; src.out = pf.Tnew;
         launches += 2;  // prepare, scan, scatter (the caller counted one)
         for (int rep = 0; rep < amax_alleles; ++rep)
@@ -725,7 +728,7 @@ struct moire_engine
         FlatSrc src{};
         src.list = pf.list; src.bounds = pf.hist + kPfScalars; src.counter = pf.hist + kPfCounters;
         src.p = v.p; src.p_stride = v.AP; src.out_locus_major = 0;
-        src.m = sf.m_new; src.log_r = sf.log_r_new; src.log_1mr = sf.log_1mr_new;
+        src.ss = sf.ss; src.binom_rows = v.max_coi;
         src.round_flags = nullptr; src.out = sf.Tn;
         launch_flat_eval(src);
         k_sf_decide<KIND><<<(unsigned)(((size_t)v.T * v.N + 7) / 8), 256, 0, stream>>>(v, sf, iteration);

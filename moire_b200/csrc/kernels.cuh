@@ -47,7 +47,7 @@ constexpr int kSortBins = 12 * 64;   // (min(k, 11), m - k + 1) work classes
 struct Proposal
 {
     int valid, adapt, m_new, accept;
-    double r_new, en_new, ep_new, log_r, log_1mr;
+    double r_new, en_new, ep_new, log_r, log_1mr, odds;
     double adj;
     double pr_en_new, pr_ep_new, pr_coi_new, pr_r_new, dprior;
     double logu;
@@ -192,7 +192,7 @@ __device__ __forceinline__ int block_sort_cells(int ncell, ClassFn cls, unsigned
 // cells.  Work is handed out dynamically, heaviest first, in units of one chunk of 32
 // one-thread cells or one cooperatively evaluated cell (one warp: draws resp. subsets across
 // lanes): `next` is a shared counter the caller has zeroed before its last barrier.
-// fetch(cell, lat, prow, m, log_r, log_1mr) supplies a cell's inputs; out[cell] gets the term.
+// fetch(cell, lat, prow, m, rel) supplies a cell's inputs; out[cell] gets the term.
 // scr: kScratchSlots rows of blockDim.x + 1 doubles.  No block barrier inside.
 template <class Fetch>
 __device__ __forceinline__ void block_eval_transmissions(const unsigned short *order, int nwork,
@@ -226,23 +226,21 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
         unsigned long long lat;
         const double *prow;
         int m;
-        double log_r, log_1mr;
+        Rel rel;
         const bool coop_egf = u >= u1 && u < u2, coop_ie = u >= u3 && u < u4;
         if (coop_egf || coop_ie)
         {
             const int cell = order[coop_egf ? 32 * egf_chunks + (u - u1)
                                             : n_egf + 32 * heavy_chunks + (u - u3)];
-            fetch(cell, lat, prow, m, log_r, log_1mr);
+            fetch(cell, lat, prow, m, rel);
             const int k = __popcll(lat);
             double T;
             if (k > m)
                 T = NAN;
             else if (coop_egf)
-                T = transmission_ll_egf_coop(lat, prow, m, log_r, log_1mr, allow_rel, scr + warp * 32,
-                                             ST, lgam);
+                T = transmission_ll_egf_coop(lat, prow, m, rel, allow_rel, scr + warp * 32, ST, lgam, nullptr);
             else
-                T = transmission_ll_coop(lat, prow, m, log_r, log_1mr, allow_rel, scr + warp * 32,
-                                         ST, lgam);
+                T = transmission_ll_coop(lat, prow, m, rel, allow_rel, scr + warp * 32, ST, lgam, nullptr);
             if (lane == 0) out[cell] = T;
         }
         else
@@ -267,9 +265,10 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
             if (w < end)
             {
                 const int cell = order[w];
-                fetch(cell, lat, prow, m, log_r, log_1mr);
-                out[cell] = transmission_ll(lat, prow, m, log_r, log_1mr, allow_rel, scr + tid, ST,
-                                            lgam, callers);
+                fetch(cell, lat, prow, m, rel);
+                double pv[kGather];
+                gather_freqs(lat, prow, pv);
+                out[cell] = transmission_ll(lat, prow, pv, m, rel, allow_rel, scr + tid, ST, lgam, nullptr, callers);
             }
         }
         __syncwarp();
@@ -301,6 +300,7 @@ __device__ __forceinline__ Proposal draw_sample_proposal(const View &v, int t, i
     P.ep_new = v.eps_pos[si];
     P.log_r = v.log_r[si];
     P.log_1mr = v.log_1mr[si];
+    P.odds = v.odds[si];
     P.adj = 0.0;
     P.dprior = 0.0;
     P.pr_en_new = P.pr_ep_new = P.pr_coi_new = P.pr_r_new = 0.0;
@@ -368,6 +368,7 @@ __device__ __forceinline__ Proposal draw_sample_proposal(const View &v, int t, i
         P.dprior += P.pr_r_new - v.pr_r[si];
         P.log_r = cold_log(P.r_new);
         P.log_1mr = cold_log(1.0 - P.r_new);
+        P.odds = P.r_new / (1.0 - P.r_new);
     }
     if (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
     {
@@ -423,6 +424,7 @@ __device__ __forceinline__ void decide_sample(const View &v, Proposal &P, int t,
             v.r[si] = P.r_new;
             v.log_r[si] = P.log_r;
             v.log_1mr[si] = P.log_1mr;
+            v.odds[si] = P.odds;
             v.pr_r[si] = P.pr_r_new;
         }
         if (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES)
@@ -569,15 +571,15 @@ __global__ void __launch_bounds__(kThreads, MOIRE_MIN_BLOCKS_S * (256 / kThreads
             return work_class(__popcll(s_nlat[cell]), P.m_new);
         };
         const int nwork = block_sort_cells(ncell, cls, s_hist, s_order, s_tmp);
-        auto fetch = [&](int cell, unsigned long long &lat, const double *&prow, int &m,
-                         double &log_r, double &log_1mr) {
+        auto fetch = [&](int cell, unsigned long long &lat, const double *&prow, int &m, Rel &rel) {
             const int sl = cell / L, j = cell - sl * L;
             const Proposal &P = s_prop[sl];
             lat = s_nlat[cell];
             prow = v.p + ((size_t)t * L + j) * v.AP;
             m = P.m_new;
-            log_r = P.log_r;
-            log_1mr = P.log_1mr;
+            rel.log_r = P.log_r;
+            rel.log_1mr = P.log_1mr;
+            rel.odds = P.odds;
         };
         block_eval_transmissions(s_order, nwork, (int)s_tmp[33], (int)s_tmp[34], fetch, s_T, s_qs,
                                  s_lgam, v.allow_rel != 0, &s_next);
@@ -746,14 +748,14 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 512 ? 1 : MOIRE_MIN_BLOCKS_P *
     };
     const int nwork = block_sort_cells(N, cls, s_hist, s_order, s_tmp);
     const int n_egf = (int)s_tmp[33], coop_end = (int)s_tmp[34];
-    auto fetch = [&](int i, unsigned long long &lat, const double *&prow_, int &m, double &log_r,
-                     double &log_1mr) {
+    auto fetch = [&](int i, unsigned long long &lat, const double *&prow_, int &m, Rel &rel) {
         const size_t si = (size_t)t * N + i;
         lat = s_lat[i];
         prow_ = s_pprop;
         m = s_m[i];
-        log_r = v.log_r[si];
-        log_1mr = v.log_1mr[si];
+        rel.log_r = v.log_r[si];
+        rel.log_1mr = v.log_1mr[si];
+        rel.odds = v.odds[si];
     };
 
     unsigned long long evals = 0;
@@ -1034,8 +1036,12 @@ __global__ void __launch_bounds__(kThreads)
         const size_t si = (size_t)t * v.N + i;
         EpsLogs el;
         build_eps_logs(el, v.eps_neg[si], v.eps_pos[si], v.max_eps_neg, v.max_eps_pos, v.nall[j]);
-        T = transmission_ll(v.latent[gi], v.p + ((size_t)t * v.L + j) * v.AP, v.m[si], v.log_r[si],
-                            v.log_1mr[si], v.allow_rel != 0, s_qs + tid, kThreads + 1, s_lgam, callers);
+        const Rel rel{v.log_r[si], v.log_1mr[si], v.odds[si]};
+        const double *prow = v.p + ((size_t)t * v.L + j) * v.AP;
+        double pv[kGather];
+        gather_freqs(v.latent[gi], prow, pv);
+        T = transmission_ll(v.latent[gi], prow, pv, v.m[si], rel, v.allow_rel != 0, s_qs + tid,
+                            kThreads + 1, s_lgam, nullptr, callers);
         O = observation_ll(v.latent[gi], v.obs[cell], v.nall[j], el);
     }
     v.cellT[gi] = T;
@@ -1054,6 +1060,7 @@ __global__ void k_eval_priors(const View v, const int chain_sel, const int use_a
     const double lambda = v.mean_coi[t];
     v.log_r[si] = log(v.r[si]);
     v.log_1mr[si] = log(1.0 - v.r[si]);
+    v.odds[si] = v.r[si] / (1.0 - v.r[si]);
     v.pr_eps_neg[si] = dbeta_log(v.eps_neg[si], v.eps_neg_a, v.eps_neg_b, v.eps_neg_lbeta);
     v.pr_eps_pos[si] = dbeta_log(v.eps_pos[si], v.eps_pos_a, v.eps_pos_b, v.eps_pos_lbeta);
     v.pr_r[si] = dbeta_log(v.r[si], v.r_a, v.r_b, v.r_lbeta);

@@ -282,6 +282,39 @@ __device__ __forceinline__ void egf_band(uint64_t latent, const double *prow, do
     }
 }
 
+// What a cell needs of its sample's relatedness r: log r, log(1 - r) (the reference's terms,
+// src/chain.cpp:903-914) and the odds r / (1 - r) that the linear-domain mixture runs on.
+struct Rel
+{
+    double log_r, log_1mr, odds;
+};
+
+// x^n, n >= 0, by square and multiply.
+__device__ __forceinline__ double pow_uint(double x, int n)
+{
+    // n < 128 (a COI): seven rounds, no branches
+    double r = (n & 1) ? x : 1.0;
+#pragma unroll
+    for (int b = 1; b < 7; ++b)
+    {
+        x = __dmul_rn(x, x);
+        const double rx = __dmul_rn(r, x);
+        r = (n >> b) & 1 ? rx : r;
+    }
+    return r;
+}
+
+// m log(total) + log(s), s > 0: ONE logarithm, of total^m * s, while total^m is comfortably a normal
+// number (it nearly always is: total is a sum of allele frequencies, m a COI), else the two
+// logarithms.  Which form runs depends on (total, m) only, so every evaluator takes the same one for
+// a given cell.  The two differ by rounding (~1e-16 relative).
+__device__ __forceinline__ double log_total_pow_times(double total, int m, double s)
+{
+    const double tm = pow_uint(total, m);
+    if (tm >= 1e-250) return hot_log(__dmul_rn(tm, s));
+    return __dadd_rn(__dmul_rn((double)m, cold_log(total)), cold_log(s));
+}
+
 // Sampler::dbinom (src/sampler.cpp:44-50); lgam[i] = lgamma(i + 1).
 __device__ __forceinline__ double dbinom_log(int x, int size, double log_p, double log_1mp,
                                              const double *lgam)
@@ -291,46 +324,55 @@ __device__ __forceinline__ double dbinom_log(int x, int size, double log_p, doub
     return __dadd_rn(lp, lc);
 }
 
-// Relatedness mixture + log-sum-exp (src/chain.cpp:903-920, src/mcmc_utils.h:382-397), rolled.
-// On entry val[t * ST] = PAM(n = k + t), t < cnt; term i = 0..cnt-1 uses n = m - i, i.e.
-// t = cnt - 1 - i.  The terms are overwritten in place.
-__device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, int cnt,
-                                                      double log_total, double log_r,
-                                                      double log_1mr, const double *lgam)
+// Relatedness mixture (src/chain.cpp:903-920, src/mcmc_utils.h:382-397).
+// On entry val[t * ST] = PAM(n = k + t), t < cnt (val == nullptr: every PAM is exactly 0, the
+// k = 1 case); term i = 0..cnt-1 uses n = m - i, i.e. t = cnt - 1 - i.
+//
+// The same sum with the common factor of term i = 0 taken out instead of the largest term:
+//   sum_i C(m-1,i) r^i (1-r)^(m-1-i) total^(m-i) (1 - pam_i)
+//     = (1-r)^(m-1) total^m * S,   S = sum_i C(m-1,i) q^i (1 - pam_i),  q = odds / total,
+// so log(sum) = (m-1) log(1-r) + log(total^m S): one division and one logarithm per CELL in place
+// of one log and one exp per TERM plus log(total) (round 1: 37 % of the evaluator's instructions
+// went there; round 2 dropped the exp and the second log: -60 instructions per cell).  S has only
+// positive terms (no cancellation) and starts at 1 - pam_0 >= eps; the weights stay finite while
+// q^(cnt-1) <= 2^850 (C(m-1,i) < 2^124), otherwise the reference's log-sum-exp form below runs.
+// Difference from the reference's order of operations: rounding level (<= ~1e-14 relative,
+// tolerance 1e-9).  binom_s: rows [m - 1][i < kBinomCols] of g_binom staged in
+// shared memory by the caller (or nullptr).
+constexpr int kBinomCols = 16;
+__device__ __noinline__ double relatedness_mixture(const double *val, int ST, int m, int cnt,
+                                                   double total, const Rel rel, const double *lgam,
+                                                   const double *binom_s)
 {
-    // The same sum with the common factor of term i = 0 taken out instead of the largest term:
-    //   sum_i C(m-1,i) r^i (1-r)^(m-1-i) total^(m-i) (1 - pam_i)
-    //     = (1-r)^(m-1) total^m * S,   S = sum_i C(m-1,i) q^i (1 - pam_i),  q = r / ((1-r) total)
-    // so log(sum) = (m-1) log(1-r) + m log(total) + log(S): one exp and one log per cell in place
-    // of one log and one exp per TERM (they were 37 % of the evaluator's instructions).  S has
-    // only positive terms (no cancellation) and starts at 1 - pam_0 >= eps; the weights stay
-    // finite while |log q| (cnt-1) <= 600 (C <= 2^63), otherwise the log-sum-exp form below runs.
-    // Difference from the reference's order of operations: rounding level (<= ~1e-14 relative,
-    // tolerance 1e-9).
-    if (cnt > 1)
+    const double lead = __dmul_rn((double)(m - 1), rel.log_1mr);
+    if (cnt == 1)
     {
-        const double lq = __dsub_rn(__dsub_rn(log_r, log_1mr), log_total);
-        if (fabs(lq) * (double)(cnt - 1) <= 600.0)
-        {
-            const double q = exp(lq);
-            const double *cb = g_binom + (m - 1) * (kMaxCoi + 1);
-            double qi = 1.0, S = 0.0;
-            for (int i = 0; i < cnt; ++i)  // i ascending, as the reference sums; t = cnt - 1 - i
-            {
-                const double pam = clamp_pam(val[(cnt - 1 - i) * ST]);
-                S = __dadd_rn(S, __dmul_rn(__dmul_rn(cb[i], qi), __dsub_rn(1.0, pam)));
-                qi = __dmul_rn(qi, q);
-            }
-            const double lead = __dadd_rn(__dmul_rn((double)(m - 1), log_1mr),
-                                          __dmul_rn((double)m, log_total));
-            return __dadd_rn(lead, hot_log(S));
-        }
+        // m == k: the single term i = 0 (its binomial log-pmf is (m-1) log(1-r))
+        const double pam = val ? clamp_pam(val[0]) : 0.0;
+        return __dadd_rn(lead, log_total_pow_times(total, m, __dsub_rn(1.0, pam)));
     }
-    // the reference's log-sum-exp form (val[] is left untouched: the terms are recomputed for the sum)
+    const double q = __ddiv_rn(rel.odds, total);
+    const int e2 = ((__double2hiint(q) >> 20) & 0x7ff) - 1022;  // q < 2^e2 (NaN / inf: 1025)
+    if ((cnt - 1) * max(e2, 0) <= 850)
+    {
+        const double *cb = g_binom + (m - 1) * (kMaxCoi + 1);
+        const double *cs = binom_s ? binom_s + (m - 1) * kBinomCols : cb;
+        double qi = 1.0, S = 0.0;
+        for (int i = 0; i < cnt; ++i)  // i ascending, as the reference sums; t = cnt - 1 - i
+        {
+            const double pam = val ? clamp_pam(val[(cnt - 1 - i) * ST]) : 0.0;
+            const double c = i < kBinomCols ? cs[i] : cb[i];
+            S = __dadd_rn(S, __dmul_rn(__dmul_rn(c, qi), __dsub_rn(1.0, pam)));
+            qi = __dmul_rn(qi, q);
+        }
+        return __dadd_rn(lead, log_total_pow_times(total, m, S));
+    }
+    // the reference's log-sum-exp form (the terms are recomputed for the sum)
+    const double log_total = cold_log(total);
     auto term = [&](int t) -> double {
         const int i = cnt - 1 - t;
-        const double pr = dbinom_log(i, m - 1, log_r, log_1mr, lgam);
-        const double pam = clamp_pam(val[t * ST]);
+        const double pr = dbinom_log(i, m - 1, rel.log_r, rel.log_1mr, lgam);
+        const double pam = val ? clamp_pam(val[t * ST]) : 0.0;
         const double i_res = __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)(m - i)));
         return __dadd_rn(pr, i_res);
     };
@@ -341,7 +383,6 @@ __device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, i
         mx = (mx < v) ? v : mx;  // std::max_element semantics
     }
     if (mx == -INFINITY) return -INFINITY;
-    if (cnt == 1) return mx;  // exp(0) = 1, log(1) = 0: the sum is the term itself
     double sum = 0.0;
     for (int t = cnt - 1; t >= 0; --t)  // i ascending, as the reference sums
     {
@@ -349,6 +390,12 @@ __device__ __noinline__ double relatedness_mixture(double *val, int ST, int m, i
         sum = __dadd_rn(sum, dv == 0.0 ? 1.0 : cold_exp(dv));
     }
     return __dadd_rn(mx, cold_log(sum));
+}
+
+// Relatedness off: log1p(-pam) + m log(total) (src/chain.cpp:895-899), as one logarithm.
+__device__ __forceinline__ double norel_term(double pam, double total, int m)
+{
+    return log_total_pow_times(total, m, __dsub_rn(1.0, clamp_pam(pam)));
 }
 
 constexpr int kMaxAcc = 16;  // accumulators kept in registers
@@ -399,12 +446,21 @@ struct SmallSubsets
 };
 
 template <int K, int NACC>
+__device__ __forceinline__ void ie_small_regs(const double (&q)[K], double (&acc)[NACC]);
+
+template <int K, int NACC>
 __device__ __forceinline__ void ie_small(const double *scr, int ST, double (&acc)[NACC])
 {
-    constexpr SmallSubsets<K> ord{};
     double q[K];
 #pragma unroll
     for (int e = 0; e < K; ++e) q[e] = scr[e * ST];
+    ie_small_regs<K, NACC>(q, acc);
+}
+
+template <int K, int NACC>
+__device__ __forceinline__ void ie_small_regs(const double (&q)[K], double (&acc)[NACC])
+{
+    constexpr SmallSubsets<K> ord{};
 #pragma unroll
     for (int t = 0; t < NACC; ++t) acc[t] = 0.0;
 #pragma unroll
@@ -495,20 +551,20 @@ __device__ __noinline__ void ie_pams(double *scr, int ST, int k, int cnt, unsign
 #undef MOIRE_IE_STORE
 }
 
-__device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, int m,
-                                                   double log_total, double log_r, double log_1mr,
-                                                   const double *lgam, unsigned lanes)
+__device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, int m, double total,
+                                                   const Rel rel, const double *lgam,
+                                                   const double *binom_s, unsigned lanes)
 {
     const int cnt = m - k + 1;
     ie_pams(scr, ST, k, cnt, lanes);
-    return relatedness_mixture(scr, ST, m, cnt, log_total, log_r, log_1mr, lgam);
+    return relatedness_mixture(scr, ST, m, cnt, total, rel, lgam, binom_s);
 }
 
 // m - k >= kMaxAcc (rare: a COI far above the number of distinct alleles): the accumulators are
 // produced kMaxAcc at a time and parked in local memory.
 __device__ __noinline__ double transmission_rel_ie_wide(double *scr, int ST, int k, int m,
-                                                        double log_total, double log_r,
-                                                        double log_1mr, const double *lgam)
+                                                        double total, const Rel rel,
+                                                        const double *lgam, const double *binom_s)
 {
     double v[kMaxCoi];
     const int cnt = m - k + 1;
@@ -520,35 +576,31 @@ __device__ __noinline__ double transmission_rel_ie_wide(double *scr, int ST, int
         for (int j = 0; j < kMaxAcc; ++j)
             if (t0 + j < cnt) v[t0 + j] = acc[j];
     }
-    return relatedness_mixture(v, 1, m, cnt, log_total, log_r, log_1mr, lgam);
+    return relatedness_mixture(v, 1, m, cnt, total, rel, lgam, binom_s);
 }
 
 // EGF branch (k > 10) of one cell on one thread: the band in the thread's scratch column while it
 // fits (m - k < kScratchSlots: nearly always), else in local memory; then the same mixture as every
 // other path.
 __device__ __noinline__ double transmission_egf(uint64_t latent, const double *prow, double total,
-                                                int k, int m, double log_total, double log_r,
-                                                double log_1mr, bool allow_relatedness, double *scr,
-                                                int ST, const double *lgam)
+                                                int k, int m, const Rel rel, bool allow_relatedness,
+                                                double *scr, int ST, const double *lgam,
+                                                const double *binom_s)
 {
     const int D = m - k;
     double local_band[kMaxCoi + 1];
     double *band = D < kScratchSlots ? scr : local_band;
     const int BS = D < kScratchSlots ? ST : 1;
     egf_band(latent, prow, total, D, band, BS);
-    if (!allow_relatedness)
-    {
-        // src/chain.cpp:895-899 with probAnyMissingFunctor::operator() (prob_any_missing.cpp:149-153)
-        const double pam = clamp_pam(pam_from_coverage(band[D * BS]));
-        return __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)m));
-    }
+    // src/chain.cpp:895-899 with probAnyMissingFunctor::operator() (prob_any_missing.cpp:149-153)
+    if (!allow_relatedness) return norel_term(pam_from_coverage(band[D * BS]), total, m);
     for (int d = 0; d <= D; ++d) band[d * BS] = pam_from_coverage(band[d * BS]);
-    return relatedness_mixture(band, BS, m, D + 1, log_total, log_r, log_1mr, lgam);
+    return relatedness_mixture(band, BS, m, D + 1, total, rel, lgam, binom_s);
 }
 
 // Relatedness off and n == k: 1 - k! * prod(q) in double (src/prob_any_missing.cpp:139-148).
 __device__ __forceinline__ double transmission_norel_exact_cover(uint64_t latent, const double *prow,
-                                                                 double total, double log_total, int k)
+                                                                 double total, int k)
 {
     double cov = 1.0;
     uint64_t rest = latent;
@@ -559,28 +611,63 @@ __device__ __forceinline__ double transmission_norel_exact_cover(uint64_t latent
         cov = __dmul_rn(cov, __ddiv_rn(prow[al], total));
     }
     for (int i = 2; i <= k; ++i) cov = __dmul_rn(cov, (double)i);
-    const double pam = clamp_pam(pam_from_coverage(cov));
-    return __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)k));
+    return norel_term(pam_from_coverage(cov), total, k);
+}
+
+// The first kGather allele frequencies of a latent genotype, ascending allele order.  The loads do
+// not depend on one another (an exhausted genotype re-reads entry 0), so they are in flight
+// together: one trip to L2 instead of k dependent ones in front of every cell (the evaluator's
+// top stall was the long scoreboard).
+constexpr int kGather = 6;
+__device__ __forceinline__ void gather_freqs(uint64_t latent, const double *prow, double (&pv)[kGather])
+{
+    uint64_t rest = latent;
+#pragma unroll
+    for (int e = 0; e < kGather; ++e)
+    {
+        const int al = rest ? __ffsll((long long)rest) - 1 : 0;
+        pv[e] = prow[al];
+        rest &= rest - 1;
+    }
 }
 
 // ---- a2: transmission process of one cell, one thread -------------------------------------------
 // prow: allele frequencies of the locus; scr: the thread's scratch column (kScratchSlots slots,
-// stride ST); lgam: lgamma(i + 1), i < 128.  `callers`: the lanes of the warp that make this call
-// together (a __ballot_sync the caller takes BEFORE branching into the call).
-__device__ __forceinline__ double transmission_ll(uint64_t latent, const double *prow, int m,
-                                                  double log_r, double log_1mr,
+// stride ST); lgam: lgamma(i + 1), i < 128; binom_s: see relatedness_mixture.  `callers`: the lanes
+// of the warp that make this call together (a __ballot_sync the caller takes BEFORE branching
+// into the call).
+__device__ __forceinline__ double transmission_ll(uint64_t latent, const double *prow,
+                                                  const double (&pv)[kGather], int m, const Rel rel,
                                                   bool allow_relatedness, double *scr, int ST,
-                                                  const double *lgam, unsigned callers)
+                                                  const double *lgam, const double *binom_s,
+                                                  unsigned callers)
 {
     const int k = __popcll(latent);
     // the lanes that will reach the register-tier inclusion-exclusion sums, agreed on while the
     // callers are still together (the branches below diverge by k and m)
     const unsigned ie_lanes = __ballot_sync(
-        callers, allow_relatedness && k >= 1 && k <= m && k <= kIeMax && m - k + 1 <= kMaxAcc);
+        callers, allow_relatedness && k >= 2 && k <= m && k <= kIeMax && m - k + 1 <= kMaxAcc);
     if (k == 0 || k > m) return NAN;  // unreachable for states the sampler produces
-    double total = 0.0;
+    if (k == 1)
     {
-        uint64_t rest = latent;
+        // One latent allele: q = p / p = 1 exactly, every base 1 - q is exactly 0 and so is every
+        // PAM (in each of the reference's branches) -- the subset sums have nothing to add.
+        const double total = __dadd_rn(0.0, pv[0]);
+        if (!allow_relatedness) return norel_term(0.0, total, m);
+        return relatedness_mixture(nullptr, 0, m, m, total, rel, lgam, binom_s);
+    }
+    // the frequency sum in ascending allele order: the gathered ones, then any further ones
+    double total = 0.0;
+    uint64_t tail = latent;
+#pragma unroll
+    for (int e = 0; e < kGather; ++e)
+    {
+        if (e < k) total = __dadd_rn(total, pv[e]);
+        tail &= tail - 1;
+    }
+    if (k > kGather)
+    {
+        uint64_t rest = tail;
         while (rest)
         {
             const int al = __ffsll((long long)rest) - 1;
@@ -588,33 +675,115 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
             total = __dadd_rn(total, prow[al]);
         }
     }
-    const double log_total = hot_log(total);
     if (k <= kIeMax)
     {
-        uint64_t rest = latent;
-        int e = 0;
-        while (rest)
+#pragma unroll
+        for (int e = 0; e < kGather; ++e)
+            if (e < k) scr[e * ST] = __ddiv_rn(pv[e], total);
+        if (k > kGather)
         {
-            const int al = __ffsll((long long)rest) - 1;
-            rest &= rest - 1;
-            scr[e * ST] = __ddiv_rn(prow[al], total);
-            ++e;
+            uint64_t rest = tail;
+            int e = kGather;
+            while (rest)
+            {
+                const int al = __ffsll((long long)rest) - 1;
+                rest &= rest - 1;
+                scr[e * ST] = __ddiv_rn(prow[al], total);
+                ++e;
+            }
         }
     }
     if (!allow_relatedness)
     {
         // src/chain.cpp:895-899 with probAnyMissingFunctor::operator() (prob_any_missing.cpp:131-154)
-        if (m == k) return transmission_norel_exact_cover(latent, prow, total, log_total, k);
-        if (k > kIeMax)
-            return transmission_egf(latent, prow, total, k, m, log_total, log_r, log_1mr, false, scr, ST, lgam);
-        const double pam = clamp_pam(ie_scalar(scr, ST, k, m));
-        return __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)m));
+        if (m == k) return transmission_norel_exact_cover(latent, prow, total, k);
+        if (k > kIeMax) return transmission_egf(latent, prow, total, k, m, rel, false, scr, ST, lgam, binom_s);
+        return norel_term(ie_scalar(scr, ST, k, m), total, m);
     }
-    if (k > kIeMax)
-        return transmission_egf(latent, prow, total, k, m, log_total, log_r, log_1mr, true, scr, ST, lgam);
-    if (m - k + 1 <= kMaxAcc)
-        return transmission_rel_ie(scr, ST, k, m, log_total, log_r, log_1mr, lgam, ie_lanes);
-    return transmission_rel_ie_wide(scr, ST, k, m, log_total, log_r, log_1mr, lgam);
+    if (k > kIeMax) return transmission_egf(latent, prow, total, k, m, rel, true, scr, ST, lgam, binom_s);
+    if (m - k + 1 <= kMaxAcc) return transmission_rel_ie(scr, ST, k, m, total, rel, lgam, binom_s, ie_lanes);
+    return transmission_rel_ie_wide(scr, ST, k, m, total, rel, lgam, binom_s);
+}
+
+// ---- a2, class-uniform small cells, fully in registers ---------------------------------------------
+// ncu, round 2 (profiles/r02g): at the benchmark shapes the subset sums themselves are ~13 % of the
+// evaluator's instructions; the rest is everything around them -- 64-bit bit scans, predicated
+// gathers, q and the sums travelling through shared memory between out-of-line functions, the
+// generic mixture loop.  A chunk whose 32 cells share k <= kSmallK (nearly every chunk: the list is
+// class-sorted) takes this path instead: K known at compile time, the K frequencies loaded
+// together, q, the accumulators and the mixture terms in registers, one call-free stretch of
+// straight code per (K, tier).  Same operations in the same order as the generic path (the sums
+// are ie_small's, the mixture is relatedness_mixture's fast branch; its rare fallback is called
+// with the sums parked in the scratch column), so a cell gets the same bits whichever path its
+// neighbours send it down.
+constexpr int kSmallK = 6;      // <= MOIRE_SMALL_K
+constexpr int kSmallCnt = 8;    // mixture terms handled in registers
+
+template <int K, int NACC>
+__device__ __forceinline__ double small_cell_tail(const double (&q)[K], double total, int m, int cnt,
+                                                  const Rel rel, double *scr, int ST, const double *lgam,
+                                                  const double *binom_s)
+{
+    double acc[NACC];
+    if (K >= 2)
+        ie_small_regs<K, NACC>(q, acc);
+    else
+    {
+#pragma unroll
+        for (int t = 0; t < NACC; ++t) acc[t] = 0.0;  // one latent allele: every PAM is exactly 0
+    }
+    const double lead = __dmul_rn((double)(m - 1), rel.log_1mr);
+    if (cnt == 1)
+        return __dadd_rn(lead, log_total_pow_times(total, m, __dsub_rn(1.0, clamp_pam(acc[0]))));
+    const double qr = __ddiv_rn(rel.odds, total);
+    const int e2 = ((__double2hiint(qr) >> 20) & 0x7ff) - 1022;
+    if ((cnt - 1) * max(e2, 0) > 850)
+    {
+        // weights could overflow: the generic function's log-sum-exp branch, sums via the scratch column
+#pragma unroll
+        for (int t = 0; t < NACC; ++t) scr[t * ST] = acc[t];
+        return relatedness_mixture(scr, ST, m, cnt, total, rel, lgam, binom_s);
+    }
+    const double *cs = binom_s + (m - 1) * kBinomCols;  // cnt <= kSmallCnt <= kBinomCols
+    double qi = 1.0, S = 0.0;
+    // term i = cnt - 1 - t uses acc[t]: t descending is i ascending, the order of the generic loop
+#pragma unroll
+    for (int t = NACC - 1; t >= 0; --t)
+        if (t < cnt)
+        {
+            S = __dadd_rn(S, __dmul_rn(__dmul_rn(cs[cnt - 1 - t], qi), __dsub_rn(1.0, clamp_pam(acc[t]))));
+            qi = __dmul_rn(qi, qr);
+        }
+    return __dadd_rn(lead, log_total_pow_times(total, m, S));
+}
+
+// lat32: the latent genotype (all alleles below 32); cnt_hi: the largest m - k + 1 among the lanes
+// that call together (warp-uniform).  All of them have exactly K latent alleles.
+template <int K>
+__device__ __forceinline__ double small_cell(unsigned lat32, const double *prow, int m, int cnt_hi,
+                                             const Rel rel, double *scr, int ST, const double *lgam,
+                                             const double *binom_s)
+{
+    double q[K];
+    unsigned rest = lat32;
+#pragma unroll
+    for (int e = 0; e < K; ++e)
+    {
+        q[e] = prow[__ffs(rest) - 1];
+        rest &= rest - 1u;
+    }
+    double total = 0.0;
+#pragma unroll
+    for (int e = 0; e < K; ++e) total = __dadd_rn(total, q[e]);
+    if (K >= 2)
+    {
+#pragma unroll
+        for (int e = 0; e < K; ++e) q[e] = __ddiv_rn(q[e], total);
+    }
+    const int cnt = m - K + 1;
+    if (cnt_hi <= 2) return small_cell_tail<K, 2>(q, total, m, cnt, rel, scr, ST, lgam, binom_s);
+    if (cnt_hi <= 4) return small_cell_tail<K, 4>(q, total, m, cnt, rel, scr, ST, lgam, binom_s);
+    return small_cell_tail<K, kSmallCnt>(q, total, m, cnt, rel, scr, ST, lgam, binom_s);
 }
 
 // ---- a2, warp-cooperative: one cell, 32 lanes ---------------------------------------------------
@@ -632,9 +801,9 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
 #endif
 constexpr int kCoopMinK = MOIRE_COOP_MIN_K;
 __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const double *prow, int m,
-                                                       double log_r, double log_1mr,
-                                                       bool allow_relatedness, double *wscr, int ST,
-                                                       const double *lgam)
+                                                       const Rel rel, bool allow_relatedness,
+                                                       double *wscr, int ST, const double *lgam,
+                                                       const double *binom_s)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -649,9 +818,7 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
             total = __dadd_rn(total, prow[al]);
         }
     }
-    const double log_total = cold_log(total);
-    if (!allow_relatedness && m == k)
-        return transmission_norel_exact_cover(latent, prow, total, log_total, k);
+    if (!allow_relatedness && m == k) return transmission_norel_exact_cover(latent, prow, total, k);
     double *q = wscr + 16 * ST;
     {
         // lane e normalises element e
@@ -733,11 +900,7 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
             }
         }
     }
-    if (!allow_relatedness)
-    {
-        const double pam = clamp_pam(__shfl_sync(FULL, acc[0], 0));
-        return __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)m));
-    }
+    if (!allow_relatedness) return norel_term(__shfl_sync(FULL, acc[0], 0), total, m);
     // The mixture through the same function, in the same order of operations, as the one-thread
     // path: which evaluator a cell lands in depends on the launch (the cooperative threshold
     // follows the work per thread, so it changes with the number of chains on the device) and must
@@ -750,7 +913,7 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
             const int top = min(16, cnt - 16 * ch);
             for (int t = 0; t < top; ++t) pams[16 * ch + t] = __shfl_sync(FULL, acc[ch], t);
         }
-    return relatedness_mixture(pams, 1, m, cnt, log_total, log_r, log_1mr, lgam);
+    return relatedness_mixture(pams, 1, m, cnt, total, rel, lgam, binom_s);
 }
 
 // ---- a2 for k > 10, warp-cooperative: the band with its rows across lanes ---------------------
@@ -759,9 +922,9 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
 // in the warp's scratch rows.  Every lane then gathers the band and runs the one mixture function.
 // All lanes must call with identical arguments; every lane returns the value.
 __device__ MOIRE_COOP_INLINE double transmission_ll_egf_coop(uint64_t latent, const double *prow, int m,
-                                                           double log_r, double log_1mr,
-                                                           bool allow_relatedness, double *wscr,
-                                                           int ST, const double *lgam)
+                                                           const Rel rel, bool allow_relatedness,
+                                                           double *wscr, int ST, const double *lgam,
+                                                           const double *binom_s)
 {
     constexpr int CS = kMaxCoi + 1;
     const int lane = threadIdx.x & 31;
@@ -777,7 +940,6 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_egf_coop(uint64_t latent, co
             total = __dadd_rn(total, prow[al]);
         }
     }
-    const double log_total = cold_log(total);
     // band[d] at wscr[(d >> 5) * ST + (d & 31)], d <= D < 128: rows 0..3
     auto B = [&](int d) -> double & { return wscr[(d >> 5) * ST + (d & 31)]; };
     for (int d = lane; d <= D; d += 32) B(d) = d == 0 ? 1.0 : 0.0;
@@ -816,15 +978,11 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_egf_coop(uint64_t latent, co
         }
         __syncwarp();
     }
-    if (!allow_relatedness)
-    {
-        const double pam = clamp_pam(pam_from_coverage(B(D)));
-        return __dadd_rn(cold_log1m(pam), __dmul_rn(log_total, (double)m));
-    }
+    if (!allow_relatedness) return norel_term(pam_from_coverage(B(D)), total, m);
     double pams[kMaxCoi];
     for (int d = 0; d <= D; ++d) pams[d] = pam_from_coverage(B(d));
     __syncwarp();
-    return relatedness_mixture(pams, 1, m, D + 1, log_total, log_r, log_1mr, lgam);
+    return relatedness_mixture(pams, 1, m, D + 1, total, rel, lgam, binom_s);
 }
 
 // ---- a8: latent-genotype proposal ------------------------------------------------------------

@@ -1256,6 +1256,14 @@ int moire_mcmc_run(moire_mcmc *h, moire_progress_fn progress, void *ctx,
     });
 }
 
+int moire_mcmc_get_mode(moire_mcmc *h, int32_t *device_ladder, int32_t *step_graph)
+{
+    return guarded(h, [&] {
+        if (device_ladder) *device_ladder = h->dev_mode ? 1 : 0;
+        if (step_graph) *step_graph = h->dev_mode && h->graph_ok && (h->step_graph[0] || h->step_graph[1]) ? 1 : 0;
+    });
+}
+
 int moire_mcmc_get_sizes(moire_mcmc *h, moire_mcmc_sizes *out)
 {
     return guarded(h, [&] {

@@ -22,9 +22,18 @@
 
 namespace moire
 {
+// What the evaluator needs of a cell's sample, one 32-byte sector per gather.
+struct alignas(32) SampleScal
+{
+    double log_r, log_1mr, odds;
+    int m, pad;
+};
+
 struct PFlat
 {
-    uint4 *list;         // [cells] {latent genotype lo, hi, t * L + j, t * N + i}, sorted by cost class
+    uint4 *list;         // [cells] {latent genotype lo, hi, (t << 16) | j, i}, sorted by cost class
+                         // (t: chain of this engine, j: locus, i: sample)
+    SampleScal *ss;      // [T * N] current (m, r) of every sample, for the duration of update_p
     unsigned int *hist;  // [kSortBins] counts, [kSortBins] running offsets, 4 scalars, task counters
     double *Tcur, *Tnew; // [T][L][N] transmission terms, locus-major, for the duration of the update
     double *pprop;       // [T * L][AP] proposed frequencies
@@ -33,7 +42,7 @@ struct PFlat
     const int *nonmiss;  // [L] non-missing cells of a locus
 };
 constexpr unsigned kPfActive = 1u, kPfBroken = 2u;
-constexpr int kPfScalars = 2 * kSortBins;  // hist[kPfScalars + 0..2] = n_egf, coop_end, nwork
+constexpr int kPfScalars = 2 * kSortBins;  // hist[kPfScalars + 0..3] = n_egf, coop_end, nwork, mid_end
 constexpr int kPfCounters = kPfScalars + 4;  // one task counter per evaluator launch of an update
 constexpr int kPfHistWords = kPfCounters + 72;
 
@@ -141,6 +150,17 @@ __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
         const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
         const unsigned t = tl / v.L, j = tl - t * v.L;
         const size_t cell = ((size_t)t * v.N + i) * v.L + j;
+        if (j == 0)
+        {
+            const size_t tn = (size_t)t * v.N + i;
+            SampleScal sc;
+            sc.log_r = v.log_r[tn];
+            sc.log_1mr = v.log_1mr[tn];
+            sc.odds = v.odds[tn];
+            sc.m = v.m[tn];
+            sc.pad = 0;
+            f.ss[tn] = sc;
+        }
         if (v.missing[(size_t)i * v.L + j] == 0)
         {
             f.Tcur[loc] = v.cellT[cell];
@@ -198,17 +218,26 @@ __global__ void __launch_bounds__(256) k_pf_scan(const PFlat f)
     float total_work = 0.f;
     for (int w = 0; w < 8; ++w) total_work += s_work[w];
     // cooperative above this much one-thread work: a share of the launch's work per thread
+    // Two boundaries.  thr (as tuned in round 1): classes above it are worth a cooperating warp when
+    // they are RARE -- too few cells to fill class-uniform chunks -- and run one cell per thread
+    // when plentiful.  thr_hi: a cell whose one-thread work exceeds the launch's work per thread would
+    // outlast everything else on its own (a small shard of a high-COI ladder: one k = 10 cell with
+    // 30 mixture terms is ~10^5 dependent instructions, ~1 ms, while the launch's share per thread is
+    // a tenth of that), so it ALWAYS goes to a warp.
     const float share = MOIRE_COOP_WORK_SHARE * total_work / (float)f.eval_threads;
     const float thr = fminf(MOIRE_COOP_WORK_MAX, fmaxf(MOIRE_COOP_WORK_MIN, share));
+    const float thr_hi = fmaxf(thr, share);
     unsigned int base = s_part[tid >> 5] + x - local;
     for (int q = 0; q < per; ++q)
     {
         const int b = tid * per + q;
         f.hist[kSortBins + b] = base;
         if (b == kClassCoopBegin) f.hist[kPfScalars + 0] = base;
-        // ranks >= 64 are sorted by estimate, descending: the first one below the threshold
-        if (b >= kClassCoopBegin && c_flat_est[b] < thr && (b == kClassCoopBegin || c_flat_est[b - 1] >= thr))
+        // ranks >= 64 are sorted by estimate, descending: the first one below each threshold
+        if (b >= kClassCoopBegin && c_flat_est[b] < thr_hi && (b == kClassCoopBegin || c_flat_est[b - 1] >= thr_hi))
             f.hist[kPfScalars + 1] = base;
+        if (b >= kClassCoopBegin && c_flat_est[b] < thr && (b == kClassCoopBegin || c_flat_est[b - 1] >= thr))
+            f.hist[kPfScalars + 3] = base;
         base += h[q];
     }
     if (tid == 0) f.hist[kPfScalars + 2] = s_part[8];
@@ -263,7 +292,7 @@ __global__ void __launch_bounds__(256) k_pf_scatter(const View v, const PFlat f)
         const unsigned tn = t * v.N + i;
         const unsigned long long lat = v.latent[cell];
         cls = work_class_flat(__popcll(lat), v.m[tn]);
-        entry = make_uint4((unsigned)lat, (unsigned)(lat >> 32), tl, tn);
+        entry = make_uint4((unsigned)lat, (unsigned)(lat >> 32), (t << 16) | j, i);
         return true;
     };
     block_scatter(total, cell_fn, f.hist + kSortBins, f.list);
@@ -422,18 +451,18 @@ __global__ void __launch_bounds__(kPfRoundThreads) k_pf_round(const View v, cons
 // shapes); otherwise a chunk of 1023-subset cells would outlast everything else.
 struct FlatSrc
 {
-    const uint4 *list;                  // {latent genotype (two words), p-row index t * L + j,
-                                        //  sample index t * N + i}: the genotype travels in the
-                                        //  list, so a unit's loads are list -> frequencies only
-    const unsigned int *bounds;         // [3] n_egf, coop_end, nwork
+    const uint4 *list;                  // {latent genotype (two words), (t << 16) | j, i}: the
+                                        //  genotype travels in the list, so a unit's loads are
+                                        //  list -> frequencies / sample scalars only
+    const unsigned int *bounds;         // [4] n_egf, coop_end, nwork, mid_end
     unsigned int *counter;              // task counter, zero at launch
-    const double *p;                    // row list.z, p_stride doubles apart
+    const double *p;                    // row t * L + j, p_stride doubles apart
     int p_stride;
-    const int *m;                       // [list.w]
-    const double *log_r, *log_1mr;      // [list.w]
-    const double *round_flags;          // null, or [list.z * 4 + 3] & kPfActive says "evaluate"
+    const SampleScal *ss;               // [t * N + i]
+    const double *round_flags;          // null, or [(t * L + j) * 4 + 3] & kPfActive says "evaluate"
     double *out;                        // locus-major [t][j][i] (p rounds) or sample-major [t][i][j]
     int out_locus_major;
+    int binom_rows;                     // rows of g_binom staged in shared memory (= max_coi)
 };
 
 #ifndef MOIRE_PF_THREADS
@@ -455,28 +484,41 @@ __host__ __device__ inline int pf_tasks(int cells, bool chunked, bool light)
     const int upb = pf_units_per_task(light);
     return (units + upb - 1) / upb;
 }
+__host__ __device__ inline size_t pf_eval_smem_doubles(int binom_rows)
+{
+    return 128 + (size_t)binom_rows * kBinomCols + scratch_doubles(kEvalThreads);
+}
 
+// Sections of the list, heaviest first (k_pf_scan): [0, n_egf) k > 10; [n_egf, coop_end) cells that
+// would outlast the launch on one thread: always one warp per cell; [coop_end, mid_end) heavy
+// classes: a warp per cell while they are rare, chunks of 32 when they hold a large share of all
+// cells (high-COI shapes); [mid_end, nwork) light cells in chunks.
 __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval(const View v, const FlatSrc f)
 {
     extern __shared__ double smem[];
     double *s_lgam = smem;
-    double *s_scr = smem + 128;
+    double *s_scr = smem + 128;                                   // fixed offsets for the hot arrays
+    double *s_binom = s_scr + scratch_doubles(kEvalThreads);
     __shared__ int s_task;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int ST = kEvalThreads + 1;
     for (int i = tid; i < 128; i += kEvalThreads) s_lgam[i] = v.lgam[i];
+    for (int i = tid; i < f.binom_rows * kBinomCols; i += kEvalThreads)
+        s_binom[i] = g_binom[(i / kBinomCols) * (kMaxCoi + 1) + (i % kBinomCols)];
     const bool allow_rel = v.allow_rel != 0;
     const unsigned N = (unsigned)v.N, L = (unsigned)v.L;
     const bool locus_major = f.out_locus_major != 0;
-    auto out_index = [&](unsigned tl, unsigned tn) -> size_t {
-        const unsigned t = tl / L;
-        return locus_major ? (size_t)tl * N + (tn - t * N) : (size_t)tn * L + (tl - t * L);
-    };
-    const int n_egf = (int)f.bounds[0], coop_end = (int)f.bounds[1], nwork = (int)f.bounds[2];
-    const bool chunked_heavy = (size_t)coop_end * 4 > (size_t)nwork;
-    const int t_egf = pf_tasks(n_egf, chunked_heavy, false);
-    const int t_heavy = pf_tasks(coop_end - n_egf, chunked_heavy, false);
-    const int tasks = t_egf + t_heavy + pf_tasks(nwork - coop_end, true, true);
+    const int n_egf = (int)f.bounds[0], coop_end = (int)f.bounds[1], nwork = (int)f.bounds[2],
+              mid_end = (int)f.bounds[3];
+    // a section is cut into chunks of 32 one-thread cells once it holds enough cells for the chunks
+    // to be class-uniform and to spread over the grid; a handful of heavy cells get a warp each
+    const size_t enough = (size_t)gridDim.x * kEvalThreads / 8;
+    const bool chunked_egf = (size_t)n_egf >= enough;
+    const bool chunked_mid = (size_t)(mid_end - coop_end) >= enough;
+    const int t_egf = pf_tasks(n_egf, chunked_egf, false);
+    const int t_strag = pf_tasks(coop_end - n_egf, false, false);
+    const int t_mid = pf_tasks(mid_end - coop_end, chunked_mid, false);
+    const int tasks = t_egf + t_strag + t_mid + pf_tasks(nwork - mid_end, true, true);
     for (;;)
     {
         __syncthreads();
@@ -490,20 +532,27 @@ __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval
         {
             lo = 0;
             hi = n_egf;
-            coop = !chunked_heavy;
+            coop = !chunked_egf;
             egf = true;
         }
-        else if (b < t_egf + t_heavy)
+        else if (b < t_egf + t_strag)
         {
             b -= t_egf;
             lo = n_egf;
             hi = coop_end;
-            coop = !chunked_heavy;
+            coop = true;
+        }
+        else if (b < t_egf + t_strag + t_mid)
+        {
+            b -= t_egf + t_strag;
+            lo = coop_end;
+            hi = mid_end;
+            coop = !chunked_mid;
         }
         else
         {
-            b -= t_egf + t_heavy;
-            lo = coop_end;
+            b -= t_egf + t_strag + t_mid;
+            lo = mid_end;
             hi = nwork;
             coop = false;
             light = true;
@@ -517,21 +566,22 @@ __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval
                 const int w = lo + unit;
                 if (w >= hi) break;
                 const uint4 e = f.list[w];
-                if (f.round_flags && ((unsigned)f.round_flags[(size_t)e.z * 4 + 3] & kPfActive) == 0)
+                const unsigned t = e.z >> 16, j = e.z & 0xffffu, tl = t * L + j, tn = t * N + e.w;
+                if (f.round_flags && ((unsigned)f.round_flags[(size_t)tl * 4 + 3] & kPfActive) == 0)
                     continue;
                 const unsigned long long lat = ((unsigned long long)e.y << 32) | e.x;
-                const int m = f.m[e.w], k = __popcll(lat);
-                const double *prow = f.p + (size_t)e.z * f.p_stride;
+                const SampleScal sc = f.ss[tn];
+                const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
+                const int m = sc.m, k = __popcll(lat);
+                const double *prow = f.p + (size_t)tl * f.p_stride;
                 double T;
                 if (k > m)
                     T = NAN;
                 else if (egf)
-                    T = transmission_ll_egf_coop(lat, prow, m, f.log_r[e.w], f.log_1mr[e.w], allow_rel,
-                                                 s_scr + warp * 32, ST, s_lgam);
+                    T = transmission_ll_egf_coop(lat, prow, m, rel, allow_rel, s_scr + warp * 32, ST, s_lgam, s_binom);
                 else
-                    T = transmission_ll_coop(lat, prow, m, f.log_r[e.w], f.log_1mr[e.w], allow_rel,
-                                             s_scr + warp * 32, ST, s_lgam);
-                if (lane == 0) f.out[out_index(e.z, e.w)] = T;
+                    T = transmission_ll_coop(lat, prow, m, rel, allow_rel, s_scr + warp * 32, ST, s_lgam, s_binom);
+                if (lane == 0) f.out[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + j] = T;
                 __syncwarp();
             }
             else
@@ -540,18 +590,67 @@ __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval
                 if (w0 >= hi) break;
                 const int w = w0 + lane;
                 bool go = w < hi;
-                uint4 e = make_uint4(0u, 0u, 0u, 0u);
-                if (go)
+                uint4 e = make_uint4(1u, 0u, 0u, 0u);
+                if (go) e = f.list[w];
+                // -- class-uniform chunk of small cells: the register path (likelihood.cuh)
                 {
-                    e = f.list[w];
-                    go = !f.round_flags || ((unsigned)f.round_flags[(size_t)e.z * 4 + 3] & kPfActive);
+                    const unsigned in = __ballot_sync(0xffffffffu, go);
+                    const int k = __popc(e.x);
+                    const bool small = allow_rel && in != 0 &&
+                                       __all_sync(0xffffffffu, !go || (e.y == 0 && k <= kSmallK && k >= 1)) &&
+                                       __reduce_max_sync(0xffffffffu, go ? k : 0) ==
+                                           __reduce_min_sync(0xffffffffu, go ? k : kSmallK + 1);
+                    if (small)
+                    {
+                        const int K = __shfl_sync(0xffffffffu, k, __ffs(in) - 1);
+                        const unsigned tl = (e.z >> 16) * L + (e.z & 0xffffu), tn = (e.z >> 16) * N + e.w;
+                        const double flagword = f.round_flags ? f.round_flags[(size_t)tl * 4 + 3] : (double)kPfActive;
+                        const SampleScal sc = f.ss[tn];
+                        const double *prow = f.p + (size_t)tl * f.p_stride;
+                        const int cnt = sc.m - K + 1;
+                        const int cnt_hi = __reduce_max_sync(0xffffffffu, go ? cnt : 0);
+                        const int cnt_lo = __reduce_min_sync(0xffffffffu, go ? cnt : 1);
+                        if (cnt_hi <= kSmallCnt && cnt_lo >= 1)
+                        {
+                            if (go && ((unsigned)flagword & kPfActive))
+                            {
+                                const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
+                                double T;
+                                switch (K)
+                                {
+                                    case 1: T = small_cell<1>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom); break;
+                                    case 2: T = small_cell<2>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom); break;
+                                    case 3: T = small_cell<3>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom); break;
+                                    case 4: T = small_cell<4>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom); break;
+                                    case 5: T = small_cell<5>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom); break;
+                                    default: T = small_cell<6>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom); break;
+                                }
+                                f.out[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] = T;
+                            }
+                            __syncwarp();
+                            continue;
+                        }
+                    }
                 }
+                // everything the cell needs hangs off the list entry: issue it all at once -- the
+                // round flag, the sample's scalars, the gathered frequencies -- and only then look
+                // at the flag (two trips to L2 per cell instead of 3 + k)
+                const unsigned tl = (e.z >> 16) * L + (e.z & 0xffffu), tn = (e.z >> 16) * N + e.w;
+                const unsigned long long lat = ((unsigned long long)e.y << 32) | e.x;
+                const double *prow = f.p + (size_t)tl * f.p_stride;
+                const double flagword = f.round_flags ? f.round_flags[(size_t)tl * 4 + 3] : (double)kPfActive;
+                const SampleScal sc = f.ss[tn];
+                double pv[kGather];
+                gather_freqs(lat, prow, pv);
+                go = go && ((unsigned)flagword & kPfActive);
                 const unsigned callers = __ballot_sync(0xffffffffu, go);
                 if (go)
-                    f.out[out_index(e.z, e.w)] =
-                        transmission_ll(((unsigned long long)e.y << 32) | e.x,
-                                        f.p + (size_t)e.z * f.p_stride, f.m[e.w], f.log_r[e.w],
-                                        f.log_1mr[e.w], allow_rel, s_scr + tid, ST, s_lgam, callers);
+                {
+                    const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
+                    f.out[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] =
+                        transmission_ll(lat, prow, pv, sc.m, rel, allow_rel, s_scr + tid, ST, s_lgam, s_binom,
+                                        callers);
+                }
                 __syncwarp();
             }
         }

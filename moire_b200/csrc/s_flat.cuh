@@ -23,7 +23,7 @@ struct SFlat
 {
     Proposal *prop;                  // [T * N]
     int *m_new;                      // [T * N] proposed COI
-    double *log_r_new, *log_1mr_new; // [T * N]
+    SampleScal *ss;                  // [T * N] the proposal's (m, r) as the evaluator gathers it
     EpsLogs *elogs;                  // [T * N][nA] logs of the proposed error rates
     unsigned long long *lat;         // [T][N][L] proposed latent genotypes
     double *adj;                     // [T][N][L] their log proposal densities
@@ -48,8 +48,13 @@ __global__ void __launch_bounds__(kDrawThreads) k_sf_draw(const View v, const SF
         const Proposal P = draw_sample_proposal<KIND>(v, t, i, iteration, v.lgam);
         sf.prop[si] = P;
         sf.m_new[si] = P.m_new;
-        sf.log_r_new[si] = P.log_r;
-        sf.log_1mr_new[si] = P.log_1mr;
+        SampleScal sc;
+        sc.log_r = P.log_r;
+        sc.log_1mr = P.log_1mr;
+        sc.odds = P.odds;
+        sc.m = P.m_new;
+        sc.pad = 0;
+        sf.ss[si] = sc;
         s_en[tid] = P.en_new;
         s_ep[tid] = P.ep_new;
         s_valid[tid] = P.valid;
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(256) k_sf_scatter(const View v, const SFlat sf
         if (!sf.prop[tn].valid || v.missing[(size_t)i * v.L + j] != 0) return false;
         const unsigned long long lat = RESAMPLE ? sf.lat[gi] : v.latent[gi];
         cls = work_class_flat(__popcll(lat), sf.m_new[tn]);
-        entry = make_uint4((unsigned)lat, (unsigned)(lat >> 32), t * v.L + j, tn);
+        entry = make_uint4((unsigned)lat, (unsigned)(lat >> 32), (t << 16) | j, i);
         return true;
     };
     block_scatter(total, cell_fn, pf.hist + kSortBins, pf.list);

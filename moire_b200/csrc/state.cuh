@@ -40,7 +40,7 @@ struct View
 
     // per sample [T][N]
     int *m;
-    double *r, *log_r, *log_1mr;
+    double *r, *log_r, *log_1mr, *odds;  // odds = r / (1 - r), what the linear-domain mixture uses
     double *eps_pos, *eps_neg;
     double *sd_eps_neg, *sd_eps_pos, *sd_r, *sd_mr;
     int *acc_eps_neg, *acc_eps_pos, *acc_m, *acc_r, *acc_mr, *acc_samples;

@@ -295,6 +295,14 @@ class MCMC:
                  "run")
         return bool(reached.value), float(minutes.value)
 
+    def mode(self):
+        """'device ladder, step graph' | 'device ladder, plain launches' | 'host ladder'."""
+        a, b = C.c_int32(), C.c_int32()
+        self._ck(self.lib.moire_mcmc_get_mode(self._h, C.byref(a), C.byref(b)), "get_mode")
+        if not a.value:
+            return "host ladder"
+        return "device ladder, " + ("step graph" if b.value else "plain launches")
+
     # ---- results ----
     def sizes(self):
         s = _lib.MoireMcmcSizes()

@@ -14,8 +14,12 @@ rep, lib, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-cub = [f for f in os.listdir(tmp) if f.endswith(".cubin") and "mcmc_driver" not in f][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+dis = ""
+for cub in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    out = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+    if kname in out:
+        dis = out
+        break
 lines, cur, active = [], None, False
 for ln in dis.splitlines():
     if ".section" in ln and ".text." in ln:
