@@ -41,6 +41,13 @@ extern "C" {
 #define MOIRE_PIPELINE_AUTO 0
 #define MOIRE_PIPELINE_FLAT 1
 #define MOIRE_PIPELINE_FUSED 2
+/* OR-ed into moire_params::pipeline: emulate the one place where the shipped (float) reference and
+ * an fp64 evaluation differ to leading order -- P(any missing) is rounded to float and clamped at
+ * 1 - FLT_EPSILON (src/chain.cpp:888-893, src/prob_any_missing.cpp:99-112) instead of
+ * 1 - DBL_EPSILON, which floors a cell's log(1 - PAM) at log(2^-23).  For attributing posterior
+ * differences to the reference's precision; the default (off) is the fp64 evaluation whose cells
+ * match the reference's double variant to 1e-9.  Process-wide: the last created engine decides. */
+#define MOIRE_NUMERICS_REF32 0x100
 
 /* The 8 Metropolis updates in the order MCMC::burnin runs them (src/mcmc.cpp:162-173). */
 enum moire_update_kind
@@ -140,6 +147,14 @@ int32_t moire_engine_num_chains(const moire_engine *e);
 int moire_engine_init_chains(moire_engine *e, int32_t max_tries, int32_t *ill_count,
                              int32_t *still_ill, int32_t *first_bad_sample,
                              int32_t *first_bad_locus, int32_t *prior_nonfinite);
+
+/* Chain::first_nonfinite_genotyping_term and Chain::collect_nonfinite_prior_terms
+ * (src/chain.cpp:1032-1081) of one chain's CURRENT state, whenever asked (init_chains calls the same
+ * routine for every failed attempt): the 1-based (sample, locus) of the first cell, in the
+ * reference's sample-major order, whose log-likelihood is not finite (0, 0 if none) and the counts
+ * of non-finite prior terms [5] (eps_neg, eps_pos, relatedness, coi, mean_coi_hyper).  NULL = skip. */
+int moire_engine_diagnose(moire_engine *e, int32_t chain, int32_t *first_bad_sample,
+                          int32_t *first_bad_locus, int32_t *prior_nonfinite);
 
 /* Every ill-conditioned start seen by the last moire_engine_init_chains, in attempt order:
  * records of (local chain, 1-based sample, 1-based locus), (chain, 0, 0) when no genotyping term
@@ -243,6 +258,19 @@ int moire_engine_synchronize(moire_engine *e);
  * out[i], i < 2^k - 1: bits 0..k-1 = elements of the i-th subset, bit 15 = its term is subtracted.
  * Must match the reference's sequences bit for bit (tests/test_gpu_parity.py). */
 int moire_engine_subset_order(moire_engine *e, int32_t which, int32_t k, uint16_t *out);
+
+/* Synthetic genotyping data generated on the device: the per-cell part of the reference's
+ * simulate_data (R/simulator.R:154-212) -- strains per cell, their alleles, the false-negative /
+ * false-positive observation process and missingness -- given the per-locus allele frequencies
+ * [L][a_pad], per-sample COIs and within-host relatedness (drawn by the caller: a few thousand
+ * numbers).  Outputs are HOST arrays in the engine's input layout: obs_mask [N][L], is_missing
+ * [N][L], and (optional) true_mask [N][L] = the alleles actually present.  Streams are keyed by
+ * (seed, sample, locus): the result does not depend on the launch shape. */
+int moire_simulate_data(int32_t num_samples, int32_t num_loci, const int32_t *num_alleles,
+                        const double *allele_freqs, int32_t a_pad, const int32_t *sample_cois,
+                        const double *sample_relatedness, double epsilon_pos, double epsilon_neg,
+                        double missingness, uint64_t seed, int32_t device_id, uint64_t *obs_mask,
+                        uint8_t *is_missing, uint64_t *true_mask);
 
 /* Philox4x32-10 block (counter, key) -> 4 words; exported so tests can pin the generator against
  * the Random123 known-answer vectors. */

@@ -101,6 +101,7 @@ ENGINE_SYMBOLS = {
     "moire_engine_num_chains": (i32, [vp]),
     "moire_engine_init_chains": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
     "moire_engine_read_init_log": (C.c_int, [vp, vp, i32, vp]),
+    "moire_engine_diagnose": (C.c_int, [vp, i32, vp, vp, vp]),
     "moire_engine_step": (C.c_int, [vp, i32]),
     "moire_engine_update": (C.c_int, [vp, i32, i32]),
     "moire_engine_eval_all": (C.c_int, [vp]),
@@ -131,6 +132,7 @@ ENGINE_SYMBOLS = {
     "moire_engine_add_launches": (C.c_int, [vp, C.c_int64]),
     "moire_engine_get_timing": (C.c_int, [vp, C.POINTER(i32)]),
     "moire_engine_enqueue_record_draw": (C.c_int, [vp, vp, vp]),
+    "moire_simulate_data": (C.c_int, [i32, i32, vp, vp, i32, vp, vp, dbl, dbl, dbl, u64, i32, vp, vp, vp]),
     "moire_philox4x32": (None, [vp, vp, vp]),
 }
 

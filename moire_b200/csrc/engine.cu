@@ -242,6 +242,52 @@ __global__ void __launch_bounds__(256) k_record_draw(const moire::View v, const 
         for (size_t i = g0; i < NL; i += stride) st.latent[slot * NL + i] = v.latent[t * NL + i];
 }
 
+// ---- synthetic data on the device (row f2; R/simulator.R:154-212) ---------------------------------
+// One thread per (sample, locus) cell, its own Philox stream: related strains ~ Binom(coi - 1, r)
+// (:63-65), the coi - related unrelated strains each draw an allele from the locus' frequencies
+// (the multinomial of :66-69, one categorical draw per strain by inverse CDF), then the observation
+// process (:85-107): a present allele is seen w.p. 1 - eps_neg / A, an absent one w.p. eps_pos / A,
+// the whole cell is blanked w.p. `missingness`; is_missing = nothing observed (:195-199).
+__global__ void __launch_bounds__(256) k_simulate_cells(const int N, const int L, const int AP, const int *nall,
+                                                        const double *freqs, const int *coi, const double *rel,
+                                                        const double eps_pos, const double eps_neg,
+                                                        const double missingness, const unsigned long long seed,
+                                                        unsigned long long *obs, unsigned char *missing,
+                                                        unsigned long long *truth)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)N * L) return;
+    const int i = (int)(g / L), j = (int)(g - (size_t)i * L);
+    const int A = nall[j];
+    const double *f = freqs + (size_t)j * AP;
+    moire::Stream rng;
+    rng.open(seed, 0x51D0u, moire::KIND_INIT_SAMPLE, 0u, (uint32_t)i, (uint32_t)(j + 1));
+    int related = 0;
+    const double r = rel[i];
+    for (int s = 0; s < coi[i] - 1; ++s) related += rng.next_uniform() < r;
+    unsigned long long present = 0;
+    for (int s = 0; s < coi[i] - related; ++s)
+    {
+        const double u = rng.next_uniform();
+        double c = 0.0;
+        int a = 0;
+        for (; a < A - 1; ++a)
+        {
+            c += f[a];
+            if (u < c) break;
+        }
+        present |= 1ull << a;
+    }
+    unsigned long long seen = 0;
+    const double p_hit = 1.0 - eps_neg / (double)A, p_false = eps_pos / (double)A;
+    for (int a = 0; a < A; ++a)
+        if (rng.next_uniform() < ((present >> a) & 1ull ? p_hit : p_false)) seen |= 1ull << a;
+    if (rng.next_uniform() < missingness) seen = 0;
+    obs[g] = seen;
+    missing[g] = seen == 0;
+    if (truth) truth[g] = present;
+}
+
 template <int K>
 __device__ void dump_small_subsets(unsigned short *out)
 {
@@ -555,9 +601,17 @@ struct moire_engine
         if (const char *env = std::getenv("MOIRE_B200_FLAT_MIN_CELLS")) flat_min_cells = (size_t)std::atoll(env);
         p_fused = std::getenv("MOIRE_B200_P_FUSED") != nullptr || TNL < flat_min_cells;
         // moire_params::pipeline overrides the size rule (tests run both generations on one shape)
-        if (prm->pipeline == MOIRE_PIPELINE_FLAT) p_fused = false;
-        if (prm->pipeline == MOIRE_PIPELINE_FUSED) p_fused = true;
-        if (prm->pipeline < 0 || prm->pipeline > MOIRE_PIPELINE_FUSED) throw InvalidArg{"unknown pipeline"};
+        const int pipeline = prm->pipeline & 0xff;
+        if (pipeline == MOIRE_PIPELINE_FLAT) p_fused = false;
+        if (pipeline == MOIRE_PIPELINE_FUSED) p_fused = true;
+        if (prm->pipeline < 0 || pipeline > MOIRE_PIPELINE_FUSED || (prm->pipeline & ~(0xff | MOIRE_NUMERICS_REF32)))
+            throw InvalidArg{"unknown pipeline / numerics flags"};
+        {
+            const int pam_float = (prm->pipeline & MOIRE_NUMERICS_REF32) != 0;
+            const double max_pam = pam_float ? 1.0 - (double)FLT_EPSILON : 1.0 - DBL_EPSILON;
+            CUDA_TRY(cudaMemcpyToSymbol(moire::c_max_pam, &max_pam, sizeof(double)));
+            CUDA_TRY(cudaMemcpyToSymbol(moire::c_pam_float, &pam_float, sizeof(int)));
+        }
         if (!p_fused && TNL >= (1ull << 32))
             throw InvalidArg{"num_chains * num_samples * num_loci must stay below 2^32 per engine "
                              "(32-bit cell lists): shard the ladder over more engines"};
@@ -1432,6 +1486,67 @@ int moire_engine_synchronize(moire_engine *e)
     return guarded(e, [&] {
         if (!e) throw InvalidArg{"null engine"};
         CUDA_TRY(cudaStreamSynchronize(e->stream));
+    });
+}
+
+int moire_simulate_data(int32_t num_samples, int32_t num_loci, const int32_t *num_alleles,
+                        const double *allele_freqs, int32_t a_pad, const int32_t *sample_cois,
+                        const double *sample_relatedness, double epsilon_pos, double epsilon_neg,
+                        double missingness, uint64_t seed, int32_t device_id, uint64_t *obs_mask,
+                        uint8_t *is_missing, uint64_t *true_mask)
+{
+    return guarded(nullptr, [&] {
+        if (!num_alleles || !allele_freqs || !sample_cois || !sample_relatedness || !obs_mask || !is_missing)
+            throw InvalidArg{"null argument"};
+        if (num_samples < 1 || num_loci < 1 || a_pad < 1) throw InvalidArg{"empty shape"};
+        for (int j = 0; j < num_loci; ++j)
+            if (num_alleles[j] < 2 || num_alleles[j] > MOIRE_MAX_ALLELES || num_alleles[j] > a_pad)
+                throw InvalidArg{"num_alleles outside 2..64 / a_pad"};
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw CudaError{"no CUDA device -- libmoire_b200 has no CPU fallback"};
+        if (device_id < 0 || device_id >= ndev) throw InvalidArg{"device_id out of range"};
+        CUDA_TRY(cudaSetDevice(device_id));
+        const size_t N = num_samples, L = num_loci, NL = N * L;
+        DevBuf<int> nall, coi;
+        DevBuf<double> freqs, rel;
+        DevBuf<unsigned long long> obs, truth;
+        DevBuf<unsigned char> miss;
+        auto release = [&] { nall.release(); coi.release(); freqs.release(); rel.release(); obs.release(); truth.release(); miss.release(); };
+        try
+        {
+            nall.alloc(L); coi.alloc(N); freqs.alloc(L * a_pad); rel.alloc(N); obs.alloc(NL); truth.alloc(NL); miss.alloc(NL);
+            nall.upload(num_alleles, L, nullptr);
+            coi.upload(sample_cois, N, nullptr);
+            freqs.upload(allele_freqs, L * a_pad, nullptr);
+            rel.upload(sample_relatedness, N, nullptr);
+            k_simulate_cells<<<(unsigned)((NL + 255) / 256), 256>>>(num_samples, num_loci, a_pad, nall.ptr, freqs.ptr,
+                                                                     coi.ptr, rel.ptr, epsilon_pos, epsilon_neg,
+                                                                     missingness, seed, obs.ptr, miss.ptr, truth.ptr);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpy(obs_mask, obs.ptr, NL * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(is_missing, miss.ptr, NL, cudaMemcpyDeviceToHost));
+            if (true_mask) CUDA_TRY(cudaMemcpy(true_mask, truth.ptr, NL * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        }
+        catch (...)
+        {
+            release();
+            throw;
+        }
+        release();
+    });
+}
+
+int moire_engine_diagnose(moire_engine *e, int32_t chain, int32_t *first_bad_sample,
+                          int32_t *first_bad_locus, int32_t *prior_nonfinite)
+{
+    return guarded(e, [&] {
+        need_chain(e, chain);
+        if (prior_nonfinite) std::fill(prior_nonfinite, prior_nonfinite + 5, 0);
+        int32_t bs = 0, bl = 0;
+        e->diagnose(chain, &bs, &bl, prior_nonfinite);
+        if (first_bad_sample) *first_bad_sample = bs;
+        if (first_bad_locus) *first_bad_locus = bl;
     });
 }
 

@@ -91,12 +91,22 @@ __device__ __forceinline__ double observation_ll(uint64_t latent, uint64_t obs, 
     return res;
 }
 
+// Numerics switch (moire_params::pipeline, MOIRE_NUMERICS_REF32): the shipped reference computes
+// this path in float, and what that does to a posterior is, to leading order, ONE thing -- its clamp
+// max_pam = 1 - FLT_EPSILON (src/chain.cpp:888-893) floors log(1 - PAM) at log(2^-23) = -15.9, so
+// every cell whose coverage probability is below ~1e-7 gets the same likelihood.  With
+// the switch on, PAM is rounded to float and clamped at 1 - FLT_EPSILON exactly there; everything
+// else stays fp64.  It exists to attribute posterior differences between the fp32 package and an
+// fp64 engine (scripts/posterior_study.py); per process, set at engine creation.
+__constant__ double c_max_pam = 1.0 - DBL_EPSILON;
+__constant__ int c_pam_float = 0;
+
 __device__ __forceinline__ double clamp_pam(double x)
 {
     // src/chain.cpp:890-893 in double: min(1 - eps, max(0, x))
-    const double max_pam = 1.0 - DBL_EPSILON;
-    const double lo = x > 0.0 ? x : 0.0;  // std::max(0., x): NaN -> 0
-    return max_pam < lo ? max_pam : lo;
+    double lo = x > 0.0 ? x : 0.0;  // std::max(0., x): NaN -> 0
+    if (c_pam_float) lo = (double)(float)lo;
+    return c_max_pam < lo ? c_max_pam : lo;
 }
 
 __device__ __forceinline__ double pam_from_coverage(double cov)

@@ -24,6 +24,7 @@ DEFAULT_MODEL = dict(allow_relatedness=True, burnin=10000, max_coi=40, mean_coi_
 
 # moire_params.pipeline (include/moire_engine.h): kernel generation, "auto" = by problem size
 PIPELINES = dict(auto=0, flat=1, fused=2)
+NUMERICS_REF32 = 0x100   # MOIRE_NUMERICS_REF32: float-rounded PAM clamped at 1 - FLT_EPSILON
 
 
 class MoireError(RuntimeError):
@@ -38,7 +39,7 @@ class Engine:
     """``num_chains`` tempered chains [chain_offset, chain_offset + num_chains) on one device."""
 
     def __init__(self, data: PackedData, temps, seed=1, device=0, chain_offset=0, pipeline="auto",
-                 **model):
+                 ref32_emulation=False, **model):
         self._h = None
         self.lib = _lib.load()
         prm = dict(DEFAULT_MODEL)
@@ -59,7 +60,8 @@ class Engine:
         d = _lib.MoireData(self.N, self.L, _ptr(self._keep["na"]), _ptr(self._keep["obs"]),
                            _ptr(self._keep["mis"]), _ptr(self._keep["coi"]))
         p = _lib.MoireParams(int(bool(prm["allow_relatedness"])), int(prm["burnin"]),
-                             int(prm["max_coi"]), PIPELINES[pipeline], prm["mean_coi_shape"], prm["mean_coi_scale"],
+                             int(prm["max_coi"]), PIPELINES[pipeline] | (NUMERICS_REF32 if ref32_emulation else 0),
+                             prm["mean_coi_shape"], prm["mean_coi_scale"],
                              prm["max_eps_pos"], prm["eps_pos_alpha"], prm["eps_pos_beta"],
                              prm["max_eps_neg"], prm["eps_neg_alpha"], prm["eps_neg_beta"],
                              prm["r_alpha"], prm["r_beta"])
@@ -99,6 +101,15 @@ class Engine:
             _ptr(out["first_bad_sample"]), _ptr(out["first_bad_locus"]),
             _ptr(out["prior_nonfinite"])), "init_chains")
         return out
+
+    def diagnose(self, chain=0):
+        """(first_bad_sample, first_bad_locus, prior_nonfinite[5]) of the chain's current state:
+        Chain::first_nonfinite_genotyping_term / collect_nonfinite_prior_terms, 1-based, 0 = none."""
+        bs, bl = C.c_int32(), C.c_int32()
+        pri = np.zeros(5, np.int32)
+        self._ck(self.lib.moire_engine_diagnose(self._h, chain, C.byref(bs), C.byref(bl), _ptr(pri)),
+                 "diagnose")
+        return int(bs.value), int(bl.value), pri
 
     # ---- MCMC::burnin / sample loop body ----
     def step(self, iteration):

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib
 from .data import PackedData, pack_data
-from .engine import DEFAULT_MODEL, PIPELINES, Engine, MoireError, _ptr
+from .engine import DEFAULT_MODEL, NUMERICS_REF32, PIPELINES, Engine, MoireError, _ptr
 
 PRIOR_TERMS = ("eps_neg", "eps_pos", "relatedness", "coi", "mean_coi_hyper")
 
@@ -144,7 +144,7 @@ class MCMC:
     def __init__(self, data: PackedData, pt_chains, *, burnin, samples, thin=1, adapt_temp=True,
                  pre_adapt_steps=25, temp_adapt_steps=25, max_initialization_tries=10000,
                  record_latent_genotypes=False, max_runtime=math.inf, seed=1, device=0, rank=0,
-                 world_size=1, allgather=None, pipeline="auto", **model):
+                 world_size=1, allgather=None, pipeline="auto", ref32_emulation=False, **model):
         self._h = None
         self.lib = _lib.load()
         prm = dict(DEFAULT_MODEL)
@@ -168,7 +168,8 @@ class MCMC:
         d = _lib.MoireData(self.N, self.L, _ptr(self._keep["na"]), _ptr(self._keep["obs"]),
                            _ptr(self._keep["mis"]), _ptr(self._keep["coi"]))
         p = _lib.MoireParams(int(bool(prm["allow_relatedness"])), int(burnin), int(prm["max_coi"]),
-                             PIPELINES[pipeline], prm["mean_coi_shape"], prm["mean_coi_scale"], prm["max_eps_pos"],
+                             PIPELINES[pipeline] | (NUMERICS_REF32 if ref32_emulation else 0),
+                             prm["mean_coi_shape"], prm["mean_coi_scale"], prm["max_eps_pos"],
                              prm["eps_pos_alpha"], prm["eps_pos_beta"], prm["max_eps_neg"],
                              prm["eps_neg_alpha"], prm["eps_neg_beta"], prm["r_alpha"],
                              prm["r_beta"])
@@ -489,7 +490,7 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
              record_latent_genotypes=False, num_chains=1, num_cores=1, pt_chains=1, pt_grad=1,
              pt_num_threads=1, adapt_temp=True, pre_adapt_steps=25, temp_adapt_steps=25,
              max_initialization_tries=10000, max_runtime=math.inf, *, seed=1, device=0,
-             distributed=None, progress=None, pipeline="auto"):
+             distributed=None, progress=None, pipeline="auto", ref32_emulation=False):
     """Same arguments and result as ``moire::run_mcmc`` (R/mcmc.R:76-182): returns
     ``dict(runtime, chains=[...], args)`` whose ``chains[i]`` holds the 23 fields of
     src/main.cpp:138-189 plus ``mean_coi``.
@@ -501,7 +502,8 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
     seeds from ``std::random_device``), ``device``, ``distributed`` -- ``True`` to shard the ladder
     over the ranks of an initialised ``torch.distributed`` group (every rank returns the full
     result) --, ``progress(phase, step, posterior, hot_chain)`` and ``pipeline`` ("auto", "flat",
-    "fused": the kernel generation, include/moire_engine.h).
+    "fused": the kernel generation, include/moire_engine.h) and ``ref32_emulation`` (float-rounded
+    P(any missing) clamped at 1 - FLT_EPSILON like the shipped float reference; off = fp64).
 
     Engine limits the reference does not have (``MoireError`` when exceeded): at most
     MOIRE_MAX_ALLELES alleles per locus, ``max_coi`` <= MOIRE_MAX_COI, and
@@ -552,7 +554,8 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
                   max_initialization_tries=int(max_initialization_tries),
                   record_latent_genotypes=record_latent_genotypes, max_runtime=max_runtime,
                   seed=int(seed) + 7919 * (chain_number - 1), device=device, rank=rank,
-                  world_size=world, allgather=gather, pipeline=pipeline, **model)
+                  world_size=world, allgather=gather, pipeline=pipeline,
+                  ref32_emulation=ref32_emulation, **model)
         try:
             if native:
                 mc.init_nccl(device)     # falls back to the callback if NCCL cannot be bound

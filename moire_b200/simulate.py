@@ -84,3 +84,50 @@ def simulate_data(mean_coi=None, num_samples=None, epsilon_pos=0.0, epsilon_neg=
                 loci=[f"L{j + 1}" for j in range(L)], is_missing=is_missing,
                 allele_freqs=allele_freqs, sample_cois=sample_cois,
                 sample_relatedness=internal_relatedness, true_genotypes=true_genotypes)
+
+
+def simulate_data_gpu(mean_coi=None, num_samples=None, epsilon_pos=0.0, epsilon_neg=0.0,
+                      sample_cois=None, locus_freq_alphas=None, allele_freqs=None,
+                      internal_relatedness_alpha=0.0, internal_relatedness_beta=1.0,
+                      internal_relatedness=None, missingness=0.0, seed=0, device=0):
+    """``simulate_data`` with the per-cell work (N x L x A_j: strains, alleles, observation noise,
+    missingness) on the GPU (``moire_simulate_data``); the per-locus frequencies and per-sample
+    COIs / relatedness -- a few thousand numbers -- are drawn here exactly as ``simulate_data``
+    draws them.  Returns the packed masks the engine consumes plus the truth:
+    ``dict(packed=PackedData, true_mask, allele_freqs, sample_cois, sample_relatedness)``.
+    Same model, different random streams: the two generators agree in distribution."""
+    import ctypes as C
+
+    from . import _lib
+    from .data import PackedData
+    rng = np.random.Generator(np.random.Philox(seed))
+    if allele_freqs is None:
+        allele_freqs = [rng.dirichlet(np.asarray(a, dtype=np.float64)) for a in locus_freq_alphas]
+    else:
+        allele_freqs = [np.asarray(f, dtype=np.float64) for f in allele_freqs]
+    L = len(allele_freqs)
+    if sample_cois is None:
+        sample_cois = simulate_sample_coi(num_samples, mean_coi, rng)
+    sample_cois = np.ascontiguousarray(sample_cois, dtype=np.int32)
+    N = len(sample_cois)
+    if internal_relatedness is None:
+        internal_relatedness = (np.zeros(N) if internal_relatedness_alpha <= 0 else
+                                rng.beta(internal_relatedness_alpha, internal_relatedness_beta, size=N))
+    rel = np.ascontiguousarray(internal_relatedness, dtype=np.float64)
+    na = np.array([len(f) for f in allele_freqs], dtype=np.int32)
+    AP = int(na.max())
+    fr = np.zeros((L, AP))
+    for j, f in enumerate(allele_freqs):
+        fr[j, :len(f)] = f
+    obs, tru = np.zeros((N, L), np.uint64), np.zeros((N, L), np.uint64)
+    mis = np.zeros((N, L), np.uint8)
+    lib = _lib.load()
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.moire_simulate_data(N, L, ptr(na), ptr(fr), AP, ptr(sample_cois), ptr(rel), float(epsilon_pos),
+                                 float(epsilon_neg), float(missingness), int(seed), int(device), ptr(obs),
+                                 ptr(mis), ptr(tru))
+    if rc != 0:
+        raise RuntimeError(f"moire_simulate_data failed ({rc}): {lib.moire_last_error().decode()}")
+    coi = np.vectorize(lambda x: bin(int(x)).count("1"))(obs).max(axis=1).astype(np.int32)
+    return dict(packed=PackedData(N, L, na, obs, mis, coi), true_mask=tru, allele_freqs=allele_freqs,
+                sample_cois=sample_cois, sample_relatedness=rel)

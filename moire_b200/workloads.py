@@ -70,3 +70,34 @@ def make_workload(name: str):
     nominal = (6 * pk.num_samples * pk.num_loci + pk.num_samples * sum_alleles) * nonmissing
     return dict(name=name, sim=d, packed=pk, temps=ladder(T), model=model,
                 nominal_evals_per_chain_step=nominal)
+
+
+def make_posterior_shape(name: str):
+    """The hard shapes of BASELINE.json scaled to what the reference's CPU sampler finishes in
+    minutes (scripts/posterior_reference.py mints the reference side, tests/test_gpu_posterior.py
+    and scripts/posterior_study.py run the engine on the same data): ``c3s`` is C3-shaped (A = 10,
+    COI <= 10 from a zero-truncated Poisson(4), sparse relatedness) at 500 samples x 40 loci;
+    ``c5s`` is C5-shaped (A = 30, COI uniform on 1..30, relatedness Beta(1, 1): cells with more than
+    ten latent alleles, coverage probabilities far below the fp32 reference's 2^-23 floor) at
+    150 samples x 20 loci.  One chain (T = 1), ``max_coi`` 40."""
+    name = name.lower()
+    if name == "c3s":
+        rng = np.random.Generator(np.random.Philox(17325 + 33))
+        coi = np.minimum(simulate_sample_coi(500, 4.0, rng), 10)
+        sim = dict(sample_cois=coi, epsilon_pos=.01, epsilon_neg=.1,
+                   locus_freq_alphas=[np.ones(10)] * 40,
+                   internal_relatedness_alpha=.1, internal_relatedness_beta=1, seed=17325 + 33)
+        burnin, samples = 1000, 1000
+    elif name == "c5s":
+        rng = np.random.Generator(np.random.Philox(17325 + 55))
+        coi = rng.integers(1, 31, size=150)
+        sim = dict(sample_cois=coi, epsilon_pos=.01, epsilon_neg=.1,
+                   locus_freq_alphas=[np.ones(30)] * 20,
+                   internal_relatedness_alpha=1, internal_relatedness_beta=1, seed=17325 + 55)
+        burnin, samples = 700, 700
+    else:
+        raise ValueError(f"unknown posterior shape {name!r}")
+    d = simulate_data(**sim)
+    pk = pack_data(d["data"], d["is_missing"])
+    return dict(name=name, sim=d, packed=pk, temps=np.array([1.0]), burnin=burnin, samples=samples,
+                model=dict(allow_relatedness=True, max_coi=40))

@@ -300,3 +300,81 @@ def test_update_p_adaptation_matches_stepper(oracle, pipeline):
         assert np.array_equal(dg["p_prop_var"], frozen[c])       # no adaptation after burn-in
         assert (dg["p_accept"] <= dg["p_attempt"]).all()
     eng.close()
+
+
+def test_nonfinite_state_is_located_like_the_reference(oracle):
+    """Row f4: Chain::first_nonfinite_genotyping_term / collect_nonfinite_prior_terms
+    (src/chain.cpp:1032-1081) on a LIVE failure: a state whose log-likelihood is not finite is put
+    through the engine (load_state -> every cache rebuilt, as Chain::initialize_likelihood does) and
+    the engine must name the first offending (sample, locus) in the reference's sample-major order
+    and count the non-finite prior terms by kind."""
+    from moire_b200.data import pack_data
+    from moire_b200.simulate import simulate_data
+    d = simulate_data(mean_coi=3, num_samples=30, epsilon_pos=.02, epsilon_neg=.15,
+                      locus_freq_alphas=[np.ones(6)] * 9, internal_relatedness_alpha=.2,
+                      internal_relatedness_beta=1, missingness=.05, seed=13)
+    pk = pack_data(d["data"], d["is_missing"])
+    for pipeline in PIPELINES:
+        eng, _ = engine_for(pk, temps=(1.0, 0.4), pipeline=pipeline)
+        assert not eng.init_chains()["still_ill"].any()
+        assert eng.diagnose(0)[:2] == (0, 0) and not eng.diagnose(0)[2].any()
+        st = eng.dump_state(1)
+        # a false negative (latent allele that was not observed) under eps_neg = 0: log(0)
+        fn = np.vectorize(lambda l, o: bin(int(l) & ~int(o)).count("1"))(st["latent"], pk.obs_mask)
+        fn[pk.is_missing != 0] = 0
+        rows, cols = np.nonzero(fn)
+        s_bad = int(rows[len(rows) // 2])
+        l_bad = int(cols[rows == s_bad].min())
+        bad = dict(st)
+        bad["eps_neg"] = st["eps_neg"].copy()
+        bad["eps_neg"][s_bad] = 0.0
+        bad["r"] = st["r"].copy()
+        bad["r"][[2, 7]] = 1.5                         # outside Beta's support: prior -inf, twice
+        eng.load_state(1, {k: bad[k] for k in ("m", "r", "eps_pos", "eps_neg", "p", "latent", "lg_adj", "mean_coi")})
+        llik, prior = eng.scalars()
+        assert not np.isfinite(llik[1]) and np.isfinite(llik[0])
+        # earlier samples may be hit by r = 1.5 (log(1 - r) = NaN in their transmission terms)
+        first = min([s_bad] + [s for s in (2, 7) if (pk.is_missing[s] == 0).any()])
+        want_locus = l_bad if first == s_bad else int(np.nonzero(pk.is_missing[first] == 0)[0][0])
+        bs, bl, pri = eng.diagnose(1)
+        assert (bs, bl) == (first + 1, want_locus + 1), (bs, bl, first, want_locus)
+        assert pri.tolist() == [0, 0, 2, 0, 0]          # eps_neg = 0 has a finite Beta(1,1) log-density; r = 1.5 has none
+        assert eng.diagnose(0)[:2] == (0, 0)           # the other chain is untouched
+        # the oracle agrees on which cells are not finite
+        t, o = oracle.eval_cells(64, pk.num_alleles, pk.obs_mask, pk.is_missing, bad["latent"], bad["m"],
+                                 bad["r"], bad["eps_neg"], bad["eps_pos"], bad["p"][:, :pk.max_alleles], 1)
+        out = eng.dump_state(1)
+        assert np.array_equal(np.isfinite(t + o), np.isfinite(out["cell_t"] + out["cell_o"]))
+        eng.close()
+
+
+def test_ref32_emulation_floors_tiny_coverage_like_the_float_reference(oracle):
+    """MOIRE_NUMERICS_REF32: where the coverage probability of a cell is far below 2^-23 the shipped
+    float reference returns log(FLT_EPSILON) + m log(sum p) (its clamp, src/chain.cpp:888-893) and an
+    fp64 evaluation the true value; the switch reproduces the float answer there and leaves
+    well-conditioned cells at the fp64 value."""
+    from moire_b200.data import PackedData
+    from moire_b200.engine import Engine
+    N, L, A = 4, 2, 8
+    obs = np.full((N, L), 0b00011111, np.uint64)
+    pk = PackedData(N, L, np.full(L, A, np.int32), obs, np.zeros((N, L), np.uint8), np.full(N, 5, np.int32))
+    p = np.zeros((L, A))
+    p[0] = [1e-10, .1, .1, .1, .1, .2, .2, .2]                 # coverage of {0..4} in 5 draws ~ 6e-11
+    p[1] = [.1, .2, .1, .15, .05, .2, .1, .1]                  # well conditioned
+    st = dict(m=np.full(N, 5, np.int32), r=np.full(N, .3), eps_pos=np.full(N, .02), eps_neg=np.full(N, .05),
+              p=p, latent=obs.copy(), lg_adj=np.zeros((N, L)), mean_coi=3.0)
+    out = {}
+    for mode in (False, True):
+        eng = Engine(pk, [1.0], pipeline="flat", ref32_emulation=mode)
+        eng.load_state(0, st)
+        out[mode] = eng.dump_state(0)["cell_t"]
+        eng.close()
+    idx = [0, 1, 2, 3, 4]
+    t64 = [oracle.transmission(64, idx, p[j], 5, .3, 1) for j in range(L)]
+    t32 = [oracle.transmission(32, idx, p[j].astype(np.float32), 5, .3, 1) for j in range(L)]
+    assert abs(t64[0] - t32[0]) > 5                            # the float floor is what differs
+    assert np.allclose(out[False][:, 0], t64[0], rtol=1e-9) and np.allclose(out[False][:, 1], t64[1], rtol=1e-9)
+    assert np.allclose(out[True][:, 0], t32[0], rtol=1e-5), (out[True][:, 0], t32[0])
+    assert np.allclose(out[True][:, 1], t64[1], rtol=1e-6)
+    eng = Engine(pk, [1.0])                                    # leaves the process in fp64 mode
+    eng.close()

@@ -266,3 +266,40 @@ def test_many_samples_need_no_shared_memory_budget():
     check_invariants(eng, pk, 0)
     check_invariants(eng, pk, 1)
     eng.close()
+
+
+def test_simulate_data_on_the_device_follows_the_generative_model():
+    """Row f2: the device generator against the NumPy restatement of R/simulator.R:154-212 on the
+    same frequencies, COIs and relatedness -- two independent random streams, so the comparison is
+    distributional: per-allele observation rates, strains per cell, missingness, and the exact
+    structural facts (no bits above A_j, is_missing == nothing observed, present alleles <= COI)."""
+    from moire_b200.data import pack_data
+    from moire_b200.simulate import simulate_data, simulate_data_gpu
+    rng = np.random.default_rng(7)
+    alphas = [np.ones(a) for a in (2, 5, 12, 30, 64)]
+    freqs = [rng.dirichlet(a) for a in alphas]
+    N = 6000
+    coi = rng.integers(1, 9, size=N)
+    rel = rng.beta(.5, 2, size=N)
+    kw = dict(sample_cois=coi, allele_freqs=freqs, internal_relatedness=rel, epsilon_pos=.4, epsilon_neg=.5,
+              missingness=.07)
+    g = simulate_data_gpu(seed=5, **kw)
+    c = simulate_data(seed=5, **kw)
+    pk, cp = g["packed"], pack_data(c["data"], c["is_missing"])
+    assert pk.obs_mask.shape == (N, 5) and np.array_equal(pk.num_alleles, cp.num_alleles)
+    assert np.array_equal(pk.is_missing != 0, pk.obs_mask == 0)
+    pop = np.vectorize(lambda x: bin(int(x)).count("1"))
+    present = pop(g["true_mask"])
+    assert (present >= 1).all() and (present <= coi[:, None]).all()
+    for j, A in enumerate(pk.num_alleles):
+        assert A == 64 or not (pk.obs_mask[:, j] >> np.uint64(A)).any()
+        bits_g = ((pk.obs_mask[:, j][:, None] >> np.arange(A, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(float)
+        bits_c = ((cp.obs_mask[:, j][:, None] >> np.arange(A, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(float)
+        se = np.sqrt((bits_c.var(0) + bits_g.var(0)) / N) + 1e-9
+        assert (np.abs(bits_g.mean(0) - bits_c.mean(0)) < 5 * se).all(), j      # per-allele observation rate
+        truth_c = (np.asarray(c["true_genotypes"][j]) > 0).sum(1)
+        assert abs(present[:, j].mean() - truth_c.mean()) < 5 * np.sqrt(2 * truth_c.var() / N)
+    assert abs(pk.is_missing.mean() - cp.is_missing.mean()) < 0.01
+    # the generator's output drives the engine like any other data
+    again = simulate_data_gpu(seed=5, **kw)["packed"]
+    assert np.array_equal(again.obs_mask, pk.obs_mask)          # same seed, same data
