@@ -48,6 +48,39 @@ constexpr int kIeMax = 10;      // src/prob_any_missing.cpp:11
 constexpr int kMaxCoi = 127;    // MOIRE_MAX_COI: the reference's lgamma LUT bound (src/sampler.cpp:22-25)
 constexpr int kLogCDim = 65;    // logC[n][k], 0 <= k <= n <= 64 (alleles of a locus)
 
+// x^n, n >= 0, by square and multiply.
+__device__ __forceinline__ double pow_uint(double x, int n)
+{
+    // n < 128 (a COI): seven rounds, no branches
+    double r = (n & 1) ? x : 1.0;
+#pragma unroll
+    for (int b = 1; b < 7; ++b)
+    {
+        x = __dmul_rn(x, x);
+        const double rx = __dmul_rn(r, x);
+        r = (n >> b) & 1 ? rx : r;
+    }
+    return r;
+}
+
+// Binomial(n, pr) by inversion of ONE uniform: pmf(0) = (1 - pr)^n, pmf(k) = pmf(k-1) odds (n-k+1)/k.
+// The latent-genotype proposal counts its false negatives / false positives this way (one Philox
+// word each instead of one per candidate allele); every operation is an IEEE multiply / divide /
+// add in a fixed order, so the CPU stepper reproduces the draw bit for bit.  q = 1 - pr,
+// odds = pr / (1 - pr).
+__device__ __forceinline__ int binom_inverse(double u, int n, double q, double odds)
+{
+    double pmf = pow_uint(q, n), cdf = pmf;
+    int k = 0;
+    while (u >= cdf && k < n)
+    {
+        ++k;
+        pmf = __dmul_rn(__dmul_rn(pmf, odds), __ddiv_rn((double)(n - k + 1), (double)k));
+        cdf = __dadd_rn(cdf, pmf);
+    }
+    return k;
+}
+
 // Per (sample, distinct allele count) logs, built once per tile.
 struct EpsLogs
 {
@@ -55,6 +88,8 @@ struct EpsLogs
     double o_tp, o_fn, o_tn, o_fp;
     // sample_latent_genotype: log(en/A), log(1 - en/A), log(ep/A), log(1 - ep/A), en/A, ep/A
     double l_en, l_1men, l_ep, l_1mep, pr_en, pr_ep;
+    // binom_inverse: 1 - en/A, (en/A) / (1 - en/A), and the same for ep
+    double q_en, odds_en, q_ep, odds_ep;
 };
 
 __device__ __noinline__ void build_eps_logs(EpsLogs &e, double eps_neg, double eps_pos,
@@ -73,6 +108,10 @@ __device__ __noinline__ void build_eps_logs(EpsLogs &e, double eps_neg, double e
     e.l_1men = cold_log(__dsub_rn(1.0, e.pr_en));
     e.l_ep = cold_log(e.pr_ep);
     e.l_1mep = cold_log(__dsub_rn(1.0, e.pr_ep));
+    e.q_en = __dsub_rn(1.0, e.pr_en);
+    e.odds_en = __ddiv_rn(e.pr_en, e.q_en);
+    e.q_ep = __dsub_rn(1.0, e.pr_ep);
+    e.odds_ep = __ddiv_rn(e.pr_ep, e.q_ep);
 }
 
 // ---- a7: observation process on masks --------------------------------------------------------
@@ -298,21 +337,6 @@ struct Rel
 {
     double log_r, log_1mr, odds;
 };
-
-// x^n, n >= 0, by square and multiply.
-__device__ __forceinline__ double pow_uint(double x, int n)
-{
-    // n < 128 (a COI): seven rounds, no branches
-    double r = (n & 1) ? x : 1.0;
-#pragma unroll
-    for (int b = 1; b < 7; ++b)
-    {
-        x = __dmul_rn(x, x);
-        const double rx = __dmul_rn(r, x);
-        r = (n >> b) & 1 ? rx : r;
-    }
-    return r;
-}
 
 // m log(total) + log(s), s > 0: ONE logarithm, of total^m * s, while total^m is comfortably a normal
 // number (it nearly always is: total is a sum of allele frequencies, m a COI), else the two
@@ -1003,6 +1027,16 @@ __device__ __forceinline__ uint64_t choose_bits(Stream &rng, uint64_t set, int n
 {
     if (need <= 0) return 0;
     if (need >= n) return set;
+    if (need == 1 || need == n - 1)
+    {
+        // keep one / drop one (what a proposal with a single false positive or false negative
+        // needs -- nearly every proposal that needs a choice at all): one uniform picks the allele
+        const int idx = (int)(rng.next_uniform() * (double)n);
+        uint64_t s = set;
+        for (int i = 0; i < idx; ++i) s &= s - 1;
+        const uint64_t bit = s & (0ull - s);
+        return need == 1 ? bit : set ^ bit;
+    }
     uint64_t out = 0;
     int remaining = n;
     while (need > 0)
@@ -1025,24 +1059,12 @@ __device__ __forceinline__ uint64_t choose_bits(Stream &rng, uint64_t set, int n
     return out;
 }
 
-// The uniform of a word w is (w + 0.5) 2^-32 (exact in double), so "uniform < pr" is the integer
-// test w < ceil(pr 2^32 - 0.5); pr 2^32 is exact too.  pr >= 1 would accept every word: those
-// proposals are rejected before any cell is drawn (eps in (0, 1), A >= 2).
-__device__ __forceinline__ uint32_t bernoulli_threshold(double pr)
-{
-    const double x = ceil(pr * 4294967296.0 - 0.5);
-    return x <= 0.0 ? 0u : (x >= 4294967295.0 ? 4294967295u : (uint32_t)x);
-}
-
-// The three phases of the draw (false negatives, false positives, which alleles) each start on a
-// fresh Philox block (MOIRE_RNG_ALIGN, mirrored by the CPU stepper): the lanes of a warp consume
-// different numbers of words per phase, and without this they refill at different times, each
-// refill running for a fraction of the warp (-20 us per resampling kernel at C3).
-#ifndef MOIRE_RNG_ALIGN
-#define MOIRE_RNG_ALIGN 1
-#endif
 // Draws the proposal and returns its mask; *log_prob gets the log proposal density.
-// logC[n * 65 + k] = log(C(n, k)).
+// logC[n * 65 + k] = log(C(n, k)).  Stream use: word 0 -> the number of false negatives, word 1 -> the
+// number of false positives (both by inversion, always consumed), then one word per visited allele
+// while the two uniform choices are still open (none when every observed allele is kept and no
+// false negative was drawn -- the usual cell): one Philox block per cell, where the round-1 sampler
+// (a Bernoulli word per candidate allele, each phase on a fresh block) used three.
 __device__ __forceinline__ uint64_t sample_latent_genotype(Stream &rng, uint64_t obs, int A,
                                                            int coi, const EpsLogs &e,
                                                            const double *__restrict__ logC,
@@ -1053,13 +1075,9 @@ __device__ __forceinline__ uint64_t sample_latent_genotype(Stream &rng, uint64_t
     const int obs_neg = A - obs_pos;
     const int min_fn = obs_pos == 0;
     const int max_fn = max(min_fn, min(coi, obs_neg));
-    int fn = min_fn;
-    // (w + 0.5) 2^-32 < pr  <=>  w < ceil(pr 2^32 - 0.5): the same Bernoulli draws on the raw words
-    const uint32_t thr_en = bernoulli_threshold(e.pr_en);
-    for (int ii = min_fn; ii < max_fn; ++ii) fn += (rng.next_u32() < thr_en);
-#if MOIRE_RNG_ALIGN
-    rng.have = 0;  // every phase starts on a fresh block: the lanes of a warp refill together
-#endif
+    const double u_fn = rng.next_uniform();
+    const double u_fp = rng.next_uniform();
+    const int fn = min_fn + binom_inverse(u_fn, max_fn - min_fn, e.q_en, e.odds_en);
     const int tn = obs_neg - fn;
     const double lp_fn =
         __dadd_rn(__dadd_rn(logC[obs_neg * kLogCDim + (fn - min_fn)],
@@ -1072,12 +1090,7 @@ __device__ __forceinline__ uint64_t sample_latent_genotype(Stream &rng, uint64_t
         *log_prob = -INFINITY;
         return 0;
     }
-    int fp = min_fp;
-    const uint32_t thr_ep = bernoulli_threshold(e.pr_ep);
-    for (int ii = min_fp; ii < max_fp; ++ii) fp += (rng.next_u32() < thr_ep);
-#if MOIRE_RNG_ALIGN
-    rng.have = 0;
-#endif
+    const int fp = min_fp + binom_inverse(u_fp, max_fp - min_fp, e.q_ep, e.odds_ep);
     const int tp = obs_pos - fp;
     const double lp_fp =
         __dadd_rn(__dadd_rn(logC[obs_pos * kLogCDim + (fp - min_fp)],

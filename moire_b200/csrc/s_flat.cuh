@@ -78,7 +78,7 @@ __host__ __device__ inline unsigned sf_cell_blocks(size_t total)
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(256) k_sf_cells(const View v, const SFlat sf, const PFlat pf, const int iteration_arg)
+__global__ void __launch_bounds__(256, 4) k_sf_cells(const View v, const SFlat sf, const PFlat pf, const int iteration_arg)
 {
     const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);

@@ -94,6 +94,15 @@ static uint64_t stp_choose_bits(stp_stream *s, uint64_t set, int n, int need)
 {
     if (need <= 0) return 0;
     if (need >= n) return set;
+    if (need == 1 || need == n - 1)
+    {
+        /* keep one / drop one: one uniform picks the allele (the engine's choose_bits) */
+        const int idx = (int)(stp_uniform(s) * (double)n);
+        uint64_t r = set;
+        for (int i = 0; i < idx; ++i) r &= r - 1;
+        const uint64_t bit = r & (0ull - r);
+        return need == 1 ? bit : set ^ bit;
+    }
     uint64_t out = 0;
     int remaining = n;
     while (need > 0)
@@ -116,6 +125,34 @@ static uint64_t stp_choose_bits(stp_stream *s, uint64_t set, int n, int need)
     return out;
 }
 
+/* the engine's pow_uint / binom_inverse (likelihood.cuh), operation for operation */
+static double stp_pow_uint(double x, int n)
+{
+    double r = (n & 1) ? x : 1.0;
+    for (int b = 1; b < 7; ++b)
+    {
+        x = x * x;
+        const double rx = r * x;
+        r = ((n >> b) & 1) ? rx : r;
+    }
+    return r;
+}
+
+static int stp_binom_inverse(double u, int n, double q, double odds)
+{
+    double pmf = stp_pow_uint(q, n), cdf = pmf;
+    int k = 0;
+    while (u >= cdf && k < n)
+    {
+        ++k;
+        const double ratio = (double)(n - k + 1) / (double)k;
+        const double po = pmf * odds;
+        pmf = po * ratio;
+        cdf = cdf + pmf;
+    }
+    return k;
+}
+
 /* Sampler::sample_latent_genotype (src/sampler.cpp:230-340) on masks */
 static uint64_t stp_sample_latent(stp_stream *s, uint64_t obs, int A, int coi, double eps_pos,
                                   double eps_neg, double *log_prob)
@@ -126,9 +163,11 @@ static uint64_t stp_sample_latent(stp_stream *s, uint64_t obs, int A, int coi, d
     const int min_fn = obs_pos == 0;
     int max_fn = coi < obs_neg ? coi : obs_neg;
     if (max_fn < min_fn) max_fn = min_fn;
-    int fn = min_fn;
-    for (int ii = min_fn; ii < max_fn; ++ii) fn += (stp_uniform(s) < eps_neg / (double)A);
-    s->have = 0; /* the engine starts every phase of the draw on a fresh Philox block */
+    /* counts by inversion, one uniform each, always consumed in this order (the engine's stream use) */
+    const double u_fn = stp_uniform(s), u_fp = stp_uniform(s);
+    const double pr_en = eps_neg / (double)A, pr_ep = eps_pos / (double)A;
+    const double q_en = 1.0 - pr_en, q_ep = 1.0 - pr_ep;
+    const int fn = min_fn + stp_binom_inverse(u_fn, max_fn - min_fn, q_en, pr_en / q_en);
     int min_fp = obs_pos + fn - coi;
     if (min_fp < 0) min_fp = 0;
     int max_fp = obs_pos + fn - 1;
@@ -138,9 +177,7 @@ static uint64_t stp_sample_latent(stp_stream *s, uint64_t obs, int A, int coi, d
         *log_prob = -INFINITY;
         return 0;
     }
-    int fp = min_fp;
-    for (int ii = min_fp; ii < max_fp; ++ii) fp += (stp_uniform(s) < eps_pos / (double)A);
-    s->have = 0;
+    const int fp = min_fp + stp_binom_inverse(u_fp, max_fp - min_fp, q_ep, pr_ep / q_ep);
     const uint64_t pos = stp_choose_bits(s, obs, obs_pos, obs_pos - fp);
     const uint64_t neg = stp_choose_bits(s, ~obs & all, obs_neg, fn);
     *log_prob = latent_log_prob_f64(A, obs_pos, fn, fp, coi, eps_pos, eps_neg);

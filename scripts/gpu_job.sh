@@ -1,3 +1,6 @@
 set -x
-python -m pytest tests/test_gpu_posterior.py -m gpu -q > gpurun_out/r2m_pytest_post.log 2>&1; tail -5 gpurun_out/r2m_pytest_post.log
-python scripts/posterior_study.py c3s c5s > gpurun_out/r2m_posterior_study.json 2> gpurun_out/r2m_posterior_study.err; tail -3 gpurun_out/r2m_posterior_study.err
+( time python -m pytest tests -m gpu -q ) > gpurun_out/r2q_pytest.log 2>&1
+tail -12 gpurun_out/r2q_pytest.log | cut -c1-300
+for c in c2 c3; do python scripts/kind_timing.py --config $c >> gpurun_out/r2q_kind.log 2>&1; done; grep config gpurun_out/r2q_kind.log
+python scripts/kind_timing.py --config c3 --steps 1 --warmup 1 > gpurun_out/r2q_plain_c3.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'k_sf_cells' -s 3 -c 3 -o gpurun_out/r2q_c3_cells python scripts/kind_timing.py --config c3 --steps 1 --warmup 1 > gpurun_out/r2q_ncu_c3.log 2>&1

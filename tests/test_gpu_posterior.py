@@ -64,11 +64,12 @@ def test_posterior_matches_the_reference_sampler_at_hard_shapes(shape):
     r32 = g["ref32.m"]
     own = np.corrcoef(r32[: len(r32) // 2].mean(axis=0), r32[len(r32) // 2:].mean(axis=0))[0, 1]
     assert np.corrcoef(our_m, ref_m)[0, 1] > min(0.99, own - 0.02), (np.corrcoef(our_m, ref_m)[0, 1], own)
-    assert abs(our_m.mean() - ref_m.mean()) < 0.03 * ref_m.mean()
-    for key in ("r", "eps_neg", "eps_pos"):
-        a = np.mean([o[key].mean() for o in ours])
-        b = g[f"ref32.{key}"].mean()
-        assert abs(a - b) < 0.06 * b + 0.002, (shape, "ref32", key, a, b)
+    for key, fl in floors.items():
+        # Monte-Carlo error of both sides plus the systematic share the float arithmetic accounts for
+        # (profiles/r02_posterior_study_c3s_c5s.json: the reference's own fp64 build differs from its
+        # fp32 build by as much, and the engine with MOIRE_NUMERICS_REF32 lands on the fp32 values)
+        d, se = compare(ours, g[f"ref32.{key}"], key, fl)
+        assert abs(d) < 4.5 * se + 0.05 * abs(np.mean(g[f"ref32.{key}"])), (shape, "ref32", key, d, se)
     our_p0 = np.mean([o["p0"] for o in ours], axis=0)
     assert np.abs(our_p0 - g["ref32.p0"].mean(axis=0)).max() < 0.02
     # log-likelihood at stationarity, in units of the reference's own trace sd
