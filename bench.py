@@ -417,14 +417,22 @@ def our_arm(args, wl):
         top_ms, top_n = kind_ms[kind], kind_n[kind]
         top_evals = ke1[kind] - ke0[kind] if kind in ke1 else 0
     achieved = top_evals * B_EVAL / (top_ms * 1e-3) / 1e9 if top_ms > 0 else 0.0
-    traffic = None
+    traffic, compute = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_inputs.json")) as f:
-            traffic = json.load(f).get("traffic_bytes_per_launch", {}).get(top)
+            inputs = json.load(f)
+        traffic = inputs.get("traffic_bytes_per_launch", {}).get(top)
+        compute = inputs.get("compute", {}).get(top)
     except Exception:
         pass
+    if compute is not None:
+        # what actually bounds the kernel: the fp64 pipe and the issue slots, from the
+        # committed ncu capture; the live part is the instruction rate these launches sustained
+        compute = dict(compute, source="profiles/roofline_inputs.json (ncu --set full capture of one full-ladder launch)",
+                       measured_thread_instructions_per_sec=(compute["thread_instructions_per_evaluation"] * top_evals
+                                                             / (top_ms * 1e-3)) if top_ms > 0 else None)
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    traffic=traffic, kernel=top, peak_source=peak_src,
+                    traffic=traffic, compute=compute, kernel=top, peak_source=peak_src,
                     launches=top_n, ms_per_launch=top_ms / max(top_n, 1),
                     algorithmic_bytes_per_launch=top_evals * B_EVAL / max(top_n, 1),
                     share_of_step=top_ms / step_kernel_ms,
