@@ -404,6 +404,9 @@ struct moire_engine
     ~moire_engine()
     {
         cudaSetDevice(device);
+        // The buffers go back to a per-process cache, not to cudaFree (which would wait for the
+        // device): nothing of this engine may still be running when the next engine picks them up.
+        if (stream) cudaStreamSynchronize(stream);
         for (auto &t : pending)
         {
             cudaEventDestroy(t.a);

@@ -368,6 +368,7 @@ struct moire_mcmc
 
     ~moire_mcmc()
     {
+        if (stream) cudaStreamSynchronize(stream);  // queued steps still write the ladder and the draw store
         for (auto &g : step_graph)
             if (g) cudaGraphExecDestroy(g);
         for (void *p : dev_allocs) cudaFree(p);

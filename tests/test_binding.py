@@ -122,8 +122,12 @@ def test_binding_matches_python_run_mcmc_on_the_gpu(monkeypatch):
     T = 3
     names = b.run(sim, np.linspace(1, 0, T), burnin=40, samples=20, thin=2, record_latent_genotypes=1)
     idx = {n: i for i, n in enumerate(names)}
+    # the reference's Parameters holds its reals as float (src/parameters.h:31-47): the binding hands
+    # the engine 0.1f for mean_coi_shape, so does this call
+    f32 = lambda x: float(np.float32(x))
     ch = run_mcmc(sim, sim["is_missing"], burnin=40, samples_per_chain=20, thin=2, pt_chains=np.linspace(1, 0, T),
                   max_coi=20, pre_adapt_steps=5, temp_adapt_steps=4, max_initialization_tries=100,
+                  mean_coi_shape=f32(DEFAULTS["mean_coi_shape"]), mean_coi_scale=f32(DEFAULTS["mean_coi_scale"]),
                   record_latent_genotypes=True, verbose=False, seed=9)["chains"][0]
     for k in ("llik_burnin", "llik_sample", "prior_sample", "posterior_burnin", "lam_coi", "swap_store",
               "temp_gradient", "swap_barriers", "swap_acceptances", "observed_coi"):
