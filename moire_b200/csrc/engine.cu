@@ -634,6 +634,17 @@ struct moire_engine
             pf.list = pf_list.ptr; pf.hist = pf_hist.ptr; pf.Tcur = pf_Tcur.ptr; pf.Tnew = pf_Tnew.ptr;
             pf.pprop = pf_pprop.ptr; pf.round = pf_round.ptr; pf.nonmiss = pf_nonmiss.ptr;
             p_smem = 0;  // the fused kernel's per-block arrays are not needed
+            {
+                // k_pf_round: one block per (chain, locus), about as many threads in all as the device
+                // holds at 64 registers each (one warp per locus at the benchmark ladder, 512 threads
+                // for a few dozen loci with thousands of samples)
+                cudaDeviceProp pr;
+                CUDA_TRY(cudaGetDeviceProperties(&pr, device));
+                const size_t want = (size_t)pr.multiProcessorCount * 1024 / ((size_t)T * L);
+                pf_round_threads = 32;
+                while (pf_round_threads < 1024 && (size_t)pf_round_threads * 2 <= want && pf_round_threads * 4 <= N)
+                    pf_round_threads *= 2;
+            }
             // the per-sample updates share the list, the histogram and the two term arrays
             sf_prop.alloc(TN); sf_m.alloc(TN); sf_ss.alloc(TN); pf_ss.alloc(TN);
             pf.ss = pf_ss.ptr;
@@ -742,6 +753,7 @@ struct moire_engine
     }
 
     // update_p as sort-once + (round, eval) per proposal (p_flat.cuh); nothing returns to the host
+    int pf_round_threads = 32;  // k_pf_round: threads of the block that owns a (chain, locus)
     void update_p_flat(int iteration)
     {
         using namespace moire;
@@ -759,12 +771,12 @@ struct moire_engine
         launches += 2;  // prepare, scan, scatter (the caller counted one)
         for (int rep = 0; rep < amax_alleles; ++rep)
         {
-            k_pf_round<<<(v.T * v.L + kPfRoundThreads / 32 - 1) / (kPfRoundThreads / 32), kPfRoundThreads, 0, stream>>>(v, pf, iteration, rep);
+            k_pf_round<<<(unsigned)(v.T * v.L), pf_round_threads, 0, stream>>>(v, pf, iteration, rep);
             src.counter = pf.hist + kPfCounters + rep;
             launch_flat_eval(src);
             launches += 2;
         }
-        k_pf_round<<<(v.T * v.L + kPfRoundThreads / 32 - 1) / (kPfRoundThreads / 32), kPfRoundThreads, 0, stream>>>(v, pf, iteration, amax_alleles);
+        k_pf_round<<<(unsigned)(v.T * v.L), pf_round_threads, 0, stream>>>(v, pf, iteration, amax_alleles);
         k_pf_finish<<<cell_blocks, 256, 0, stream>>>(v, pf);
         launches += 2;
         CUDA_TRY(cudaGetLastError());

@@ -7,8 +7,8 @@
 // kernel on an instruction-fetch-bound path (profiles/README.md).  Here the work is cut the other
 // way: the latent genotypes do not change during update_p, so ALL cells of ALL chains are sorted
 // ONCE by cost class (device-wide counting sort), and every proposal round is
-//   k_pf_round  one warp per (chain, locus): decide the previous proposal, commit, draw the next
-//               SALT proposal                                             (tiny, serial math)
+//   k_pf_round  one block per (chain, locus): sum and decide the previous proposal, commit, draw
+//               the next SALT proposal                        (one latency chain per locus)
 //   k_flat_eval a persistent grid over the sorted cell list: warps with identical (k, m - k + 1) in
 //               every lane, no block barrier, only the evaluator's code   (all the arithmetic)
 // Rounds = max_j A_j; loci with fewer alleles (or that hit the 1e-12 floor) sit out.  Streams,
@@ -298,50 +298,55 @@ __global__ void __launch_bounds__(256) k_pf_scatter(const View v, const PFlat f)
     block_scatter(total, cell_fn, f.hist + kSortBins, f.list);
 }
 
-// ---- once per proposal round: decide the previous proposal, draw the next ----------------------
-// One warp per (chain, locus), no block barriers: the decision and the proposal are one warp's
-// serial math, so the kernel is latency bound and wants as many independent warps in flight as
-// the SM holds (ncu, block-per-locus version: 51 us per round at 27 % issue, 36 % warps active).
-// Tcur / Tnew hold 0 at missing cells (k_pf_prepare), so the sum needs no mask.
-constexpr int kPfRoundThreads = 128;
-__global__ void __launch_bounds__(kPfRoundThreads) k_pf_round(const View v, const PFlat f, const int iteration_arg,
-                                                  const int rep)
+// ---- once per proposal round: decide the previous proposal, draw the next -----------------------
+// One block per (chain, locus); the block size follows the shape (engine.cu: about as many threads
+// as the device holds, spread over T * L loci: 64 at the benchmark ladder, 1024 for a few loci with
+// thousands of samples) and the registers are capped at 64, so every locus of a round is resident at
+// once -- the kernel is one latency chain per locus (sum, decision, commit, proposal), not
+// throughput.  Tcur / Tnew hold 0 at missing cells (k_pf_prepare), so the sum needs no mask.
+__global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat f, const int iteration_arg,
+                                                    const int rep)
 {
+    __shared__ double s_part[32];
+    __shared__ int s_accept;
     const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     const int N = v.N, L = v.L, AP = v.AP;
-    const int lane = threadIdx.x & 31;
-    const int tl = blockIdx.x * (kPfRoundThreads / 32) + (threadIdx.x >> 5);
-    if (tl >= v.T * L) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, B = blockDim.x;
+    const int tl = blockIdx.x;
     const int t = tl / L, j = tl - t * L;
     const int A = v.nall[j];
     const size_t prow = (size_t)tl * AP;
     double *st = f.round + (size_t)tl * 4;
     unsigned flags = rep == 0 ? 0u : (unsigned)st[3];
+    double *tn = f.Tnew + (size_t)tl * N, *tc = f.Tcur + (size_t)tl * N;
 
     if (flags & kPfActive)
     {
-        // -- the change of the locus' log-likelihood under proposal rep - 1
+        // -- the change of the locus' log-likelihood under proposal rep - 1: thread-strided partial
+        // sums (four loads in flight per array), the shuffle tree, then the warp sums in warp order
         double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-        const double *tn = f.Tnew + (size_t)tl * N, *tc = f.Tcur + (size_t)tl * N;
-        int i = lane;
-        for (; i + 96 < N; i += 128)
+        int i = tid;
+        for (; i + 3 * B < N; i += 4 * B)
         {
-            const double a0 = tn[i], a1 = tn[i + 32], a2 = tn[i + 64], a3 = tn[i + 96];
-            const double b0 = tc[i], b1 = tc[i + 32], b2 = tc[i + 64], b3 = tc[i + 96];
+            const double a0 = tn[i], a1 = tn[i + B], a2 = tn[i + 2 * B], a3 = tn[i + 3 * B];
+            const double b0 = tc[i], b1 = tc[i + B], b2 = tc[i + 2 * B], b3 = tc[i + 3 * B];
             d0 += a0 - b0;
             d1 += a1 - b1;
             d2 += a2 - b2;
             d3 += a3 - b3;
         }
-        for (; i < N; i += 32) d0 += tn[i] - tc[i];
-        const double d = warp_sum((d0 + d1) + (d2 + d3));
-        int accept = 0;
-        if (lane == 0)
+        for (; i < N; i += B) d0 += tn[i] - tc[i];
+        const double dw = warp_sum((d0 + d1) + (d2 + d3));
+        if (lane == 0) s_part[warp] = dw;
+        __syncthreads();
+        if (tid == 0)
         {
+            double d = 0.0;
+            for (int w = 0; w < (B >> 5); ++w) d += s_part[w];
             const int idx = (int)st[2];
             const double dpost = v.temp[t] * d;  // the priors do not depend on p
             const double ratio = dpost + st[0];
-            accept = !(isnan(dpost) || st[1] > ratio);
+            const int accept = !(isnan(dpost) || st[1] > ratio);
             if (accept) ++v.p_acc[prow + idx];
             if (iteration < v.burnin && v.p_att[prow + idx] > 15)
             {
@@ -352,22 +357,23 @@ __global__ void __launch_bounds__(kPfRoundThreads) k_pf_round(const View v, cons
                 v.p_sd[prow + idx] = sd > .01 ? sd : .01;
             }
             atomicAdd(v.evals + KIND_P, (unsigned long long)f.nonmiss[j]);
+            s_accept = accept;
         }
-        accept = __shfl_sync(0xffffffffu, accept, 0);
-        if (accept)
+        __syncthreads();
+        if (s_accept)
         {
-            double *tcw = f.Tcur + (size_t)tl * N;
-            for (int q = lane; q < N; q += 32) tcw[q] = tn[q];
-            for (int a = lane; a < A; a += 32) v.p[prow + a] = f.pprop[prow + a];
+            for (int q = tid; q < N; q += B) tc[q] = tn[q];
+            for (int a = tid; a < A; a += B) v.p[prow + a] = f.pprop[prow + a];
         }
-        __syncwarp();
+        __syncthreads();
     }
     flags &= ~kPfActive;
     if (rep >= A || (flags & kPfBroken))
     {
-        if (lane == 0) st[3] = (double)flags;
+        if (tid == 0) st[3] = (double)flags;
         return;
     }
+    if (warp != 0) return;
     // -- proposal `rep`, lanes across alleles (same arithmetic as k_update_p)
     {
         Stream rng;
