@@ -48,6 +48,17 @@ extern "C" {
  * differences to the reference's precision; the default (off) is the fp64 evaluation whose cells
  * match the reference's double variant to 1e-9.  Process-wide: the last created engine decides. */
 #define MOIRE_NUMERICS_REF32 0x100
+/* OR-ed into moire_params::pipeline: update_p's PAM cache (flat pipelines only).  SALT
+ * (src/mcmc_utils.h:252-300) moves one allele frequency and rescales the others by a common factor,
+ * so a cell whose latent genotype does not hold the proposed allele keeps its normalised frequencies
+ * and every P(any missing); with the cache ON such a cell re-runs only the relatedness mixture on
+ * the new frequency sum, and only the cells that hold the proposed allele (a fraction k / A_j) are
+ * evaluated from scratch each round.  Default (neither bit): OFF -- a cached vector was computed
+ * from frequencies that have been rescaled since, equal to the last bits, and a cell whose coverage
+ * probability is tiny amplifies that difference (observed: 2.6e-9 relative on a cell term, past the
+ * 1e-9 the from-scratch evaluation holds).  Costs 16 B x max_coi per cell of device memory. */
+#define MOIRE_P_CACHE_ON 0x200
+#define MOIRE_P_CACHE_OFF 0x400
 
 /* The 8 Metropolis updates in the order MCMC::burnin runs them (src/mcmc.cpp:162-173). */
 enum moire_update_kind

@@ -353,6 +353,7 @@ __global__ void k_dump_subset_order(const int which, const int k, unsigned short
 
 struct moire_engine
 {
+    static constexpr size_t kTraceWords = 1024 * 256;  // MOIRE_B200_TRACE: 256 words per evaluator block
     moire::View v{};
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -374,6 +375,12 @@ struct moire_engine
     DevBuf<int> pf_nonmiss;
     int amax_alleles = 0;
     bool p_fused = false;
+    // update_p's PAM cache (p_flat.cuh: k_pc_sweep)
+    bool p_cache = false;
+    DevBuf<unsigned long long> pf_latLM;
+    DevBuf<double> red_part;          // k_reduce: per-part sums
+    DevBuf<unsigned int> red_done;    //           parts finished, per chain
+    DevBuf<double> pf_Wcur, pf_Wnew;
     // the step as a CUDA graph: ~55 launches replayed with one call, iteration read from iter_dev
     DevBuf<int> iter_dev;
     cudaGraphExec_t step_graph = nullptr;
@@ -418,13 +425,14 @@ struct moire_engine
         aclass.release(); avals.release(); obs_coi.release(); m.release(); acc6.release();
         p_acc.release(); p_att.release(); active.release(); logC.release(); lgam.release();
         pf_list.release(); pf_hist.release(); pf_Tcur.release(); pf_Tnew.release(); pf_pprop.release();
-        pf_round.release(); pf_nonmiss.release();
+        red_part.release(); red_done.release();
+        pf_round.release(); pf_nonmiss.release(); pf_latLM.release(); pf_Wcur.release(); pf_Wnew.release();
         sf_prop.release(); sf_m.release(); sf_ss.release(); pf_ss.release(); sf_lat.release(); sf_adj.release(); sf_elogs.release();
         lgadj.release(); cellT.release(); cellO.release(); persample.release(); p.release();
         p_sd.release(); perchain.release(); scratchN.release();
         if (v.trace && std::getenv("MOIRE_B200_TRACE"))
         {
-            std::vector<unsigned long long> h(64 * 16 * 16 * 2);
+            std::vector<unsigned long long> h(kTraceWords);
             if (cudaMemcpy(h.data(), v.trace, h.size() * sizeof(h[0]), cudaMemcpyDeviceToHost) == cudaSuccess)
                 if (FILE *f = std::fopen(std::getenv("MOIRE_B200_TRACE"), "wb"))
                 {
@@ -520,6 +528,8 @@ struct moire_engine
         m.alloc(TN); acc6.alloc(6 * TN); persample.alloc(14 * TN);
         p.alloc(TLA); p_sd.alloc(TLA); p_acc.alloc(TLA); p_att.alloc(TLA);
         perchain.alloc(7 * (size_t)T); active.alloc(T); evals.alloc(16); iter_dev.alloc(1); scratchN.alloc(N);
+        red_part.alloc((size_t)T * moire::kReduceParts * 2); red_done.alloc(T);
+        CUDA_TRY(cudaMemsetAsync(red_done.ptr, 0, (size_t)T * sizeof(unsigned int), stream));
 
         std::vector<double> logC_h(moire::kLogCDim * moire::kLogCDim, -INFINITY), lgam_h(128);
         for (int n = 0; n < moire::kLogCDim; ++n)
@@ -582,7 +592,8 @@ struct moire_engine
         v.trace = nullptr;
         if (std::getenv("MOIRE_B200_TRACE"))  // tuning aid: per-warp clocks of update_p
         {
-            trace.alloc(64 * 16 * 16 * 2);
+            trace.alloc(kTraceWords);
+            CUDA_TRY(cudaMemsetAsync(trace.ptr, 0, kTraceWords * sizeof(unsigned long long), stream));
             v.trace = trace.ptr;
         }
         CUDA_TRY(cudaMemcpyAsync(v.temp, temps, T * sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -607,7 +618,9 @@ struct moire_engine
         const int pipeline = prm->pipeline & 0xff;
         if (pipeline == MOIRE_PIPELINE_FLAT) p_fused = false;
         if (pipeline == MOIRE_PIPELINE_FUSED) p_fused = true;
-        if (prm->pipeline < 0 || pipeline > MOIRE_PIPELINE_FUSED || (prm->pipeline & ~(0xff | MOIRE_NUMERICS_REF32)))
+        if (prm->pipeline < 0 || pipeline > MOIRE_PIPELINE_FUSED ||
+            (prm->pipeline & ~(0xff | MOIRE_NUMERICS_REF32 | MOIRE_P_CACHE_ON | MOIRE_P_CACHE_OFF)) ||
+            ((prm->pipeline & MOIRE_P_CACHE_ON) && (prm->pipeline & MOIRE_P_CACHE_OFF)))
             throw InvalidArg{"unknown pipeline / numerics flags"};
         {
             const int pam_float = (prm->pipeline & MOIRE_NUMERICS_REF32) != 0;
@@ -625,7 +638,7 @@ struct moire_engine
         if (!p_fused)
         {
             pf_list.alloc(TNL); pf_hist.alloc(moire::kPfHistWords);
-            pf_Tcur.alloc(TNL); pf_Tnew.alloc(TNL);
+            pf_Tcur.alloc(TNL); pf_Tnew.alloc(TNL); pf_latLM.alloc(TNL); pf.latLM = pf_latLM.ptr;
             pf_pprop.alloc(TLA); pf_round.alloc((size_t)T * L * 4); pf_nonmiss.alloc(L);
             std::vector<int> nm(L, 0);
             for (int i = 0; i < N; ++i)
@@ -634,6 +647,26 @@ struct moire_engine
             pf.list = pf_list.ptr; pf.hist = pf_hist.ptr; pf.Tcur = pf_Tcur.ptr; pf.Tnew = pf_Tnew.ptr;
             pf.pprop = pf_pprop.ptr; pf.round = pf_round.ptr; pf.nonmiss = pf_nonmiss.ptr;
             p_smem = 0;  // the fused kernel's per-block arrays are not needed
+            {
+                // update_p's PAM cache: two [max_coi][cells] arrays + a locus-major genotype copy
+                const size_t wbytes = 2 * (size_t)v.max_coi * TNL * sizeof(double);
+                size_t budget = (size_t)48 << 30;
+                if (const char *env = std::getenv("MOIRE_B200_P_CACHE_MAX_GB")) budget = (size_t)std::atoll(env) << 30;
+                const bool on = (prm->pipeline & MOIRE_P_CACHE_ON) != 0, off = (prm->pipeline & MOIRE_P_CACHE_OFF) != 0;
+                if (on && wbytes > budget)
+                    throw InvalidArg{"MOIRE_P_CACHE_ON needs " + std::to_string(wbytes >> 20) + " MiB for the PAM cache; budget " +
+                                     std::to_string(budget >> 20) + " MiB (MOIRE_B200_P_CACHE_MAX_GB)"};
+                // off unless asked for: a cached PAM comes from frequencies that were rescaled since, and
+                // a cell whose coverage probability is tiny amplifies that last-bit difference past the
+                // 1e-9 the from-scratch evaluation holds against the reference
+                (void)off;
+                p_cache = on;
+                if (p_cache)
+                {
+                    pf_Wcur.alloc((size_t)v.max_coi * TNL); pf_Wnew.alloc((size_t)v.max_coi * TNL);
+                    pf.Wcur = pf_Wcur.ptr; pf.Wnew = pf_Wnew.ptr; pf.wstride = TNL;
+                }
+            }
             {
                 // k_pf_round: one block per (chain, locus), about as many threads in all as the device
                 // holds at 64 registers each (one warp per locus at the benchmark ladder, 512 threads
@@ -679,10 +712,11 @@ struct moire_engine
             CUDA_TRY(cudaFuncSetAttribute(k_update_p<MOIRE_P_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
             CUDA_TRY(cudaFuncSetAttribute(k_update_p<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
         }
-        CUDA_TRY(cudaFuncSetAttribute(k_flat_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
+        CUDA_TRY(cudaFuncSetAttribute(k_flat_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
+        CUDA_TRY(cudaFuncSetAttribute(k_flat_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
         {
             int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flat_eval, kEvalThreads, pf_eval_smem()));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flat_eval<false>, kEvalThreads, pf_eval_smem()));
             cudaDeviceProp prop1;
             CUDA_TRY(cudaGetDeviceProperties(&prop1, device));
             flat_grid = std::max(1, per_sm) * prop1.multiProcessorCount;
@@ -735,7 +769,7 @@ struct moire_engine
     size_t pf_eval_smem() const { return moire::pf_eval_smem_doubles(v.max_coi) * sizeof(double); }
     int flat_grid = 0;  // persistent evaluator grid: resident blocks of the device
 
-    void launch_flat_eval(const moire::FlatSrc &src)
+    void launch_flat_eval(const moire::FlatSrc &src, bool cache = false)
     {
         cudaEvent_t a = nullptr, b = nullptr;
         if (timing)
@@ -744,7 +778,10 @@ struct moire_engine
             CUDA_TRY(cudaEventCreate(&b));
             CUDA_TRY(cudaEventRecord(a, stream));
         }
-        moire::k_flat_eval<<<flat_grid, moire::kEvalThreads, pf_eval_smem(), stream>>>(v, src);
+        if (cache)
+            moire::k_flat_eval<true><<<flat_grid, moire::kEvalThreads, pf_eval_smem(), stream>>>(v, src);
+        else
+            moire::k_flat_eval<false><<<flat_grid, moire::kEvalThreads, pf_eval_smem(), stream>>>(v, src);
         if (timing)
         {
             CUDA_TRY(cudaEventRecord(b, stream));
@@ -760,7 +797,8 @@ struct moire_engine
         const size_t total = (size_t)v.T * v.L * v.N;
         const unsigned cell_blocks = (unsigned)((total + 255) / 256);
         CUDA_TRY(cudaMemsetAsync(pf.hist, 0, kPfHistWords * sizeof(unsigned int), stream));
-        k_pf_prepare<<<cell_blocks, 256, 0, stream>>>(v, pf);
+        const unsigned tile_blocks = (unsigned)v.T * pf_tiles(v.N, v.L);
+        k_pf_prepare<<<tile_blocks, 256, 0, stream>>>(v, pf);
         k_pf_scan<<<1, 256, 0, stream>>>(pf);
         k_pf_scatter<<<scatter_blocks(total), 256, 0, stream>>>(v, pf);
         FlatSrc src{};
@@ -769,6 +807,30 @@ struct moire_engine
         src.ss = pf.ss; src.binom_rows = v.max_coi;
         src.round_flags = pf.round; src.out = pf.Tnew;
         launches += 2;  // prepare, scan, scatter (the caller counted one)
+        if (p_cache)
+        {
+            // the PAM vectors of the current state: one evaluation of every cell at the accepted p
+            src.p = v.p; src.round_flags = nullptr; src.counter = pf.hist + kPfCounters;
+            src.pam_out = pf.Wcur; src.pam_stride = pf.wstride;
+            launch_flat_eval(src, true);
+            src.p = pf.pprop; src.pam_out = pf.Wnew;
+            const unsigned list_blocks = scatter_blocks(total);
+            for (int rep = 0; rep < amax_alleles; ++rep)
+            {
+                k_pf_round<<<(unsigned)(v.T * v.L), pf_round_threads, 0, stream>>>(v, pf, iteration, rep);
+                k_pc_sweep<<<cell_blocks, 256, 0, stream>>>(v, pf);
+                k_pf_scan<<<1, 256, 0, stream>>>(pf);
+                k_pc_scatter<<<list_blocks, 256, 0, stream>>>(v, pf);
+                src.counter = pf.hist + kPfCounters + 1 + rep;
+                launch_flat_eval(src, true);
+                launches += 5;
+            }
+            k_pf_round<<<(unsigned)(v.T * v.L), pf_round_threads, 0, stream>>>(v, pf, iteration, amax_alleles);
+            k_pf_finish<<<tile_blocks, 256, 0, stream>>>(v, pf);
+            launches += 3;
+            CUDA_TRY(cudaGetLastError());
+            return;
+        }
         for (int rep = 0; rep < amax_alleles; ++rep)
         {
             k_pf_round<<<(unsigned)(v.T * v.L), pf_round_threads, 0, stream>>>(v, pf, iteration, rep);
@@ -777,7 +839,7 @@ struct moire_engine
             launches += 2;
         }
         k_pf_round<<<(unsigned)(v.T * v.L), pf_round_threads, 0, stream>>>(v, pf, iteration, amax_alleles);
-        k_pf_finish<<<cell_blocks, 256, 0, stream>>>(v, pf);
+        k_pf_finish<<<tile_blocks, 256, 0, stream>>>(v, pf);
         launches += 2;
         CUDA_TRY(cudaGetLastError());
     }
@@ -876,7 +938,7 @@ struct moire_engine
     void reduce()
     {
         Timed tm(this, 8);
-        moire::k_reduce<<<v.T, 1024, 0, stream>>>(v);
+        moire::k_reduce<<<v.T * moire::kReduceParts, 1024, 0, stream>>>(v, red_part.ptr, red_done.ptr);
         tm.done();
     }
 

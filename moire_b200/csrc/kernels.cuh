@@ -238,9 +238,9 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
             if (k > m)
                 T = NAN;
             else if (coop_egf)
-                T = transmission_ll_egf_coop(lat, prow, m, rel, allow_rel, scr + warp * 32, ST, lgam, nullptr);
+                T = transmission_ll_egf_coop<false>(lat, prow, m, rel, allow_rel, scr + warp * 32, ST, lgam, nullptr, PamOut{});
             else
-                T = transmission_ll_coop(lat, prow, m, rel, allow_rel, scr + warp * 32, ST, lgam, nullptr);
+                T = transmission_ll_coop<false>(lat, prow, m, rel, allow_rel, scr + warp * 32, ST, lgam, nullptr, PamOut{});
             if (lane == 0) out[cell] = T;
         }
         else
@@ -268,7 +268,7 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
                 fetch(cell, lat, prow, m, rel);
                 double pv[kGather];
                 gather_freqs(lat, prow, pv);
-                out[cell] = transmission_ll(lat, prow, pv, m, rel, allow_rel, scr + tid, ST, lgam, nullptr, callers);
+                out[cell] = transmission_ll<false>(lat, prow, pv, m, rel, allow_rel, scr + tid, ST, lgam, nullptr, callers, PamOut{});
             }
         }
         __syncwarp();
@@ -958,19 +958,23 @@ __global__ void __launch_bounds__(kThreads) k_update_mean_coi(const View v, cons
 }
 
 // ---- per-chain sums (calc_new_likelihood / calc_new_prior, src/chain.cpp:978-1026) ------------
-__global__ void __launch_bounds__(1024) k_reduce(const View v)
+// kReduceParts blocks per chain (one block per chain left most of the device idle: 24 us for the
+// 40-chain ladder, as long again for a 5-chain shard): part g sums the cells c = g B + tid (mod
+// kReduceParts B) in a fixed order, and the last part to finish adds the parts in index order -- the
+// result does not depend on which block that is.
+constexpr int kReduceParts = 8;
+__global__ void __launch_bounds__(1024) k_reduce(const View v, double *part, unsigned int *done)
 {
     __shared__ double s_red[40];
-    const int tid = threadIdx.x, t = blockIdx.x;
+    const int tid = threadIdx.x, t = blockIdx.x / kReduceParts, g = blockIdx.x % kReduceParts;
     const size_t ncell = (size_t)v.N * v.L;
     const double *cT = v.cellT + (size_t)t * ncell;
     const double *cO = v.cellO + (size_t)t * ncell;
     double s = 0.0;
     {
-        // a thread's cells in its fixed order, eight loads in flight (one chain per block: the
-        // kernel is latency bound)
-        const size_t B = blockDim.x;
-        size_t c = tid;
+        // a thread's cells in its fixed order, eight loads in flight
+        const size_t B = (size_t)blockDim.x * kReduceParts;
+        size_t c = (size_t)g * blockDim.x + tid;
         for (; c + 3 * B < ncell; c += 4 * B)
         {
             const double a0 = cT[c], a1 = cT[c + B], a2 = cT[c + 2 * B], a3 = cT[c + 3 * B];
@@ -983,17 +987,32 @@ __global__ void __launch_bounds__(1024) k_reduce(const View v)
         for (; c < ncell; c += B) s += __dadd_rn(cT[c], cO[c]);
     }
     const double llik = block_sum(s, s_red);
-    double q = 0.0;
-    for (int i = tid; i < v.N; i += blockDim.x)
+    double prior = 0.0;
+    if (g == 0)
     {
-        const size_t si = (size_t)t * v.N + i;
-        q += ((v.pr_eps_neg[si] + v.pr_eps_pos[si]) + v.pr_r[si]) + v.pr_coi[si];
+        double q = 0.0;
+        for (int i = tid; i < v.N; i += blockDim.x)
+        {
+            const size_t si = (size_t)t * v.N + i;
+            q += ((v.pr_eps_neg[si] + v.pr_eps_pos[si]) + v.pr_r[si]) + v.pr_coi[si];
+        }
+        prior = block_sum(q, s_red);
     }
-    const double prior = block_sum(q, s_red);
     if (tid == 0)
     {
-        v.llik[t] = llik;
-        v.prior[t] = prior + v.hyper[t];
+        double *mine = part + ((size_t)t * kReduceParts + g) * 2;
+        mine[0] = llik;
+        if (g == 0) mine[1] = prior;
+        __threadfence();
+        if (atomicAdd(&done[t], 1u) == kReduceParts - 1)
+        {
+            __threadfence();
+            double l = 0.0;
+            for (int q = 0; q < kReduceParts; ++q) l += __ldcg(part + ((size_t)t * kReduceParts + q) * 2);
+            v.llik[t] = l;
+            v.prior[t] = __ldcg(part + (size_t)t * kReduceParts * 2 + 1) + v.hyper[t];
+            done[t] = 0;  // ready for the next launch
+        }
     }
 }
 
@@ -1040,8 +1059,8 @@ __global__ void __launch_bounds__(kThreads)
         const double *prow = v.p + ((size_t)t * v.L + j) * v.AP;
         double pv[kGather];
         gather_freqs(v.latent[gi], prow, pv);
-        T = transmission_ll(v.latent[gi], prow, pv, v.m[si], rel, v.allow_rel != 0, s_qs + tid,
-                            kThreads + 1, s_lgam, nullptr, callers);
+        T = transmission_ll<false>(v.latent[gi], prow, pv, v.m[si], rel, v.allow_rel != 0, s_qs + tid,
+                                   kThreads + 1, s_lgam, nullptr, callers, PamOut{});
         O = observation_ll(v.latent[gi], v.obs[cell], v.nall[j], el);
     }
     v.cellT[gi] = T;

@@ -434,6 +434,28 @@ __device__ __forceinline__ double norel_term(double pam, double total, int m)
 
 constexpr int kMaxAcc = 16;  // accumulators kept in registers
 
+// update_p's PAM cache (p_flat.cuh): an evaluator compiled with CACHE leaves the raw PAM vector of
+// the cell -- exactly what it hands to relatedness_mixture / norel_term -- at w[t * stride],
+// t < m - k + 1 (relatedness off: w[0]), so that a later proposal that does not touch the cell's
+// latent alleles (q unchanged, only their sum moves) re-runs the mixture alone.
+struct PamOut
+{
+    double *w;
+    size_t stride;
+};
+template <bool CACHE>
+__device__ __forceinline__ void pam_store(const PamOut po, const double *val, int ST, int cnt)
+{
+    if (CACHE)
+        for (int t = 0; t < cnt; ++t) po.w[(size_t)t * po.stride] = val[t * ST];
+}
+template <bool CACHE>
+__device__ __forceinline__ double norel_term_c(double pam, double total, int m, const PamOut po)
+{
+    if (CACHE) po.w[0] = pam;
+    return norel_term(pam, total, m);
+}
+
 // The subset sums of one cell, accumulators dumped to scr[t * ST], then the mixture.
 // All lanes that arrive together run the accumulator tier of the largest count among them (the
 // extra accumulators of a lane with fewer mixture terms are simply never read), so lanes with
@@ -585,20 +607,24 @@ __device__ __noinline__ void ie_pams(double *scr, int ST, int k, int cnt, unsign
 #undef MOIRE_IE_STORE
 }
 
+template <bool CACHE>
 __device__ __noinline__ double transmission_rel_ie(double *scr, int ST, int k, int m, double total,
                                                    const Rel rel, const double *lgam,
-                                                   const double *binom_s, unsigned lanes)
+                                                   const double *binom_s, unsigned lanes, const PamOut po)
 {
     const int cnt = m - k + 1;
     ie_pams(scr, ST, k, cnt, lanes);
+    pam_store<CACHE>(po, scr, ST, cnt);
     return relatedness_mixture(scr, ST, m, cnt, total, rel, lgam, binom_s);
 }
 
 // m - k >= kMaxAcc (rare: a COI far above the number of distinct alleles): the accumulators are
 // produced kMaxAcc at a time and parked in local memory.
+template <bool CACHE>
 __device__ __noinline__ double transmission_rel_ie_wide(double *scr, int ST, int k, int m,
                                                         double total, const Rel rel,
-                                                        const double *lgam, const double *binom_s)
+                                                        const double *lgam, const double *binom_s,
+                                                        const PamOut po)
 {
     double v[kMaxCoi];
     const int cnt = m - k + 1;
@@ -610,16 +636,18 @@ __device__ __noinline__ double transmission_rel_ie_wide(double *scr, int ST, int
         for (int j = 0; j < kMaxAcc; ++j)
             if (t0 + j < cnt) v[t0 + j] = acc[j];
     }
+    pam_store<CACHE>(po, v, 1, cnt);
     return relatedness_mixture(v, 1, m, cnt, total, rel, lgam, binom_s);
 }
 
 // EGF branch (k > 10) of one cell on one thread: the band in the thread's scratch column while it
 // fits (m - k < kScratchSlots: nearly always), else in local memory; then the same mixture as every
 // other path.
+template <bool CACHE>
 __device__ __noinline__ double transmission_egf(uint64_t latent, const double *prow, double total,
                                                 int k, int m, const Rel rel, bool allow_relatedness,
                                                 double *scr, int ST, const double *lgam,
-                                                const double *binom_s)
+                                                const double *binom_s, const PamOut po)
 {
     const int D = m - k;
     double local_band[kMaxCoi + 1];
@@ -627,14 +655,16 @@ __device__ __noinline__ double transmission_egf(uint64_t latent, const double *p
     const int BS = D < kScratchSlots ? ST : 1;
     egf_band(latent, prow, total, D, band, BS);
     // src/chain.cpp:895-899 with probAnyMissingFunctor::operator() (prob_any_missing.cpp:149-153)
-    if (!allow_relatedness) return norel_term(pam_from_coverage(band[D * BS]), total, m);
+    if (!allow_relatedness) return norel_term_c<CACHE>(pam_from_coverage(band[D * BS]), total, m, po);
     for (int d = 0; d <= D; ++d) band[d * BS] = pam_from_coverage(band[d * BS]);
+    pam_store<CACHE>(po, band, BS, D + 1);
     return relatedness_mixture(band, BS, m, D + 1, total, rel, lgam, binom_s);
 }
 
 // Relatedness off and n == k: 1 - k! * prod(q) in double (src/prob_any_missing.cpp:139-148).
+template <bool CACHE>
 __device__ __forceinline__ double transmission_norel_exact_cover(uint64_t latent, const double *prow,
-                                                                 double total, int k)
+                                                                 double total, int k, const PamOut po)
 {
     double cov = 1.0;
     uint64_t rest = latent;
@@ -645,7 +675,7 @@ __device__ __forceinline__ double transmission_norel_exact_cover(uint64_t latent
         cov = __dmul_rn(cov, __ddiv_rn(prow[al], total));
     }
     for (int i = 2; i <= k; ++i) cov = __dmul_rn(cov, (double)i);
-    return norel_term(pam_from_coverage(cov), total, k);
+    return norel_term_c<CACHE>(pam_from_coverage(cov), total, k, po);
 }
 
 // The first kGather allele frequencies of a latent genotype, ascending allele order.  The loads do
@@ -670,11 +700,12 @@ __device__ __forceinline__ void gather_freqs(uint64_t latent, const double *prow
 // stride ST); lgam: lgamma(i + 1), i < 128; binom_s: see relatedness_mixture.  `callers`: the lanes
 // of the warp that make this call together (a __ballot_sync the caller takes BEFORE branching
 // into the call).
+template <bool CACHE>
 __device__ __forceinline__ double transmission_ll(uint64_t latent, const double *prow,
                                                   const double (&pv)[kGather], int m, const Rel rel,
                                                   bool allow_relatedness, double *scr, int ST,
                                                   const double *lgam, const double *binom_s,
-                                                  unsigned callers)
+                                                  unsigned callers, const PamOut po)
 {
     const int k = __popcll(latent);
     // the lanes that will reach the register-tier inclusion-exclusion sums, agreed on while the
@@ -687,7 +718,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
         // One latent allele: q = p / p = 1 exactly, every base 1 - q is exactly 0 and so is every
         // PAM (in each of the reference's branches) -- the subset sums have nothing to add.
         const double total = __dadd_rn(0.0, pv[0]);
-        if (!allow_relatedness) return norel_term(0.0, total, m);
+        if (!allow_relatedness) return norel_term_c<CACHE>(0.0, total, m, po);
         return relatedness_mixture(nullptr, 0, m, m, total, rel, lgam, binom_s);
     }
     // the frequency sum in ascending allele order: the gathered ones, then any further ones
@@ -730,13 +761,13 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
     if (!allow_relatedness)
     {
         // src/chain.cpp:895-899 with probAnyMissingFunctor::operator() (prob_any_missing.cpp:131-154)
-        if (m == k) return transmission_norel_exact_cover(latent, prow, total, k);
-        if (k > kIeMax) return transmission_egf(latent, prow, total, k, m, rel, false, scr, ST, lgam, binom_s);
-        return norel_term(ie_scalar(scr, ST, k, m), total, m);
+        if (m == k) return transmission_norel_exact_cover<CACHE>(latent, prow, total, k, po);
+        if (k > kIeMax) return transmission_egf<CACHE>(latent, prow, total, k, m, rel, false, scr, ST, lgam, binom_s, po);
+        return norel_term_c<CACHE>(ie_scalar(scr, ST, k, m), total, m, po);
     }
-    if (k > kIeMax) return transmission_egf(latent, prow, total, k, m, rel, true, scr, ST, lgam, binom_s);
-    if (m - k + 1 <= kMaxAcc) return transmission_rel_ie(scr, ST, k, m, total, rel, lgam, binom_s, ie_lanes);
-    return transmission_rel_ie_wide(scr, ST, k, m, total, rel, lgam, binom_s);
+    if (k > kIeMax) return transmission_egf<CACHE>(latent, prow, total, k, m, rel, true, scr, ST, lgam, binom_s, po);
+    if (m - k + 1 <= kMaxAcc) return transmission_rel_ie<CACHE>(scr, ST, k, m, total, rel, lgam, binom_s, ie_lanes, po);
+    return transmission_rel_ie_wide<CACHE>(scr, ST, k, m, total, rel, lgam, binom_s, po);
 }
 
 // ---- a2, class-uniform small cells, fully in registers ---------------------------------------------
@@ -753,14 +784,22 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
 constexpr int kSmallK = 6;      // <= MOIRE_SMALL_K
 constexpr int kSmallCnt = 8;    // mixture terms handled in registers
 
-template <int K, int NACC>
+template <int K, int NACC, bool CACHE>
 __device__ __forceinline__ double small_cell_tail(const double (&q)[K], double total, int m, int cnt,
                                                   const Rel rel, double *scr, int ST, const double *lgam,
-                                                  const double *binom_s)
+                                                  const double *binom_s, const PamOut po)
 {
     double acc[NACC];
     if (K >= 2)
+    {
         ie_small_regs<K, NACC>(q, acc);
+        if (CACHE)
+        {
+#pragma unroll
+            for (int t = 0; t < NACC; ++t)
+                if (t < cnt) po.w[(size_t)t * po.stride] = acc[t];
+        }
+    }
     else
     {
 #pragma unroll
@@ -793,10 +832,10 @@ __device__ __forceinline__ double small_cell_tail(const double (&q)[K], double t
 
 // lat32: the latent genotype (all alleles below 32); cnt_hi: the largest m - k + 1 among the lanes
 // that call together (warp-uniform).  All of them have exactly K latent alleles.
-template <int K>
+template <int K, bool CACHE>
 __device__ __forceinline__ double small_cell(unsigned lat32, const double *prow, int m, int cnt_hi,
                                              const Rel rel, double *scr, int ST, const double *lgam,
-                                             const double *binom_s)
+                                             const double *binom_s, const PamOut po)
 {
     double q[K];
     unsigned rest = lat32;
@@ -815,9 +854,9 @@ __device__ __forceinline__ double small_cell(unsigned lat32, const double *prow,
         for (int e = 0; e < K; ++e) q[e] = __ddiv_rn(q[e], total);
     }
     const int cnt = m - K + 1;
-    if (cnt_hi <= 2) return small_cell_tail<K, 2>(q, total, m, cnt, rel, scr, ST, lgam, binom_s);
-    if (cnt_hi <= 4) return small_cell_tail<K, 4>(q, total, m, cnt, rel, scr, ST, lgam, binom_s);
-    return small_cell_tail<K, kSmallCnt>(q, total, m, cnt, rel, scr, ST, lgam, binom_s);
+    if (cnt_hi <= 2) return small_cell_tail<K, 2, CACHE>(q, total, m, cnt, rel, scr, ST, lgam, binom_s, po);
+    if (cnt_hi <= 4) return small_cell_tail<K, 4, CACHE>(q, total, m, cnt, rel, scr, ST, lgam, binom_s, po);
+    return small_cell_tail<K, kSmallCnt, CACHE>(q, total, m, cnt, rel, scr, ST, lgam, binom_s, po);
 }
 
 // ---- a2, warp-cooperative: one cell, 32 lanes ---------------------------------------------------
@@ -834,10 +873,11 @@ __device__ __forceinline__ double small_cell(unsigned lat32, const double *prow,
 #define MOIRE_COOP_MIN_K 8
 #endif
 constexpr int kCoopMinK = MOIRE_COOP_MIN_K;
+template <bool CACHE>
 __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const double *prow, int m,
                                                        const Rel rel, bool allow_relatedness,
                                                        double *wscr, int ST, const double *lgam,
-                                                       const double *binom_s)
+                                                       const double *binom_s, const PamOut po)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -852,7 +892,7 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
             total = __dadd_rn(total, prow[al]);
         }
     }
-    if (!allow_relatedness && m == k) return transmission_norel_exact_cover(latent, prow, total, k);
+    if (!allow_relatedness && m == k) return transmission_norel_exact_cover<CACHE>(latent, prow, total, k, po);
     double *q = wscr + 16 * ST;
     {
         // lane e normalises element e
@@ -934,7 +974,7 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
             }
         }
     }
-    if (!allow_relatedness) return norel_term(__shfl_sync(FULL, acc[0], 0), total, m);
+    if (!allow_relatedness) return norel_term_c<CACHE>(__shfl_sync(FULL, acc[0], 0), total, m, po);
     // The mixture through the same function, in the same order of operations, as the one-thread
     // path: which evaluator a cell lands in depends on the launch (the cooperative threshold
     // follows the work per thread, so it changes with the number of chains on the device) and must
@@ -947,6 +987,8 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
             const int top = min(16, cnt - 16 * ch);
             for (int t = 0; t < top; ++t) pams[16 * ch + t] = __shfl_sync(FULL, acc[ch], t);
         }
+    if (CACHE)  // every lane holds the vector: lane t stores entries t, t + 32, ...
+        for (int t = lane; t < cnt; t += 32) po.w[(size_t)t * po.stride] = pams[t];
     return relatedness_mixture(pams, 1, m, cnt, total, rel, lgam, binom_s);
 }
 
@@ -955,10 +997,11 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
 // l + 32, ... for bands wider than a warp), each as the sequential sum of egf_band; the band lives
 // in the warp's scratch rows.  Every lane then gathers the band and runs the one mixture function.
 // All lanes must call with identical arguments; every lane returns the value.
+template <bool CACHE>
 __device__ MOIRE_COOP_INLINE double transmission_ll_egf_coop(uint64_t latent, const double *prow, int m,
                                                            const Rel rel, bool allow_relatedness,
                                                            double *wscr, int ST, const double *lgam,
-                                                           const double *binom_s)
+                                                           const double *binom_s, const PamOut po)
 {
     constexpr int CS = kMaxCoi + 1;
     const int lane = threadIdx.x & 31;
@@ -1012,10 +1055,12 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_egf_coop(uint64_t latent, co
         }
         __syncwarp();
     }
-    if (!allow_relatedness) return norel_term(pam_from_coverage(B(D)), total, m);
+    if (!allow_relatedness) return norel_term_c<CACHE>(pam_from_coverage(B(D)), total, m, po);
     double pams[kMaxCoi];
     for (int d = 0; d <= D; ++d) pams[d] = pam_from_coverage(B(d));
     __syncwarp();
+    if (CACHE)
+        for (int d = lane; d <= D; d += 32) po.w[(size_t)d * po.stride] = pams[d];
     return relatedness_mixture(pams, 1, m, D + 1, total, rel, lgam, binom_s);
 }
 

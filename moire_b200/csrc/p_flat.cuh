@@ -40,8 +40,15 @@ struct PFlat
     int eval_threads;   // threads of one evaluator launch (sets the cooperative threshold)
     double *round;       // [T * L][4] logAdj, log u, allele index, flags
     const int *nonmiss;  // [L] non-missing cells of a locus
+    unsigned long long *latLM;  // [T][L][N] latent genotypes, locus-major, 0 at missing cells
+    // update_p's PAM cache (null unless the update runs in cache mode, see k_pc_sweep)
+    double *Wcur, *Wnew;        // [max_coi][T * L * N] PAM vectors: accepted state / current proposal
+    size_t wstride;             // T * L * N
 };
 constexpr unsigned kPfActive = 1u, kPfBroken = 2u;
+// cache mode: the previous proposal of the locus was accepted (bit 2) and which allele it moved
+// (bits 8..15) -- k_pc_sweep commits the PAM vectors of the cells that held it
+constexpr unsigned kPfAccepted = 4u;
 constexpr int kPfScalars = 2 * kSortBins;  // hist[kPfScalars + 0..3] = n_egf, coop_end, nwork, mid_end
 constexpr int kPfCounters = kPfScalars + 4;  // one task counter per evaluator launch of an update
 constexpr int kPfHistWords = kPfCounters + 72;
@@ -138,42 +145,82 @@ inline void build_flat_classes(std::vector<unsigned short> &rank, std::vector<fl
     }
 }
 
+// The cache is sample-major ([t][i][j], like the reference's), update_p works locus-major
+// ([t][j][i]): 32 x 32 tiles go through shared memory so that both sides are read / written along
+// their fast index (ncu, thread-per-cell version: every 8-byte load of the strided side cost a
+// 32-byte sector, 101 us at the benchmark ladder).  One block per (chain, tile of samples, tile of loci).
+__host__ __device__ inline unsigned pf_tiles(int N, int L) { return (unsigned)(((N + 31) / 32) * ((L + 31) / 32)); }
+struct PfTile
+{
+    int t, i0, j0;
+};
+__device__ __forceinline__ PfTile pf_tile_of_block(const View &v)
+{
+    const int tiles_j = (v.L + 31) / 32, tiles_i = (v.N + 31) / 32;
+    int b = blockIdx.x;
+    PfTile r;
+    r.j0 = (b % tiles_j) * 32;
+    b /= tiles_j;
+    r.i0 = (b % tiles_i) * 32;
+    r.t = b / tiles_i;
+    return r;
+}
+
 __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
 {
     __shared__ unsigned int s_hist[kSortBins];
-    for (int b = threadIdx.x; b < kSortBins; b += blockDim.x) s_hist[b] = 0;
+    __shared__ double s_T[32][33];
+    __shared__ unsigned long long s_lat[32][33];
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    for (int b = tid; b < kSortBins; b += blockDim.x) s_hist[b] = 0;
     __syncthreads();
-    const size_t total = (size_t)v.T * v.L * v.N;
-    const size_t loc = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (loc < total)
+    const PfTile tile = pf_tile_of_block(v);
+    const int N = v.N, L = v.L, t = tile.t;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
     {
-        const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
-        const unsigned t = tl / v.L, j = tl - t * v.L;
-        const size_t cell = ((size_t)t * v.N + i) * v.L + j;
-        if (j == 0)
+        const int li = ty + 8 * r, i = tile.i0 + li, j = tile.j0 + tx;
+        double T = 0.0;  // missing cells: never listed, never evaluated: a zero term on both sides
+        unsigned long long lat = 0ull;
+        if (i < N && j < L)
         {
-            const size_t tn = (size_t)t * v.N + i;
-            SampleScal sc;
-            sc.log_r = v.log_r[tn];
-            sc.log_1mr = v.log_1mr[tn];
-            sc.odds = v.odds[tn];
-            sc.m = v.m[tn];
-            sc.pad = 0;
-            f.ss[tn] = sc;
+            const size_t tn = (size_t)t * N + i;
+            if (j == 0)
+            {
+                SampleScal sc;
+                sc.log_r = v.log_r[tn];
+                sc.log_1mr = v.log_1mr[tn];
+                sc.odds = v.odds[tn];
+                sc.m = v.m[tn];
+                sc.pad = 0;
+                f.ss[tn] = sc;
+            }
+            if (v.missing[(size_t)i * L + j] == 0)
+            {
+                const size_t cell = tn * L + j;
+                lat = v.latent[cell];
+                T = v.cellT[cell];
+                atomicAdd(&s_hist[work_class_flat(__popcll(lat), v.m[tn])], 1u);
+            }
         }
-        if (v.missing[(size_t)i * v.L + j] == 0)
-        {
-            f.Tcur[loc] = v.cellT[cell];
-            atomicAdd(&s_hist[work_class_flat(__popcll(v.latent[cell]), v.m[(size_t)t * v.N + i])], 1u);
-        }
-        else
-        {
-            f.Tcur[loc] = 0.0;  // never listed, never evaluated: a zero term on both sides
-            f.Tnew[loc] = 0.0;
-        }
+        s_T[li][tx] = T;
+        s_lat[li][tx] = lat;
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < kSortBins; b += blockDim.x)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+        const int lj = ty + 8 * r, j = tile.j0 + lj, i = tile.i0 + tx;
+        if (i < N && j < L)
+        {
+            const size_t loc = ((size_t)t * L + j) * N + i;
+            const unsigned long long lat = s_lat[tx][lj];
+            f.Tcur[loc] = s_T[tx][lj];
+            f.latLM[loc] = lat;  // 0 marks a missing cell (a latent genotype is never empty)
+            if (lat == 0ull) f.Tnew[loc] = 0.0;
+        }
+    }
+    for (int b = tid; b < kSortBins; b += blockDim.x)
         if (s_hist[b]) atomicAdd(&f.hist[b], s_hist[b]);
 }
 
@@ -285,13 +332,11 @@ __global__ void __launch_bounds__(256) k_pf_scatter(const View v, const PFlat f)
 {
     const size_t total = (size_t)v.T * v.L * v.N;
     auto cell_fn = [&](size_t loc, int &cls, uint4 &entry) -> bool {
+        const unsigned long long lat = f.latLM[loc];  // locus-major copy of k_pf_prepare: coalesced
+        if (lat == 0ull) return false;                // missing
         const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
         const unsigned t = tl / v.L, j = tl - t * v.L;
-        if (v.missing[(size_t)i * v.L + j] != 0) return false;
-        const size_t cell = ((size_t)t * v.N + i) * v.L + j;
-        const unsigned tn = t * v.N + i;
-        const unsigned long long lat = v.latent[cell];
-        cls = work_class_flat(__popcll(lat), v.m[tn]);
+        cls = work_class_flat(__popcll(lat), v.m[t * v.N + i]);
         entry = make_uint4((unsigned)lat, (unsigned)(lat >> 32), (t << 16) | j, i);
         return true;
     };
@@ -319,6 +364,9 @@ __global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat 
     double *st = f.round + (size_t)tl * 4;
     unsigned flags = rep == 0 ? 0u : (unsigned)st[3];
     double *tn = f.Tnew + (size_t)tl * N, *tc = f.Tcur + (size_t)tl * N;
+    // cache mode: every round sorts its own list (k_pc_sweep counts into these bins)
+    if (f.Wcur && blockIdx.x == 0)
+        for (int b = tid; b < kSortBins; b += B) f.hist[b] = 0;
 
     if (flags & kPfActive)
     {
@@ -367,7 +415,12 @@ __global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat 
         }
         __syncthreads();
     }
-    flags &= ~kPfActive;
+    {
+        // cache mode: what k_pc_sweep has to commit before the next proposal is evaluated
+        const bool was_active = (flags & kPfActive) != 0;
+        flags &= ~(kPfActive | kPfAccepted | 0xff00u);
+        if (f.Wcur && was_active && s_accept) flags |= kPfAccepted | ((unsigned)st[2] << 8);
+    }
     if (rep >= A || (flags & kPfBroken))
     {
         if (tid == 0) st[3] = (double)flags;
@@ -447,6 +500,167 @@ __global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat 
     }
 }
 
+// ---- cache mode: a round evaluates from scratch only the cells that hold the proposed allele -----
+// SALT moves ONE frequency and rescales all others by a common factor (src/mcmc_utils.h:252-300),
+// so for a cell whose latent genotype does not contain the proposed allele the normalised
+// frequencies q_a = p_a / sum -- and with them every PAM -- are unchanged (to the last bits of the
+// rescaling); only the sum enters the mixture anew.  With A_j alleles per locus and k of them in a
+// cell that is a fraction 1 - k / A_j of the cells of every round.  In cache mode update_p keeps the
+// PAM vector of every cell (Wcur: accepted state, Wnew: the proposal's, for the cells evaluated from
+// scratch; committed by the next round's k_pc_sweep when k_pf_round accepted the proposal), filled by one evaluation of the current
+// state at the start of the update, and each round is
+//   k_pf_round   decide / commit the previous proposal, draw the next          (as before)
+//   k_pc_sweep   every cell of an active locus, in memory order: cells without the proposed allele
+//                get their term from the cached PAMs -- the fresh sum of the proposed frequencies
+//                through the SAME mixture function the evaluators end in -- the others are counted
+//                by cost class
+//   k_pf_scan, k_pc_scatter   the round's own sorted list of from-scratch cells
+//   k_flat_eval<true>         evaluates that list, terms to Tnew, PAM vectors to Wnew
+// What changes numerically: a cached PAM was computed from q of an earlier p of the same update
+// (rescaled since, so equal to rounding); the from-scratch value (k_eval_cells) stays the truth the
+// tests bound the difference against (tests/test_gpu_shapes.py).
+__device__ __forceinline__ bool pc_fresh(unsigned long long S, int idx, int k, int m)
+{
+    return ((S >> idx) & 1ull) || k > m;
+}
+
+// relatedness_mixture for at most eight mixture terms with the PAMs in registers: the loop of
+// small_cell_tail (likelihood.cuh), i.e. the same operations in the same order as the generic
+// function's fast branch; its rare fallbacks go through the generic function.
+__device__ __forceinline__ double mixture_regs8(const double (&pam)[8], int m, int cnt, double total,
+                                                const Rel rel, const double *lgam)
+{
+    const double lead = __dmul_rn((double)(m - 1), rel.log_1mr);
+    if (cnt == 1)
+        return __dadd_rn(lead, log_total_pow_times(total, m, __dsub_rn(1.0, clamp_pam(pam[0]))));
+    const double qr = __ddiv_rn(rel.odds, total);
+    const int e2 = ((__double2hiint(qr) >> 20) & 0x7ff) - 1022;
+    if ((cnt - 1) * max(e2, 0) > 850)
+    {
+        double w[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) w[t] = pam[t];
+        return relatedness_mixture(w, 1, m, cnt, total, rel, lgam, nullptr);
+    }
+    const double *cb = g_binom + (m - 1) * (kMaxCoi + 1);
+    double qi = 1.0, S = 0.0;
+#pragma unroll
+    for (int t = 7; t >= 0; --t)
+        if (t < cnt)
+        {
+            S = __dadd_rn(S, __dmul_rn(__dmul_rn(cb[cnt - 1 - t], qi), __dsub_rn(1.0, clamp_pam(pam[t]))));
+            qi = __dmul_rn(qi, qr);
+        }
+    return __dadd_rn(lead, log_total_pow_times(total, m, S));
+}
+
+__global__ void __launch_bounds__(256) k_pc_sweep(const View v, const PFlat f)
+{
+    __shared__ unsigned int s_hist[kSortBins];
+    for (int b = threadIdx.x; b < kSortBins; b += blockDim.x) s_hist[b] = 0;
+    __syncthreads();
+    const size_t total = (size_t)v.T * v.L * v.N;
+    const size_t loc = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (loc < total)
+    {
+        const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
+        const double *st = f.round + (size_t)tl * 4;
+        const unsigned long long S = f.latLM[loc];
+        const unsigned fl = (unsigned)st[3];
+        if ((fl & kPfActive) && S)
+        {
+            const unsigned t = tl / v.L;
+            const size_t tn = (size_t)t * v.N + i;
+            const int idx = (int)st[2], k = __popcll(S);
+            const SampleScal sc = f.ss[tn];
+            const int m = sc.m;
+            const bool rel_on = v.allow_rel != 0;
+            const int nw = rel_on ? (k >= 2 ? m - k + 1 : 0) : 1;  // cached PAMs of the cell
+            // the previous proposal of this locus was accepted and this cell held its allele: the
+            // PAM vector the evaluator left in Wnew is the accepted state's now
+            const bool commit = (fl & kPfAccepted) && ((S >> ((fl >> 8) & 0xffu)) & 1ull) && k <= m;
+            const bool fresh = pc_fresh(S, idx, k, m);
+            const double *wsrc = (commit ? f.Wnew : f.Wcur) + loc;
+            if (fresh)
+            {
+                atomicAdd(&s_hist[work_class_flat(k, m)], 1u);
+                if (commit)
+                    for (int q = 0; q < nw; ++q) f.Wcur[(size_t)q * f.wstride + loc] = wsrc[(size_t)q * f.wstride];
+            }
+            else
+            {
+                // the sum of the proposed frequencies of the latent alleles, ascending allele order
+                // (the evaluators' order)
+                const double *prow = f.pprop + (size_t)tl * v.AP;
+                double tot = 0.0;
+                unsigned long long rest = S;
+                while (rest)
+                {
+                    const int al = __ffsll((long long)rest) - 1;
+                    rest &= rest - 1;
+                    tot = __dadd_rn(tot, prow[al]);
+                }
+                double T;
+                if (!rel_on)
+                {
+                    const double pam = wsrc[0];
+                    if (commit) f.Wcur[loc] = pam;
+                    T = norel_term(pam, tot, m);
+                }
+                else
+                {
+                    const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
+                    if (k == 1)
+                        T = relatedness_mixture(nullptr, 0, m, m, tot, rel, v.lgam, nullptr);
+                    else if (nw <= 8)
+                    {
+                        double w[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) w[q] = q < nw ? wsrc[(size_t)q * f.wstride] : 0.0;
+                        if (commit)
+                        {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                if (q < nw) f.Wcur[(size_t)q * f.wstride + loc] = w[q];
+                        }
+                        T = mixture_regs8(w, m, nw, tot, rel, v.lgam);
+                    }
+                    else
+                    {
+                        double w[kMaxCoi];
+                        for (int q = 0; q < nw; ++q) w[q] = wsrc[(size_t)q * f.wstride];
+                        if (commit)
+                            for (int q = 0; q < nw; ++q) f.Wcur[(size_t)q * f.wstride + loc] = w[q];
+                        T = relatedness_mixture(w, 1, m, nw, tot, rel, v.lgam, nullptr);
+                    }
+                }
+                f.Tnew[loc] = T;
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kSortBins; b += blockDim.x)
+        if (s_hist[b]) atomicAdd(&f.hist[b], s_hist[b]);
+}
+
+__global__ void __launch_bounds__(256) k_pc_scatter(const View v, const PFlat f)
+{
+    const size_t total = (size_t)v.T * v.L * v.N;
+    auto cell_fn = [&](size_t loc, int &cls, uint4 &entry) -> bool {
+        const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
+        const double *st = f.round + (size_t)tl * 4;
+        const unsigned long long S = f.latLM[loc];
+        if (((unsigned)st[3] & kPfActive) == 0 || S == 0) return false;
+        const unsigned t = tl / v.L, j = tl - t * v.L;
+        const int m = v.m[(size_t)t * v.N + i], k = __popcll(S);
+        if (!pc_fresh(S, (int)st[2], k, m)) return false;
+        cls = work_class_flat(k, m);
+        entry = make_uint4((unsigned)S, (unsigned)(S >> 32), (t << 16) | j, i);
+        return true;
+    };
+    block_scatter(total, cell_fn, f.hist + kSortBins, f.list);
+}
+
 // ---- the flat evaluator: every listed cell, from the sorted list ---------------------------------
 // Sections of the list: [0, n_egf) k > 10, [n_egf, coop_end) the classes above the launch's
 // cooperative threshold (k_pf_scan), the rest light.
@@ -469,6 +683,8 @@ struct FlatSrc
     double *out;                        // locus-major [t][j][i] (p rounds) or sample-major [t][i][j]
     int out_locus_major;
     int binom_rows;                     // rows of g_binom staged in shared memory (= max_coi)
+    double *pam_out;                    // CACHE evaluators: PAM vectors, [t][pam_stride] + locus-major cell
+    size_t pam_stride;
 };
 
 #ifndef MOIRE_PF_THREADS
@@ -495,24 +711,127 @@ __host__ __device__ inline size_t pf_eval_smem_doubles(int binom_rows)
     return 128 + (size_t)binom_rows * kBinomCols + scratch_doubles(kEvalThreads);
 }
 
+// One unit of the list: a cooperative cell (all lanes of the warp on one cell) or a chunk of 32
+// one-thread cells starting at lo + 32 * unit.  CACHE: the evaluator also leaves every cell's PAM
+// vector in update_p's cache (likelihood.cuh: PamOut), at the cell's locus-major index.
+template <bool CACHE>
+__device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const int lo, const int hi,
+                                          const bool coop, const bool egf, const int unit, double *s_scr,
+                                          const double *s_lgam, const double *s_binom, const bool allow_rel,
+                                          const bool locus_major)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int ST = kEvalThreads + 1;
+    const unsigned N = (unsigned)v.N, L = (unsigned)v.L;
+    if (coop)
+    {
+        const int w = lo + unit;
+        if (w >= hi) return;
+        const uint4 e = f.list[w];
+        const unsigned t = e.z >> 16, j = e.z & 0xffffu, tl = t * L + j, tn = t * N + e.w;
+        if (f.round_flags && ((unsigned)f.round_flags[(size_t)tl * 4 + 3] & kPfActive) == 0) return;
+        const unsigned long long lat = ((unsigned long long)e.y << 32) | e.x;
+        const SampleScal sc = f.ss[tn];
+        const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
+        const int m = sc.m, k = __popcll(lat);
+        const double *prow = f.p + (size_t)tl * f.p_stride;
+        const PamOut po{CACHE ? f.pam_out + ((size_t)tl * N + e.w) : nullptr, f.pam_stride};
+        double T;
+        if (k > m)
+            T = NAN;
+        else if (egf)
+            T = transmission_ll_egf_coop<CACHE>(lat, prow, m, rel, allow_rel, s_scr + warp * 32, ST, s_lgam, s_binom, po);
+        else
+            T = transmission_ll_coop<CACHE>(lat, prow, m, rel, allow_rel, s_scr + warp * 32, ST, s_lgam, s_binom, po);
+        if (lane == 0) f.out[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + j] = T;
+        __syncwarp();
+        return;
+    }
+    const int w0 = lo + unit * 32;
+    if (w0 >= hi) return;
+    const int w = w0 + lane;
+    bool go = w < hi;
+    uint4 e = make_uint4(1u, 0u, 0u, 0u);
+    if (go) e = f.list[w];
+    // -- class-uniform chunk of small cells: the register path (likelihood.cuh)
+    {
+        const unsigned in = __ballot_sync(0xffffffffu, go);
+        const int k = __popc(e.x);
+        const bool small = allow_rel && in != 0 &&
+                           __all_sync(0xffffffffu, !go || (e.y == 0 && k <= kSmallK && k >= 1)) &&
+                           __reduce_max_sync(0xffffffffu, go ? k : 0) ==
+                               __reduce_min_sync(0xffffffffu, go ? k : kSmallK + 1);
+        if (small)
+        {
+            const int K = __shfl_sync(0xffffffffu, k, __ffs(in) - 1);
+            const unsigned tl = (e.z >> 16) * L + (e.z & 0xffffu), tn = (e.z >> 16) * N + e.w;
+            const double flagword = f.round_flags ? f.round_flags[(size_t)tl * 4 + 3] : (double)kPfActive;
+            const SampleScal sc = f.ss[tn];
+            const double *prow = f.p + (size_t)tl * f.p_stride;
+            const int cnt = sc.m - K + 1;
+            const int cnt_hi = __reduce_max_sync(0xffffffffu, go ? cnt : 0);
+            const int cnt_lo = __reduce_min_sync(0xffffffffu, go ? cnt : 1);
+            if (cnt_hi <= kSmallCnt && cnt_lo >= 1)
+            {
+                if (go && ((unsigned)flagword & kPfActive))
+                {
+                    const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
+                    const PamOut po{CACHE ? f.pam_out + ((size_t)tl * N + e.w) : nullptr, f.pam_stride};
+                    double T;
+                    switch (K)
+                    {
+                        case 1: T = small_cell<1, CACHE>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom, po); break;
+                        case 2: T = small_cell<2, CACHE>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom, po); break;
+                        case 3: T = small_cell<3, CACHE>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom, po); break;
+                        case 4: T = small_cell<4, CACHE>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom, po); break;
+                        case 5: T = small_cell<5, CACHE>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom, po); break;
+                        default: T = small_cell<6, CACHE>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom, po); break;
+                    }
+                    f.out[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] = T;
+                }
+                __syncwarp();
+                return;
+            }
+        }
+    }
+    // everything the cell needs hangs off the list entry: issue it all at once -- the
+    // round flag, the sample's scalars, the gathered frequencies -- and only then look
+    // at the flag (two trips to L2 per cell instead of 3 + k)
+    const unsigned tl = (e.z >> 16) * L + (e.z & 0xffffu), tn = (e.z >> 16) * N + e.w;
+    const unsigned long long lat = ((unsigned long long)e.y << 32) | e.x;
+    const double *prow = f.p + (size_t)tl * f.p_stride;
+    const double flagword = f.round_flags ? f.round_flags[(size_t)tl * 4 + 3] : (double)kPfActive;
+    const SampleScal sc = f.ss[tn];
+    double pv[kGather];
+    gather_freqs(lat, prow, pv);
+    go = go && ((unsigned)flagword & kPfActive);
+    const unsigned callers = __ballot_sync(0xffffffffu, go);
+    if (go)
+    {
+        const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
+        const PamOut po{CACHE ? f.pam_out + ((size_t)tl * N + e.w) : nullptr, f.pam_stride};
+        f.out[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] =
+            transmission_ll<CACHE>(lat, prow, pv, sc.m, rel, allow_rel, s_scr + tid, ST, s_lgam, s_binom, callers, po);
+    }
+    __syncwarp();
+}
+
 // Sections of the list, heaviest first (k_pf_scan): [0, n_egf) k > 10; [n_egf, coop_end) cells that
 // would outlast the launch on one thread: always one warp per cell; [coop_end, mid_end) heavy
 // classes: a warp per cell while they are rare, chunks of 32 when they hold a large share of all
 // cells (high-COI shapes); [mid_end, nwork) light cells in chunks.
+template <bool CACHE>
 __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval(const View v, const FlatSrc f)
 {
     extern __shared__ double smem[];
     double *s_lgam = smem;
     double *s_scr = smem + 128;                                   // fixed offsets for the hot arrays
     double *s_binom = s_scr + scratch_doubles(kEvalThreads);
-    __shared__ int s_task;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int ST = kEvalThreads + 1;
+    const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < 128; i += kEvalThreads) s_lgam[i] = v.lgam[i];
     for (int i = tid; i < f.binom_rows * kBinomCols; i += kEvalThreads)
         s_binom[i] = g_binom[(i / kBinomCols) * (kMaxCoi + 1) + (i % kBinomCols)];
     const bool allow_rel = v.allow_rel != 0;
-    const unsigned N = (unsigned)v.N, L = (unsigned)v.L;
     const bool locus_major = f.out_locus_major != 0;
     const int n_egf = (int)f.bounds[0], coop_end = (int)f.bounds[1], nwork = (int)f.bounds[2],
               mid_end = (int)f.bounds[3];
@@ -521,6 +840,14 @@ __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval
     const size_t enough = (size_t)gridDim.x * kEvalThreads / 8;
     const bool chunked_egf = (size_t)n_egf >= enough;
     const bool chunked_mid = (size_t)(mid_end - coop_end) >= enough;
+    __shared__ int s_task;
+#ifdef MOIRE_EVAL_TRACE
+    // tuning aid: per block {entry, after the prologue, then per task: claimed at, task id}
+    unsigned long long *tr = (v.trace && blockIdx.x < 1024) ? v.trace + (size_t)blockIdx.x * 256 : nullptr;
+    int ntr = 2;
+    auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if (tr && tid == 0) tr[0] = now();
+#endif
     const int t_egf = pf_tasks(n_egf, chunked_egf, false);
     const int t_strag = pf_tasks(coop_end - n_egf, false, false);
     const int t_mid = pf_tasks(mid_end - coop_end, chunked_mid, false);
@@ -528,9 +855,20 @@ __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval
     for (;;)
     {
         __syncthreads();
+#ifdef MOIRE_EVAL_TRACE
+        if (tr && tid == 0 && ntr + 3 <= 256) tr[ntr++] = now();  // the block is done with its previous task
+#endif
         if (tid == 0) s_task = (int)atomicAdd(f.counter, 1u);
         __syncthreads();
         int b = s_task;
+#ifdef MOIRE_EVAL_TRACE
+        if (tr && tid == 0 && ntr + 2 <= 256)
+        {
+            tr[ntr++] = now();  // claimed
+            tr[ntr++] = (unsigned long long)b;
+            tr[1] = (unsigned long long)ntr;
+        }
+#endif
         if (b >= tasks) break;
         int lo, hi;
         bool coop, egf = false, light = false;
@@ -565,112 +903,39 @@ __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval
         }
         const int upb = pf_units_per_task(light);
         for (int u = warp; u < upb; u += kEvalWarps)
-        {
-            const int unit = b * upb + u;
-            if (coop)
-            {
-                const int w = lo + unit;
-                if (w >= hi) break;
-                const uint4 e = f.list[w];
-                const unsigned t = e.z >> 16, j = e.z & 0xffffu, tl = t * L + j, tn = t * N + e.w;
-                if (f.round_flags && ((unsigned)f.round_flags[(size_t)tl * 4 + 3] & kPfActive) == 0)
-                    continue;
-                const unsigned long long lat = ((unsigned long long)e.y << 32) | e.x;
-                const SampleScal sc = f.ss[tn];
-                const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
-                const int m = sc.m, k = __popcll(lat);
-                const double *prow = f.p + (size_t)tl * f.p_stride;
-                double T;
-                if (k > m)
-                    T = NAN;
-                else if (egf)
-                    T = transmission_ll_egf_coop(lat, prow, m, rel, allow_rel, s_scr + warp * 32, ST, s_lgam, s_binom);
-                else
-                    T = transmission_ll_coop(lat, prow, m, rel, allow_rel, s_scr + warp * 32, ST, s_lgam, s_binom);
-                if (lane == 0) f.out[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + j] = T;
-                __syncwarp();
-            }
-            else
-            {
-                const int w0 = lo + unit * 32;
-                if (w0 >= hi) break;
-                const int w = w0 + lane;
-                bool go = w < hi;
-                uint4 e = make_uint4(1u, 0u, 0u, 0u);
-                if (go) e = f.list[w];
-                // -- class-uniform chunk of small cells: the register path (likelihood.cuh)
-                {
-                    const unsigned in = __ballot_sync(0xffffffffu, go);
-                    const int k = __popc(e.x);
-                    const bool small = allow_rel && in != 0 &&
-                                       __all_sync(0xffffffffu, !go || (e.y == 0 && k <= kSmallK && k >= 1)) &&
-                                       __reduce_max_sync(0xffffffffu, go ? k : 0) ==
-                                           __reduce_min_sync(0xffffffffu, go ? k : kSmallK + 1);
-                    if (small)
-                    {
-                        const int K = __shfl_sync(0xffffffffu, k, __ffs(in) - 1);
-                        const unsigned tl = (e.z >> 16) * L + (e.z & 0xffffu), tn = (e.z >> 16) * N + e.w;
-                        const double flagword = f.round_flags ? f.round_flags[(size_t)tl * 4 + 3] : (double)kPfActive;
-                        const SampleScal sc = f.ss[tn];
-                        const double *prow = f.p + (size_t)tl * f.p_stride;
-                        const int cnt = sc.m - K + 1;
-                        const int cnt_hi = __reduce_max_sync(0xffffffffu, go ? cnt : 0);
-                        const int cnt_lo = __reduce_min_sync(0xffffffffu, go ? cnt : 1);
-                        if (cnt_hi <= kSmallCnt && cnt_lo >= 1)
-                        {
-                            if (go && ((unsigned)flagword & kPfActive))
-                            {
-                                const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
-                                double T;
-                                switch (K)
-                                {
-                                    case 1: T = small_cell<1>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom); break;
-                                    case 2: T = small_cell<2>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom); break;
-                                    case 3: T = small_cell<3>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom); break;
-                                    case 4: T = small_cell<4>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom); break;
-                                    case 5: T = small_cell<5>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom); break;
-                                    default: T = small_cell<6>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom); break;
-                                }
-                                f.out[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] = T;
-                            }
-                            __syncwarp();
-                            continue;
-                        }
-                    }
-                }
-                // everything the cell needs hangs off the list entry: issue it all at once -- the
-                // round flag, the sample's scalars, the gathered frequencies -- and only then look
-                // at the flag (two trips to L2 per cell instead of 3 + k)
-                const unsigned tl = (e.z >> 16) * L + (e.z & 0xffffu), tn = (e.z >> 16) * N + e.w;
-                const unsigned long long lat = ((unsigned long long)e.y << 32) | e.x;
-                const double *prow = f.p + (size_t)tl * f.p_stride;
-                const double flagword = f.round_flags ? f.round_flags[(size_t)tl * 4 + 3] : (double)kPfActive;
-                const SampleScal sc = f.ss[tn];
-                double pv[kGather];
-                gather_freqs(lat, prow, pv);
-                go = go && ((unsigned)flagword & kPfActive);
-                const unsigned callers = __ballot_sync(0xffffffffu, go);
-                if (go)
-                {
-                    const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
-                    f.out[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] =
-                        transmission_ll(lat, prow, pv, sc.m, rel, allow_rel, s_scr + tid, ST, s_lgam, s_binom,
-                                        callers);
-                }
-                __syncwarp();
-            }
-        }
+            flat_unit<CACHE>(v, f, lo, hi, coop, egf, b * upb + u, s_scr, s_lgam, s_binom, allow_rel, locus_major);
     }
 }
 
 // ---- once per update: the accepted terms back into the sample-major cache -----------------------
 __global__ void __launch_bounds__(256) k_pf_finish(const View v, const PFlat f)
 {
-    const size_t total = (size_t)v.T * v.L * v.N;
-    const size_t loc = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (loc >= total) return;
-    const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
-    const unsigned t = tl / v.L, j = tl - t * v.L;
-    if (v.missing[(size_t)i * v.L + j] == 0) v.cellT[((size_t)t * v.N + i) * v.L + j] = f.Tcur[loc];
+    __shared__ double s_T[32][33];
+    __shared__ unsigned char s_in[32][33];
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const PfTile tile = pf_tile_of_block(v);
+    const int N = v.N, L = v.L, t = tile.t;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+        const int lj = ty + 8 * r, j = tile.j0 + lj, i = tile.i0 + tx;
+        bool in = false;
+        double T = 0.0;
+        if (i < N && j < L)
+        {
+            const size_t loc = ((size_t)t * L + j) * N + i;
+            in = f.latLM[loc] != 0ull;
+            T = f.Tcur[loc];
+        }
+        s_T[lj][tx] = T;
+        s_in[lj][tx] = in;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+        const int li = ty + 8 * r, i = tile.i0 + li, j = tile.j0 + tx;
+        if (i < N && j < L && s_in[tx][li]) v.cellT[((size_t)t * N + i) * L + j] = s_T[tx][li];
+    }
 }
 }  // namespace moire

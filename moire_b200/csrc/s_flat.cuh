@@ -167,7 +167,9 @@ __global__ void __launch_bounds__(256) k_sf_decide(const View v, const SFlat sf,
     double d = 0.0, a = 0.0;
     if (valid)
     {
-        // four loci per lane in flight (the loads of a chunk are issued before its sums)
+        // four loci per lane in flight (the loads of a chunk are issued before its sums).  Tried:
+        // every load issued unconditionally, ahead of the validity and missing flags -- 74 registers
+        // instead of 48, fewer resident warps, 68 -> 91 us (profiles/README.md, r3k)
         for (int j0 = 0; j0 < L; j0 += 128)
         {
             double vT[4], vO[4], vTn[4], vOn[4], va[4], vb[4];
@@ -234,34 +236,35 @@ __global__ void __launch_bounds__(256) k_eps_cells(const View v, const SFlat sf,
     const int N = v.N, L = v.L, nA = v.nA;
     const int t = (int)(si / N), i = (int)(si - (size_t)t * N);
     const size_t base = si * L, data_base = (size_t)i * L;
-    const bool valid = sf.prop[si].valid != 0;
+    const int valid_word = sf.prop[si].valid;
     const EpsLogs *el = sf.elogs + si * nA;
     double d = 0.0;
     unsigned n_eval = 0;
-    if (valid)
     {
+        // as in k_sf_decide: every load of a chunk is issued before anything that depends on one
         for (int j0 = 0; j0 < L; j0 += 128)
         {
             double vT[4], vO[4];
             unsigned long long vl[4], vo[4];
             int vA[4], vc[4];
-            bool use[4];
+            unsigned char vm[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
             {
                 const int j = j0 + 32 * u + lane;
-                use[u] = j < L && v.missing[data_base + (j < L ? j : 0)] == 0;
-                const int jj = use[u] ? j : 0;
-                vT[u] = use[u] ? v.cellT[base + jj] : 0.0;
-                vO[u] = use[u] ? v.cellO[base + jj] : 0.0;
-                vl[u] = use[u] ? v.latent[base + jj] : 0ull;
-                vo[u] = use[u] ? v.obs[data_base + jj] : 0ull;
+                const int jj = j < L ? j : 0;
+                vm[u] = v.missing[data_base + jj];
+                vT[u] = v.cellT[base + jj];
+                vO[u] = v.cellO[base + jj];
+                vl[u] = v.latent[base + jj];
+                vo[u] = v.obs[data_base + jj];
                 vA[u] = v.nall[jj];
                 vc[u] = v.aclass[jj];
             }
+            const bool valid = valid_word != 0;
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (use[u])
+                if (valid && j0 + 32 * u + lane < L && vm[u] == 0)
                 {
                     const double O = observation_ll(vl[u], vo[u], vA[u], el[vc[u]]);
                     d += __dadd_rn(vT[u], O) - __dadd_rn(vT[u], vO[u]);

@@ -25,6 +25,18 @@ DEFAULT_MODEL = dict(allow_relatedness=True, burnin=10000, max_coi=40, mean_coi_
 # moire_params.pipeline (include/moire_engine.h): kernel generation, "auto" = by problem size
 PIPELINES = dict(auto=0, flat=1, fused=2)
 NUMERICS_REF32 = 0x100   # MOIRE_NUMERICS_REF32: float-rounded PAM clamped at 1 - FLT_EPSILON
+P_CACHE_ON, P_CACHE_OFF = 0x200, 0x400   # MOIRE_P_CACHE_*: update_p's PAM cache (default: by shape)
+
+
+def pipeline_flags(pipeline, ref32_emulation=False):
+    """moire_params.pipeline from "auto" | "flat" | "fused", optionally followed by "+cache" /
+    "-cache" (update_p's PAM cache forced on / off; flat pipelines only)."""
+    name, flags = pipeline, 0
+    if pipeline.endswith("+cache"):
+        name, flags = pipeline[:-6], P_CACHE_ON
+    elif pipeline.endswith("-cache"):
+        name, flags = pipeline[:-6], P_CACHE_OFF
+    return PIPELINES[name] | flags | (NUMERICS_REF32 if ref32_emulation else 0)
 
 
 class MoireError(RuntimeError):
@@ -60,7 +72,7 @@ class Engine:
         d = _lib.MoireData(self.N, self.L, _ptr(self._keep["na"]), _ptr(self._keep["obs"]),
                            _ptr(self._keep["mis"]), _ptr(self._keep["coi"]))
         p = _lib.MoireParams(int(bool(prm["allow_relatedness"])), int(prm["burnin"]),
-                             int(prm["max_coi"]), PIPELINES[pipeline] | (NUMERICS_REF32 if ref32_emulation else 0),
+                             int(prm["max_coi"]), pipeline_flags(pipeline, ref32_emulation),
                              prm["mean_coi_shape"], prm["mean_coi_scale"],
                              prm["max_eps_pos"], prm["eps_pos_alpha"], prm["eps_pos_beta"],
                              prm["max_eps_neg"], prm["eps_neg_alpha"], prm["eps_neg_beta"],

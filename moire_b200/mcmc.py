@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib
 from .data import PackedData, pack_data
-from .engine import DEFAULT_MODEL, NUMERICS_REF32, PIPELINES, Engine, MoireError, _ptr
+from .engine import DEFAULT_MODEL, Engine, MoireError, _ptr, pipeline_flags
 
 PRIOR_TERMS = ("eps_neg", "eps_pos", "relatedness", "coi", "mean_coi_hyper")
 
@@ -168,7 +168,7 @@ class MCMC:
         d = _lib.MoireData(self.N, self.L, _ptr(self._keep["na"]), _ptr(self._keep["obs"]),
                            _ptr(self._keep["mis"]), _ptr(self._keep["coi"]))
         p = _lib.MoireParams(int(bool(prm["allow_relatedness"])), int(burnin), int(prm["max_coi"]),
-                             PIPELINES[pipeline] | (NUMERICS_REF32 if ref32_emulation else 0),
+                             pipeline_flags(pipeline, ref32_emulation),
                              prm["mean_coi_shape"], prm["mean_coi_scale"], prm["max_eps_pos"],
                              prm["eps_pos_alpha"], prm["eps_pos_beta"], prm["max_eps_neg"],
                              prm["eps_neg_alpha"], prm["eps_neg_beta"], prm["r_alpha"],

@@ -1,8 +1,7 @@
-( time python -m pytest tests -m gpu -q -x ) > gpurun_out/r3b_pytest.log 2>&1
-tail -3 gpurun_out/r3b_pytest.log
-for c in c2 c3 c5; do python scripts/kind_timing.py --config $c >> gpurun_out/r3b_kind.log 2>&1; done
-grep -E "config" gpurun_out/r3b_kind.log | cut -c1-600
-python scripts/class_census.py c2 40 > gpurun_out/r3b_census_c2.log 2>&1; cat gpurun_out/r3b_census_c2.log
-python scripts/class_census.py c3 40 > gpurun_out/r3b_census_c3.log 2>&1; cat gpurun_out/r3b_census_c3.log
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r3b_launches_c2.csv python scripts/kind_timing.py --config c2 --steps 1 --warmup 1 > gpurun_out/r3b_ncu_c2.log 2>&1
-python scripts/seq_summary.py gpurun_out/r3b_launches_c2.csv 30
+( time python -m pytest tests -m gpu -q -x 2>&1 | grep -v "^$" ) > gpurun_out/r3k_pytest.log 2>&1
+tail -6 gpurun_out/r3k_pytest.log | cut -c1-300
+for c in c2 c3 c5; do python scripts/kind_timing.py --config $c >> gpurun_out/r3k_kind.log 2>&1; done
+python scripts/kind_timing.py --config c3 --chains 5 >> gpurun_out/r3k_kind.log 2>&1
+grep -E "config|Error|error" gpurun_out/r3k_kind.log | cut -c1-420
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r3k_launches_c3.csv python scripts/kind_timing.py --config c3 --steps 1 --warmup 1 > gpurun_out/r3k_ncu_c3.log 2>&1
+python scripts/launch_summary.py gpurun_out/r3k_launches_c3.csv 2>&1 | head -36

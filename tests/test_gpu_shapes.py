@@ -215,6 +215,74 @@ def test_flat_and_fused_pipelines_agree_on_ragged_data_with_missing_cells(monkey
                 assert np.allclose(x, y, rtol=1e-9, atol=1e-12, equal_nan=True), key
 
 
+@pytest.mark.parametrize("shape", ["ragged", "c5-like", "norel"])
+def test_update_p_pam_cache_stays_on_the_from_scratch_chain(oracle, shape):
+    """update_p's PAM cache (MOIRE_P_CACHE_ON, opt-in): cells that do not hold the proposed allele
+    re-run only the mixture on cached P(any missing) vectors.  The cached vectors come from
+    frequencies that were rescaled since (equal to the last bits), so the terms differ from a
+    from-scratch evaluation by rounding x the cell's conditioning.  On a well-conditioned shape
+    (ragged A_j, COI ~ 3) the run is the cache-off run: identical integer state and counters,
+    floating state to 1e-9.  On COI-30 data (EGF cells, cooperative cells, coverage probabilities
+    down to 1e-12) the terms are held to the oracle's from-scratch values with the bound that
+    conditioning allows: 99 % of the cells within 1e-9, every cell within 1e-4, and a from-scratch
+    re-evaluation on the device (eval_all) agrees with the oracle to 1e-9 again."""
+    from moire_b200.data import pack_data
+    from moire_b200.engine import DEFAULT_MODEL, Engine
+    from moire_b200.simulate import simulate_data
+    rng = np.random.default_rng(3)
+    if shape == "ragged":
+        L, N = 13, 157
+        num_alleles = rng.integers(2, 41, size=L)
+        sim = simulate_data(mean_coi=3.0, num_samples=N, epsilon_pos=.02, epsilon_neg=.05,
+                            locus_freq_alphas=[np.full(int(a), .5) for a in num_alleles], seed=4)
+        pk = pack_data(sim["data"], rng.random((L, N)) < .15)
+        model = dict(DEFAULT_MODEL, max_coi=12, burnin=100)
+    else:
+        sim = simulate_data(sample_cois=rng.integers(1, 31, size=120), epsilon_pos=.01, epsilon_neg=.1,
+                            locus_freq_alphas=[np.ones(30)] * 9, internal_relatedness_alpha=1,
+                            internal_relatedness_beta=1, seed=8)
+        pk = pack_data(sim["data"], sim["is_missing"])
+        model = dict(DEFAULT_MODEL, max_coi=40, burnin=100, allow_relatedness=shape != "norel")
+    allow = int(model["allow_relatedness"])
+    temps = np.array([1.0, .6, .2])
+    runs = {}
+    for pipeline in ("flat-cache", "flat+cache"):
+        eng = Engine(pk, temps, seed=21, pipeline=pipeline, **model)
+        assert not eng.init_chains()["still_ill"].any()
+        for it in range(5):
+            eng.step(it)
+        states = [eng.dump_state(c) for c in range(len(temps))]
+        diags = [eng.diagnostics(c) for c in range(len(temps))]
+        if pipeline == "flat+cache":
+            worst = 0.0
+            for c, st in enumerate(states):
+                check_invariants(eng, pk, c)
+                t, o = oracle.eval_cells(64, pk.num_alleles, pk.obs_mask, pk.is_missing, st["latent"],
+                                         st["m"], st["r"], st["eps_neg"], st["eps_pos"],
+                                         st["p"][:, :pk.max_alleles], allow)
+                err = np.abs(st["cell_t"] - t) / np.maximum(1.0, np.abs(t))
+                assert (err < 1e-9).mean() > .99 and err.max() < 1e-4, (err.max(), (err < 1e-9).mean())
+                assert np.array_equal(st["cell_o"], o) or np.allclose(st["cell_o"], o, rtol=1e-12)
+                worst = max(worst, float(err.max()))
+            print(f"PAM cache, {shape}: largest relative difference of a cached term {worst:.3g}")
+            eng.eval_all()
+            for c in range(len(temps)):
+                check_invariants(eng, pk, c, oracle, allow=allow, ncheck=2000, seed=c)
+        runs[pipeline] = (states, diags)
+        eng.close()
+    if shape != "ragged":
+        return
+    (sa_all, da_all), (sb_all, db_all) = runs["flat-cache"], runs["flat+cache"]
+    for sa, sb, da, db in zip(sa_all, sb_all, da_all, db_all):
+        for a, b in ((sa, sb), (da, db)):
+            for key in a:
+                x, y = np.asarray(a[key]), np.asarray(b[key])
+                if x.dtype.kind in "iu":
+                    assert np.array_equal(x, y), key
+                else:
+                    assert np.allclose(x, y, rtol=1e-9, atol=1e-12, equal_nan=True), key
+
+
 def test_step_graph_replays_the_plain_launch_sequence(monkeypatch):
     """moire_engine_step replays a captured CUDA graph; with MOIRE_B200_NO_GRAPH it issues the same
     kernels one by one.  Same state, bit for bit, and the same launch count."""
