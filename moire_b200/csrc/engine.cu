@@ -805,15 +805,16 @@ struct moire_engine
         src.list = pf.list; src.bounds = pf.hist + kPfScalars;
         src.p = pf.pprop; src.p_stride = v.AP; src.out_locus_major = 1;
         src.ss = pf.ss; src.binom_rows = v.max_coi;
-        src.round_flags = pf.round; src.out = pf.Tnew;
+        src.round_flags = pf.round; src.out = pf.Tnew; src.out_flip = pf.Tcur;
         launches += 2;  // prepare, scan, scatter (the caller counted one)
         if (p_cache)
         {
             // the PAM vectors of the current state: one evaluation of every cell at the accepted p
-            src.p = v.p; src.round_flags = nullptr; src.counter = pf.hist + kPfCounters;
+            // (its terms land in Tnew, which every round overwrites; no locus is swapped yet)
+            src.p = v.p; src.round_flags = nullptr; src.out_flip = nullptr; src.counter = pf.hist + kPfCounters;
             src.pam_out = pf.Wcur; src.pam_stride = pf.wstride;
             launch_flat_eval(src, true);
-            src.p = pf.pprop; src.pam_out = pf.Wnew;
+            src.p = pf.pprop; src.pam_out = pf.Wnew; src.round_flags = pf.round; src.out_flip = pf.Tcur;
             const unsigned list_blocks = scatter_blocks(total);
             for (int rep = 0; rep < amax_alleles; ++rep)
             {

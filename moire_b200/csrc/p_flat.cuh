@@ -49,6 +49,14 @@ constexpr unsigned kPfActive = 1u, kPfBroken = 2u;
 // cache mode: the previous proposal of the locus was accepted (bit 2) and which allele it moved
 // (bits 8..15) -- k_pc_sweep commits the PAM vectors of the cells that held it
 constexpr unsigned kPfAccepted = 4u;
+// The two term arrays of update_p swap roles per locus instead of being copied when a proposal is
+// accepted: bit 3 set = the accepted terms of the locus live in PFlat::Tnew and the next proposal's
+// go to PFlat::Tcur (the 8 KB copy sat on the one-warp-per-locus latency chain of k_pf_round).
+constexpr unsigned kPfFlip = 8u;
+__device__ __forceinline__ double *pf_terms(const PFlat &f, unsigned flags, bool proposed)
+{
+    return (((flags & kPfFlip) != 0) != proposed) ? f.Tnew : f.Tcur;
+}
 constexpr int kPfScalars = 2 * kSortBins;  // hist[kPfScalars + 0..3] = n_egf, coop_end, nwork, mid_end
 constexpr int kPfCounters = kPfScalars + 4;  // one task counter per evaluator launch of an update
 constexpr int kPfHistWords = kPfCounters + 72;
@@ -363,7 +371,34 @@ __global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat 
     const size_t prow = (size_t)tl * AP;
     double *st = f.round + (size_t)tl * 4;
     unsigned flags = rep == 0 ? 0u : (unsigned)st[3];
-    double *tn = f.Tnew + (size_t)tl * N, *tc = f.Tcur + (size_t)tl * N;
+    const double *tn = pf_terms(f, flags, true) + (size_t)tl * N, *tc = pf_terms(f, flags, false) + (size_t)tl * N;
+    // the scalars of the decision, in flight together with the sum's loads (thread 0)
+    double e_adj = 0.0, e_logu = 0.0, e_temp = 0.0, e_sd = 0.0;
+    int e_idx = 0, e_att = 0, e_acc = 0;
+    if ((flags & kPfActive) && tid == 0)
+    {
+        e_idx = (int)st[2];
+        e_adj = st[0];
+        e_logu = st[1];
+        e_temp = v.temp[t];
+        e_att = v.p_att[prow + e_idx];
+        e_acc = v.p_acc[prow + e_idx];
+        e_sd = v.p_sd[prow + e_idx];
+    }
+    // the draws of proposal `rep` depend on nothing the decision changes: before the sum, so that
+    // their arithmetic runs while its loads are in flight
+    const bool will_propose = rep < A && !(flags & kPfBroken) && warp == 0;
+    int n_idx = 0;
+    double n_z = 0.0, n_logu = 0.0;
+    if (will_propose)
+    {
+        Stream rng;
+        rng.open(v.seed, (uint32_t)iteration, KIND_P, (unsigned)(v.chain_offset + t), (uint32_t)j,
+                 (uint32_t)rep);
+        n_idx = (int)mulhi32(rng.next_u32(), (uint32_t)A);
+        n_z = next_normal(rng);
+        n_logu = cold_log(rng.next_uniform());
+    }
     // cache mode: every round sorts its own list (k_pc_sweep counts into these bins)
     if (f.Wcur && blockIdx.x == 0)
         for (int b = tid; b < kSortBins; b += B) f.hist[b] = 0;
@@ -391,17 +426,17 @@ __global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat 
         {
             double d = 0.0;
             for (int w = 0; w < (B >> 5); ++w) d += s_part[w];
-            const int idx = (int)st[2];
-            const double dpost = v.temp[t] * d;  // the priors do not depend on p
-            const double ratio = dpost + st[0];
-            const int accept = !(isnan(dpost) || st[1] > ratio);
-            if (accept) ++v.p_acc[prow + idx];
-            if (iteration < v.burnin && v.p_att[prow + idx] > 15)
+            const int idx = e_idx;
+            const double dpost = e_temp * d;  // the priors do not depend on p
+            const double ratio = dpost + e_adj;
+            const int accept = !(isnan(dpost) || e_logu > ratio);
+            if (accept) v.p_acc[prow + idx] = ++e_acc;
+            if (iteration < v.burnin && e_att > 15)
             {
                 // src/chain.cpp:555-562
-                const double att = (double)v.p_att[prow + idx];
-                const double rate = ((double)v.p_acc[prow + idx] + 1.0) / (att + 1.0);
-                const double sd = v.p_sd[prow + idx] + (rate - .23) / sqrt(att + 1.0);
+                const double att = (double)e_att;
+                const double rate = ((double)e_acc + 1.0) / (att + 1.0);
+                const double sd = e_sd + (rate - .23) / sqrt(att + 1.0);
                 v.p_sd[prow + idx] = sd > .01 ? sd : .01;
             }
             atomicAdd(v.evals + KIND_P, (unsigned long long)f.nonmiss[j]);
@@ -409,17 +444,15 @@ __global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat 
         }
         __syncthreads();
         if (s_accept)
-        {
-            for (int q = tid; q < N; q += B) tc[q] = tn[q];
             for (int a = tid; a < A; a += B) v.p[prow + a] = f.pprop[prow + a];
-        }
         __syncthreads();
     }
     {
-        // cache mode: what k_pc_sweep has to commit before the next proposal is evaluated
-        const bool was_active = (flags & kPfActive) != 0;
+        const bool accepted = (flags & kPfActive) && s_accept;
         flags &= ~(kPfActive | kPfAccepted | 0xff00u);
-        if (f.Wcur && was_active && s_accept) flags |= kPfAccepted | ((unsigned)st[2] << 8);
+        if (accepted) flags ^= kPfFlip;  // the proposal's terms are the locus' terms now: no copy
+        // cache mode: what k_pc_sweep has to commit before the next proposal is evaluated
+        if (f.Wcur && accepted) flags |= kPfAccepted | ((unsigned)e_idx << 8);  // thread 0's word is the one stored
     }
     if (rep >= A || (flags & kPfBroken))
     {
@@ -429,12 +462,8 @@ __global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat 
     if (warp != 0) return;
     // -- proposal `rep`, lanes across alleles (same arithmetic as k_update_p)
     {
-        Stream rng;
-        rng.open(v.seed, (uint32_t)iteration, KIND_P, (unsigned)(v.chain_offset + t), (uint32_t)j,
-                 (uint32_t)rep);
-        const int idx = (int)mulhi32(rng.next_u32(), (uint32_t)A);
-        const double z = next_normal(rng);
-        const double logu = cold_log(rng.next_uniform());
+        const int idx = n_idx;
+        const double z = n_z, logu = n_logu;
         double lg[2], lp[2], lq[2];
         bool rest[2];
 #pragma unroll
@@ -634,7 +663,7 @@ __global__ void __launch_bounds__(256) k_pc_sweep(const View v, const PFlat f)
                         T = relatedness_mixture(w, 1, m, nw, tot, rel, v.lgam, nullptr);
                     }
                 }
-                f.Tnew[loc] = T;
+                pf_terms(f, fl, true)[loc] = T;
             }
         }
     }
@@ -681,6 +710,8 @@ struct FlatSrc
     const SampleScal *ss;               // [t * N + i]
     const double *round_flags;          // null, or [(t * L + j) * 4 + 3] & kPfActive says "evaluate"
     double *out;                        // locus-major [t][j][i] (p rounds) or sample-major [t][i][j]
+    double *out_flip;                   // p rounds: where the terms of a locus whose arrays are swapped go
+                                        // (kPfFlip in its round flags); null otherwise
     int out_locus_major;
     int binom_rows;                     // rows of g_binom staged in shared memory (= max_coi)
     double *pam_out;                    // CACHE evaluators: PAM vectors, [t][pam_stride] + locus-major cell
@@ -729,7 +760,9 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
         if (w >= hi) return;
         const uint4 e = f.list[w];
         const unsigned t = e.z >> 16, j = e.z & 0xffffu, tl = t * L + j, tn = t * N + e.w;
-        if (f.round_flags && ((unsigned)f.round_flags[(size_t)tl * 4 + 3] & kPfActive) == 0) return;
+        const unsigned fl = f.round_flags ? (unsigned)f.round_flags[(size_t)tl * 4 + 3] : kPfActive;
+        if ((fl & kPfActive) == 0) return;
+        double *const outp = (f.out_flip && (fl & kPfFlip)) ? f.out_flip : f.out;
         const unsigned long long lat = ((unsigned long long)e.y << 32) | e.x;
         const SampleScal sc = f.ss[tn];
         const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
@@ -743,7 +776,7 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
             T = transmission_ll_egf_coop<CACHE>(lat, prow, m, rel, allow_rel, s_scr + warp * 32, ST, s_lgam, s_binom, po);
         else
             T = transmission_ll_coop<CACHE>(lat, prow, m, rel, allow_rel, s_scr + warp * 32, ST, s_lgam, s_binom, po);
-        if (lane == 0) f.out[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + j] = T;
+        if (lane == 0) outp[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + j] = T;
         __syncwarp();
         return;
     }
@@ -787,7 +820,8 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
                         case 5: T = small_cell<5, CACHE>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom, po); break;
                         default: T = small_cell<6, CACHE>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom, po); break;
                     }
-                    f.out[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] = T;
+                    double *const outp = (f.out_flip && ((unsigned)flagword & kPfFlip)) ? f.out_flip : f.out;
+                    outp[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] = T;
                 }
                 __syncwarp();
                 return;
@@ -810,7 +844,8 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
     {
         const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
         const PamOut po{CACHE ? f.pam_out + ((size_t)tl * N + e.w) : nullptr, f.pam_stride};
-        f.out[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] =
+        double *const outp = (f.out_flip && ((unsigned)flagword & kPfFlip)) ? f.out_flip : f.out;
+        outp[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] =
             transmission_ll<CACHE>(lat, prow, pv, sc.m, rel, allow_rel, s_scr + tid, ST, s_lgam, s_binom, callers, po);
     }
     __syncwarp();
@@ -925,7 +960,7 @@ __global__ void __launch_bounds__(256) k_pf_finish(const View v, const PFlat f)
         {
             const size_t loc = ((size_t)t * L + j) * N + i;
             in = f.latLM[loc] != 0ull;
-            T = f.Tcur[loc];
+            T = pf_terms(f, (unsigned)f.round[((size_t)t * L + j) * 4 + 3], false)[loc];
         }
         s_T[lj][tx] = T;
         s_in[lj][tx] = in;
