@@ -78,9 +78,6 @@ constexpr int kPfHistWords = kPfCounters + 72;
 #ifndef MOIRE_COOP_WORK_MAX
 #define MOIRE_COOP_WORK_MAX 8000.f
 #endif
-#ifndef MOIRE_COOP_WORK_MIN
-#define MOIRE_COOP_WORK_MIN 3000.f
-#endif
 #ifndef MOIRE_COOP_WORK_SHARE
 #define MOIRE_COOP_WORK_SHARE 1.2f
 #endif
@@ -232,70 +229,163 @@ __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
         if (s_hist[b]) atomicAdd(&f.hist[b], s_hist[b]);
 }
 
+// One block: the exclusive scan of the class counts (the list offsets) and the section bounds.
+// Where the one-thread / cooperative boundary goes is decided per launch from a cost model of the
+// evaluator (calibrated on its per-block trace, scripts/eval_trace_digest.py; unit = one dependent
+// instruction of a resident warp, ~11 ns with eight warps per scheduler):
+//   a chunk of 32 one-thread cells of a class costs its warp  est           (and is one latency chain)
+//   a cooperative cell costs its warp                         est / 4 + 300
+// With the boundary in front of class b (classes are ranked by est, heaviest first) the launch takes
+//   T(b) = max( (sum_{c < b} n_c (est_c / 4 + 300) + sum_{c >= b} n_c est_c / 32) / warps ,  est_b )
+// -- throughput against the longest one-thread chain -- and the populated b with the smallest T(b)
+// wins, capped at MOIRE_COOP_WORK_MAX.  A full benchmark ladder lands where round 1 tuned it by hand
+// (~8000: the work per warp is that large); a 5-chain shard of it near 3000; the Namibia shape
+// (work per warp ~400, a few hundred cells of 1000..3000) moves down to ~1000, where the fixed 3000
+// left 30 us one-thread chains in a launch with 5 us of work (profiles/README.md, round 2).
 __global__ void __launch_bounds__(256) k_pf_scan(const PFlat f)
 {
     __shared__ unsigned int s_part[9];
-    __shared__ float s_work[8];
+    __shared__ float s_work[8], s_lw[9], s_cw[9], s_bestT[8];
+    __shared__ int s_bestB[8];
     const int tid = threadIdx.x;
     constexpr int per = kSortBins / 256;  // 3
     unsigned int local = 0, h[per];
-    float work = 0.f;
+    float work = 0.f, lw[per], cw[per], lsum = 0.f, csum = 0.f;
     for (int q = 0; q < per; ++q)
     {
-        h[q] = f.hist[tid * per + q];
+        const int b = tid * per + q;
+        h[q] = f.hist[b];
         local += h[q];
-        work += (float)h[q] * c_flat_est[tid * per + q];
+        const float est = c_flat_est[b];
+        work += (float)h[q] * est;
+        const bool ie = b >= kClassCoopBegin;  // the EGF classes (ranks < 64) have their own section
+        lw[q] = ie ? (float)h[q] * est * (1.f / 32.f) : 0.f;
+        cw[q] = ie ? (float)h[q] * (est * .25f + 300.f) : 0.f;
+        lsum += lw[q];
+        csum += cw[q];
     }
     unsigned int x = local;
+    float xl = lsum, xc = csum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
     {
         const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
-        if ((tid & 31) >= o) x += y;
+        const float yl = __shfl_up_sync(0xffffffffu, xl, o), yc = __shfl_up_sync(0xffffffffu, xc, o);
+        if ((tid & 31) >= o)
+        {
+            x += y;
+            xl += yl;
+            xc += yc;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) work += __shfl_xor_sync(0xffffffffu, work, o);
-    if ((tid & 31) == 31) s_part[tid >> 5] = x;
+    if ((tid & 31) == 31)
+    {
+        s_part[tid >> 5] = x;
+        s_lw[tid >> 5] = xl;
+        s_cw[tid >> 5] = xc;
+    }
     if ((tid & 31) == 0) s_work[tid >> 5] = work;
     __syncthreads();
     if (tid == 0)
     {
         unsigned int run = 0;
+        float rl = 0.f, rc = 0.f;
         for (int w = 0; w < 8; ++w)
         {
             const unsigned int c = s_part[w];
+            const float cl = s_lw[w], cc = s_cw[w];
             s_part[w] = run;
+            s_lw[w] = rl;
+            s_cw[w] = rc;
             run += c;
+            rl += cl;
+            rc += cc;
         }
         s_part[8] = run;
+        s_lw[8] = rl;
+        s_cw[8] = rc;
     }
     __syncthreads();
     float total_work = 0.f;
     for (int w = 0; w < 8; ++w) total_work += s_work[w];
-    // cooperative above this much one-thread work: a share of the launch's work per thread
-    // Two boundaries.  thr (as tuned in round 1): classes above it are worth a cooperating warp when
-    // they are RARE -- too few cells to fill class-uniform chunks -- and run one cell per thread
-    // when plentiful.  thr_hi: a cell whose one-thread work exceeds the launch's work per thread would
-    // outlast everything else on its own (a small shard of a high-COI ladder: one k = 10 cell with
-    // 30 mixture terms is ~10^5 dependent instructions, ~1 ms, while the launch's share per thread is
-    // a tenth of that), so it ALWAYS goes to a warp.
+    const float warps = (float)f.eval_threads * (1.f / 32.f);
+    // a cell whose one-thread work exceeds the launch's work per thread would outlast everything else
+    // on its own (a small shard of a high-COI ladder: one k = 10 cell with 30 mixture terms is ~10^5
+    // dependent instructions, ~1 ms, while the launch's share per thread is a tenth of that), so it
+    // ALWAYS goes to a warp: the classes above `share`
     const float share = MOIRE_COOP_WORK_SHARE * total_work / (float)f.eval_threads;
-    const float thr = fminf(MOIRE_COOP_WORK_MAX, fmaxf(MOIRE_COOP_WORK_MIN, share));
-    const float thr_hi = fmaxf(thr, share);
+    // -- T(b) of this thread's populated classes
+    float bestT = 3.0e38f;
+    int bestB = kSortBins;
+    {
+        float coop_before = s_cw[tid >> 5] + xc - csum, light_before = s_lw[tid >> 5] + xl - lsum;
+        const float light_total = s_lw[8];
+        for (int q = 0; q < per; ++q)
+        {
+            const int b = tid * per + q;
+            if (b >= kClassCoopBegin && h[q] && c_flat_est[b] <= MOIRE_COOP_WORK_MAX)
+            {
+                const float T = fmaxf((coop_before + (light_total - light_before)) / warps, c_flat_est[b]);
+                if (T < bestT)  // ties: the first (heaviest) class, i.e. fewer cooperative cells
+                {
+                    bestT = T;
+                    bestB = b;
+                }
+            }
+            coop_before += cw[q];
+            light_before += lw[q];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        const float oT = __shfl_xor_sync(0xffffffffu, bestT, o);
+        const int oB = __shfl_xor_sync(0xffffffffu, bestB, o);
+        if (oT < bestT || (oT == bestT && oB < bestB))
+        {
+            bestT = oT;
+            bestB = oB;
+        }
+    }
+    if ((tid & 31) == 0)
+    {
+        s_bestT[tid >> 5] = bestT;
+        s_bestB[tid >> 5] = bestB;
+    }
+    __syncthreads();
+    for (int w = 0; w < 8; ++w)
+        if (s_bestT[w] < bestT || (s_bestT[w] == bestT && s_bestB[w] < bestB))
+        {
+            bestT = s_bestT[w];
+            bestB = s_bestB[w];
+        }
+    // bestB: the first class that runs one cell per thread (kSortBins: every populated class is above
+    // MOIRE_COOP_WORK_MAX or the list holds EGF cells only)
+    if (tid == 0)
+    {
+        // defaults (no class below the boundary): everything is cooperative
+        f.hist[kPfScalars + 1] = s_part[8];
+        f.hist[kPfScalars + 2] = s_part[8];
+        f.hist[kPfScalars + 3] = s_part[8];
+    }
+    __syncthreads();
     unsigned int base = s_part[tid >> 5] + x - local;
     for (int q = 0; q < per; ++q)
     {
         const int b = tid * per + q;
         f.hist[kSortBins + b] = base;
         if (b == kClassCoopBegin) f.hist[kPfScalars + 0] = base;
-        // ranks >= 64 are sorted by estimate, descending: the first one below each threshold
-        if (b >= kClassCoopBegin && c_flat_est[b] < thr_hi && (b == kClassCoopBegin || c_flat_est[b - 1] >= thr_hi))
+        // ranks >= 64 are sorted by estimate, descending.  [n_egf, coop_end): est >= share and above the
+        // boundary: always a warp per cell; [coop_end, mid_end): above the boundary but below the
+        // launch's share: a warp per cell while rare, chunks when plentiful
+        if (b >= kClassCoopBegin && (c_flat_est[b] < share || b >= bestB) &&
+            (b == kClassCoopBegin || !(c_flat_est[b - 1] < share || b - 1 >= bestB)))
             f.hist[kPfScalars + 1] = base;
-        if (b >= kClassCoopBegin && c_flat_est[b] < thr && (b == kClassCoopBegin || c_flat_est[b - 1] >= thr))
-            f.hist[kPfScalars + 3] = base;
+        if (b >= kClassCoopBegin && b == max(bestB, kClassCoopBegin) && b < kSortBins) f.hist[kPfScalars + 3] = base;
         base += h[q];
     }
-    if (tid == 0) f.hist[kPfScalars + 2] = s_part[8];
 }
 
 // Scatter of one block's cells into the sorted list: ranks inside the block come from a
