@@ -995,6 +995,21 @@ __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval
         }
 #endif
         if (b >= tasks) break;
+        // Claim order: the cooperative tasks (heaviest first) and the one-thread tasks (heaviest
+        // first) ALTERNATE while both last.  The heaviest one-thread chunks are the longest single
+        // chains of the launch (the trace of a 5-chain shard: 37 us, started 16 us late behind 660
+        // cooperative tasks -- the launch ended when they did), so they start with the first wave.
+        // (Not when a heavy section runs as one-thread chunks itself -- high-COI shapes: those chunks
+        // are longer than anything in the light section and must not wait: c5 lost 4 % with it.)
+        const int t_heavy = t_egf + t_strag + t_mid;
+        const int t_pair = (chunked_egf || chunked_mid) ? 0 : min(t_heavy, tasks - t_heavy);
+        if (t_pair == 0)
+            ;
+        else if (b < 2 * t_pair)
+            b = (b & 1) ? t_heavy + (b >> 1) : (b >> 1);
+        else if (t_heavy > t_pair)
+            b -= t_pair;  // the one-thread tasks are used up: b - 2 t_pair cooperative tasks beyond t_pair
+        // else: the cooperative tasks are used up and b already is the task's own index
         int lo, hi;
         bool coop, egf = false, light = false;
         if (b < t_egf)
@@ -1011,7 +1026,7 @@ __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval
             hi = coop_end;
             coop = true;
         }
-        else if (b < t_egf + t_strag + t_mid)
+        else if (b < t_heavy)
         {
             b -= t_egf + t_strag;
             lo = coop_end;
@@ -1020,7 +1035,7 @@ __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval
         }
         else
         {
-            b -= t_egf + t_strag + t_mid;
+            b -= t_heavy;
             lo = mid_end;
             hi = nwork;
             coop = false;
