@@ -387,12 +387,18 @@ def our_arm(args, wl):
     # ---- the multi-GPU shapes of BASELINE.json on the same ranks (configs[3], configs[4])
     other = {}
     if world > 1 and wl["name"] == "c3" and not args.no_other_workloads:
-        for key, name, T in (("c4", "c4", 64), ("c5_T16", "c5", 16), ("c5_T32", "c5", 32), ("c5_T64", "c5", 64)):
+        # ... and the benchmark shape with the ladder grown with the box (40 temperatures per GPU): the
+        # headline line above cuts a fixed 40-temperature ladder N ways (strong scaling); this one
+        # keeps every GPU's share fixed (weak scaling); chain_steps_per_sec = steps/s x temperatures
+        shapes = [("c4", "c4", 64, 5), ("c5_T16", "c5", 16, 5), ("c5_T32", "c5", 32, 5), ("c5_T64", "c5", 64, 5),
+                  (f"c3_weak_T{40 * world}", "c3", 40 * world, 30)]
+        for key, name, T, nsteps in shapes:
             if T < world:
                 continue
             try:
-                other[key] = timed_workload(name, T, steps=5, warmup=3, world=world, rank=rank, local=local,
+                other[key] = timed_workload(name, T, steps=nsteps, warmup=3, world=world, rank=rank, local=local,
                                             dev=dev, seed=args.seed)
+                other[key]["chain_steps_per_sec"] = other[key]["value"] * T
             except Exception as exc:  # a shape that does not fit is reported, not fatal
                 other[key] = dict(error=repr(exc))
     if rank != 0:

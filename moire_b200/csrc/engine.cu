@@ -851,7 +851,8 @@ struct moire_engine
     {
         using namespace moire;
         const size_t total = (size_t)v.T * v.N * v.L;
-        const unsigned draw_blocks = (unsigned)(((size_t)v.T * v.N + kDrawThreads - 1) / kDrawThreads);
+        const size_t draw_spb = (size_t)sf_draw_units_per_block(v.nA, KIND != KIND_R);
+        const unsigned draw_blocks = (unsigned)(((size_t)v.T * v.N + draw_spb - 1) / draw_spb);
         CUDA_TRY(cudaMemsetAsync(pf.hist, 0, kPfHistWords * sizeof(unsigned int), stream));
         k_sf_draw<KIND><<<draw_blocks, kDrawThreads, 0, stream>>>(v, sf, iteration);
         k_sf_cells<KIND><<<sf_cell_blocks(total), 256, 0, stream>>>(v, sf, pf, iteration);
@@ -876,8 +877,8 @@ struct moire_engine
             if (!p_fused)
             {
                 const size_t units = (size_t)v.T * v.N;
-                moire::k_sf_draw<KIND><<<(unsigned)((units + moire::kDrawThreads - 1) / moire::kDrawThreads),
-                                         moire::kDrawThreads, 0, stream>>>(v, sf, iteration);
+                const size_t spb = (size_t)moire::sf_draw_units_per_block(v.nA, true);
+                moire::k_sf_draw<KIND><<<(unsigned)((units + spb - 1) / spb), moire::kDrawThreads, 0, stream>>>(v, sf, iteration);
                 moire::k_eps_cells<KIND><<<(unsigned)((units + 7) / 8), 256, 0, stream>>>(v, sf, iteration);
                 launches += 1;  // two kernels; the caller counts one
                 return;

@@ -392,7 +392,10 @@ __global__ void __launch_bounds__(256) k_pf_scan(const PFlat f)
 // shared-memory histogram, and the block reserves its range of every class with ONE global atomic
 // per class (a global atomic per cell on ~50 hot counters cost 200 us per 800 K cells).
 // cell_fn(idx, cls, entry) returns false for cells that are not listed.
-constexpr int kScatterCellsPerThread = 4;
+#ifndef MOIRE_SCATTER_CPT
+#define MOIRE_SCATTER_CPT 4
+#endif
+constexpr int kScatterCellsPerThread = MOIRE_SCATTER_CPT;
 template <class CellFn>
 __device__ __forceinline__ void block_scatter(size_t total, CellFn cell_fn, unsigned int *offsets,
                                               uint4 *list)

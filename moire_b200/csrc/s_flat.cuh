@@ -32,6 +32,16 @@ struct SFlat
 
 constexpr int kDrawThreads = 128;
 
+// A block draws the proposals of `spb` consecutive (chain, sample) units -- one thread each, a serial
+// chain of ~15 double-precision transcendentals -- and then builds the observation logs of the
+// proposed error rates, one thread per (unit, distinct allele count).  spb = kDrawThreads / nA
+// (sf_draw_units_per_block), so the second phase is one pair per thread whatever the number of
+// distinct allele counts (the Namibia shape has 20: with 128 units per block a thread built 20 sets of
+// logs in turn, 65 us per launch where the benchmark shape, one allele count, takes 15).
+__host__ __device__ inline int sf_draw_units_per_block(int nA, bool logs)
+{
+    return logs ? max(1, kDrawThreads / max(1, nA)) : kDrawThreads;
+}
 template <int KIND>
 __global__ void __launch_bounds__(kDrawThreads) k_sf_draw(const View v, const SFlat sf, const int iteration_arg)
 {
@@ -39,10 +49,11 @@ __global__ void __launch_bounds__(kDrawThreads) k_sf_draw(const View v, const SF
     constexpr bool LOGS = KIND != KIND_R;  // the kinds that recompute observation terms
     __shared__ double s_en[kDrawThreads], s_ep[kDrawThreads];
     __shared__ int s_valid[kDrawThreads];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nA = v.nA;
+    const int spb = sf_draw_units_per_block(nA, LOGS);
     const size_t total = (size_t)v.T * v.N;
-    const size_t si0 = (size_t)blockIdx.x * kDrawThreads, si = si0 + tid;
-    if (si < total)
+    const size_t si0 = (size_t)blockIdx.x * spb, si = si0 + tid;
+    if (tid < spb && si < total)
     {
         const int t = (int)(si / v.N), i = (int)(si - (size_t)t * v.N);
         const Proposal P = draw_sample_proposal<KIND>(v, t, i, iteration, v.lgam);
@@ -61,7 +72,7 @@ __global__ void __launch_bounds__(kDrawThreads) k_sf_draw(const View v, const SF
     }
     if (!LOGS) return;
     __syncthreads();
-    const int n = (int)min((size_t)kDrawThreads, total - si0), nA = v.nA;
+    const int n = (int)min((size_t)spb, total - si0);
     for (int e = tid; e < n * nA; e += kDrawThreads)
     {
         const int sl = e / nA, a = e - sl * nA;
