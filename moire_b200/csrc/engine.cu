@@ -594,6 +594,13 @@ struct moire_engine
         {
             trace.alloc(kTraceWords);
             CUDA_TRY(cudaMemsetAsync(trace.ptr, 0, kTraceWords * sizeof(unsigned long long), stream));
+#ifdef MOIRE_EVAL_TRACE
+            {
+                // cooperative cells' phase clocks go behind the per-block records (block 600 on)
+                unsigned long long *coop = trace.ptr + 600 * 256;
+                CUDA_TRY(cudaMemcpyToSymbol(moire::g_coop_trace, &coop, sizeof(coop)));
+            }
+#endif
             v.trace = trace.ptr;
         }
         CUDA_TRY(cudaMemcpyAsync(v.temp, temps, T * sizeof(double), cudaMemcpyHostToDevice, stream));

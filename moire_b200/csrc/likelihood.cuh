@@ -872,6 +872,9 @@ __device__ __forceinline__ double small_cell(unsigned lat32, const double *prow,
 #ifndef MOIRE_COOP_MIN_K
 #define MOIRE_COOP_MIN_K 8
 #endif
+#ifdef MOIRE_EVAL_TRACE
+__device__ unsigned long long *g_coop_trace = nullptr;  // tuning aid: phase clocks of cooperative cells
+#endif
 constexpr int kCoopMinK = MOIRE_COOP_MIN_K;
 template <bool CACHE>
 __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const double *prow, int m,
@@ -882,25 +885,26 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int k = __popcll(latent);  // 1 <= k <= kIeMax, k <= m guaranteed by the caller
-    double total = 0.0;
+#ifdef MOIRE_EVAL_TRACE
+    long long tc0 = clock64(), tc1 = 0, tc2 = 0, tc3 = 0;
+#endif
+    // lane e < k fetches the frequency of element e (the k loads are in flight together: the trace
+    // showed ~3000 cycles for k dependent trips to L2 in front of every cooperative cell); the sum is
+    // then taken in ascending allele order, as everywhere
+    double total = 0.0, p_mine = 0.0;
     {
         uint64_t rest = latent;
-        while (rest)
-        {
-            const int al = __ffsll((long long)rest) - 1;
-            rest &= rest - 1;
-            total = __dadd_rn(total, prow[al]);
-        }
+        for (int e = 0; e < lane && rest; ++e) rest &= rest - 1;
+        if (lane < k) p_mine = prow[__ffsll((long long)rest) - 1];
+        for (int e = 0; e < k; ++e) total = __dadd_rn(total, __shfl_sync(FULL, p_mine, e));
     }
     if (!allow_relatedness && m == k) return transmission_norel_exact_cover<CACHE>(latent, prow, total, k, po);
     double *q = wscr + 16 * ST;
-    {
-        // lane e normalises element e
-        uint64_t rest = latent;
-        for (int e = 0; e < lane && rest; ++e) rest &= rest - 1;
-        if (lane < k) q[lane] = __ddiv_rn(prow[__ffsll((long long)rest) - 1], total);
-    }
+    if (lane < k) q[lane] = __ddiv_rn(p_mine, total);  // lane e normalises element e
     __syncwarp();
+#ifdef MOIRE_EVAL_TRACE
+    tc1 = clock64();
+#endif
     const unsigned short *masks = g_sub_mask + subset_block(k);
     const int nsub = (1 << k) - 1;
     const int cnt = allow_relatedness ? m - k + 1 : 1;
@@ -964,6 +968,17 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
 #pragma unroll
                         for (int l = 0; l < 32; ++l) a = __dadd_rn(a, term[l]);
                     }
+                    else if (nv >= 16)
+                    {
+                        // a short last batch (2^k - 1 is never a multiple of 32) the same way, padded with
+                        // zeros: x + 0 is x -- at most the sign of a zero sum changes, and a PAM of +-0
+                        // clamps to 0
+                        double term[32];
+#pragma unroll
+                        for (int l = 0; l < 32; ++l) term[l] = row[l];
+#pragma unroll
+                        for (int l = 0; l < 32; ++l) a = __dadd_rn(a, l < nv ? term[l] : 0.0);
+                    }
                     else
                     {
                         for (int l = 0; l < nv; ++l) a = __dadd_rn(a, row[l]);
@@ -974,7 +989,52 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
             }
         }
     }
+#ifdef MOIRE_EVAL_TRACE
+    tc2 = clock64();
+#endif
     if (!allow_relatedness) return norel_term_c<CACHE>(__shfl_sync(FULL, acc[0], 0), total, m, po);
+    // Up to 32 mixture terms: lane L builds term i = cnt - 1 - L (its own q^i by the same chain of
+    // multiplications, its own clamp) and the terms are then added in the order i = 0, 1, ... through
+    // shuffles -- the operations and the order of relatedness_mixture's linear branch, bit for bit,
+    // without every lane walking the whole vector through local memory (trace: gather + mixture were
+    // ~45 % of a cooperative cell's 23 000 cycles).  Its other branches (one term, weights that could
+    // overflow) go through the function itself, below.
+    if (cnt > 1 && cnt <= 32)
+    {
+        const double qr = __ddiv_rn(rel.odds, total);
+        const int e2 = ((__double2hiint(qr) >> 20) & 0x7ff) - 1022;
+        if ((cnt - 1) * max(e2, 0) <= 850)
+        {
+            const double v0 = __shfl_sync(FULL, acc[0], lane & 15), v1 = __shfl_sync(FULL, acc[1], lane & 15);
+            const double pam = (lane >> 4) ? v1 : v0;  // PAM(n = k + lane)
+            if (CACHE && lane < cnt) po.w[(size_t)lane * po.stride] = pam;
+            const int i = cnt - 1 - lane;  // this lane's term (negative: none)
+            double qi = 1.0;
+            for (int j = 0; j < cnt - 1; ++j)
+                if (j < i) qi = __dmul_rn(qi, qr);
+            double term = 0.0;
+            if (i >= 0)
+            {
+                const double c = g_binom[(m - 1) * (kMaxCoi + 1) + i];
+                term = __dmul_rn(__dmul_rn(c, qi), __dsub_rn(1.0, clamp_pam(pam)));
+            }
+            double S = 0.0;
+            for (int j = 0; j < cnt; ++j) S = __dadd_rn(S, __shfl_sync(FULL, term, cnt - 1 - j));
+            const double lead = __dmul_rn((double)(m - 1), rel.log_1mr);
+#ifdef MOIRE_EVAL_TRACE
+            if (g_coop_trace && lane == 0)
+            {
+                const unsigned slot = atomicAdd((unsigned int *)g_coop_trace, 1u);
+                if (slot < 8000)
+                {
+                    unsigned long long *r = g_coop_trace + 8 + (size_t)slot * 8;
+                    r[0] = k; r[1] = cnt; r[2] = tc1 - tc0; r[3] = tc2 - tc1; r[4] = 0; r[5] = clock64() - tc2;
+                }
+            }
+#endif
+            return __dadd_rn(lead, log_total_pow_times(total, m, S));
+        }
+    }
     // The mixture through the same function, in the same order of operations, as the one-thread
     // path: which evaluator a cell lands in depends on the launch (the cooperative threshold
     // follows the work per thread, so it changes with the number of chains on the device) and must
@@ -989,7 +1049,22 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
         }
     if (CACHE)  // every lane holds the vector: lane t stores entries t, t + 32, ...
         for (int t = lane; t < cnt; t += 32) po.w[(size_t)t * po.stride] = pams[t];
+#ifdef MOIRE_EVAL_TRACE
+    tc3 = clock64();
+    const double res_traced = relatedness_mixture(pams, 1, m, cnt, total, rel, lgam, binom_s);
+    if (g_coop_trace && lane == 0)
+    {
+        const unsigned slot = atomicAdd((unsigned int *)g_coop_trace, 1u);
+        if (slot < 8000)
+        {
+            unsigned long long *r = g_coop_trace + 8 + (size_t)slot * 8;
+            r[0] = k; r[1] = cnt; r[2] = tc1 - tc0; r[3] = tc2 - tc1; r[4] = tc3 - tc2; r[5] = clock64() - tc3;
+        }
+    }
+    return res_traced;
+#else
     return relatedness_mixture(pams, 1, m, cnt, total, rel, lgam, binom_s);
+#endif
 }
 
 // ---- a2 for k > 10, warp-cooperative: the band with its rows across lanes ---------------------

@@ -75,6 +75,12 @@ constexpr int kPfHistWords = kPfCounters + 72;
 // path has the shorter critical path but the lower throughput (lanes idle in its sums), so a full
 // ladder wants it for the few heaviest cells only (8000 instructions ~ k >= 8, the tuned optimum
 // at 40 chains) and a small shard for many more.
+#ifndef MOIRE_COOP_COST_SLOPE
+#define MOIRE_COOP_COST_SLOPE .25f
+#endif
+#ifndef MOIRE_COOP_COST_FIXED
+#define MOIRE_COOP_COST_FIXED 300.f
+#endif
 #ifndef MOIRE_COOP_WORK_MAX
 #define MOIRE_COOP_WORK_MAX 8000.f
 #endif
@@ -260,7 +266,7 @@ __global__ void __launch_bounds__(256) k_pf_scan(const PFlat f)
         work += (float)h[q] * est;
         const bool ie = b >= kClassCoopBegin;  // the EGF classes (ranks < 64) have their own section
         lw[q] = ie ? (float)h[q] * est * (1.f / 32.f) : 0.f;
-        cw[q] = ie ? (float)h[q] * (est * .25f + 300.f) : 0.f;
+        cw[q] = ie ? (float)h[q] * (est * MOIRE_COOP_COST_SLOPE + MOIRE_COOP_COST_FIXED) : 0.f;
         lsum += lw[q];
         csum += cw[q];
     }

@@ -4,7 +4,7 @@ usage: eval_trace_digest.py trace.bin"""
 import sys
 import numpy as np
 a = np.fromfile(sys.argv[1], dtype=np.uint64).reshape(1024, 256).astype(np.int64)
-blocks = [b for b in range(1024) if a[b, 0] > 0 and a[b, 1] >= 5]
+blocks = [b for b in range(600) if a[b, 0] > 0 and a[b, 1] >= 5]
 t0 = min(a[b, 0] for b in blocks)
 rows = []
 for b in blocks:
@@ -39,3 +39,12 @@ if len(at):
     for lo in range(0, 10):
         seg = at[len(at) * lo // 10: len(at) * (lo + 1) // 10]
         print(f"  tasks {int(seg[0, 0]):6d}..{int(seg[-1, 0]):6d}: mean {seg[:, 1].mean() * us:6.2f} us max {seg[:, 1].max() * us:6.2f}  started {seg[:, 2].min() * us:6.1f}..{seg[:, 2].max() * us:6.1f} us")
+# cooperative cells' phase clocks (cycles): {k, cnt, normalise, subset terms + ordered sums, gather, mixture}
+c = a.reshape(-1)[600 * 256:]
+n = int(c[0])
+if n:
+    r = c[8:8 + 8 * min(n, 8000)].reshape(-1, 8).astype(np.float64)
+    print(f"cooperative cells traced: {len(r)} (of {n}); cycles per phase, mean by k:")
+    for k in sorted(set(r[:, 0].astype(int))):
+        s = r[r[:, 0] == k]
+        print(f"  k {k:2d}: {len(s):5d} cells, cnt mean {s[:, 1].mean():5.1f}  normalise {s[:, 2].mean():7.0f}  subsets+sums {s[:, 3].mean():8.0f}  gather {s[:, 4].mean():6.0f}  mixture {s[:, 5].mean():7.0f}  total {s[:, 2:6].sum(1).mean():8.0f} (max {s[:, 2:6].sum(1).max():8.0f})")
