@@ -51,14 +51,15 @@ constexpr int kLogCDim = 65;    // logC[n][k], 0 <= k <= n <= 64 (alleles of a l
 // x^n, n >= 0, by square and multiply.
 __device__ __forceinline__ double pow_uint(double x, int n)
 {
-    // n < 128 (a COI): seven rounds, no branches
+    // n < 128 (a COI): at most seven rounds, as many as n has bits (the lanes of a class-uniform
+    // chunk share n up to the COI's spread, so the exit is all but uniform; a COI below 8 takes two
+    // rounds where the branch-free version always ran six)
     double r = (n & 1) ? x : 1.0;
-#pragma unroll
-    for (int b = 1; b < 7; ++b)
+#pragma unroll 1
+    for (n >>= 1; n; n >>= 1)
     {
         x = __dmul_rn(x, x);
-        const double rx = __dmul_rn(r, x);
-        r = (n >> b) & 1 ? rx : r;
+        if (n & 1) r = __dmul_rn(r, x);
     }
     return r;
 }
@@ -194,7 +195,9 @@ __device__ __forceinline__ void ie_vectorized(double *scr, int ST, int k, int t0
     for (int t = 0; t < NACC; ++t) acc[t] = 0.0;
     const unsigned short *tab = c_sub_tail + subset_block(k);
     const int nsub = (1 << k) - 1;
-    const int lead = k - 1 + t0;
+    // sign * base is exact, so the chain starts at +-base and one leading multiplication is saved
+    // (k >= 2 here: at least one is due)
+    const int lead = k - 2 + t0;
 #pragma unroll 1
     for (int idx = 0; idx < nsub; ++idx)
     {
@@ -212,7 +215,7 @@ __device__ __forceinline__ void ie_vectorized(double *scr, int ST, int k, int t0
             scr[(kPartBase + pos) * ST] = base;
             ++pos;
         }
-        double r = (e & 0x4000u) ? -1.0 : 1.0;
+        double r = (e & 0x4000u) ? -base : base;
         // r *= base, `lead` times: a jump into a straight run of multiplications (lead <= 9
         // unless this is a later pass of the wide path)
         switch (lead)
@@ -516,6 +519,7 @@ __device__ __forceinline__ void ie_small(const double *scr, int ST, double (&acc
 template <int K, int NACC>
 __device__ __forceinline__ void ie_small_regs(const double (&q)[K], double (&acc)[NACC])
 {
+    static_assert(K >= 2, "one latent allele has no subset sums (every PAM is exactly 0)");
     constexpr SmallSubsets<K> ord{};
 #pragma unroll
     for (int t = 0; t < NACC; ++t) acc[t] = 0.0;
@@ -532,9 +536,11 @@ __device__ __forceinline__ void ie_small_regs(const double (&q)[K], double (&acc
                 base = __dsub_rn(base, q[e]);
                 ++size;
             }
-        double r = (size & 1) ? 1.0 : -1.0;
+        // sign * base is exact (no rounding), so the chain of K - 1 leading multiplications starts at
+        // +-base: one multiplication and one constant fewer per subset, the same bits
+        double r = (size & 1) ? base : -base;
 #pragma unroll
-        for (int j = 0; j < K - 1; ++j) r = __dmul_rn(r, base);
+        for (int j = 0; j < K - 2; ++j) r = __dmul_rn(r, base);
 #pragma unroll
         for (int t = 0; t < NACC; ++t)
         {
@@ -790,7 +796,7 @@ __device__ __forceinline__ double small_cell_tail(const double (&q)[K], double t
                                                   const double *binom_s, const PamOut po)
 {
     double acc[NACC];
-    if (K >= 2)
+    if constexpr (K >= 2)
     {
         ie_small_regs<K, NACC>(q, acc);
         if (CACHE)
@@ -935,7 +941,8 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
                     if (allow_relatedness)
                     {
                         const int lead = k - 1 + t0;
-                        for (int j = 0; j < lead; ++j) r = __dmul_rn(r, base);
+                        if (lead > 0) r = neg ? -base : base;  // sign * base, exact
+                        for (int j = 1; j < lead; ++j) r = __dmul_rn(r, base);
                         for (int t = 0; t < cc; ++t)
                         {
                             r = __dmul_rn(r, base);
