@@ -36,6 +36,10 @@ namespace moire
 // below, i.e. the term differs from log1p(-pam) by at most ~2e-16 in absolute value -- ulp-level,
 // like the difference between CUDA's and glibc's log1p -- while the 250-instruction log1p body
 // cost 13 % of the step when it sat in the hot loop (profiles/variants_o.log).
+// (Tried, round 2: a leaner logarithm for the one log of a cell -- atanh series on the hardware's
+// reciprocal seed, ~35 instructions where CUDA's log() showed as ~20 % of the evaluator's executed
+// instructions.  It measured 0.4 % of a step: the evaluator is bound by stalls, not by issue slots.
+// Not kept; profiles/README.md.)
 __device__ __forceinline__ double hot_log(double x) { return log(x); }
 __device__ __noinline__ double cold_log(double x) { return log(x); }
 __device__ __noinline__ double cold_log1p(double x) { return log1p(x); }
@@ -143,10 +147,12 @@ __constant__ int c_pam_float = 0;
 
 __device__ __forceinline__ double clamp_pam(double x)
 {
-    // src/chain.cpp:890-893 in double: min(1 - eps, max(0, x))
-    double lo = x > 0.0 ? x : 0.0;  // std::max(0., x): NaN -> 0
+    // src/chain.cpp:890-893 in double: min(1 - eps, max(0, x)).  fmax / fmin are one instruction each
+    // and return the other operand for a NaN, which is std::max(0., x)'s NaN -> 0 (the compare-and-select
+    // spelling was 11 % of the evaluator's instructions); a -0 may come out as -0: only 1 - pam is used
+    double lo = fmax(x, 0.0);
     if (c_pam_float) lo = (double)(float)lo;
-    return c_max_pam < lo ? c_max_pam : lo;
+    return fmin(lo, c_max_pam);
 }
 
 __device__ __forceinline__ double pam_from_coverage(double cov)
