@@ -103,16 +103,21 @@ Rcpp::List run_mcmc(Rcpp::List args)
     // ---- GenotypingData -> SoA bit masks (moire_data, include/moire_engine.h)
     const int N = (int)gd.num_samples, L = (int)gd.num_loci;
     std::vector<int32_t> num_alleles(gd.num_alleles.begin(), gd.num_alleles.end());
+    // allele sets are W 64-bit words each: W = 1 in libmoire_b200.so, 2 in libmoire_b200_w128.so (link the
+    // latter for data with a locus of 65..128 alleles; include/moire_engine.h, "Mask width")
+    const size_t W = (size_t)moire_engine_mask_words();
     for (int a : num_alleles)
-        if (a > MOIRE_MAX_ALLELES) Rcpp::stop("libmoire_b200 supports at most 64 alleles per locus");
-    std::vector<uint64_t> obs((size_t)N * L, 0);
+        if (a > moire_engine_max_alleles())
+            Rcpp::stop("this build of libmoire_b200 holds at most " + std::to_string(moire_engine_max_alleles()) +
+                       " alleles per locus (libmoire_b200_w128: 128)");
+    std::vector<uint64_t> obs((size_t)N * L * W, 0);
     std::vector<uint8_t> missing((size_t)N * L, 0);
     for (int j = 0; j < L; ++j)
         for (int i = 0; i < N; ++i)
         {
             const std::vector<int> &o = gd.get_observed_alleles(j, i);  // src/genotyping_data.cpp:49
             for (size_t a = 0; a < o.size(); ++a)
-                if (o[a]) obs[(size_t)i * L + j] |= 1ull << a;
+                if (o[a]) obs[((size_t)i * L + j) * W + (a >> 6)] |= 1ull << (a & 63);
             missing[(size_t)i * L + j] = gd.is_missing(j, i);           // src/genotyping_data.cpp:55
         }
     std::vector<int32_t> obs_coi(gd.observed_coi.begin(), gd.observed_coi.end());
@@ -191,7 +196,7 @@ Rcpp::List run_mcmc(Rcpp::List args)
     std::vector<int32_t> draw_step(D), coi((size_t)D * N);
     std::vector<double> freqs((size_t)D * L * AP), eps_neg((size_t)D * N), eps_pos((size_t)D * N),
         rel((size_t)D * N), data_llik((size_t)D * N), lam(D);
-    std::vector<uint64_t> latent(params.record_latent_genotypes ? (size_t)D * N * L : 0);
+    std::vector<uint64_t> latent(params.record_latent_genotypes ? (size_t)D * N * L * W : 0);
     check(moire_mcmc_get_draws(h, draw_step.data(), freqs.data(), coi.data(), eps_neg.data(), eps_pos.data(),
                                rel.data(), data_llik.data(), lam.data(),
                                params.record_latent_genotypes ? latent.data() : nullptr), h, "get_draws");
@@ -219,8 +224,9 @@ Rcpp::List run_mcmc(Rcpp::List args)
                 for (int j = 0; j < L; ++j)
                 {
                     std::vector<int> idx;
-                    for (uint64_t msk = latent[((size_t)dr * N + i) * L + j]; msk; msk &= msk - 1)
-                        idx.push_back(__builtin_ctzll(msk));
+                    for (size_t w = 0; w < W; ++w)
+                        for (uint64_t msk = latent[(((size_t)dr * N + i) * L + j) * W + w]; msk; msk &= msk - 1)
+                            idx.push_back((int)(64 * w) + __builtin_ctzll(msk));
                     latent_store[i][j].push_back(idx);
                 }
 

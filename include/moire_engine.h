@@ -14,8 +14,17 @@
  *
  * Layouts (sample-major, like the reference's genotyping_llik_new[sample * L + locus],
  * src/chain.cpp:1116):  per-cell arrays are [N][L]; per-sample arrays [N]; allele frequencies
- * [L][a_pad] with a_pad = moire_engine_a_pad().  Allele sets (observed and latent) are 64-bit
- * masks, bit a = allele a (sorted index list of the reference == ascending bit order).
+ * [L][a_pad] with a_pad = moire_engine_a_pad().  Allele sets (observed and latent) are bit
+ * masks, bit a = allele a (sorted index list of the reference == ascending bit order), of
+ * W = moire_engine_mask_words() 64-bit words each, word 0 = alleles 0..63.
+ *
+ * Mask width.  The reference keeps allele sets as vectors of any length
+ * (src/genotyping_data.cpp:17-48).  This ABI is built twice from the same sources:
+ *   libmoire_b200.so       W = 1: up to 64 alleles per locus (every shape BASELINE.json names);
+ *   libmoire_b200_w128.so  W = 2: up to 128 alleles per locus, flat pipelines only.
+ * Same entry points, same structs; every `uint64_t *` mask array below is [..][W].  A caller picks
+ * the library by the widest locus of its data (moire_b200/_lib.py does) and can ask either one with
+ * moire_engine_mask_words() / moire_engine_max_alleles().
  */
 #ifndef MOIRE_ENGINE_H
 #define MOIRE_ENGINE_H
@@ -32,7 +41,7 @@ extern "C" {
 #define MOIRE_ENOMEM (-3)
 #define MOIRE_ESTATE (-4)   /* call order (e.g. step before init) */
 
-#define MOIRE_MAX_ALLELES 64 /* alleles per locus (one mask word) */
+#define MOIRE_MAX_ALLELES 64 /* alleles per locus PER MASK WORD: the limit is 64 * moire_engine_mask_words() */
 #define MOIRE_MAX_COI 127    /* the reference's own bound: its lgamma table (src/sampler.cpp:22-25) */
 
 /* Kernel generation: AUTO picks the flat pipelines (device-wide cost-class sort + persistent
@@ -78,8 +87,8 @@ typedef struct moire_data
 {
     int32_t num_samples;          /* N */
     int32_t num_loci;             /* L */
-    const int32_t *num_alleles;   /* [L], 2..64 */
-    const uint64_t *obs_mask;     /* [N][L] observed alleles */
+    const int32_t *num_alleles;   /* [L], 2..64 W */
+    const uint64_t *obs_mask;     /* [N][L][W] observed alleles */
     const uint8_t *is_missing;    /* [N][L] 0/1 */
     const int32_t *observed_coi;  /* [N] or NULL (then derived as max_j popcount(obs_mask)) */
 } moire_data;
@@ -108,7 +117,7 @@ typedef struct moire_chain_state
     double *eps_pos;    /* [N] */
     double *eps_neg;    /* [N] */
     double *p;          /* [L][a_pad] allele frequencies (entries a >= A_j are 0) */
-    uint64_t *latent;   /* [N][L] latent genotypes */
+    uint64_t *latent;   /* [N][L][W] latent genotypes */
     double *lg_adj;     /* [N][L] log proposal density of the current latent genotype */
     double *mean_coi;   /* [1] */
     /* output only */
@@ -145,6 +154,10 @@ int moire_engine_create(const moire_data *data, const moire_params *params, int3
 int moire_engine_destroy(moire_engine *e);
 
 int32_t moire_engine_a_pad(const moire_engine *e);
+/* Mask width of THIS library: 64-bit words per allele set (1 or 2) and the alleles a locus may have
+ * (64 or 128).  The reference has no such limit (src/genotyping_data.cpp:17-48): see "Mask width". */
+int32_t moire_engine_mask_words(void);
+int32_t moire_engine_max_alleles(void);
 int32_t moire_engine_num_chains(const moire_engine *e);
 
 /* Chain::initialize_parameters with the retry loop of MCMC::MCMC (src/mcmc.cpp:68-104): draws a
@@ -235,7 +248,7 @@ typedef struct moire_draw_store
     int32_t *m;           /* [capacity][N] */
     double *eps_neg, *eps_pos, *r, *sample_llik; /* [capacity][N] */
     double *mean_coi;     /* [capacity] */
-    uint64_t *latent;     /* [capacity][N][L] or NULL */
+    uint64_t *latent;     /* [capacity][N][L][W] or NULL */
     int32_t capacity;
 } moire_draw_store;
 int moire_engine_enqueue_record_draw(moire_engine *e, const int32_t *dev_sel,

@@ -12,6 +12,9 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # MOIRE_B200_LIB: an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("MOIRE_B200_LIB") or os.path.join(HERE, "libmoire_b200.so")
+# the same sources built with two-word allele masks (loci with 65..128 alleles, include/moire_engine.h
+# "Mask width"); the one-word library serves everything else
+LIB_PATH_W128 = os.environ.get("MOIRE_B200_LIB_W128") or os.path.join(HERE, "libmoire_b200_w128.so")
 
 vp, i32, u64, dbl = C.c_void_p, C.c_int32, C.c_uint64, C.c_double
 
@@ -98,6 +101,8 @@ ENGINE_SYMBOLS = {
                                       i32, u64, C.POINTER(vp)]),
     "moire_engine_destroy": (C.c_int, [vp]),
     "moire_engine_a_pad": (i32, [vp]),
+    "moire_engine_mask_words": (i32, []),
+    "moire_engine_max_alleles": (i32, []),
     "moire_engine_num_chains": (i32, [vp]),
     "moire_engine_init_chains": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
     "moire_engine_read_init_log": (C.c_int, [vp, vp, i32, vp]),
@@ -136,22 +141,32 @@ ENGINE_SYMBOLS = {
     "moire_philox4x32": (None, [vp, vp, vp]),
 }
 
-_lib = None
+_libs = {}
 
 
-def load():
-    """Returns the ctypes handle of libmoire_b200.so with every prototype set."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def load(mask_words: int = 1):
+    """Returns the ctypes handle of libmoire_b200.so (``mask_words`` = 1: up to 64 alleles per
+    locus) or libmoire_b200_w128.so (2: up to 128) with every prototype set."""
+    if mask_words in _libs:
+        return _libs[mask_words]
+    if mask_words not in (1, 2):
+        raise ValueError("mask_words must be 1 or 2 (at most 128 alleles per locus)")
+    path = LIB_PATH if mask_words == 1 else LIB_PATH_W128
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: build the CUDA engine first "
+            f"{path} is missing: build the CUDA engine first "
             "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in list(ENGINE_SYMBOLS.items()) + list(MCMC_SYMBOLS.items()):
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    if lib.moire_engine_mask_words() != mask_words:
+        raise ImportError(f"{path} was built with {lib.moire_engine_mask_words()}-word masks")
+    _libs[mask_words] = lib
     return lib
+
+
+def words_for(max_alleles: int) -> int:
+    """Mask words (= which library) a data set with this widest locus needs."""
+    return 1 if max_alleles <= 64 else 2

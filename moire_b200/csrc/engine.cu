@@ -239,7 +239,10 @@ __global__ void __launch_bounds__(256) k_record_draw(const moire::View v, const 
     }
     if (g0 == 0) st.mean_coi[slot] = v.mean_coi[t];
     if (st.latent)
-        for (size_t i = g0; i < NL; i += stride) st.latent[slot * NL + i] = v.latent[t * NL + i];
+    {
+        moire::mask_t *dst = reinterpret_cast<moire::mask_t *>(st.latent);  // [capacity][N][L] masks of W words
+        for (size_t i = g0; i < NL; i += stride) dst[slot * NL + i] = v.latent[t * NL + i];
+    }
 }
 
 // ---- synthetic data on the device (row f2; R/simulator.R:154-212) ---------------------------------
@@ -252,8 +255,8 @@ __global__ void __launch_bounds__(256) k_simulate_cells(const int N, const int L
                                                         const double *freqs, const int *coi, const double *rel,
                                                         const double eps_pos, const double eps_neg,
                                                         const double missingness, const unsigned long long seed,
-                                                        unsigned long long *obs, unsigned char *missing,
-                                                        unsigned long long *truth)
+                                                        moire::mask_t *obs, unsigned char *missing,
+                                                        moire::mask_t *truth)
 {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (size_t)N * L) return;
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(256) k_simulate_cells(const int N, const int L
     int related = 0;
     const double r = rel[i];
     for (int s = 0; s < coi[i] - 1; ++s) related += rng.next_uniform() < r;
-    unsigned long long present = 0;
+    moire::mask_t present = 0;
     for (int s = 0; s < coi[i] - related; ++s)
     {
         const double u = rng.next_uniform();
@@ -276,12 +279,12 @@ __global__ void __launch_bounds__(256) k_simulate_cells(const int N, const int L
             c += f[a];
             if (u < c) break;
         }
-        present |= 1ull << a;
+        present |= moire::mbit(a);
     }
-    unsigned long long seen = 0;
+    moire::mask_t seen = 0;
     const double p_hit = 1.0 - eps_neg / (double)A, p_false = eps_pos / (double)A;
     for (int a = 0; a < A; ++a)
-        if (rng.next_uniform() < ((present >> a) & 1ull ? p_hit : p_false)) seen |= 1ull << a;
+        if (rng.next_uniform() < (moire::mtest(present, a) ? p_hit : p_false)) seen |= moire::mbit(a);
     if (rng.next_uniform() < missingness) seen = 0;
     obs[g] = seen;
     missing[g] = seen == 0;
@@ -366,10 +369,11 @@ struct moire_engine
     int p_threads = 256;
 
     // allocations
-    DevBuf<unsigned long long> obs, latent, evals, trace;
+    DevBuf<moire::mask_t> obs, latent;
+    DevBuf<unsigned long long> evals, trace;
     // flat update_p pipeline (p_flat.cuh)
     moire::PFlat pf{};
-    DevBuf<uint4> pf_list;
+    DevBuf<moire::ListEntry> pf_list;
     DevBuf<unsigned int> pf_hist;
     DevBuf<double> pf_Tcur, pf_Tnew, pf_pprop, pf_round;
     DevBuf<int> pf_nonmiss;
@@ -377,7 +381,7 @@ struct moire_engine
     bool p_fused = false;
     // update_p's PAM cache (p_flat.cuh: k_pc_sweep)
     bool p_cache = false;
-    DevBuf<unsigned long long> pf_latLM;
+    DevBuf<moire::mask_t> pf_latLM;
     DevBuf<double> red_part;          // k_reduce: per-part sums
     DevBuf<unsigned int> red_done;    //           parts finished, per chain
     DevBuf<double> pf_Wcur, pf_Wnew;
@@ -391,7 +395,7 @@ struct moire_engine
     DevBuf<int> sf_m;
     DevBuf<double> sf_adj;
     DevBuf<moire::SampleScal> sf_ss, pf_ss;
-    DevBuf<unsigned long long> sf_lat;
+    DevBuf<moire::mask_t> sf_lat;
     DevBuf<moire::EpsLogs> sf_elogs;
     DevBuf<unsigned char> missing;
     DevBuf<int> nall, aclass, avals, obs_coi, m, acc6, p_acc, p_att, active;
@@ -464,9 +468,13 @@ struct moire_engine
         for (int j = 0; j < L; ++j)
         {
             const int A = d->num_alleles[j];
-            if (A < 2 || A > MOIRE_MAX_ALLELES)
+            if (A < 2 || A > moire::kMaskBits)
                 throw InvalidArg{"num_alleles[" + std::to_string(j) + "] = " + std::to_string(A) +
-                                 " outside 2.." + std::to_string(MOIRE_MAX_ALLELES)};
+                                 " outside 2.." + std::to_string(moire::kMaskBits) +
+                                 (MOIRE_MASK_WORDS == 1 ? " (one-word masks: loci with up to " +
+                                                              std::to_string(MOIRE_MAX_ALLELES) +
+                                                              " alleles need libmoire_b200_w128)"
+                                                        : std::string())};
             amax = std::max(amax, A);
             auto it = std::find(avals_h.begin(), avals_h.end(), A);
             if (it == avals_h.end())
@@ -481,10 +489,11 @@ struct moire_engine
         {
             for (int j = 0; j < L; ++j)
             {
-                const unsigned long long o = d->obs_mask[(size_t)i * L + j];
+                const uint64_t *w = d->obs_mask + ((size_t)i * L + j) * MOIRE_MASK_WORDS;
+                const moire::mask_t o = moire::mfrom_words(w[0], MOIRE_MASK_WORDS > 1 ? w[MOIRE_MASK_WORDS - 1] : 0);
                 const int A = d->num_alleles[j];
-                if (A < 64 && (o >> A) != 0) throw InvalidArg{"obs_mask has bits above num_alleles"};
-                coi_h[i] = std::max(coi_h[i], __builtin_popcountll(o));
+                if (A < moire::kMaskBits && (o >> A) != 0) throw InvalidArg{"obs_mask has bits above num_alleles"};
+                coi_h[i] = std::max(coi_h[i], moire::mpopc(o));
             }
             if (d->observed_coi) coi_h[i] = d->observed_coi[i];
         }
@@ -562,7 +571,7 @@ struct moire_engine
             }
             CUDA_TRY(cudaMemcpyToSymbol(moire::g_binom, binom_h.data(), binom_h.size() * sizeof(double)));
         }
-        obs.upload((const unsigned long long *)d->obs_mask, NL, stream);
+        obs.upload((const moire::mask_t *)d->obs_mask, NL, stream);  // [N][L][words], word 0 = alleles 0..63
         missing.upload(d->is_missing, NL, stream);
         nall.upload(d->num_alleles, L, stream);
         aclass.upload(aclass_h.data(), L, stream);
@@ -625,6 +634,13 @@ struct moire_engine
         const int pipeline = prm->pipeline & 0xff;
         if (pipeline == MOIRE_PIPELINE_FLAT) p_fused = false;
         if (pipeline == MOIRE_PIPELINE_FUSED) p_fused = true;
+#if MOIRE_MASK_WORDS > 1
+        // two-word masks: the flat pipelines only (the fused tiny-problem kernels keep one-word
+        // per-block genotype arrays and two alleles per lane)
+        if (pipeline == MOIRE_PIPELINE_FUSED || std::getenv("MOIRE_B200_P_FUSED"))
+            throw InvalidArg{"the fused kernels are built for one-word masks only (libmoire_b200.so)"};
+        p_fused = false;
+#endif
         if (prm->pipeline < 0 || pipeline > MOIRE_PIPELINE_FUSED ||
             (prm->pipeline & ~(0xff | MOIRE_NUMERICS_REF32 | MOIRE_P_CACHE_ON | MOIRE_P_CACHE_OFF)) ||
             ((prm->pipeline & MOIRE_P_CACHE_ON) && (prm->pipeline & MOIRE_P_CACHE_OFF)))
@@ -1160,7 +1176,7 @@ struct moire_engine
         d2h(o->eps_pos, v.eps_pos + t * N, N);
         d2h(o->eps_neg, v.eps_neg + t * N, N);
         d2h(o->p, v.p + t * LA, LA);
-        d2h((unsigned long long *)o->latent, v.latent + t * NL, NL);
+        d2h((moire::mask_t *)o->latent, v.latent + t * NL, NL);
         d2h(o->lg_adj, v.lgadj + t * NL, NL);
         d2h(o->mean_coi, v.mean_coi + t, 1);
         d2h(o->cell_t, v.cellT + t * NL, NL);
@@ -1181,7 +1197,7 @@ struct moire_engine
         h2d(v.eps_pos + t * N, in->eps_pos, N);
         h2d(v.eps_neg + t * N, in->eps_neg, N);
         h2d(v.p + t * LA, in->p, LA);
-        h2d(v.latent + t * NL, (const unsigned long long *)in->latent, NL);
+        h2d(v.latent + t * NL, (const moire::mask_t *)in->latent, NL);
         h2d(v.lgadj + t * NL, in->lg_adj, NL);
         h2d(v.mean_coi + t, in->mean_coi, 1);
         CUDA_TRY(cudaStreamSynchronize(stream));  // host buffers may go away after return
@@ -1303,6 +1319,8 @@ int moire_engine_destroy(moire_engine *e)
 }
 
 int32_t moire_engine_a_pad(const moire_engine *e) { return e ? e->v.AP : 0; }
+int32_t moire_engine_mask_words(void) { return MOIRE_MASK_WORDS; }
+int32_t moire_engine_max_alleles(void) { return moire::kMaskBits; }
 int32_t moire_engine_num_chains(const moire_engine *e) { return e ? e->v.T : 0; }
 
 int moire_engine_init_chains(moire_engine *e, int32_t max_tries, int32_t *ill_count,
@@ -1477,7 +1495,7 @@ int moire_engine_record_draw(moire_engine *e, int32_t chain, double *p, int32_t 
         e->d2h(r, v.r + t * N, N);
         e->d2h(sample_llik, e->scratchN.ptr, N);
         e->d2h(mean_coi, v.mean_coi + t, 1);
-        e->d2h((unsigned long long *)latent, v.latent + t * NL, NL);
+        e->d2h((moire::mask_t *)latent, v.latent + t * NL, NL);
         CUDA_TRY(cudaStreamSynchronize(e->stream));
     });
 }
@@ -1586,8 +1604,8 @@ int moire_simulate_data(int32_t num_samples, int32_t num_loci, const int32_t *nu
             throw InvalidArg{"null argument"};
         if (num_samples < 1 || num_loci < 1 || a_pad < 1) throw InvalidArg{"empty shape"};
         for (int j = 0; j < num_loci; ++j)
-            if (num_alleles[j] < 2 || num_alleles[j] > MOIRE_MAX_ALLELES || num_alleles[j] > a_pad)
-                throw InvalidArg{"num_alleles outside 2..64 / a_pad"};
+            if (num_alleles[j] < 2 || num_alleles[j] > moire::kMaskBits || num_alleles[j] > a_pad)
+                throw InvalidArg{"num_alleles outside 2.." + std::to_string(moire::kMaskBits) + " / a_pad"};
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
             throw CudaError{"no CUDA device -- libmoire_b200 has no CPU fallback"};
@@ -1596,7 +1614,7 @@ int moire_simulate_data(int32_t num_samples, int32_t num_loci, const int32_t *nu
         const size_t N = num_samples, L = num_loci, NL = N * L;
         DevBuf<int> nall, coi;
         DevBuf<double> freqs, rel;
-        DevBuf<unsigned long long> obs, truth;
+        DevBuf<moire::mask_t> obs, truth;
         DevBuf<unsigned char> miss;
         auto release = [&] { nall.release(); coi.release(); freqs.release(); rel.release(); obs.release(); truth.release(); miss.release(); };
         try
@@ -1610,9 +1628,9 @@ int moire_simulate_data(int32_t num_samples, int32_t num_loci, const int32_t *nu
                                                                      coi.ptr, rel.ptr, epsilon_pos, epsilon_neg,
                                                                      missingness, seed, obs.ptr, miss.ptr, truth.ptr);
             CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaMemcpy(obs_mask, obs.ptr, NL * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(obs_mask, obs.ptr, NL * sizeof(moire::mask_t), cudaMemcpyDeviceToHost));
             CUDA_TRY(cudaMemcpy(is_missing, miss.ptr, NL, cudaMemcpyDeviceToHost));
-            if (true_mask) CUDA_TRY(cudaMemcpy(true_mask, truth.ptr, NL * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+            if (true_mask) CUDA_TRY(cudaMemcpy(true_mask, truth.ptr, NL * sizeof(moire::mask_t), cudaMemcpyDeviceToHost));
         }
         catch (...)
         {

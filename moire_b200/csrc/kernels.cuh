@@ -223,7 +223,7 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
         if (lane == 0) u = (int)atomicAdd(next, 1u);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= units) break;
-        unsigned long long lat;
+        mask_t lat;
         const double *prow;
         int m;
         Rel rel;
@@ -233,7 +233,7 @@ __device__ __forceinline__ void block_eval_transmissions(const unsigned short *o
             const int cell = order[coop_egf ? 32 * egf_chunks + (u - u1)
                                             : n_egf + 32 * heavy_chunks + (u - u3)];
             fetch(cell, lat, prow, m, rel);
-            const int k = __popcll(lat);
+            const int k = mpopc(lat);
             double T;
             if (k > m)
                 T = NAN;
@@ -483,8 +483,8 @@ __global__ void __launch_bounds__(kThreads, MOIRE_MIN_BLOCKS_S * (256 / kThreads
     const int C = S * v.L;
     double *s_lgam = smem;
     double *s_qs = s_lgam + 128;
-    unsigned long long *s_nlat =
-        reinterpret_cast<unsigned long long *>(s_qs + (NEED_T ? scratch_doubles(kThreads) : 0));
+    mask_t *s_nlat =
+        reinterpret_cast<mask_t *>(s_qs + (NEED_T ? scratch_doubles(kThreads) : 0));
     double *s_nadj = reinterpret_cast<double *>(s_nlat + C);
     double *s_T = s_nadj + (NEED_T ? C : 0);  // the error-rate updates keep only latent and O
     double *s_O = s_T + (NEED_T ? C : 0);
@@ -533,10 +533,10 @@ __global__ void __launch_bounds__(kThreads, MOIRE_MIN_BLOCKS_S * (256 / kThreads
         const int sl = cell / L, j = cell - sl * L;
         const Proposal &P = s_prop[sl];
         if (!P.valid) continue;
-        const unsigned long long obs = v.obs[data_base + cell];
+        const mask_t obs = v.obs[data_base + cell];
         const bool miss = v.missing[data_base + cell] != 0;
         const int A = v.nall[j];
-        unsigned long long lat;
+        mask_t lat;
         const EpsLogs *el = NEED_O ? &s_elogs[sl * nA + v.aclass[j]] : nullptr;
         if (RESAMPLE)
         {
@@ -568,10 +568,10 @@ __global__ void __launch_bounds__(kThreads, MOIRE_MIN_BLOCKS_S * (256 / kThreads
             const int sl = cell / L;
             const Proposal &P = s_prop[sl];
             if (!P.valid || v.missing[data_base + cell] != 0) return -1;
-            return work_class(__popcll(s_nlat[cell]), P.m_new);
+            return work_class(mpopc(s_nlat[cell]), P.m_new);
         };
         const int nwork = block_sort_cells(ncell, cls, s_hist, s_order, s_tmp);
-        auto fetch = [&](int cell, unsigned long long &lat, const double *&prow, int &m, Rel &rel) {
+        auto fetch = [&](int cell, mask_t &lat, const double *&prow, int &m, Rel &rel) {
             const int sl = cell / L, j = cell - sl * L;
             const Proposal &P = s_prop[sl];
             lat = s_nlat[cell];
@@ -702,7 +702,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 512 ? 1 : MOIRE_MIN_BLOCKS_P *
     const int N = v.N, L = v.L, AP = v.AP, B = blockDim.x;
     double *s_lgam = smem;
     double *s_qs = s_lgam + 128;
-    unsigned long long *s_lat = reinterpret_cast<unsigned long long *>(s_qs + scratch_doubles(B));
+    mask_t *s_lat = reinterpret_cast<mask_t *>(s_qs + scratch_doubles(B));
     double *s_Told = reinterpret_cast<double *>(s_lat + N);
     double *s_Tnew = s_Told + N;
     double *s_pcur = s_Tnew + N;
@@ -744,11 +744,11 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 512 ? 1 : MOIRE_MIN_BLOCKS_P *
     __syncthreads();
     auto cls = [&](int i) -> int {
         const int m = s_m[i];
-        return m == 0 ? -1 : work_class(__popcll(s_lat[i]), m);
+        return m == 0 ? -1 : work_class(mpopc(s_lat[i]), m);
     };
     const int nwork = block_sort_cells(N, cls, s_hist, s_order, s_tmp);
     const int n_egf = (int)s_tmp[33], coop_end = (int)s_tmp[34];
-    auto fetch = [&](int i, unsigned long long &lat, const double *&prow_, int &m, Rel &rel) {
+    auto fetch = [&](int i, mask_t &lat, const double *&prow_, int &m, Rel &rel) {
         const size_t si = (size_t)t * N + i;
         lat = s_lat[i];
         prow_ = s_pprop;

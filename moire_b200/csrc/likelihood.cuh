@@ -20,6 +20,7 @@
 #include <cmath>
 #include <cstdint>
 
+#include "mask.cuh"
 #include "rng.cuh"
 
 namespace moire
@@ -50,7 +51,7 @@ __device__ __forceinline__ double cold_log1m(double x) { return cold_log(1.0 - x
 #define MOIRE_COOP_INLINE __noinline__
 constexpr int kIeMax = 10;      // src/prob_any_missing.cpp:11
 constexpr int kMaxCoi = 127;    // MOIRE_MAX_COI: the reference's lgamma LUT bound (src/sampler.cpp:22-25)
-constexpr int kLogCDim = 65;    // logC[n][k], 0 <= k <= n <= 64 (alleles of a locus)
+constexpr int kLogCDim = kMaskBits + 1;  // logC[n][k], 0 <= k <= n <= 64 or 128 (alleles of a locus)
 
 // x^n, n >= 0, by square and multiply.
 __device__ __forceinline__ double pow_uint(double x, int n)
@@ -120,12 +121,12 @@ __device__ __noinline__ void build_eps_logs(EpsLogs &e, double eps_neg, double e
 }
 
 // ---- a7: observation process on masks --------------------------------------------------------
-__device__ __forceinline__ double observation_ll(uint64_t latent, uint64_t obs, int A,
+__device__ __forceinline__ double observation_ll(mask_t latent, mask_t obs, int A,
                                                  const EpsLogs &e)
 {
-    const int tp = __popcll(latent & obs);
-    const int fn = __popcll(latent & ~obs);
-    const int fp = __popcll(obs & ~latent);
+    const int tp = mpopc(latent & obs);
+    const int fn = mpopc(latent & ~obs);
+    const int fp = mpopc(obs & ~latent);
     const int tn = A - tp - fn - fp;
     double res = 0.0;
     res = __dadd_rn(res, __dmul_rn(e.o_tp, (double)tp));
@@ -305,16 +306,16 @@ __device__ double g_binom[(kMaxCoi + 1) * (kMaxCoi + 1)];
 // the COI.  Each sum is still the reference's: terms in j order, (comb * a) * q^j, q^j by the
 // running product q^(j-1) * q (src/prob_any_missing.cpp:68-91).
 // band[d * ST], d <= D; on return band[d * ST] = coverage(k + d).
-__device__ __forceinline__ void egf_band(uint64_t latent, const double *prow, double total, int D,
+__device__ __forceinline__ void egf_band(mask_t latent, const double *prow, double total, int D,
                                          double *band, int ST)
 {
     constexpr int CS = kMaxCoi + 1;
     for (int d = 0; d <= D; ++d) band[d * ST] = d == 0 ? 1.0 : 0.0;
-    uint64_t rest = latent;
+    mask_t rest = latent;
     int e = 0;
     while (rest)
     {
-        const int al = __ffsll((long long)rest) - 1;
+        const int al = mffs(rest) - 1;
         rest &= rest - 1;
         ++e;
         const double q = __ddiv_rn(prow[al], total);
@@ -656,7 +657,7 @@ __device__ __noinline__ double transmission_rel_ie_wide(double *scr, int ST, int
 // fits (m - k < kScratchSlots: nearly always), else in local memory; then the same mixture as every
 // other path.
 template <bool CACHE>
-__device__ __noinline__ double transmission_egf(uint64_t latent, const double *prow, double total,
+__device__ __noinline__ double transmission_egf(mask_t latent, const double *prow, double total,
                                                 int k, int m, const Rel rel, bool allow_relatedness,
                                                 double *scr, int ST, const double *lgam,
                                                 const double *binom_s, const PamOut po)
@@ -675,14 +676,14 @@ __device__ __noinline__ double transmission_egf(uint64_t latent, const double *p
 
 // Relatedness off and n == k: 1 - k! * prod(q) in double (src/prob_any_missing.cpp:139-148).
 template <bool CACHE>
-__device__ __forceinline__ double transmission_norel_exact_cover(uint64_t latent, const double *prow,
+__device__ __forceinline__ double transmission_norel_exact_cover(mask_t latent, const double *prow,
                                                                  double total, int k, const PamOut po)
 {
     double cov = 1.0;
-    uint64_t rest = latent;
+    mask_t rest = latent;
     while (rest)
     {
-        const int al = __ffsll((long long)rest) - 1;
+        const int al = mffs(rest) - 1;
         rest &= rest - 1;
         cov = __dmul_rn(cov, __ddiv_rn(prow[al], total));
     }
@@ -695,13 +696,13 @@ __device__ __forceinline__ double transmission_norel_exact_cover(uint64_t latent
 // together: one trip to L2 instead of k dependent ones in front of every cell (the evaluator's
 // top stall was the long scoreboard).
 constexpr int kGather = 6;
-__device__ __forceinline__ void gather_freqs(uint64_t latent, const double *prow, double (&pv)[kGather])
+__device__ __forceinline__ void gather_freqs(mask_t latent, const double *prow, double (&pv)[kGather])
 {
-    uint64_t rest = latent;
+    mask_t rest = latent;
 #pragma unroll
     for (int e = 0; e < kGather; ++e)
     {
-        const int al = rest ? __ffsll((long long)rest) - 1 : 0;
+        const int al = rest ? mffs(rest) - 1 : 0;
         pv[e] = prow[al];
         rest &= rest - 1;
     }
@@ -713,13 +714,13 @@ __device__ __forceinline__ void gather_freqs(uint64_t latent, const double *prow
 // of the warp that make this call together (a __ballot_sync the caller takes BEFORE branching
 // into the call).
 template <bool CACHE>
-__device__ __forceinline__ double transmission_ll(uint64_t latent, const double *prow,
+__device__ __forceinline__ double transmission_ll(mask_t latent, const double *prow,
                                                   const double (&pv)[kGather], int m, const Rel rel,
                                                   bool allow_relatedness, double *scr, int ST,
                                                   const double *lgam, const double *binom_s,
                                                   unsigned callers, const PamOut po)
 {
-    const int k = __popcll(latent);
+    const int k = mpopc(latent);
     // the lanes that will reach the register-tier inclusion-exclusion sums, agreed on while the
     // callers are still together (the branches below diverge by k and m)
     const unsigned ie_lanes = __ballot_sync(
@@ -735,7 +736,7 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
     }
     // the frequency sum in ascending allele order: the gathered ones, then any further ones
     double total = 0.0;
-    uint64_t tail = latent;
+    mask_t tail = latent;
 #pragma unroll
     for (int e = 0; e < kGather; ++e)
     {
@@ -744,10 +745,10 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
     }
     if (k > kGather)
     {
-        uint64_t rest = tail;
+        mask_t rest = tail;
         while (rest)
         {
-            const int al = __ffsll((long long)rest) - 1;
+            const int al = mffs(rest) - 1;
             rest &= rest - 1;
             total = __dadd_rn(total, prow[al]);
         }
@@ -759,11 +760,11 @@ __device__ __forceinline__ double transmission_ll(uint64_t latent, const double 
             if (e < k) scr[e * ST] = __ddiv_rn(pv[e], total);
         if (k > kGather)
         {
-            uint64_t rest = tail;
+            mask_t rest = tail;
             int e = kGather;
             while (rest)
             {
-                const int al = __ffsll((long long)rest) - 1;
+                const int al = mffs(rest) - 1;
                 rest &= rest - 1;
                 scr[e * ST] = __ddiv_rn(prow[al], total);
                 ++e;
@@ -889,14 +890,14 @@ __device__ unsigned long long *g_coop_trace = nullptr;  // tuning aid: phase clo
 #endif
 constexpr int kCoopMinK = MOIRE_COOP_MIN_K;
 template <bool CACHE>
-__device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const double *prow, int m,
+__device__ MOIRE_COOP_INLINE double transmission_ll_coop(mask_t latent, const double *prow, int m,
                                                        const Rel rel, bool allow_relatedness,
                                                        double *wscr, int ST, const double *lgam,
                                                        const double *binom_s, const PamOut po)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int k = __popcll(latent);  // 1 <= k <= kIeMax, k <= m guaranteed by the caller
+    const int k = mpopc(latent);  // 1 <= k <= kIeMax, k <= m guaranteed by the caller
 #ifdef MOIRE_EVAL_TRACE
     long long tc0 = clock64(), tc1 = 0, tc2 = 0, tc3 = 0;
 #endif
@@ -905,9 +906,9 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
     // then taken in ascending allele order, as everywhere
     double total = 0.0, p_mine = 0.0;
     {
-        uint64_t rest = latent;
+        mask_t rest = latent;
         for (int e = 0; e < lane && rest; ++e) rest &= rest - 1;
-        if (lane < k) p_mine = prow[__ffsll((long long)rest) - 1];
+        if (lane < k) p_mine = prow[mffs(rest) - 1];
         for (int e = 0; e < k; ++e) total = __dadd_rn(total, __shfl_sync(FULL, p_mine, e));
     }
     if (!allow_relatedness && m == k) return transmission_norel_exact_cover<CACHE>(latent, prow, total, k, po);
@@ -1086,21 +1087,21 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_coop(uint64_t latent, const 
 // in the warp's scratch rows.  Every lane then gathers the band and runs the one mixture function.
 // All lanes must call with identical arguments; every lane returns the value.
 template <bool CACHE>
-__device__ MOIRE_COOP_INLINE double transmission_ll_egf_coop(uint64_t latent, const double *prow, int m,
+__device__ MOIRE_COOP_INLINE double transmission_ll_egf_coop(mask_t latent, const double *prow, int m,
                                                            const Rel rel, bool allow_relatedness,
                                                            double *wscr, int ST, const double *lgam,
                                                            const double *binom_s, const PamOut po)
 {
     constexpr int CS = kMaxCoi + 1;
     const int lane = threadIdx.x & 31;
-    const int k = __popcll(latent);
+    const int k = mpopc(latent);
     const int D = m - k;
     double total = 0.0;
     {
-        uint64_t rest = latent;
+        mask_t rest = latent;
         while (rest)
         {
-            const int al = __ffsll((long long)rest) - 1;
+            const int al = mffs(rest) - 1;
             rest &= rest - 1;
             total = __dadd_rn(total, prow[al]);
         }
@@ -1109,11 +1110,11 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_egf_coop(uint64_t latent, co
     auto B = [&](int d) -> double & { return wscr[(d >> 5) * ST + (d & 31)]; };
     for (int d = lane; d <= D; d += 32) B(d) = d == 0 ? 1.0 : 0.0;
     __syncwarp();
-    uint64_t rest = latent;
+    mask_t rest = latent;
     int e = 0;
     while (rest)
     {
-        const int al = __ffsll((long long)rest) - 1;
+        const int al = mffs(rest) - 1;
         rest &= rest - 1;
         ++e;
         const double q = __ddiv_rn(prow[al], total);
@@ -1156,7 +1157,7 @@ __device__ MOIRE_COOP_INLINE double transmission_ll_egf_coop(uint64_t latent, co
 // Uniform choice of `need` of the `n` set bits of `set` (selection sampling; consumes one
 // uniform per visited bit while the outcome is still open).  Distributionally what the
 // reference's shuffle + prefix does (src/sampler.cpp:312-322).
-__device__ __forceinline__ uint64_t choose_bits(Stream &rng, uint64_t set, int n, int need)
+__device__ __forceinline__ mask_t choose_bits(Stream &rng, mask_t set, int n, int need)
 {
     if (need <= 0) return 0;
     if (need >= n) return set;
@@ -1165,12 +1166,12 @@ __device__ __forceinline__ uint64_t choose_bits(Stream &rng, uint64_t set, int n
         // keep one / drop one (what a proposal with a single false positive or false negative
         // needs -- nearly every proposal that needs a choice at all): one uniform picks the allele
         const int idx = (int)(rng.next_uniform() * (double)n);
-        uint64_t s = set;
+        mask_t s = set;
         for (int i = 0; i < idx; ++i) s &= s - 1;
-        const uint64_t bit = s & (0ull - s);
+        const mask_t bit = mlowest(s);
         return need == 1 ? bit : set ^ bit;
     }
-    uint64_t out = 0;
+    mask_t out = 0;
     int remaining = n;
     while (need > 0)
     {
@@ -1179,7 +1180,7 @@ __device__ __forceinline__ uint64_t choose_bits(Stream &rng, uint64_t set, int n
             out |= set;
             break;
         }
-        const uint64_t low = set & (0ull - set);
+        const mask_t low = mlowest(set);
         set ^= low;
         const double u = rng.next_uniform();
         if (u * (double)remaining < (double)need)
@@ -1193,18 +1194,18 @@ __device__ __forceinline__ uint64_t choose_bits(Stream &rng, uint64_t set, int n
 }
 
 // Draws the proposal and returns its mask; *log_prob gets the log proposal density.
-// logC[n * 65 + k] = log(C(n, k)).  Stream use: word 0 -> the number of false negatives, word 1 -> the
+// logC[n * kLogCDim + k] = log(C(n, k)).  Stream use: word 0 -> the number of false negatives, word 1 -> the
 // number of false positives (both by inversion, always consumed), then one word per visited allele
 // while the two uniform choices are still open (none when every observed allele is kept and no
 // false negative was drawn -- the usual cell): one Philox block per cell, where the round-1 sampler
 // (a Bernoulli word per candidate allele, each phase on a fresh block) used three.
-__device__ __forceinline__ uint64_t sample_latent_genotype(Stream &rng, uint64_t obs, int A,
+__device__ __forceinline__ mask_t sample_latent_genotype(Stream &rng, mask_t obs, int A,
                                                            int coi, const EpsLogs &e,
                                                            const double *__restrict__ logC,
                                                            double *log_prob)
 {
-    const uint64_t all = A >= 64 ? ~0ull : ((1ull << A) - 1ull);
-    const int obs_pos = __popcll(obs);
+    const mask_t all = mall(A);
+    const int obs_pos = mpopc(obs);
     const int obs_neg = A - obs_pos;
     const int min_fn = obs_pos == 0;
     const int max_fn = max(min_fn, min(coi, obs_neg));
@@ -1229,8 +1230,8 @@ __device__ __forceinline__ uint64_t sample_latent_genotype(Stream &rng, uint64_t
         __dadd_rn(__dadd_rn(logC[obs_pos * kLogCDim + (fp - min_fp)],
                             __dmul_rn((double)(fp - min_fp), e.l_ep)),
                   __dmul_rn((double)tp, e.l_1mep));
-    const uint64_t pos = choose_bits(rng, obs, obs_pos, tp);
-    const uint64_t neg = choose_bits(rng, ~obs & all, obs_neg, fn);
+    const mask_t pos = choose_bits(rng, obs, obs_pos, tp);
+    const mask_t neg = choose_bits(rng, ~obs & all, obs_neg, fn);
     const double lp_pos_idx = -logC[obs_pos * kLogCDim + tp];
     const double lp_neg_idx = -logC[obs_neg * kLogCDim + fn];
     *log_prob = __dadd_rn(__dadd_rn(__dadd_rn(lp_pos_idx, lp_neg_idx), lp_fp), lp_fn);

@@ -585,8 +585,9 @@ struct moire_mcmc
         uint64_t *lat = nullptr;
         if (prm.record_latent_genotypes)
         {
-            latent_store.resize((D + 1) * NL);
-            lat = latent_store.data() + D * NL;
+            const size_t NLW = NL * (size_t)moire_engine_mask_words();  // a genotype is W mask words
+            latent_store.resize((D + 1) * NLW);
+            lat = latent_store.data() + D * NLW;
         }
         if (!engine) return;
         ck(moire_engine_record_draw(engine, chain - first, p_store.data() + D * LA,
@@ -664,7 +665,7 @@ struct moire_mcmc
         // the draw store: as many draws as the run can produce, within ~1 GiB (then it is read
         // back when full)
         const size_t LA = (size_t)L * AP, NL = (size_t)N * L;
-        const size_t per_draw = LA * 8 + (size_t)N * (4 + 4 * 8) + 8 + (prm.record_latent_genotypes ? NL * 8 : 0);
+        const size_t per_draw = LA * 8 + (size_t)N * (4 + 4 * 8) + 8 + (prm.record_latent_genotypes ? NL * 8 * (size_t)moire_engine_mask_words() : 0);
         const size_t thin = (size_t)std::max(prm.thin, 1);
         const size_t want = ((size_t)std::max(prm.samples, 0) + thin - 1) / thin + 1;
         const size_t cap = std::max<size_t>(1, std::min(want, ((size_t)1 << 30) / std::max<size_t>(per_draw, 1)));
@@ -678,7 +679,7 @@ struct moire_mcmc
         store.r = dev_alloc<double>(cap * N);
         store.sample_llik = dev_alloc<double>(cap * N);
         store.mean_coi = dev_alloc<double>(cap);
-        store.latent = prm.record_latent_genotypes ? dev_alloc<uint64_t>(cap * NL) : nullptr;
+        store.latent = prm.record_latent_genotypes ? dev_alloc<uint64_t>(cap * NL * (size_t)moire_engine_mask_words()) : nullptr;
         dev_mode = true;
         host_dirty = true;
         batch_open = false;
@@ -796,8 +797,9 @@ struct moire_mcmc
             d2h(mean_coi_store.data() + D, store.mean_coi, nd);
             if (store.latent)
             {
-                latent_store.resize((D + nd) * NL);
-                d2h(latent_store.data() + D * NL, store.latent, nd * NL);
+                const size_t NLW = NL * (size_t)moire_engine_mask_words();
+                latent_store.resize((D + nd) * NLW);
+                d2h(latent_store.data() + D * NLW, store.latent, nd * NLW);
             }
             cu(cudaStreamSynchronize(stream), "sync");
         }

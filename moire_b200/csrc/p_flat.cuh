@@ -31,7 +31,7 @@ struct alignas(32) SampleScal
 
 struct PFlat
 {
-    uint4 *list;         // [cells] {latent genotype lo, hi, (t << 16) | j, i}, sorted by cost class
+    ListEntry *list;     // [cells] {latent genotype lo, hi, (t << 16) | j, i}, sorted by cost class
                          // (t: chain of this engine, j: locus, i: sample)
     SampleScal *ss;      // [T * N] current (m, r) of every sample, for the duration of update_p
     unsigned int *hist;  // [kSortBins] counts, [kSortBins] running offsets, 4 scalars, task counters
@@ -40,7 +40,7 @@ struct PFlat
     int eval_threads;   // threads of one evaluator launch (sets the cooperative threshold)
     double *round;       // [T * L][4] logAdj, log u, allele index, flags
     const int *nonmiss;  // [L] non-missing cells of a locus
-    unsigned long long *latLM;  // [T][L][N] latent genotypes, locus-major, 0 at missing cells
+    mask_t *latLM;              // [T][L][N] latent genotypes, locus-major, 0 at missing cells
     // update_p's PAM cache (null unless the update runs in cache mode, see k_pc_sweep)
     double *Wcur, *Wnew;        // [max_coi][T * L * N] PAM vectors: accepted state / current proposal
     size_t wstride;             // T * L * N
@@ -59,7 +59,7 @@ __device__ __forceinline__ double *pf_terms(const PFlat &f, unsigned flags, bool
 }
 constexpr int kPfScalars = 2 * kSortBins;  // hist[kPfScalars + 0..3] = n_egf, coop_end, nwork, mid_end
 constexpr int kPfCounters = kPfScalars + 4;  // one task counter per evaluator launch of an update
-constexpr int kPfHistWords = kPfCounters + 72;
+constexpr int kPfHistWords = kPfCounters + kMaskBits + 8;  // one per proposal round (as many as a locus has alleles) + the cache fill
 
 // ---- once per update: locus-major copy of the current terms, class histogram, sorted list -----
 // ---- cost classes of the flat pipelines, ranked by work ----------------------------------------
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
 {
     __shared__ unsigned int s_hist[kSortBins];
     __shared__ double s_T[32][33];
-    __shared__ unsigned long long s_lat[32][33];
+    __shared__ mask_t s_lat[32][33];
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     for (int b = tid; b < kSortBins; b += blockDim.x) s_hist[b] = 0;
     __syncthreads();
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
     {
         const int li = ty + 8 * r, i = tile.i0 + li, j = tile.j0 + tx;
         double T = 0.0;  // missing cells: never listed, never evaluated: a zero term on both sides
-        unsigned long long lat = 0ull;
+        mask_t lat = 0;
         if (i < N && j < L)
         {
             const size_t tn = (size_t)t * N + i;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
                 const size_t cell = tn * L + j;
                 lat = v.latent[cell];
                 T = v.cellT[cell];
-                atomicAdd(&s_hist[work_class_flat(__popcll(lat), v.m[tn])], 1u);
+                atomicAdd(&s_hist[work_class_flat(mpopc(lat), v.m[tn])], 1u);
             }
         }
         s_T[li][tx] = T;
@@ -225,10 +225,10 @@ __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
         if (i < N && j < L)
         {
             const size_t loc = ((size_t)t * L + j) * N + i;
-            const unsigned long long lat = s_lat[tx][lj];
+            const mask_t lat = s_lat[tx][lj];
             f.Tcur[loc] = s_T[tx][lj];
             f.latLM[loc] = lat;  // 0 marks a missing cell (a latent genotype is never empty)
-            if (lat == 0ull) f.Tnew[loc] = 0.0;
+            if (lat == 0) f.Tnew[loc] = 0.0;
         }
     }
     for (int b = tid; b < kSortBins; b += blockDim.x)
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(256) k_pf_scan(const PFlat f)
 constexpr int kScatterCellsPerThread = MOIRE_SCATTER_CPT;
 template <class CellFn>
 __device__ __forceinline__ void block_scatter(size_t total, CellFn cell_fn, unsigned int *offsets,
-                                              uint4 *list)
+                                              ListEntry *list)
 {
     __shared__ unsigned int s_cnt[kSortBins];
     const int tid = threadIdx.x;
@@ -413,7 +413,7 @@ __device__ __forceinline__ void block_scatter(size_t total, CellFn cell_fn, unsi
     const size_t first = (size_t)blockIdx.x * 256 * kScatterCellsPerThread;
     int cls[kScatterCellsPerThread];
     unsigned int rank[kScatterCellsPerThread];
-    uint4 entry[kScatterCellsPerThread];
+    ListEntry entry[kScatterCellsPerThread];
 #pragma unroll
     for (int c = 0; c < kScatterCellsPerThread; ++c)
     {
@@ -438,16 +438,27 @@ __host__ __device__ inline unsigned scatter_blocks(size_t total)
 __global__ void __launch_bounds__(256) k_pf_scatter(const View v, const PFlat f)
 {
     const size_t total = (size_t)v.T * v.L * v.N;
-    auto cell_fn = [&](size_t loc, int &cls, uint4 &entry) -> bool {
-        const unsigned long long lat = f.latLM[loc];  // locus-major copy of k_pf_prepare: coalesced
-        if (lat == 0ull) return false;                // missing
+    auto cell_fn = [&](size_t loc, int &cls, ListEntry &entry) -> bool {
+        const mask_t lat = f.latLM[loc];  // locus-major copy of k_pf_prepare: coalesced
+        if (lat == 0) return false;                // missing
         const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
         const unsigned t = tl / v.L, j = tl - t * v.L;
-        cls = work_class_flat(__popcll(lat), v.m[t * v.N + i]);
-        entry = make_uint4((unsigned)lat, (unsigned)(lat >> 32), (t << 16) | j, i);
+        cls = work_class_flat(mpopc(lat), v.m[t * v.N + i]);
+        entry = make_entry(lat, (t << 16) | j, i);
         return true;
     };
     block_scatter(total, cell_fn, f.hist + kSortBins, f.list);
+}
+
+// The SALT proposal keeps the alleles of a locus across the lanes of one warp, kAPL per lane (two with
+// one-word masks, as in round 1; four with two words).  x[slot], slot < kAPL, without dynamic indexing.
+constexpr int kAPL = kMaskBits / 32;
+__device__ __forceinline__ double lane_slot(const double (&x)[kAPL], int slot)
+{
+    double r = x[0];
+#pragma unroll
+    for (int s = 1; s < kAPL; ++s) r = slot == s ? x[s] : r;
+    return r;
 }
 
 // ---- once per proposal round: decide the previous proposal, draw the next -----------------------
@@ -563,10 +574,10 @@ __global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat 
     {
         const int idx = n_idx;
         const double z = n_z, logu = n_logu;
-        double lg[2], lp[2], lq[2];
-        bool rest[2];
+        double lg[kAPL], lp[kAPL], lq[kAPL];
+        bool rest[kAPL];
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < kAPL; ++s)
         {
             const int a = lane + 32 * s;
             const bool has = a < A;
@@ -575,7 +586,7 @@ __global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat 
             if (has) log_pq_d(lg[s], lp[s], lq[s]);
             rest[s] = has && a != idx;
         }
-        const double lg_sel = (idx >> 5) ? lg[1] : lg[0];
+        const double lg_sel = lane_slot(lg, idx >> 5);
         const double logit_curr = __shfl_sync(0xffffffffu, lg_sel, idx & 31);
         const double logit_prop = logit_curr + v.p_sd[prow + idx] * z;
         double clp, clq, plp, plq;
@@ -584,7 +595,7 @@ __global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat 
         double bv = -INFINITY;
         int ba = 1 << 30;
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < kAPL; ++s)
             if (rest[s] && (lg[s] > bv)) { bv = lg[s]; ba = lane + 32 * s; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
@@ -593,20 +604,20 @@ __global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat 
             const int oa = __shfl_xor_sync(0xffffffffu, ba, o);
             if (ov > bv || (ov == bv && oa < ba)) { bv = ov; ba = oa; }
         }
-        const double lp_sel = (ba >> 5) ? lp[1] : lp[0];
-        const double lq_sel = (ba >> 5) ? lq[1] : lq[0];
+        const double lp_sel = lane_slot(lp, ba >> 5);
+        const double lq_sel = lane_slot(lq, ba >> 5);
         const double lp1 = __shfl_sync(0xffffffffu, lp_sel, ba & 31);
         const double lq1 = __shfl_sync(0xffffffffu, lq_sel, ba & 31);
         double cum = 0.0;
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < kAPL; ++s)
             if (rest[s] && (lane + 32 * s) != ba) cum += (bv < 0.0) ? cold_exp(lp[s] - lp1) : cold_exp(lp[s]);
         cum = warp_sum(cum);
         const double lsum = (bv < 0.0) ? lp1 + cold_log1p(cum) : cold_log1p(-cold_exp(lq1) + cum);
         const double ls = plq - lsum;
         bool below = false;
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < kAPL; ++s)
         {
             const int a = lane + 32 * s;
             if (a < A)
@@ -647,9 +658,9 @@ __global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat 
 // What changes numerically: a cached PAM was computed from q of an earlier p of the same update
 // (rescaled since, so equal to rounding); the from-scratch value (k_eval_cells) stays the truth the
 // tests bound the difference against (tests/test_gpu_shapes.py).
-__device__ __forceinline__ bool pc_fresh(unsigned long long S, int idx, int k, int m)
+__device__ __forceinline__ bool pc_fresh(mask_t S, int idx, int k, int m)
 {
-    return ((S >> idx) & 1ull) || k > m;
+    return mtest(S, idx) || k > m;
 }
 
 // relatedness_mixture for at most eight mixture terms with the PAMs in registers: the loop of
@@ -693,20 +704,20 @@ __global__ void __launch_bounds__(256) k_pc_sweep(const View v, const PFlat f)
     {
         const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
         const double *st = f.round + (size_t)tl * 4;
-        const unsigned long long S = f.latLM[loc];
+        const mask_t S = f.latLM[loc];
         const unsigned fl = (unsigned)st[3];
         if ((fl & kPfActive) && S)
         {
             const unsigned t = tl / v.L;
             const size_t tn = (size_t)t * v.N + i;
-            const int idx = (int)st[2], k = __popcll(S);
+            const int idx = (int)st[2], k = mpopc(S);
             const SampleScal sc = f.ss[tn];
             const int m = sc.m;
             const bool rel_on = v.allow_rel != 0;
             const int nw = rel_on ? (k >= 2 ? m - k + 1 : 0) : 1;  // cached PAMs of the cell
             // the previous proposal of this locus was accepted and this cell held its allele: the
             // PAM vector the evaluator left in Wnew is the accepted state's now
-            const bool commit = (fl & kPfAccepted) && ((S >> ((fl >> 8) & 0xffu)) & 1ull) && k <= m;
+            const bool commit = (fl & kPfAccepted) && mtest(S, (int)((fl >> 8) & 0xffu)) && k <= m;
             const bool fresh = pc_fresh(S, idx, k, m);
             const double *wsrc = (commit ? f.Wnew : f.Wcur) + loc;
             if (fresh)
@@ -721,10 +732,10 @@ __global__ void __launch_bounds__(256) k_pc_sweep(const View v, const PFlat f)
                 // (the evaluators' order)
                 const double *prow = f.pprop + (size_t)tl * v.AP;
                 double tot = 0.0;
-                unsigned long long rest = S;
+                mask_t rest = S;
                 while (rest)
                 {
-                    const int al = __ffsll((long long)rest) - 1;
+                    const int al = mffs(rest) - 1;
                     rest &= rest - 1;
                     tot = __dadd_rn(tot, prow[al]);
                 }
@@ -774,16 +785,16 @@ __global__ void __launch_bounds__(256) k_pc_sweep(const View v, const PFlat f)
 __global__ void __launch_bounds__(256) k_pc_scatter(const View v, const PFlat f)
 {
     const size_t total = (size_t)v.T * v.L * v.N;
-    auto cell_fn = [&](size_t loc, int &cls, uint4 &entry) -> bool {
+    auto cell_fn = [&](size_t loc, int &cls, ListEntry &entry) -> bool {
         const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
         const double *st = f.round + (size_t)tl * 4;
-        const unsigned long long S = f.latLM[loc];
+        const mask_t S = f.latLM[loc];
         if (((unsigned)st[3] & kPfActive) == 0 || S == 0) return false;
         const unsigned t = tl / v.L, j = tl - t * v.L;
-        const int m = v.m[(size_t)t * v.N + i], k = __popcll(S);
+        const int m = v.m[(size_t)t * v.N + i], k = mpopc(S);
         if (!pc_fresh(S, (int)st[2], k, m)) return false;
         cls = work_class_flat(k, m);
-        entry = make_uint4((unsigned)S, (unsigned)(S >> 32), (t << 16) | j, i);
+        entry = make_entry(S, (t << 16) | j, i);
         return true;
     };
     block_scatter(total, cell_fn, f.hist + kSortBins, f.list);
@@ -799,7 +810,7 @@ __global__ void __launch_bounds__(256) k_pc_scatter(const View v, const PFlat f)
 // shapes); otherwise a chunk of 1023-subset cells would outlast everything else.
 struct FlatSrc
 {
-    const uint4 *list;                  // {latent genotype (two words), (t << 16) | j, i}: the
+    const ListEntry *list;                 // {latent genotype (two words), (t << 16) | j, i}: the
                                         //  genotype travels in the list, so a unit's loads are
                                         //  list -> frequencies / sample scalars only
     const unsigned int *bounds;         // [4] n_egf, coop_end, nwork, mid_end
@@ -857,15 +868,15 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
     {
         const int w = lo + unit;
         if (w >= hi) return;
-        const uint4 e = f.list[w];
+        const ListEntry e = f.list[w];
         const unsigned t = e.z >> 16, j = e.z & 0xffffu, tl = t * L + j, tn = t * N + e.w;
         const unsigned fl = f.round_flags ? (unsigned)f.round_flags[(size_t)tl * 4 + 3] : kPfActive;
         if ((fl & kPfActive) == 0) return;
         double *const outp = (f.out_flip && (fl & kPfFlip)) ? f.out_flip : f.out;
-        const unsigned long long lat = ((unsigned long long)e.y << 32) | e.x;
+        const mask_t lat = entry_lat(e);
         const SampleScal sc = f.ss[tn];
         const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
-        const int m = sc.m, k = __popcll(lat);
+        const int m = sc.m, k = mpopc(lat);
         const double *prow = f.p + (size_t)tl * f.p_stride;
         const PamOut po{CACHE ? f.pam_out + ((size_t)tl * N + e.w) : nullptr, f.pam_stride};
         double T;
@@ -883,14 +894,14 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
     if (w0 >= hi) return;
     const int w = w0 + lane;
     bool go = w < hi;
-    uint4 e = make_uint4(1u, 0u, 0u, 0u);
+    ListEntry e = idle_entry();
     if (go) e = f.list[w];
     // -- class-uniform chunk of small cells: the register path (likelihood.cuh)
     {
         const unsigned in = __ballot_sync(0xffffffffu, go);
         const int k = __popc(e.x);
         const bool small = allow_rel && in != 0 &&
-                           __all_sync(0xffffffffu, !go || (e.y == 0 && k <= kSmallK && k >= 1)) &&
+                           __all_sync(0xffffffffu, !go || (entry_low32(e) && k <= kSmallK && k >= 1)) &&
                            __reduce_max_sync(0xffffffffu, go ? k : 0) ==
                                __reduce_min_sync(0xffffffffu, go ? k : kSmallK + 1);
         if (small)
@@ -931,7 +942,7 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
     // round flag, the sample's scalars, the gathered frequencies -- and only then look
     // at the flag (two trips to L2 per cell instead of 3 + k)
     const unsigned tl = (e.z >> 16) * L + (e.z & 0xffffu), tn = (e.z >> 16) * N + e.w;
-    const unsigned long long lat = ((unsigned long long)e.y << 32) | e.x;
+    const mask_t lat = entry_lat(e);
     const double *prow = f.p + (size_t)tl * f.p_stride;
     const double flagword = f.round_flags ? f.round_flags[(size_t)tl * 4 + 3] : (double)kPfActive;
     const SampleScal sc = f.ss[tn];
@@ -1073,7 +1084,7 @@ __global__ void __launch_bounds__(256) k_pf_finish(const View v, const PFlat f)
         if (i < N && j < L)
         {
             const size_t loc = ((size_t)t * L + j) * N + i;
-            in = f.latLM[loc] != 0ull;
+            in = f.latLM[loc] != 0;
             T = pf_terms(f, (unsigned)f.round[((size_t)t * L + j) * 4 + 3], false)[loc];
         }
         s_T[lj][tx] = T;

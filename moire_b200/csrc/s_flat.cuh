@@ -25,7 +25,7 @@ struct SFlat
     int *m_new;                      // [T * N] proposed COI
     SampleScal *ss;                  // [T * N] the proposal's (m, r) as the evaluator gathers it
     EpsLogs *elogs;                  // [T * N][nA] logs of the proposed error rates
-    unsigned long long *lat;         // [T][N][L] proposed latent genotypes
+    mask_t *lat;                     // [T][N][L] proposed latent genotypes
     double *adj;                     // [T][N][L] their log proposal densities
     double *O, *Tn;                  // [T][N][L] observation / transmission terms of the proposal
 };
@@ -113,10 +113,10 @@ __global__ void __launch_bounds__(256, 4) k_sf_cells(const View v, const SFlat s
         const size_t di = (size_t)i * L + j;
         const bool miss = v.missing[di] != 0;
         const int m_new = sf.m_new[tn];
-        unsigned long long lat;
+        mask_t lat;
         if (RESAMPLE)
         {
-            const unsigned long long obs = v.obs[di];
+            const mask_t obs = v.obs[di];
             const int A = v.nall[j];
             const EpsLogs el = sf.elogs[(size_t)tn * nA + v.aclass[j]];
             Stream crng;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256, 4) k_sf_cells(const View v, const SFlat s
         }
         if (!miss)
         {
-            atomicAdd(&s_hist[work_class_flat(__popcll(lat), m_new)], 1u);
+            atomicAdd(&s_hist[work_class_flat(mpopc(lat), m_new)], 1u);
             ++my_evals;
         }
     }
@@ -149,13 +149,13 @@ __global__ void __launch_bounds__(256) k_sf_scatter(const View v, const SFlat sf
 {
     constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
     const size_t total = (size_t)v.T * v.N * v.L;
-    auto cell_fn = [&](size_t gi, int &cls, uint4 &entry) -> bool {
+    auto cell_fn = [&](size_t gi, int &cls, ListEntry &entry) -> bool {
         const unsigned tn = (unsigned)(gi / v.L), j = (unsigned)(gi - (size_t)tn * v.L);
         const unsigned t = tn / v.N, i = tn - t * v.N;
         if (!sf.prop[tn].valid || v.missing[(size_t)i * v.L + j] != 0) return false;
-        const unsigned long long lat = RESAMPLE ? sf.lat[gi] : v.latent[gi];
-        cls = work_class_flat(__popcll(lat), sf.m_new[tn]);
-        entry = make_uint4((unsigned)lat, (unsigned)(lat >> 32), (t << 16) | j, i);
+        const mask_t lat = RESAMPLE ? sf.lat[gi] : v.latent[gi];
+        cls = work_class_flat(mpopc(lat), sf.m_new[tn]);
+        entry = make_entry(lat, (t << 16) | j, i);
         return true;
     };
     block_scatter(total, cell_fn, pf.hist + kSortBins, pf.list);
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) k_eps_cells(const View v, const SFlat sf,
         for (int j0 = 0; j0 < L; j0 += 128)
         {
             double vT[4], vO[4];
-            unsigned long long vl[4], vo[4];
+            mask_t vl[4], vo[4];
             int vA[4], vc[4];
             unsigned char vm[4];
 #pragma unroll

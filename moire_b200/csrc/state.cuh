@@ -11,6 +11,8 @@
 #pragma once
 #include <cstdint>
 
+#include "mask.cuh"
+
 namespace moire
 {
 // kernels take the iteration by value, or read it from View::iter when handed this
@@ -23,17 +25,17 @@ struct View
     unsigned long long seed;
 
     // data (read-only)
-    const unsigned long long *obs;  // [N][L]
+    const mask_t *obs;              // [N][L] observed alleles (mask.cuh)
     const unsigned char *missing;   // [N][L]
     const int *nall;                // [L]
     const int *aclass;              // [L] index into avals
     const int *avals;               // [nA] distinct allele counts
     const int *obs_coi;             // [N]
-    const double *logC;             // [65][65] log C(n, k)
+    const double *logC;             // [kLogCDim][kLogCDim] log C(n, k)
     const double *lgam;             // [128] lgamma(i + 1)
 
     // per cell [T][N][L]
-    unsigned long long *latent;
+    mask_t *latent;
     double *lgadj;
     double *cellT;
     double *cellO;

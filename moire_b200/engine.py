@@ -53,7 +53,9 @@ class Engine:
     def __init__(self, data: PackedData, temps, seed=1, device=0, chain_offset=0, pipeline="auto",
                  ref32_emulation=False, **model):
         self._h = None
-        self.lib = _lib.load()
+        # one-word masks (libmoire_b200.so) unless a locus has more than 64 alleles
+        self.W = data.mask_words
+        self.lib = _lib.load(self.W)
         prm = dict(DEFAULT_MODEL)
         unknown = set(model) - set(prm)
         if unknown:
@@ -163,10 +165,14 @@ class Engine:
         return t
 
     # ---- state ----
+    def _mask_shape(self):
+        """[N][L] allele sets of one chain: uint64 [N][L], or [N][L][2] with two-word masks."""
+        return (self.N, self.L) if self.W == 1 else (self.N, self.L, self.W)
+
     def dump_state(self, chain=0):
         N, L, A = self.N, self.L, self.a_pad
         st = dict(m=np.zeros(N, np.int32), r=np.zeros(N), eps_pos=np.zeros(N), eps_neg=np.zeros(N),
-                  p=np.zeros((L, A)), latent=np.zeros((N, L), np.uint64), lg_adj=np.zeros((N, L)),
+                  p=np.zeros((L, A)), latent=np.zeros(self._mask_shape(), np.uint64), lg_adj=np.zeros((N, L)),
                   mean_coi=np.zeros(1), cell_t=np.zeros((N, L)), cell_o=np.zeros((N, L)),
                   prior_eps_neg=np.zeros(N), prior_eps_pos=np.zeros(N), prior_coi=np.zeros(N),
                   prior_r=np.zeros(N), mean_coi_hyper_prior=np.zeros(1))
@@ -195,7 +201,7 @@ class Engine:
         vals = dict(m=arr("m", np.int32, (N,)), r=arr("r", np.float64, (N,)),
                     eps_pos=arr("eps_pos", np.float64, (N,)),
                     eps_neg=arr("eps_neg", np.float64, (N,)), p=arr("p", np.float64, (L, A)),
-                    latent=arr("latent", np.uint64, (N, L)),
+                    latent=arr("latent", np.uint64, self._mask_shape()),
                     lg_adj=arr("lg_adj", np.float64, (N, L)))
         if "mean_coi" in st and st["mean_coi"] is not None:
             keep["mc"] = np.array([st["mean_coi"]], dtype=np.float64)
@@ -248,7 +254,7 @@ class Engine:
         N, L, A = self.N, self.L, self.a_pad
         d = dict(p=np.zeros((L, A)), m=np.zeros(N, np.int32), eps_neg=np.zeros(N),
                  eps_pos=np.zeros(N), r=np.zeros(N), sample_llik=np.zeros(N),
-                 mean_coi=np.zeros(1), latent=np.zeros((N, L), np.uint64) if latent else None)
+                 mean_coi=np.zeros(1), latent=np.zeros(self._mask_shape(), np.uint64) if latent else None)
         self._ck(self.lib.moire_engine_record_draw(
             self._h, chain, _ptr(d["p"]), _ptr(d["m"]), _ptr(d["eps_neg"]), _ptr(d["eps_pos"]),
             _ptr(d["r"]), _ptr(d["sample_llik"]), _ptr(d["mean_coi"]), _ptr(d["latent"])),

@@ -146,7 +146,8 @@ class MCMC:
                  record_latent_genotypes=False, max_runtime=math.inf, seed=1, device=0, rank=0,
                  world_size=1, allgather=None, pipeline="auto", ref32_emulation=False, **model):
         self._h = None
-        self.lib = _lib.load()
+        self.W = data.mask_words   # two-word masks (libmoire_b200_w128.so) past 64 alleles per locus
+        self.lib = _lib.load(self.W)
         prm = dict(DEFAULT_MODEL)
         unknown = set(model) - set(prm)
         if unknown:
@@ -193,7 +194,7 @@ class MCMC:
         self.engine, self.a_pad = None, 4
         if eh:
             self.engine = Engine.__new__(Engine)
-            self.engine.lib, self.engine._h = self.lib, C.c_void_p(eh)
+            self.engine.lib, self.engine._h, self.engine.W = self.lib, C.c_void_p(eh), self.W
             self.engine.N, self.engine.L, self.engine.data, self.engine.model = self.N, self.L, data, prm
             self.engine.a_pad = self.a_pad = self.lib.moire_engine_a_pad(self.engine._h)
             self.engine.T = self.lib.moire_engine_num_chains(self.engine._h)
@@ -227,7 +228,7 @@ class MCMC:
         import torch.distributed as dist
         path = nccl_library_path()
         cpath = path.encode() if path else None
-        if _NCCL_READY.get((self.world, self.rank)):     # the process keeps its communicator
+        if _NCCL_READY.get((self.W, self.world, self.rank)):     # the process keeps its communicator
             self._ck(self.lib.moire_mcmc_init_nccl(self._h, None, cpath), "init_nccl")
             return True
         idbuf = np.zeros(128, np.uint8)
@@ -242,7 +243,7 @@ class MCMC:
             return False
         idbuf = np.ascontiguousarray(t[:128])
         self._ck(self.lib.moire_mcmc_init_nccl(self._h, _ptr(idbuf), cpath), "init_nccl")
-        _NCCL_READY[(self.world, self.rank)] = True
+        _NCCL_READY[(self.W, self.world, self.rank)] = True   # per library: each keeps its own communicator
         return True
 
     def set_allgather(self, fn):
@@ -340,7 +341,8 @@ class MCMC:
                    coi=np.zeros((D, N), np.int32), eps_neg=np.zeros((D, N)),
                    eps_pos=np.zeros((D, N)), relatedness=np.zeros((D, N)),
                    data_llik=np.zeros((D, N)), lam_coi=np.zeros(D),
-                   latent=np.zeros((D, N, L), np.uint64) if self.record_latent else None)
+                   latent=np.zeros((D, N, L) if self.W == 1 else (D, N, L, self.W), np.uint64)
+                   if self.record_latent else None)
         self._ck(self.lib.moire_mcmc_get_draws(
             self._h, _ptr(out["draw_step"]), _ptr(out["allele_freqs"]), _ptr(out["coi"]),
             _ptr(out["eps_neg"]), _ptr(out["eps_pos"]), _ptr(out["relatedness"]),
@@ -449,7 +451,9 @@ def _assemble_chain(parts, N, L, num_alleles, args, record_latent):
     res["eps_pos"] = list(np.ascontiguousarray(dr["eps_pos"].T))
     res["relatedness"] = list(np.ascontiguousarray(dr["relatedness"].T))
     if record_latent and dr["latent"] is not None:
-        res["latent_genotypes"] = [[[[b for b in range(64) if int(dr["latent"][d, i, j]) >> b & 1]
+        lat = dr["latent"].reshape(D, N, L, -1)  # [..][W] mask words, word w = alleles 64 w ..
+        res["latent_genotypes"] = [[[[64 * w + b for w in range(lat.shape[3]) for b in range(64)
+                                      if int(lat[d, i, j, w]) >> b & 1]
                                      for d in range(D)] for j in range(L)] for i in range(N)]
     else:
         # nothing recorded: every (sample, locus) entry is an empty list, as in the reference's
@@ -505,9 +509,10 @@ def run_mcmc(data, is_missing=False, allow_relatedness=True, thin=1, burnin=1e4,
     "fused": the kernel generation, include/moire_engine.h) and ``ref32_emulation`` (float-rounded
     P(any missing) clamped at 1 - FLT_EPSILON like the shipped float reference; off = fp64).
 
-    Engine limits the reference does not have (``MoireError`` when exceeded): at most
-    MOIRE_MAX_ALLELES alleles per locus, ``max_coi`` <= MOIRE_MAX_COI, and
-    chains-per-GPU x samples x loci < 2^32.
+    Engine limits the reference does not have (``ValueError`` / ``MoireError`` when exceeded): at
+    most 128 alleles per locus (data with a locus of 65..128 alleles runs on the two-word build of
+    the engine, ``libmoire_b200_w128.so``, picked here from the data), ``max_coi`` <=
+    MOIRE_MAX_COI = 127 (the reference's own bound), and chains-per-GPU x samples x loci < 2^32.
     """
     t_start = time.time()
     args = dict(is_missing=is_missing, allow_relatedness=allow_relatedness, thin=thin,

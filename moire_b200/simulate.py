@@ -119,15 +119,18 @@ def simulate_data_gpu(mean_coi=None, num_samples=None, epsilon_pos=0.0, epsilon_
     fr = np.zeros((L, AP))
     for j, f in enumerate(allele_freqs):
         fr[j, :len(f)] = f
-    obs, tru = np.zeros((N, L), np.uint64), np.zeros((N, L), np.uint64)
+    W = _lib.words_for(AP)  # one mask word, or two past 64 alleles per locus
+    shape = (N, L) if W == 1 else (N, L, W)
+    obs, tru = np.zeros(shape, np.uint64), np.zeros(shape, np.uint64)
     mis = np.zeros((N, L), np.uint8)
-    lib = _lib.load()
+    lib = _lib.load(W)
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     rc = lib.moire_simulate_data(N, L, ptr(na), ptr(fr), AP, ptr(sample_cois), ptr(rel), float(epsilon_pos),
                                  float(epsilon_neg), float(missingness), int(seed), int(device), ptr(obs),
                                  ptr(mis), ptr(tru))
     if rc != 0:
         raise RuntimeError(f"moire_simulate_data failed ({rc}): {lib.moire_last_error().decode()}")
-    coi = np.vectorize(lambda x: bin(int(x)).count("1"))(obs).max(axis=1).astype(np.int32)
+    bits = np.vectorize(lambda x: bin(int(x)).count("1"))(obs)
+    coi = (bits if W == 1 else bits.sum(axis=2)).max(axis=1).astype(np.int32)
     return dict(packed=PackedData(N, L, na, obs, mis, coi), true_mask=tru, allele_freqs=allele_freqs,
                 sample_cois=sample_cois, sample_relatedness=rel)

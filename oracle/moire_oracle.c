@@ -304,5 +304,43 @@ void orc_eval_cells(int prec, int N, int L, const int *num_alleles, const uint64
     }
 }
 
+void orc_eval_cells_wide(int prec, int N, int L, int W, const int *num_alleles, const uint64_t *obs,
+                         const uint8_t *is_missing, const uint64_t *latent, const int *m,
+                         const double *r, const double *eps_neg, const double *eps_pos, const double *p,
+                         int a_pad, int allow_relatedness, double max_eps_neg, double max_eps_pos,
+                         double *t_out, double *o_out)
+{
+    for (int i = 0; i < N; ++i)
+    {
+        for (int j = 0; j < L; ++j)
+        {
+            const size_t cell = (size_t)i * (size_t)L + (size_t)j;
+            const int A = num_alleles[j];
+            const double *pj = p + (size_t)j * (size_t)a_pad;
+            t_out[cell] = o_out[cell] = 0.0;
+            if (is_missing[cell]) continue;
+            int idx[ORC_MAX_A], ov[ORC_MAX_A], k = 0;
+            for (int a = 0; a < A && a < 64 * W; ++a)
+            {
+                if (latent[cell * (size_t)W + (size_t)(a >> 6)] >> (a & 63) & 1ULL) idx[k++] = a;
+                ov[a] = (int)(obs[cell * (size_t)W + (size_t)(a >> 6)] >> (a & 63) & 1ULL);
+            }
+            if (prec == 64)
+            {
+                t_out[cell] = transmission_f64(idx, k, pj, m[i], r[i], allow_relatedness);
+                o_out[cell] = observation_f64(idx, k, ov, A, eps_neg[i], eps_pos[i], max_eps_neg, max_eps_pos);
+            }
+            else
+            {
+                float pf[ORC_MAX_A];
+                for (int a = 0; a < A; ++a) pf[a] = (float)pj[a];
+                t_out[cell] = transmission_f32(idx, k, pf, m[i], (float)r[i], allow_relatedness);
+                o_out[cell] = observation_f32(idx, k, ov, A, (float)eps_neg[i], (float)eps_pos[i],
+                                              (float)max_eps_neg, (float)max_eps_pos);
+            }
+        }
+    }
+}
+
 /* ---- the engine-semantics Metropolis stepper (fp64) ------------------------------------------ */
 #include "engine_stepper_impl.h"

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ORC_MAX_A 64   /* alleles per locus representable in one 64-bit mask */
+#define ORC_MAX_A 128  /* alleles per locus: one 64-bit mask word, or two (orc_eval_cells_wide) */
 #define ORC_MAX_N 127  /* COI bound of the reference's lgamma LUT (src/sampler.cpp:22-25) */
 #define ORC_K_IE_MAX 10 /* src/prob_any_missing.cpp:11 */
 
@@ -58,6 +58,16 @@ void orc_eval_cells(int prec, int N, int L, const int *num_alleles, const uint64
                     const double *r, const double *eps_neg, const double *eps_pos, const double *p,
                     int a_pad, int allow_relatedness, double max_eps_neg, double max_eps_pos,
                     double *t_out, double *o_out);
+
+/* The same for allele sets of W 64-bit words, [N][L][W] (word 0 = alleles 0..63): what the two-word
+ * build of the engine (libmoire_b200_w128.so, loci with 65..128 alleles) is checked against.  The
+ * reference's functions take index vectors of any length (src/chain.cpp:858-961); the masks are
+ * unpacked into exactly those. */
+void orc_eval_cells_wide(int prec, int N, int L, int W, const int *num_alleles, const uint64_t *obs,
+                         const uint8_t *is_missing, const uint64_t *latent, const int *m,
+                         const double *r, const double *eps_neg, const double *eps_pos, const double *p,
+                         int a_pad, int allow_relatedness, double max_eps_neg, double max_eps_pos,
+                         double *t_out, double *o_out);
 
 /* Philox4x32-10 of the stepper (independent of the engine's), for the known-answer test. */
 void orc_philox4x32(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);

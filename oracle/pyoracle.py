@@ -83,6 +83,8 @@ class Oracle:
         L.orc_combinations.argtypes = [i, i, vp, C.c_long, vp, vp]
         L.orc_eval_cells.argtypes = [i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, d, d,
                                      vp, vp]
+        L.orc_eval_cells_wide.argtypes = [i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, d, d,
+                                          vp, vp]
 
     # a6
     def combinations(self, n, r, max_rows=5000):
@@ -184,8 +186,10 @@ class Oracle:
 
     def eval_cells(self, prec, num_alleles, obs, is_missing, latent, m, r, eps_neg, eps_pos, p,
                    allow_relatedness, max_eps_neg=2.0, max_eps_pos=2.0):
-        """obs/latent/is_missing: [N][L]; p: [L][a_pad].  Returns (T, O) each [N][L]."""
-        N, L = obs.shape
+        """obs/latent/is_missing: [N][L] (masks of W words: [N][L][W]); p: [L][a_pad].  Returns (T, O)
+        each [N][L]."""
+        obs = np.asarray(obs)
+        N, L = obs.shape[:2]
         na = _i32(num_alleles)
         obs = np.ascontiguousarray(obs, dtype=np.uint64)
         lat = np.ascontiguousarray(latent, dtype=np.uint64)
@@ -194,6 +198,12 @@ class Oracle:
         r, en, ep, p = _f64(r), _f64(eps_neg), _f64(eps_pos), _f64(p)
         t = np.zeros((N, L))
         o = np.zeros((N, L))
+        if obs.ndim == 3:
+            assert lat.shape == obs.shape, (lat.shape, obs.shape)
+            self.lib.orc_eval_cells_wide(prec, N, L, obs.shape[2], _p(na), _p(obs), _p(mis), _p(lat),
+                                         _p(m), _p(r), _p(en), _p(ep), _p(p), p.shape[1],
+                                         int(allow_relatedness), max_eps_neg, max_eps_pos, _p(t), _p(o))
+            return t, o
         self.lib.orc_eval_cells(prec, N, L, _p(na), _p(obs), _p(mis), _p(lat), _p(m), _p(r),
                                 _p(en), _p(ep), _p(p), p.shape[1], int(allow_relatedness),
                                 max_eps_neg, max_eps_pos, _p(t), _p(o))

@@ -7,8 +7,16 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def popcount(a):
-    return np.vectorize(lambda x: bin(int(x)).count("1"))(a)
+def popcount(a, pk=None):
+    """Set bits per allele set; masks of W words ([..][W], the two-word build) are summed over words."""
+    bits = np.vectorize(lambda x: bin(int(x)).count("1"))(a)
+    return bits.sum(axis=-1) if pk is not None and pk.mask_words > 1 else bits
+
+
+def bits_above(mask_words, A):
+    """True if an allele set (its words, lowest first) has a bit at or above allele A."""
+    x = sum(int(w) << (64 * i) for i, w in enumerate(np.atleast_1d(mask_words)))
+    return (x >> int(A)) != 0
 
 
 def check_invariants(eng, pk, chain, oracle=None, allow=1, ncheck=400, seed=0):
@@ -16,10 +24,10 @@ def check_invariants(eng, pk, chain, oracle=None, allow=1, ncheck=400, seed=0):
     cell = st["cell_t"] + st["cell_o"]
     assert np.all(np.isfinite(cell))
     assert np.all(cell[pk.is_missing != 0] == 0.0)                 # missing cells contribute nothing
-    k = popcount(st["latent"])
+    k = popcount(st["latent"], pk)
     assert (k >= 1).all() and (k <= st["m"][:, None]).all()
     A = pk.num_alleles
-    assert all((int(x) >> int(A[j])) == 0 for j in range(pk.num_loci) for x in st["latent"][:, j][:50])
+    assert not any(bits_above(x, A[j]) for j in range(pk.num_loci) for x in st["latent"][:, j][:50])
     assert np.allclose(st["p"][:, :pk.max_alleles].sum(1), 1.0, atol=1e-9)
     assert (st["p"][np.arange(pk.num_loci)[:, None], np.arange(st["p"].shape[1])[None, :]]
             [np.arange(st["p"].shape[1])[None, :] >= A[:, None]] == 0).all()   # padding stays 0
@@ -98,6 +106,8 @@ def _mini(N, As, seed=3, **kw):
 @pytest.mark.parametrize("N,As,T,kw", [
     (1, [2], 1, {}),                                   # one sample, one biallelic locus, one chain
     (3, [64, 2, 33], 2, {}),                           # the widest mask word
+    (30, [100, 2, 65, 128, 64], 2, {}),                # past one word: the two-word build (128 alleles)
+    (25, [128] * 3 + [90], 2, dict(mean_coi=14, missingness=.1)),   # ... with k > 10 (EGF) cells
     (70, [5] * 3, 3, dict(missingness=1.0)),           # every cell missing
     (33, [7] * 40, 2, dict(missingness=.5)),           # half missing, ragged tile (33 = 32 + 1)
     (2049, [4, 6], 2, {}),                             # N > 2048: the 512-thread update_p variant
@@ -113,6 +123,59 @@ def test_edge_shapes(oracle, N, As, T, kw):
     for c in range(T):
         check_invariants(eng, pk, c, oracle, ncheck=300)
     eng.close()
+
+
+def test_two_word_build_runs_the_one_word_chain_bit_for_bit():
+    """libmoire_b200_w128.so is the same sources with two-word allele sets (mask.cuh).  On data whose
+    loci fit one word it must run the very chain the one-word library runs -- same Philox streams,
+    same arithmetic, same order -- so everything the one-word build is pinned to (the CPU stepper,
+    the oracle, the reference's goldens) carries over to it: every state array bit-identical after
+    several full sweeps, the second mask word empty."""
+    from moire_b200.engine import Engine
+    pk = _mini(60, [5] * 4 + [12] * 4 + [40, 64], seed=4, missingness=.1, mean_coi=4)
+    temps = [1.0, .6, .2]
+    states = []
+    for data in (pk, pk.widened(2)):
+        eng = Engine(data, temps, seed=12, burnin=40, max_coi=25, pipeline="flat")
+        assert eng.lib.moire_engine_mask_words() == data.mask_words
+        assert not eng.init_chains()["still_ill"].any()
+        for it in range(6):
+            eng.step(it)
+        states.append(([eng.dump_state(c) for c in range(len(temps))], eng.scalars(), eng.diagnostics(0)))
+        eng.close()
+    (one, sc1, dg1), (two, sc2, dg2) = states
+    for a, b in zip(one, two):
+        for name in a:
+            if name == "latent":
+                assert np.array_equal(a[name], b[name][:, :, 0]) and not b[name][:, :, 1].any()
+            else:
+                assert np.array_equal(np.asarray(a[name]), np.asarray(b[name])), name
+    assert np.array_equal(sc1[0], sc2[0]) and np.array_equal(sc1[1], sc2[1])
+    for name in dg1:
+        assert np.array_equal(dg1[name], dg2[name]), name
+
+
+def test_run_mcmc_on_a_locus_with_more_than_64_alleles():
+    """The user-facing call on data the one-word masks cannot hold (the reference has no allele limit,
+    src/genotyping_data.cpp:17-48): the 23-field result comes back, recorded latent genotypes are
+    index lists below each locus' allele count and within the sampled COI."""
+    from moire_b200.mcmc import run_mcmc
+    from moire_b200.simulate import simulate_data
+    As = [100, 8, 70]
+    d = simulate_data(mean_coi=3, num_samples=20, epsilon_pos=.02, epsilon_neg=.1,
+                      locus_freq_alphas=[np.ones(a) for a in As], seed=5)
+    res = run_mcmc(d, d["is_missing"], burnin=30, samples_per_chain=10, pt_chains=3,
+                   record_latent_genotypes=True, verbose=False)
+    ch = res["chains"][0]
+    assert [np.asarray(f[0]).shape[0] for f in ch["allele_freqs"]] == As
+    assert all(abs(np.asarray(f[-1]).sum() - 1) < 1e-9 for f in ch["allele_freqs"])
+    lg = ch["latent_genotypes"]
+    for i in range(20):
+        for j, A in enumerate(As):
+            for dr in range(10):
+                g = lg[i][j][dr]
+                assert len(g) >= 1 and all(0 <= a < A for a in g) and len(g) <= ch["coi"][i][dr]
+    assert np.all(np.isfinite(np.asarray(ch["data_llik"])))
 
 
 @pytest.mark.parametrize("max_coi,pipeline", [(64, "fused"), (100, "flat"), (127, "flat"), (127, "fused")])

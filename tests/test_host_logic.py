@@ -19,8 +19,9 @@ def test_pack_data_masks_and_observed_coi():
 def test_pack_data_rejects_single_allele_locus_and_wide_locus():
     with pytest.raises(ValueError, match="less than 2 alleles"):
         pack_data([np.ones((3, 1))])
-    with pytest.raises(ValueError, match="64"):
-        pack_data([np.ones((3, 65))])
+    assert pack_data([np.ones((3, 65))]).mask_words == 2      # past one mask word: the two-word build
+    with pytest.raises(ValueError, match="128"):
+        pack_data([np.ones((3, 129))])
     with pytest.raises(ValueError, match="is_missing"):
         pack_data([np.ones((3, 2))], np.zeros((3, 1), bool))
 
