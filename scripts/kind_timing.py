@@ -17,8 +17,12 @@ ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--chains", type=int, default=None)
 ap.add_argument("--pipeline", default="auto")
+ap.add_argument("--mask-words", type=int, default=None,
+                help="2: run the data on the two-word build (libmoire_b200_w128.so), zero-padded masks")
 a = ap.parse_args()
 wl = make_workload(a.config)
+if a.mask_words:
+    wl["packed"] = wl["packed"].widened(a.mask_words)
 temps = wl["temps"] if a.chains is None else wl["temps"][:a.chains]
 eng = Engine(wl["packed"], temps, seed=1, pipeline=a.pipeline, **wl["model"])
 t0 = time.time()
@@ -37,7 +41,7 @@ wall = time.time() - t0
 tm = eng.timing()
 ev1, _ = eng.counters()
 tot = sum(v[0] for v in tm.values())
-print(json.dumps(dict(config=a.config, pipeline=a.pipeline, chains=len(temps), steps=a.steps, wall_ms_per_step=1e3 * wall / a.steps,
+print(json.dumps(dict(config=a.config, mask_words=wl["packed"].mask_words, pipeline=a.pipeline, chains=len(temps), steps=a.steps, wall_ms_per_step=1e3 * wall / a.steps,
                       device_ms_per_step=tot / a.steps, evals_per_step=(ev1 - ev0) / a.steps,
                       kinds={k: round(v[0] / a.steps, 4) for k, v in tm.items()})))
 llik, prior = eng.scalars()

@@ -204,6 +204,13 @@ def test_argument_errors_are_reported_not_fatal():
         Engine(pk, [1.0], max_coi=128)
     with pytest.raises(MoireError, match="device_id"):
         Engine(pk, [1.0], device=99)
+    with pytest.raises(MoireError, match="one-word masks only"):      # the two-word build is flat-only
+        Engine(pk.widened(2), [1.0], pipeline="fused")
+    wide_bad = _mini(5, [70, 4])
+    wide_bad.obs_mask = wide_bad.obs_mask.copy()
+    wide_bad.obs_mask[0, 0, 1] = 1 << 20                              # allele 84 of a 70-allele locus
+    with pytest.raises(MoireError, match="bits above"):
+        Engine(wide_bad, [1.0])
     bad = _mini(5, [4, 4])
     bad.obs_mask = bad.obs_mask.copy()
     bad.obs_mask[0, 0] = 1 << 10
