@@ -456,6 +456,7 @@ struct moire_engine
                 const double *temps, int device_id, uint64_t seed)
     {
         if (!d || !prm || !temps) throw InvalidArg{"null argument"};
+        if (const char *env = std::getenv("MOIRE_B200_PDL")) pdl = std::atoi(env) != 0;
         const int N = d->num_samples, L = d->num_loci;
         if (N < 1 || L < 1 || T < 1) throw InvalidArg{"num_samples, num_loci, num_chains must be >= 1"};
         if (!d->num_alleles || !d->obs_mask || !d->is_missing) throw InvalidArg{"null data array"};
@@ -792,6 +793,26 @@ struct moire_engine
     size_t pf_eval_smem() const { return moire::pf_eval_smem_doubles(v.max_coi) * sizeof(double); }
     int flat_grid = 0;  // persistent evaluator grid: resident blocks of the device
 
+    // A kernel of the step chain: launched with the programmatic-stream-serialization attribute, so that
+    // it may become resident while the kernel in front of it finishes (every such kernel starts with
+    // pdl_enter(), state.cuh).  MOIRE_B200_PDL=0 launches them the ordinary way (A/B runs).
+    bool pdl = true;
+    template <class... P, class... A>
+    void launch_chain(void (*kernel)(P...), unsigned grid, unsigned block, size_t smem, A &&...args)
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(block);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, P(std::forward<A>(args))...));
+    }
+
     void launch_flat_eval(const moire::FlatSrc &src, bool cache = false)
     {
         cudaEvent_t a = nullptr, b = nullptr;
@@ -802,9 +823,9 @@ struct moire_engine
             CUDA_TRY(cudaEventRecord(a, stream));
         }
         if (cache)
-            moire::k_flat_eval<true><<<flat_grid, moire::kEvalThreads, pf_eval_smem(), stream>>>(v, src);
+            launch_chain(moire::k_flat_eval<true>, flat_grid, moire::kEvalThreads, pf_eval_smem(), v, src);
         else
-            moire::k_flat_eval<false><<<flat_grid, moire::kEvalThreads, pf_eval_smem(), stream>>>(v, src);
+            launch_chain(moire::k_flat_eval<false>, flat_grid, moire::kEvalThreads, pf_eval_smem(), v, src);
         if (timing)
         {
             CUDA_TRY(cudaEventRecord(b, stream));
@@ -821,9 +842,9 @@ struct moire_engine
         const unsigned cell_blocks = (unsigned)((total + 255) / 256);
         CUDA_TRY(cudaMemsetAsync(pf.hist, 0, kPfHistWords * sizeof(unsigned int), stream));
         const unsigned tile_blocks = (unsigned)v.T * pf_tiles(v.N, v.L);
-        k_pf_prepare<<<tile_blocks, 256, 0, stream>>>(v, pf);
-        k_pf_scan<<<1, 256, 0, stream>>>(pf);
-        k_pf_scatter<<<scatter_blocks(total), 256, 0, stream>>>(v, pf);
+        launch_chain(k_pf_prepare, tile_blocks, 256, 0, v, pf);
+        launch_chain(k_pf_scan, 1, 256, 0, pf);
+        launch_chain(k_pf_scatter, scatter_blocks(total), 256, 0, v, pf);
         FlatSrc src{};
         src.list = pf.list; src.bounds = pf.hist + kPfScalars;
         src.p = pf.pprop; src.p_stride = v.AP; src.out_locus_major = 1;
@@ -841,29 +862,29 @@ struct moire_engine
             const unsigned list_blocks = scatter_blocks(total);
             for (int rep = 0; rep < amax_alleles; ++rep)
             {
-                k_pf_round<<<(unsigned)(v.T * v.L), pf_round_threads, 0, stream>>>(v, pf, iteration, rep);
-                k_pc_sweep<<<cell_blocks, 256, 0, stream>>>(v, pf);
-                k_pf_scan<<<1, 256, 0, stream>>>(pf);
-                k_pc_scatter<<<list_blocks, 256, 0, stream>>>(v, pf);
+                launch_chain(k_pf_round, (unsigned)(v.T * v.L), pf_round_threads, 0, v, pf, iteration, rep);
+                launch_chain(k_pc_sweep, cell_blocks, 256, 0, v, pf);
+                launch_chain(k_pf_scan, 1, 256, 0, pf);
+                launch_chain(k_pc_scatter, list_blocks, 256, 0, v, pf);
                 src.counter = pf.hist + kPfCounters + 1 + rep;
                 launch_flat_eval(src, true);
                 launches += 5;
             }
-            k_pf_round<<<(unsigned)(v.T * v.L), pf_round_threads, 0, stream>>>(v, pf, iteration, amax_alleles);
-            k_pf_finish<<<tile_blocks, 256, 0, stream>>>(v, pf);
+            launch_chain(k_pf_round, (unsigned)(v.T * v.L), pf_round_threads, 0, v, pf, iteration, amax_alleles);
+            launch_chain(k_pf_finish, tile_blocks, 256, 0, v, pf);
             launches += 3;
             CUDA_TRY(cudaGetLastError());
             return;
         }
         for (int rep = 0; rep < amax_alleles; ++rep)
         {
-            k_pf_round<<<(unsigned)(v.T * v.L), pf_round_threads, 0, stream>>>(v, pf, iteration, rep);
+            launch_chain(k_pf_round, (unsigned)(v.T * v.L), pf_round_threads, 0, v, pf, iteration, rep);
             src.counter = pf.hist + kPfCounters + rep;
             launch_flat_eval(src);
             launches += 2;
         }
-        k_pf_round<<<(unsigned)(v.T * v.L), pf_round_threads, 0, stream>>>(v, pf, iteration, amax_alleles);
-        k_pf_finish<<<tile_blocks, 256, 0, stream>>>(v, pf);
+        launch_chain(k_pf_round, (unsigned)(v.T * v.L), pf_round_threads, 0, v, pf, iteration, amax_alleles);
+        launch_chain(k_pf_finish, tile_blocks, 256, 0, v, pf);
         launches += 2;
         CUDA_TRY(cudaGetLastError());
     }
@@ -877,17 +898,17 @@ struct moire_engine
         const size_t draw_spb = (size_t)sf_draw_units_per_block(v.nA, KIND != KIND_R);
         const unsigned draw_blocks = (unsigned)(((size_t)v.T * v.N + draw_spb - 1) / draw_spb);
         CUDA_TRY(cudaMemsetAsync(pf.hist, 0, kPfHistWords * sizeof(unsigned int), stream));
-        k_sf_draw<KIND><<<draw_blocks, kDrawThreads, 0, stream>>>(v, sf, iteration);
-        k_sf_cells<KIND><<<sf_cell_blocks(total), 256, 0, stream>>>(v, sf, pf, iteration);
-        k_pf_scan<<<1, 256, 0, stream>>>(pf);
-        k_sf_scatter<KIND><<<scatter_blocks(total), 256, 0, stream>>>(v, sf, pf);
+        launch_chain(k_sf_draw<KIND>, draw_blocks, kDrawThreads, 0, v, sf, iteration);
+        launch_chain(k_sf_cells<KIND>, sf_cell_blocks(total), 256, 0, v, sf, pf, iteration);
+        launch_chain(k_pf_scan, 1, 256, 0, pf);
+        launch_chain(k_sf_scatter<KIND>, scatter_blocks(total), 256, 0, v, sf, pf);
         FlatSrc src{};
         src.list = pf.list; src.bounds = pf.hist + kPfScalars; src.counter = pf.hist + kPfCounters;
         src.p = v.p; src.p_stride = v.AP; src.out_locus_major = 0;
         src.ss = sf.ss; src.binom_rows = v.max_coi;
         src.round_flags = nullptr; src.out = sf.Tn;
         launch_flat_eval(src);
-        k_sf_decide<KIND><<<(unsigned)(((size_t)v.T * v.N + 7) / 8), 256, 0, stream>>>(v, sf, iteration);
+        launch_chain(k_sf_decide<KIND>, (unsigned)(((size_t)v.T * v.N + 7) / 8), 256, 0, v, sf, iteration);
         launches += 5;  // draw, cells, scan, scatter, eval, decide (the caller counted one)
         CUDA_TRY(cudaGetLastError());
     }
@@ -901,8 +922,8 @@ struct moire_engine
             {
                 const size_t units = (size_t)v.T * v.N;
                 const size_t spb = (size_t)moire::sf_draw_units_per_block(v.nA, true);
-                moire::k_sf_draw<KIND><<<(unsigned)((units + spb - 1) / spb), moire::kDrawThreads, 0, stream>>>(v, sf, iteration);
-                moire::k_eps_cells<KIND><<<(unsigned)((units + 7) / 8), 256, 0, stream>>>(v, sf, iteration);
+                launch_chain(moire::k_sf_draw<KIND>, (unsigned)((units + spb - 1) / spb), moire::kDrawThreads, 0, v, sf, iteration);
+                launch_chain(moire::k_eps_cells<KIND>, (unsigned)((units + 7) / 8), 256, 0, v, sf, iteration);
                 launches += 1;  // two kernels; the caller counts one
                 return;
             }
@@ -952,7 +973,7 @@ struct moire_engine
             case MOIRE_UPDATE_MEAN_COI:
             {
                 Timed tm(this, kind);
-                k_update_mean_coi<<<v.T, kThreads, 0, stream>>>(v, iteration);
+                launch_chain(k_update_mean_coi, v.T, kThreads, 0, v, iteration);
                 tm.done();
                 break;
             }
@@ -963,7 +984,7 @@ struct moire_engine
     void reduce()
     {
         Timed tm(this, 8);
-        moire::k_reduce<<<v.T * moire::kReduceParts, 1024, 0, stream>>>(v, red_part.ptr, red_done.ptr);
+        launch_chain(moire::k_reduce, v.T * moire::kReduceParts, 1024, 0, v, red_part.ptr, red_done.ptr);
         tm.done();
     }
 

@@ -900,6 +900,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 512 ? 1 : MOIRE_MIN_BLOCKS_P *
 // ---- update_mean_coi: one block per chain (src/chain.cpp:809-856) ----------------------------
 __global__ void __launch_bounds__(kThreads) k_update_mean_coi(const View v, const int iteration_arg)
 {
+    pdl_enter();
     const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     __shared__ double s_lgam[128];
     __shared__ double s_red[40];
@@ -965,6 +966,7 @@ __global__ void __launch_bounds__(kThreads) k_update_mean_coi(const View v, cons
 constexpr int kReduceParts = 8;
 __global__ void __launch_bounds__(1024) k_reduce(const View v, double *part, unsigned int *done)
 {
+    pdl_enter();
     __shared__ double s_red[40];
     const int tid = threadIdx.x, t = blockIdx.x / kReduceParts, g = blockIdx.x % kReduceParts;
     const size_t ncell = (size_t)v.N * v.L;

@@ -179,6 +179,7 @@ __device__ __forceinline__ PfTile pf_tile_of_block(const View &v)
 
 __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
 {
+    pdl_enter();
     __shared__ unsigned int s_hist[kSortBins];
     __shared__ double s_T[32][33];
     __shared__ mask_t s_lat[32][33];
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(256) k_pf_prepare(const View v, const PFlat f)
 // left 30 us one-thread chains in a launch with 5 us of work (profiles/README.md, round 2).
 __global__ void __launch_bounds__(256) k_pf_scan(const PFlat f)
 {
+    pdl_enter();
     __shared__ unsigned int s_part[9];
     __shared__ float s_work[8], s_lw[9], s_cw[9], s_bestT[8];
     __shared__ int s_bestB[8];
@@ -437,6 +439,7 @@ __host__ __device__ inline unsigned scatter_blocks(size_t total)
 
 __global__ void __launch_bounds__(256) k_pf_scatter(const View v, const PFlat f)
 {
+    pdl_enter();
     const size_t total = (size_t)v.T * v.L * v.N;
     auto cell_fn = [&](size_t loc, int &cls, ListEntry &entry) -> bool {
         const mask_t lat = f.latLM[loc];  // locus-major copy of k_pf_prepare: coalesced
@@ -470,6 +473,7 @@ __device__ __forceinline__ double lane_slot(const double (&x)[kAPL], int slot)
 __global__ void __launch_bounds__(1024, 1) k_pf_round(const View v, const PFlat f, const int iteration_arg,
                                                     const int rep)
 {
+    pdl_enter();
     __shared__ double s_part[32];
     __shared__ int s_accept;
     const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
@@ -695,6 +699,7 @@ __device__ __forceinline__ double mixture_regs8(const double (&pam)[8], int m, i
 
 __global__ void __launch_bounds__(256) k_pc_sweep(const View v, const PFlat f)
 {
+    pdl_enter();
     __shared__ unsigned int s_hist[kSortBins];
     for (int b = threadIdx.x; b < kSortBins; b += blockDim.x) s_hist[b] = 0;
     __syncthreads();
@@ -784,6 +789,7 @@ __global__ void __launch_bounds__(256) k_pc_sweep(const View v, const PFlat f)
 
 __global__ void __launch_bounds__(256) k_pc_scatter(const View v, const PFlat f)
 {
+    pdl_enter();
     const size_t total = (size_t)v.T * v.L * v.N;
     auto cell_fn = [&](size_t loc, int &cls, ListEntry &entry) -> bool {
         const unsigned tl = (unsigned)(loc / v.N), i = (unsigned)(loc - (size_t)tl * v.N);
@@ -973,9 +979,18 @@ __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval
     double *s_scr = smem + 128;                                   // fixed offsets for the hot arrays
     double *s_binom = s_scr + scratch_doubles(kEvalThreads);
     const int tid = threadIdx.x, warp = tid >> 5;
+    // the tables staged here are constants of the engine (written once at creation), so the staging
+    // runs while the kernel in front of this one is still finishing (pdl_enter, state.cuh); everything
+    // below the wait may depend on it
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     for (int i = tid; i < 128; i += kEvalThreads) s_lgam[i] = v.lgam[i];
     for (int i = tid; i < f.binom_rows * kBinomCols; i += kEvalThreads)
         s_binom[i] = g_binom[(i / kBinomCols) * (kMaxCoi + 1) + (i % kBinomCols)];
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
     const bool allow_rel = v.allow_rel != 0;
     const bool locus_major = f.out_locus_major != 0;
     const int n_egf = (int)f.bounds[0], coop_end = (int)f.bounds[1], nwork = (int)f.bounds[2],
@@ -1070,6 +1085,7 @@ __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval
 // ---- once per update: the accepted terms back into the sample-major cache -----------------------
 __global__ void __launch_bounds__(256) k_pf_finish(const View v, const PFlat f)
 {
+    pdl_enter();
     __shared__ double s_T[32][33];
     __shared__ unsigned char s_in[32][33];
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;

@@ -45,6 +45,7 @@ __host__ __device__ inline int sf_draw_units_per_block(int nA, bool logs)
 template <int KIND>
 __global__ void __launch_bounds__(kDrawThreads) k_sf_draw(const View v, const SFlat sf, const int iteration_arg)
 {
+    pdl_enter();
     const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     constexpr bool LOGS = KIND != KIND_R;  // the kinds that recompute observation terms
     __shared__ double s_en[kDrawThreads], s_ep[kDrawThreads];
@@ -91,6 +92,7 @@ __host__ __device__ inline unsigned sf_cell_blocks(size_t total)
 template <int KIND>
 __global__ void __launch_bounds__(256, 4) k_sf_cells(const View v, const SFlat sf, const PFlat pf, const int iteration_arg)
 {
+    pdl_enter();
     const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
     __shared__ unsigned int s_hist[kSortBins];
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(256, 4) k_sf_cells(const View v, const SFlat s
 template <int KIND>
 __global__ void __launch_bounds__(256) k_sf_scatter(const View v, const SFlat sf, const PFlat pf)
 {
+    pdl_enter();
     constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
     const size_t total = (size_t)v.T * v.N * v.L;
     auto cell_fn = [&](size_t gi, int &cls, ListEntry &entry) -> bool {
@@ -166,6 +169,7 @@ __global__ void __launch_bounds__(256) k_sf_scatter(const View v, const SFlat sf
 template <int KIND>
 __global__ void __launch_bounds__(256) k_sf_decide(const View v, const SFlat sf, const int iteration_arg)
 {
+    pdl_enter();
     const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     constexpr bool RESAMPLE = (KIND == KIND_M || KIND == KIND_EFF_COI || KIND == KIND_SAMPLES);
     const int lane = threadIdx.x & 31;
@@ -239,6 +243,7 @@ __global__ void __launch_bounds__(256) k_sf_decide(const View v, const SFlat sf,
 template <int KIND>
 __global__ void __launch_bounds__(256) k_eps_cells(const View v, const SFlat sf, const int iteration_arg)
 {
+    pdl_enter();
     const int iteration = iteration_arg >= 0 ? iteration_arg : *v.iter;
     static_assert(KIND == KIND_EPS_NEG || KIND == KIND_EPS_POS, "error-rate updates only");
     const int lane = threadIdx.x & 31;

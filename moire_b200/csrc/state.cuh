@@ -15,6 +15,22 @@
 
 namespace moire
 {
+// Programmatic dependent launch (sm_90+): the kernels of a step form one chain on one stream, each a
+// few tens of microseconds at most, so the launch gap between two of them is a visible share of a
+// step on small shards (a ladder cut over 8 GPUs, Namibia-sized data).  Launched with the
+// programmatic-stream-serialization attribute (engine.cu: launch_chain) a kernel may become resident
+// while its predecessor is still running; pdl_enter() lets ITS successor do the same and then waits
+// until every predecessor has completed and flushed its memory -- nothing written by an earlier
+// kernel is read, and nothing an earlier kernel reads is written, before it.  Both instructions are
+// no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_enter()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 // kernels take the iteration by value, or read it from View::iter when handed this
 constexpr int kIterFromDevice = -1;
 
