@@ -150,7 +150,8 @@ int moire_mcmc_get_ladder(moire_mcmc *h, int32_t *swap_store, int64_t *swap_acce
 int moire_mcmc_get_hot(moire_mcmc *h, int32_t *hot);
 /* The draws stored on this rank, draw-major: draw_step [D] (sampling step of each draw),
  * allele_freqs [D][L][a_pad], coi [D][N], eps_neg/eps_pos/relatedness/data_llik [D][N],
- * lam_coi [D], latent [D][N][L] (only with record_latent_genotypes).  NULL = skip. */
+ * lam_coi [D], latent [D][N][L][W] mask words, W = moire_engine_mask_words() (only with
+ * record_latent_genotypes).  NULL = skip. */
 int moire_mcmc_get_draws(moire_mcmc *h, int32_t *draw_step, double *allele_freqs, int32_t *coi,
                          double *eps_neg, double *eps_pos, double *relatedness,
                          double *data_llik, double *lam_coi, uint64_t *latent);
