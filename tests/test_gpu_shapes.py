@@ -178,6 +178,45 @@ def test_run_mcmc_on_a_locus_with_more_than_64_alleles():
     assert np.all(np.isfinite(np.asarray(ch["data_llik"])))
 
 
+def test_salt_treats_alleles_past_the_first_mask_word_like_the_others():
+    """update_p on 100-allele loci with every cell missing: the likelihood is constant, so SALT
+    (src/chain.cpp:438-565) random-walks p under a law that is exchangeable in the alleles (the index
+    of a proposal is uniform, the update is symmetric in the others).  The two-word build keeps four
+    alleles per lane in the proposal (p_flat.cuh: kAPL); the alleles 64..99 must be proposed, accepted
+    and adapted like the alleles 0..63, hold the same mass and move as much."""
+    from moire_b200.engine import Engine
+    A, steps = 100, 160
+    pk = _mini(6, [A] * 8, missingness=1.0)
+    eng = Engine(pk, [1.0], seed=5, burnin=steps, max_coi=10)
+    assert eng.W == 2 and not eng.init_chains()["still_ill"].any()
+    trace = []
+    for it in range(steps):
+        eng.update(2, it)                     # KIND_P
+        if it >= 40:
+            trace.append(eng.dump_state(0)["p"][:, :A].copy())
+    trace = np.asarray(trace)                 # [step][locus][allele]
+    assert np.allclose(trace.sum(axis=2), 1.0, atol=1e-9) and (trace > 0).all()
+    d = eng.diagnostics(0)
+    att, acc, var = d["p_attempt"][:, :A], d["p_accept"][:, :A], d["p_prop_var"][:, :A]
+    lo, hi = slice(0, 64), slice(64, A)
+    # a locus proposes until every allele had its turn or a frequency would leave [1e-12, 1] (:503-518)
+    # (with nothing observed the frequencies wander down to that floor, so most sweeps end early)
+    assert (att.sum(axis=1) <= A * steps).all() and (att.sum(axis=1) > 10 * steps).all()
+    assert 0.9 < att[:, hi].mean() / att[:, lo].mean() < 1.1            # the index is uniform
+    per_allele = att.sum(axis=0)                                         # over the 8 loci: ~240 each
+    assert per_allele[hi].min() > 0.7 * per_allele[lo].mean() and per_allele[lo].min() > 0.7 * per_allele[hi].mean()
+    rate = acc.sum(axis=0) / att.sum(axis=0)                             # per allele, over the loci
+    assert abs(rate[hi].mean() - rate[lo].mean()) < 0.03 and rate[hi].min() > 0.05
+    assert (var[att > 16] != 1.0).all() and (att > 16).mean() > 0.9     # the scales have adapted (:555-562)
+    assert 0.8 < np.median(var[:, hi]) / np.median(var[:, lo]) < 1.25
+    # exchangeable: the two groups hold the same mass per allele and move as much
+    mean = trace.mean(axis=(0, 1))
+    assert abs(mean[hi].mean() / mean[lo].mean() - 1.0) < 0.2
+    move = np.abs(np.diff(np.log(trace), axis=0)).mean(axis=(0, 1))     # mean |step| of log p, per allele
+    assert 0.8 < move[hi].mean() / move[lo].mean() < 1.25
+    eng.close()
+
+
 @pytest.mark.parametrize("max_coi,pipeline", [(64, "fused"), (100, "flat"), (127, "flat"), (127, "fused")])
 def test_high_coi_limits(oracle, max_coi, pipeline):
     """max_coi up to the reference's own bound (127, its lgamma table, src/sampler.cpp:22-25): the
