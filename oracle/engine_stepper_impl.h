@@ -90,7 +90,27 @@ static int stp_coi_delta(stp_stream *s, double log_1mp)
     return sign * (int)floor(log(u) / log_1mp);
 }
 
-static uint64_t stp_choose_bits(stp_stream *s, uint64_t set, int n, int need)
+/* Allele sets: the stepper computes on 128-bit sets whatever the engine's build; the arrays it shares
+ * with the test are W 64-bit words per set (W = 1: libmoire_b200.so, W = 2: libmoire_b200_w128.so,
+ * word 0 = alleles 0..63). */
+typedef unsigned __int128 stp_mask;
+static int stp_popc(stp_mask x)
+{
+    return __builtin_popcountll((unsigned long long)x) + __builtin_popcountll((unsigned long long)(x >> 64));
+}
+static stp_mask stp_load(const uint64_t *a, size_t cell, int W)
+{
+    stp_mask m = a[cell * (size_t)W];
+    if (W > 1) m |= (stp_mask)a[cell * (size_t)W + 1] << 64;
+    return m;
+}
+static void stp_store(uint64_t *a, size_t cell, int W, stp_mask m)
+{
+    a[cell * (size_t)W] = (uint64_t)m;
+    if (W > 1) a[cell * (size_t)W + 1] = (uint64_t)(m >> 64);
+}
+
+static stp_mask stp_choose_bits(stp_stream *s, stp_mask set, int n, int need)
 {
     if (need <= 0) return 0;
     if (need >= n) return set;
@@ -98,12 +118,12 @@ static uint64_t stp_choose_bits(stp_stream *s, uint64_t set, int n, int need)
     {
         /* keep one / drop one: one uniform picks the allele (the engine's choose_bits) */
         const int idx = (int)(stp_uniform(s) * (double)n);
-        uint64_t r = set;
+        stp_mask r = set;
         for (int i = 0; i < idx; ++i) r &= r - 1;
-        const uint64_t bit = r & (0ull - r);
+        const stp_mask bit = r & ((stp_mask)0 - r);
         return need == 1 ? bit : set ^ bit;
     }
-    uint64_t out = 0;
+    stp_mask out = 0;
     int remaining = n;
     while (need > 0)
     {
@@ -112,7 +132,7 @@ static uint64_t stp_choose_bits(stp_stream *s, uint64_t set, int n, int need)
             out |= set;
             break;
         }
-        const uint64_t low = set & (0ull - set);
+        const stp_mask low = set & ((stp_mask)0 - set);
         set ^= low;
         const double u = stp_uniform(s);
         if (u * (double)remaining < (double)need)
@@ -154,11 +174,11 @@ static int stp_binom_inverse(double u, int n, double q, double odds)
 }
 
 /* Sampler::sample_latent_genotype (src/sampler.cpp:230-340) on masks */
-static uint64_t stp_sample_latent(stp_stream *s, uint64_t obs, int A, int coi, double eps_pos,
+static stp_mask stp_sample_latent(stp_stream *s, stp_mask obs, int A, int coi, double eps_pos,
                                   double eps_neg, double *log_prob)
 {
-    const uint64_t all = A >= 64 ? ~0ull : ((1ull << A) - 1ull);
-    const int obs_pos = __builtin_popcountll(obs);
+    const stp_mask all = A >= 128 ? ~(stp_mask)0 : (((stp_mask)1 << A) - 1);
+    const int obs_pos = stp_popc(obs);
     const int obs_neg = A - obs_pos;
     const int min_fn = obs_pos == 0;
     int max_fn = coi < obs_neg ? coi : obs_neg;
@@ -178,8 +198,8 @@ static uint64_t stp_sample_latent(stp_stream *s, uint64_t obs, int A, int coi, d
         return 0;
     }
     const int fp = min_fp + stp_binom_inverse(u_fp, max_fp - min_fp, q_ep, pr_ep / q_ep);
-    const uint64_t pos = stp_choose_bits(s, obs, obs_pos, obs_pos - fp);
-    const uint64_t neg = stp_choose_bits(s, ~obs & all, obs_neg, fn);
+    const stp_mask pos = stp_choose_bits(s, obs, obs_pos, obs_pos - fp);
+    const stp_mask neg = stp_choose_bits(s, ~obs & all, obs_neg, fn);
     *log_prob = latent_log_prob_f64(A, obs_pos, fn, fp, coi, eps_pos, eps_neg);
     return pos | neg;
 }
@@ -205,7 +225,7 @@ void orc_stp_sample_latent_many(uint64_t seed, int n, uint64_t obs, int A, int c
     {
         stp_stream s;
         stp_open(&s, seed, (uint32_t)i, 6u, 0u, (uint32_t)i >> 8, 1u);
-        masks[i] = stp_sample_latent(&s, obs, A, coi, eps_pos, eps_neg, &log_prob[i]);
+        masks[i] = (uint64_t)stp_sample_latent(&s, obs, A, coi, eps_pos, eps_neg, &log_prob[i]);
     }
 }
 
@@ -214,7 +234,7 @@ typedef struct
     /* shapes, data, model */
     int N, L, a_pad;
     const int *num_alleles;
-    const uint64_t *obs;       /* [N][L] */
+    const uint64_t *obs;       /* [N][L][W] */
     const uint8_t *is_missing; /* [N][L] */
     int allow_relatedness, burnin, max_coi;
     double mean_coi_shape, mean_coi_scale;
@@ -228,7 +248,7 @@ typedef struct
     int *m;
     double *r, *eps_pos, *eps_neg; /* [N] */
     double *p;                     /* [L][a_pad] */
-    uint64_t *latent;              /* [N][L] */
+    uint64_t *latent;              /* [N][L][W] */
     double *lg_adj, *cell_t, *cell_o;
     double *prior_eps_neg, *prior_eps_pos, *prior_coi, *prior_r; /* [N] */
     double *mean_coi, *hyper;                                    /* [1] */
@@ -239,7 +259,9 @@ typedef struct
     int *p_acc, *p_att;  /* [L][a_pad] */
     double *mean_coi_sd, *mean_coi_acc; /* [1] */
     unsigned long long evals;           /* out: non-missing cells evaluated */
+    int W;                              /* 64-bit words per allele set (0 reads as 1) */
 } stp_chain;
+static int stp_words(const stp_chain *c) { return c->W > 1 ? c->W : 1; }
 
 static double stp_adapt(double sd, double accepts, double denom, double root_arg, double floor_)
 {
@@ -249,11 +271,11 @@ static double stp_adapt(double sd, double accepts, double denom, double root_arg
     return nv > floor_ ? nv : floor_;
 }
 
-static void stp_cell(const stp_chain *c, int i, int j, uint64_t latent, int m, double r,
+static void stp_cell(const stp_chain *c, int i, int j, stp_mask latent, int m, double r,
                      double eps_neg, double eps_pos, double *t, double *o)
 {
     const size_t cell = (size_t)i * c->L + j;
-    cell_llik_f64(latent, c->obs[cell], c->num_alleles[j], 0, c->p + (size_t)j * c->a_pad, m, r,
+    cell_llik_f64(latent, stp_load(c->obs, cell, stp_words(c)), c->num_alleles[j], 0, c->p + (size_t)j * c->a_pad, m, r,
                   eps_neg, eps_pos, c->allow_relatedness, c->max_eps_neg, c->max_eps_pos, t, o);
 }
 
@@ -279,7 +301,8 @@ static void stp_update_sample_kind(stp_chain *c, int kind, int iteration)
     const int need_o = resample || kind == STP_EPS_NEG || kind == STP_EPS_POS;
     const double min_sampled = DBL_MIN;
     const double log_geom = -0.40546510810816438; /* log(1 - 1/(1+2)) */
-    uint64_t *nlat = (uint64_t *)malloc(sizeof(uint64_t) * L);
+    stp_mask *nlat = (stp_mask *)malloc(sizeof(stp_mask) * L);
+    const int W = stp_words(c);
     double *nt = (double *)malloc(sizeof(double) * L);
     double *no = (double *)malloc(sizeof(double) * L);
     double *nadj = (double *)malloc(sizeof(double) * L);
@@ -365,14 +388,14 @@ static void stp_update_sample_kind(stp_chain *c, int kind, int iteration)
             for (int j = 0; j < L; ++j)
             {
                 const size_t cell = (size_t)i * L + j;
-                uint64_t lat = c->latent[cell];
+                stp_mask lat = stp_load(c->latent, cell, W);
                 if (resample)
                 {
                     stp_stream crng;
                     stp_open(&crng, c->seed, (uint32_t)iteration, (uint32_t)kind,
                              (uint32_t)c->chain, (uint32_t)i, (uint32_t)(j + 1));
                     double lp;
-                    lat = stp_sample_latent(&crng, c->obs[cell], c->num_alleles[j], m_new, ep_new,
+                    lat = stp_sample_latent(&crng, stp_load(c->obs, cell, W), c->num_alleles[j], m_new, ep_new,
                                             en_new, &lp);
                     nlat[j] = lat;
                     nadj[j] = lp;
@@ -426,7 +449,7 @@ static void stp_update_sample_kind(stp_chain *c, int kind, int iteration)
                 const size_t cell = (size_t)i * L + j;
                 if (resample)
                 {
-                    c->latent[cell] = nlat[j];
+                    stp_store(c->latent, cell, W, nlat[j]);
                     c->lg_adj[cell] = nadj[j];
                 }
                 if (!c->is_missing[cell])
@@ -500,7 +523,7 @@ static void stp_update_p(stp_chain *c, int iteration)
                 if (!c->is_missing[cell])
                 {
                     double t, o;
-                    stp_cell(c, i, j, c->latent[cell], c->m[i], c->r[i], c->eps_neg[i],
+                    stp_cell(c, i, j, stp_load(c->latent, cell, stp_words(c)), c->m[i], c->r[i], c->eps_neg[i],
                              c->eps_pos[i], &t, &o);
                     tn[i] = t;
                     d += t - c->cell_t[cell];

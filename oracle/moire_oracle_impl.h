@@ -428,7 +428,7 @@ static REAL F(dgamma_log)(REAL x_, REAL shape_, REAL scale_)
 }
 
 /* ---- a1: Chain::calculate_genotype_likelihood (src/chain.cpp:1114-1134) on bit masks -------- */
-static REAL F(cell_llik)(uint64_t latent, uint64_t obs, int A, int is_missing, const REAL *p,
+static REAL F(cell_llik)(unsigned __int128 latent, unsigned __int128 obs, int A, int is_missing, const REAL *p,
                          int coi, REAL relatedness, REAL eps_neg, REAL eps_pos,
                          int allow_relatedness, REAL max_eps_neg, REAL max_eps_pos,
                          REAL *t_out, REAL *o_out)
@@ -443,8 +443,8 @@ static REAL F(cell_llik)(uint64_t latent, uint64_t obs, int A, int is_missing, c
     int k = 0;
     for (int a = 0; a < A; ++a)
     {
-        if (latent >> a & 1ULL) idx[k++] = a;
-        ov[a] = (int)(obs >> a & 1ULL);
+        if ((unsigned)(latent >> a) & 1u) idx[k++] = a;
+        ov[a] = (int)((unsigned)(obs >> a) & 1u);
     }
     const REAL t = F(transmission)(idx, k, p, coi, relatedness, allow_relatedness);
     const REAL o = F(observation)(idx, k, ov, A, eps_neg, eps_pos, max_eps_neg, max_eps_pos);

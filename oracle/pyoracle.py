@@ -584,7 +584,7 @@ class _StpChain(C.Structure):
                                            "acc_eps_neg", "acc_eps_pos", "acc_m", "acc_r",
                                            "acc_mr", "acc_samples", "p_sd", "p_acc", "p_att",
                                            "mean_coi_sd", "mean_coi_acc")] +
-                [("evals", C.c_ulonglong)])
+                [("evals", C.c_ulonglong), ("W", C.c_int)])
 
 
 STATE_FIELDS = ("m", "r", "eps_pos", "eps_neg", "p", "latent", "lg_adj", "cell_t", "cell_o",
@@ -648,6 +648,8 @@ class Stepper:
         for k, v in a.items():
             setattr(s, k, v.ctypes.data)
         s.evals = 0
+        s.W = 1 if a["obs"].ndim == 2 else int(a["obs"].shape[2])   # 64-bit words per allele set
+        assert a["latent"].shape == a["obs"].shape, (a["latent"].shape, a["obs"].shape)
 
     def update(self, kind, iteration):
         k = UPDATE_KINDS[kind] if isinstance(kind, str) else int(kind)

@@ -190,13 +190,15 @@ def oracle_recheck(oracle, eng, pk, chain, allow, where):
     assert rel_err(st["cell_t"], t) < RTOL and rel_err(st["cell_o"], o) < RTOL, where
 
 
-def compare_with_stepper(eng, stp, chain, where):
+def compare_with_stepper(eng, stp, chain, where, cell_t_tol=CELL_T_TOL):
     st, dg = eng.dump_state(chain), eng.diagnostics(chain)
     a = stp.a
     assert np.array_equal(st["m"], a["m"]), where
     assert np.array_equal(st["latent"], a["latent"]), where   # bit-exact index work
     for k in STATE_KEYS:
-        assert rel_err(st[k], a[k]) < (CELL_T_TOL if k == "cell_t" else RTOL), (where, k)
+        if k == "cell_t" and cell_t_tol is None:
+            continue
+        assert rel_err(st[k], a[k]) < (cell_t_tol if k == "cell_t" else RTOL), (where, k)
     assert abs(st["mean_coi"] - a["mean_coi"][0]) < RTOL * max(1, abs(st["mean_coi"])), where
     for k, sk in DIAG_MAP.items():
         if dg[k].dtype.kind == "i":
@@ -222,21 +224,44 @@ def test_metropolis_updates_match_stepper(oracle, allow, pipeline):
     iteration 15, where proposal-scale adaptation is live), against the CPU stepper that
     restates src/chain.cpp:165-856 with the engine's stream addressing: accepted proposals,
     latent genotypes, counters bit-exact; floating state to 1e-9."""
+    _updates_match_stepper(oracle, allow, pipeline,
+                           [np.ones(5)] * 4 + [np.ones(13)] * 5 + [np.ones(2)] * 2)
+
+
+@pytest.mark.parametrize("allow", [1, 0])
+def test_metropolis_updates_match_stepper_on_loci_past_64_alleles(oracle, allow):
+    """The same, on the two-word build of the engine (libmoire_b200_w128.so): loci with 100, 128 and
+    70 alleles next to small ones -- the latent-genotype proposal choosing among alleles of both mask
+    words, SALT moving alleles 64..127, observation counts over two words, all bit for bit against
+    the stepper (which computes on 128-bit sets).  With a hundred alleles of frequency ~0.01 a
+    cell's coverage probability is tiny and its inclusion-exclusion sum badly conditioned (a cell
+    with six such alleles sits at the last bits of 1 - P(any missing): first seen here as a 2 %
+    difference between terms reached through different last bits of p; on the prior chain, whose
+    frequencies wander down to 1e-12, there is nothing left to compare).  So the COI is kept below 8
+    and the terms reached through DIFFERENT last bits of p are not compared here (see CELL_T_TOL);
+    on identical inputs (oracle_recheck, after every sweep) they hold 1e-9 here too.  Everything else
+    -- every accept decision, genotype, COI, counter, and p, eps, r, priors to 1e-9 -- is."""
+    _updates_match_stepper(oracle, allow, "flat",
+                           [np.ones(5)] * 2 + [np.ones(100)] * 2 + [np.ones(128)] + [np.ones(70)] + [np.ones(2)],
+                           cell_t_tol=None, mean_coi=2, max_coi=7)
+
+
+def _updates_match_stepper(oracle, allow, pipeline, alphas, cell_t_tol=CELL_T_TOL, mean_coi=4, max_coi=25):
     from moire_b200.data import pack_data
     from moire_b200.engine import DEFAULT_MODEL
     from moire_b200.simulate import simulate_data
     from oracle.pyoracle import Stepper
-    d = simulate_data(mean_coi=4, num_samples=37, epsilon_pos=.03, epsilon_neg=.1,
-                      locus_freq_alphas=[np.ones(5)] * 4 + [np.ones(13)] * 5 + [np.ones(2)] * 2,
+    d = simulate_data(mean_coi=mean_coi, num_samples=37, epsilon_pos=.03, epsilon_neg=.1,
+                      locus_freq_alphas=alphas,
                       internal_relatedness_alpha=.3, internal_relatedness_beta=1,
                       missingness=.06, seed=23)
     pk = pack_data(d["data"], d["is_missing"])
     temps = (1.0, 0.37, 0.0)
     seed = 77
-    eng, _ = engine_for(pk, temps=temps, allow=allow, seed=seed, burnin=30, max_coi=25,
+    eng, _ = engine_for(pk, temps=temps, allow=allow, seed=seed, burnin=30, max_coi=max_coi,
                         pipeline=pipeline)
     assert not eng.init_chains()["still_ill"].any()
-    model = dict(DEFAULT_MODEL, allow_relatedness=bool(allow), burnin=30, max_coi=25)
+    model = dict(DEFAULT_MODEL, allow_relatedness=bool(allow), burnin=30, max_coi=max_coi)
     steppers = [Stepper(oracle, pk, model, seed, c, temps[c], eng.dump_state(c),
                         eng.diagnostics(c)) for c in range(3)]
     kinds = ["eps_neg", "eps_pos", "p", "m"] + (["r", "eff_coi"] if allow else []) + \
@@ -247,7 +272,7 @@ def test_metropolis_updates_match_stepper(oracle, allow, pipeline):
             eng.update(kind, it)
             for c, stp in enumerate(steppers):
                 stp.update(kind, it)
-                compare_with_stepper(eng, stp, c, (it, kind, c))
+                compare_with_stepper(eng, stp, c, (it, kind, c), cell_t_tol)
         for c in range(3):
             oracle_recheck(oracle, eng, pk, c, allow, (it, c))
     eng.reduce()
