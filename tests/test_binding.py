@@ -34,11 +34,14 @@ DEFAULTS = dict(verbose=0, simple_verbose=0, use_message=0, allow_relatedness=1,
                 max_eps_neg=2, eps_neg_alpha=1, eps_neg_beta=1, r_alpha=1, r_beta=1)
 
 
+LIB_W128 = os.path.join(ROOT, "oracle", "_ref", "libmoire_binding_w128.so")   # linked to libmoire_b200_w128.so
+
+
 class Binding:
-    def __init__(self):
-        if not os.path.exists(LIB):
-            pytest.skip("oracle/_ref/libmoire_binding.so not built (needs /root/reference: make -C oracle binding)")
-        self.lib = C.CDLL(LIB)
+    def __init__(self, lib=LIB):
+        if not os.path.exists(lib):
+            pytest.skip(f"{lib} not built (needs /root/reference: make -C oracle binding)")
+        self.lib = C.CDLL(lib)
         self.lib.binding_error.restype = C.c_char_p
         self.lib.binding_result_names.restype = C.c_char_p
         self.lib.binding_node_names.restype = C.c_char_p
@@ -149,3 +152,48 @@ def test_binding_matches_python_run_mcmc_on_the_gpu(monkeypatch):
     assert np.array_equal(b.node(idx["acceptance_rates"], 1, 1)[2], ch["acceptance_rates"][1]["coi_accept"])
     assert np.array_equal(b.node(idx["sampling_variances"], 2, 0, 3)[2],
                           ch["sampling_variances"][2]["allele_freq_var"][3])
+
+
+@pytest.mark.gpu
+def test_binding_linked_to_the_two_word_library_runs_loci_past_64_alleles(monkeypatch):
+    """The same compiled binding linked to libmoire_b200_w128.so (it reads the mask width from the
+    library): a 100-allele locus goes through GenotypingData -> two-word masks -> the engine and comes
+    back as the reference's result list, equal to what run_mcmc returns for the seed; linked to the
+    one-word library the same call stops with a message instead."""
+    from moire_b200.mcmc import run_mcmc
+    from moire_b200.simulate import simulate_data
+    monkeypatch.setenv("MOIRE_B200_DEVICE", "0")
+    monkeypatch.setenv("MOIRE_B200_SEED", "4")
+    sim = simulate_data(mean_coi=3, num_samples=15, epsilon_pos=.02, epsilon_neg=.1,
+                        locus_freq_alphas=[np.ones(100), np.ones(6), np.ones(70)], missingness=.1, seed=2)
+    T = 3
+    b = Binding(LIB_W128)
+    names = b.run(sim, np.linspace(1, 0, T), burnin=30, samples=12, record_latent_genotypes=1)
+    assert names == FIELDS
+    idx = {n: i for i, n in enumerate(names)}
+    f32 = lambda x: float(np.float32(x))
+    ch = run_mcmc(sim, sim["is_missing"], burnin=30, samples_per_chain=12, pt_chains=np.linspace(1, 0, T),
+                  max_coi=20, pre_adapt_steps=5, temp_adapt_steps=4, max_initialization_tries=100,
+                  mean_coi_shape=f32(DEFAULTS["mean_coi_shape"]), mean_coi_scale=f32(DEFAULTS["mean_coi_scale"]),
+                  record_latent_genotypes=True, verbose=False, seed=4)["chains"][0]
+    for k in ("llik_burnin", "llik_sample", "lam_coi", "swap_store", "observed_coi"):
+        assert np.array_equal(b.node(idx[k])[2], np.asarray(ch[k], float)), k
+    D = len(ch["lam_coi"])
+    assert D > 0
+    for j, A in enumerate((100, 6, 70)):
+        t, n, v = b.node(idx["allele_freqs"], j, D - 1)
+        assert n == A and np.array_equal(v, ch["allele_freqs"][j][D - 1])
+        for i in (0, 9):
+            g = b.node(idx["latent_genotypes"], i, j, D - 1)[2]
+            assert np.array_equal(g, np.asarray(ch["latent_genotypes"][i][j][D - 1], float)) and (g < A).all()
+    assert any((b.node(idx["latent_genotypes"], i, 0, d)[2] >= 64).any() for i in range(15) for d in range(D))
+    narrow = Binding()
+    data = [np.asarray(m) for m in sim["data"]]
+    na = np.array([m.shape[1] for m in data], np.int32)
+    obs = np.ascontiguousarray(np.concatenate([m.astype(np.uint8).ravel() for m in data]))
+    mis = np.ascontiguousarray(np.asarray(sim["is_missing"], np.uint8))
+    sc = np.array([float(DEFAULTS[k]) for k in SCALARS])
+    pt = np.linspace(1, 0, T)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert narrow.lib.binding_run(3, 15, p(na), p(obs), p(mis), p(sc), p(pt), T) != 0
+    assert b"at most 64 alleles" in narrow.lib.binding_error()
