@@ -701,6 +701,8 @@ struct moire_engine
                 pf_round_threads = 32;
                 while (pf_round_threads < 1024 && (size_t)pf_round_threads * 2 <= want && pf_round_threads * 4 <= N)
                     pf_round_threads *= 2;
+                if (const char *env = std::getenv("MOIRE_B200_PF_ROUND_THREADS"))  // A/B runs
+                    pf_round_threads = std::max(32, std::min(1024, std::atoi(env) / 32 * 32));
             }
             // the per-sample updates share the list, the histogram and the two term arrays
             sf_prop.alloc(TN); sf_m.alloc(TN); sf_ss.alloc(TN); pf_ss.alloc(TN);
