@@ -870,6 +870,16 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int ST = kEvalThreads + 1;
     const unsigned N = (unsigned)v.N, L = (unsigned)v.L;
+#ifndef MOIRE_PF_STASH_OUT
+#define MOIRE_PF_STASH_OUT 1
+#endif
+#if MOIRE_PF_STASH_OUT
+    // Where a one-thread cell's term goes is parked in shared memory for the length of the evaluation:
+    // held in registers it was spilled to local memory around every chunk (the evaluators need all 64),
+    // and the reload at the end of a chunk found its line gone from L1 half the time -- an extra trip
+    // to L2 per chunk, and half of the kernel's L2 traffic (ncu, profiles/README.md).
+    __shared__ double *s_dst[kEvalThreads];
+#endif
     if (coop)
     {
         const int w = lo + unit;
@@ -926,6 +936,12 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
                 {
                     const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
                     const PamOut po{CACHE ? f.pam_out + ((size_t)tl * N + e.w) : nullptr, f.pam_stride};
+#if MOIRE_PF_STASH_OUT
+                    {
+                        double *const outp0 = (f.out_flip && ((unsigned)flagword & kPfFlip)) ? f.out_flip : f.out;
+                        s_dst[tid] = outp0 + (locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu));
+                    }
+#endif
                     double T;
                     switch (K)
                     {
@@ -936,8 +952,12 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
                         case 5: T = small_cell<5, CACHE>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom, po); break;
                         default: T = small_cell<6, CACHE>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom, po); break;
                     }
+#if MOIRE_PF_STASH_OUT
+                    *(*(double *volatile *)(s_dst + tid)) = T;
+#else
                     double *const outp = (f.out_flip && ((unsigned)flagword & kPfFlip)) ? f.out_flip : f.out;
                     outp[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] = T;
+#endif
                 }
                 __syncwarp();
                 return;
@@ -961,8 +981,14 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
         const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
         const PamOut po{CACHE ? f.pam_out + ((size_t)tl * N + e.w) : nullptr, f.pam_stride};
         double *const outp = (f.out_flip && ((unsigned)flagword & kPfFlip)) ? f.out_flip : f.out;
+#if MOIRE_PF_STASH_OUT == 1
+        s_dst[tid] = outp + (locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu));
+        const double T = transmission_ll<CACHE>(lat, prow, pv, sc.m, rel, allow_rel, s_scr + tid, ST, s_lgam, s_binom, callers, po);
+        *(*(double *volatile *)(s_dst + tid)) = T;
+#else
         outp[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] =
             transmission_ll<CACHE>(lat, prow, pv, sc.m, rel, allow_rel, s_scr + tid, ST, s_lgam, s_binom, callers, po);
+#endif
     }
     __syncwarp();
 }
