@@ -912,6 +912,18 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
     bool go = w < hi;
     ListEntry e = idle_entry();
     if (go) e = f.list[w];
+#ifndef MOIRE_PF_PREFETCH
+#define MOIRE_PF_PREFETCH 1
+#endif
+#if MOIRE_PF_PREFETCH
+    // the entries this block is likely to meet next (tasks are handed out in list order, a grid's worth
+    // of tasks ahead is about one round of claims away): pulled into L2 now, so that the load at the
+    // head of that chunk -- the longest single wait of a chunk -- does not go to DRAM
+    {
+        const size_t ahead = (size_t)w + (size_t)gridDim.x * (kEvalThreads * MOIRE_PF_PREFETCH);
+        if (ahead < (size_t)hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(f.list + ahead));
+    }
+#endif
     // -- class-uniform chunk of small cells: the register path (likelihood.cuh)
     {
         const unsigned in = __ballot_sync(0xffffffffu, go);
