@@ -506,11 +506,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-workloads", action="store_true",
                     help="N > 1: skip the c4 / c5 block timed after the main workload")
+    ap.add_argument("--temperatures", type=int, default=0,
+                    help="tuning runs: a shorter ladder of the workload's shape (what one GPU of a sharded "
+                         "ladder holds); the config line says so")
     args = ap.parse_args()
     if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
         return
-    from moire_b200.workloads import make_workload
+    from moire_b200.workloads import ladder, make_workload
     wl = make_workload(args.workload)
+    if args.temperatures > 0:
+        wl["temps"] = ladder(args.temperatures)
     if args.impl == "reference":
         reference_arm(args, wl)
     else:

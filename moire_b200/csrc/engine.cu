@@ -456,6 +456,12 @@ struct moire_engine
                 const double *temps, int device_id, uint64_t seed)
     {
         if (!d || !prm || !temps) throw InvalidArg{"null argument"};
+        // Programmatic dependent launch pays where the step is launch latency (the Namibia shape: -1.8 %)
+        // and costs where kernels are long and a round's (chain, locus) blocks number thousands: the
+        // blocks of the kernel behind become resident early and wait on the SMs the running kernel
+        // needs (full C3 ladder, 4000 blocks per round: +3.5 %; 2000: +1.2 %; <= 1000: nothing either
+        // way; profiles/r02z_pdl_by_shape.log).  MOIRE_B200_PDL=0 / 1 overrides.
+        pdl = (size_t)T * (size_t)d->num_loci <= 1024;
         if (const char *env = std::getenv("MOIRE_B200_PDL")) pdl = std::atoi(env) != 0;
         const int N = d->num_samples, L = d->num_loci;
         if (N < 1 || L < 1 || T < 1) throw InvalidArg{"num_samples, num_loci, num_chains must be >= 1"};
