@@ -504,6 +504,14 @@ struct moire_engine
             }
             if (d->observed_coi) coi_h[i] = d->observed_coi[i];
         }
+        {
+            // observed COI >= 8 in more than a tenth of the samples: a high-COI data set (c5: 56 %; the
+            // other named shapes: <= 6 %)
+            size_t high = 0;
+            for (int i = 0; i < N; ++i) high += coi_h[i] >= 8;
+            eval_stash = high * 10 <= (size_t)N;
+            if (const char *env = std::getenv("MOIRE_B200_EVAL_STASH")) eval_stash = std::atoi(env) != 0;
+        }
 
         int ndev = 0;
         cudaError_t e0 = cudaGetDeviceCount(&ndev);
@@ -744,11 +752,12 @@ struct moire_engine
             CUDA_TRY(cudaFuncSetAttribute(k_update_p<MOIRE_P_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
             CUDA_TRY(cudaFuncSetAttribute(k_update_p<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
         }
-        CUDA_TRY(cudaFuncSetAttribute(k_flat_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
-        CUDA_TRY(cudaFuncSetAttribute(k_flat_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
+        CUDA_TRY(cudaFuncSetAttribute(k_flat_eval<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
+        CUDA_TRY(cudaFuncSetAttribute(k_flat_eval<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
+        CUDA_TRY(cudaFuncSetAttribute(k_flat_eval<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_eval_smem()));
         {
             int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flat_eval<false>, kEvalThreads, pf_eval_smem()));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_flat_eval<false, true>, kEvalThreads, pf_eval_smem()));
             cudaDeviceProp prop1;
             CUDA_TRY(cudaGetDeviceProperties(&prop1, device));
             flat_grid = std::max(1, per_sm) * prop1.multiProcessorCount;
@@ -805,6 +814,9 @@ struct moire_engine
     // it may become resident while the kernel in front of it finishes (every such kernel starts with
     // pdl_enter(), state.cuh).  MOIRE_B200_PDL=0 launches them the ordinary way (A/B runs).
     bool pdl = true;
+    // which evaluator runs (p_flat.cuh: STASH): the one that parks a cell's output address in shared
+    // memory unless heavy cells (k >= 8 latent alleles: long single-thread walks) are common in the data
+    bool eval_stash = true;
     template <class... P, class... A>
     void launch_chain(void (*kernel)(P...), unsigned grid, unsigned block, size_t smem, A &&...args)
     {
@@ -831,9 +843,11 @@ struct moire_engine
             CUDA_TRY(cudaEventRecord(a, stream));
         }
         if (cache)
-            launch_chain(moire::k_flat_eval<true>, flat_grid, moire::kEvalThreads, pf_eval_smem(), v, src);
+            launch_chain(moire::k_flat_eval<true, false>, flat_grid, moire::kEvalThreads, pf_eval_smem(), v, src);
+        else if (eval_stash)
+            launch_chain(moire::k_flat_eval<false, true>, flat_grid, moire::kEvalThreads, pf_eval_smem(), v, src);
         else
-            launch_chain(moire::k_flat_eval<false>, flat_grid, moire::kEvalThreads, pf_eval_smem(), v, src);
+            launch_chain(moire::k_flat_eval<false, false>, flat_grid, moire::kEvalThreads, pf_eval_smem(), v, src);
         if (timing)
         {
             CUDA_TRY(cudaEventRecord(b, stream));

@@ -861,7 +861,7 @@ __host__ __device__ inline size_t pf_eval_smem_doubles(int binom_rows)
 // One unit of the list: a cooperative cell (all lanes of the warp on one cell) or a chunk of 32
 // one-thread cells starting at lo + 32 * unit.  CACHE: the evaluator also leaves every cell's PAM
 // vector in update_p's cache (likelihood.cuh: PamOut), at the cell's locus-major index.
-template <bool CACHE>
+template <bool CACHE, bool STASH>
 __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const int lo, const int hi,
                                           const bool coop, const bool egf, const int unit, double *s_scr,
                                           const double *s_lgam, const double *s_binom, const bool allow_rel,
@@ -870,16 +870,14 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int ST = kEvalThreads + 1;
     const unsigned N = (unsigned)v.N, L = (unsigned)v.L;
-#ifndef MOIRE_PF_STASH_OUT
-#define MOIRE_PF_STASH_OUT 1
-#endif
-#if MOIRE_PF_STASH_OUT
-    // Where a one-thread cell's term goes is parked in shared memory for the length of the evaluation:
-    // held in registers it was spilled to local memory around every chunk (the evaluators need all 64),
-    // and the reload at the end of a chunk found its line gone from L1 half the time -- an extra trip
-    // to L2 per chunk, and half of the kernel's L2 traffic (ncu, profiles/README.md).
-    __shared__ double *s_dst[kEvalThreads];
-#endif
+    // STASH: where a one-thread cell's term goes is parked in shared memory for the length of the
+    // evaluation.  Held in registers it was spilled to local memory around every chunk (the
+    // evaluators need all 64), and the reload at the end of a chunk found its line gone from L1 half
+    // the time -- an extra trip to L2 per chunk, and half of the kernel's L2 traffic (ncu,
+    // profiles/README.md): -3 % of a step at the benchmark shapes.  The register allocation it leaves
+    // is worse for the long single-thread walks of heavy cells (a high-COI shard of 2 chains: 20 -> 30
+    // ms per step), so the engine picks the variant from the data (engine.cu: eval_stash).
+    __shared__ double *s_dst[STASH ? kEvalThreads : 1];
     if (coop)
     {
         const int w = lo + unit;
@@ -948,12 +946,11 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
                 {
                     const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
                     const PamOut po{CACHE ? f.pam_out + ((size_t)tl * N + e.w) : nullptr, f.pam_stride};
-#if MOIRE_PF_STASH_OUT
+                    if constexpr (STASH)
                     {
                         double *const outp0 = (f.out_flip && ((unsigned)flagword & kPfFlip)) ? f.out_flip : f.out;
                         s_dst[tid] = outp0 + (locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu));
                     }
-#endif
                     double T;
                     switch (K)
                     {
@@ -964,12 +961,13 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
                         case 5: T = small_cell<5, CACHE>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom, po); break;
                         default: T = small_cell<6, CACHE>(e.x, prow, sc.m, cnt_hi, rel, s_scr + tid, ST, s_lgam, s_binom, po); break;
                     }
-#if MOIRE_PF_STASH_OUT
-                    *(*(double *volatile *)(s_dst + tid)) = T;
-#else
-                    double *const outp = (f.out_flip && ((unsigned)flagword & kPfFlip)) ? f.out_flip : f.out;
-                    outp[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] = T;
-#endif
+                    if constexpr (STASH)
+                        *(*(double *volatile *)(s_dst + tid)) = T;
+                    else
+                    {
+                        double *const outp = (f.out_flip && ((unsigned)flagword & kPfFlip)) ? f.out_flip : f.out;
+                        outp[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] = T;
+                    }
                 }
                 __syncwarp();
                 return;
@@ -993,14 +991,15 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
         const Rel rel{sc.log_r, sc.log_1mr, sc.odds};
         const PamOut po{CACHE ? f.pam_out + ((size_t)tl * N + e.w) : nullptr, f.pam_stride};
         double *const outp = (f.out_flip && ((unsigned)flagword & kPfFlip)) ? f.out_flip : f.out;
-#if MOIRE_PF_STASH_OUT == 1
-        s_dst[tid] = outp + (locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu));
-        const double T = transmission_ll<CACHE>(lat, prow, pv, sc.m, rel, allow_rel, s_scr + tid, ST, s_lgam, s_binom, callers, po);
-        *(*(double *volatile *)(s_dst + tid)) = T;
-#else
-        outp[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] =
-            transmission_ll<CACHE>(lat, prow, pv, sc.m, rel, allow_rel, s_scr + tid, ST, s_lgam, s_binom, callers, po);
-#endif
+        if constexpr (STASH)
+        {
+            s_dst[tid] = outp + (locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu));
+            const double T = transmission_ll<CACHE>(lat, prow, pv, sc.m, rel, allow_rel, s_scr + tid, ST, s_lgam, s_binom, callers, po);
+            *(*(double *volatile *)(s_dst + tid)) = T;
+        }
+        else
+            outp[locus_major ? (size_t)tl * N + e.w : (size_t)tn * L + (e.z & 0xffffu)] =
+                transmission_ll<CACHE>(lat, prow, pv, sc.m, rel, allow_rel, s_scr + tid, ST, s_lgam, s_binom, callers, po);
     }
     __syncwarp();
 }
@@ -1009,7 +1008,7 @@ __device__ __forceinline__ void flat_unit(const View &v, const FlatSrc &f, const
 // would outlast the launch on one thread: always one warp per cell; [coop_end, mid_end) heavy
 // classes: a warp per cell while they are rare, chunks of 32 when they hold a large share of all
 // cells (high-COI shapes); [mid_end, nwork) light cells in chunks.
-template <bool CACHE>
+template <bool CACHE, bool STASH>
 __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval(const View v, const FlatSrc f)
 {
     extern __shared__ double smem[];
@@ -1116,7 +1115,7 @@ __global__ void __launch_bounds__(kEvalThreads, MOIRE_PF_MIN_BLOCKS) k_flat_eval
         }
         const int upb = pf_units_per_task(light);
         for (int u = warp; u < upb; u += kEvalWarps)
-            flat_unit<CACHE>(v, f, lo, hi, coop, egf, b * upb + u, s_scr, s_lgam, s_binom, allow_rel, locus_major);
+            flat_unit<CACHE, STASH>(v, f, lo, hi, coop, egf, b * upb + u, s_scr, s_lgam, s_binom, allow_rel, locus_major);
     }
 }
 
